@@ -1,0 +1,146 @@
+// Per-source-point body of the ICP Gauss-Newton accumulation (kernel K3 of SURVEY.md §2.3):
+// transform -> exact k-NN in the voxel-hash map -> (plane fit) -> gates -> J, r -> H += J^T J, B += -J^T r.
+// Restates the loop bodies of IcpRegistration::CaculateMatrixHAndBP2P (icp_registration.cpp:62-92)
+// and ::CaculateMatrixHAndBP2Plane (icp_registration.cpp:166-202) for one point.
+#pragma once
+#include "la.cuh"
+#include "voxel_map.cuh"
+
+namespace locreg {
+
+enum Method : int { kIcpP2P = 0, kIcpP2Line = 1, kIcpP2Plane = 2, kNdtDirect = 3 };
+
+struct IcpParams {
+    double max_nn_distance;     // IcpOptions::max_nn_distance_ (compared against a SQUARED distance, quirk Q6)
+    double max_plane_distance;  // IcpOptions::max_plane_distance_
+    double plane_fit_eps;       // math::FitPlane's eps (1e-2, math_utils.h:113)
+    double eps;                 // IcpOptions::eps_
+    int max_iteration;
+    int min_effective_pts;
+};
+
+// gate codes written by the debug probe (same meaning as oracle_icp_compute_hb's gate[])
+enum Gate : unsigned char { kGateSkipped = 0, kGateFitFailed = 1, kGateResidual = 2, kGateInlier = 3 };
+
+// H += J^T J (upper triangle), B += -J^T r, for a 1x6 Jacobian row
+LR_HD void accum_rank1(Accum& a, const double (&J)[6], double r) {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = i; j < 6; ++j) a.v[k++] += J[i] * J[j];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a.v[21 + i] += -J[i] * r;
+}
+
+// Point-to-plane (icp_registration.cpp:166-202).  Returns the gate code; nn_out (5 ints, may be
+// nullptr) receives the neighbour indices in (dis2, index) order.
+LR_HD unsigned char icp_point_p2plane(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy,
+                                      float sz, Accum& acc, int* nn_out) {
+    if (nn_out) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) nn_out[j] = -1;
+    }
+    if (!finite3(sx, sy, sz)) return kGateSkipped;  // deviation D1: the reference would poison H with NaN
+    const double qx = sx, qy = sy, qz = sz;
+    double wx, wy, wz;
+    pose_apply(T, qx, qy, qz, wx, wy, wz);  // qs = predict_pose * q  (:169)
+    KnnResult<5> nn;
+    knn_query<5>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn);  // (:170)
+    if (nn_out) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) nn_out[j] = nn.idx[j] != 0x7fffffff ? nn.idx[j] : -1;
+    }
+    // a map with fewer than 5 leaves makes KdTree::GetClosestPoint refuse (kdtree.cpp:149): no neighbours
+    if (knn_count(nn) < 5) return kGateSkipped;
+    double P[5][3];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float4 p = map.pts[nn.pos[j]];
+        P[j][0] = p.x; P[j][1] = p.y; P[j][2] = p.z;
+    }
+    double n[4];
+    plane_svd5(P, n);  // math::FitPlane (:179)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const double err = n[0] * P[j][0] + n[1] * P[j][1] + n[2] * P[j][2] + n[3];
+        if (err * err > prm.plane_fit_eps) return kGateFitFailed;
+    }
+    acc.n_eff += 1u;  // quirk Q4: counted before the distance gate (:184)
+    const double dis = n[0] * wx + n[1] * wy + n[2] * wz + n[3];
+    if (fabs(dis) > prm.max_plane_distance) return kGateResidual;
+    // J = [ -n^T R hat(q) , n^T ]  (:193-195): with m = R^T n, -m^T hat(q) = (q x m)^T
+    const double mx = T.R[0] * n[0] + T.R[3] * n[1] + T.R[6] * n[2];
+    const double my = T.R[1] * n[0] + T.R[4] * n[1] + T.R[7] * n[2];
+    const double mz = T.R[2] * n[0] + T.R[5] * n[1] + T.R[8] * n[2];
+    const double J[6] = {qy * mz - qz * my, qz * mx - qx * mz, qx * my - qy * mx, n[0], n[1], n[2]};
+    accum_rank1(acc, J, dis);
+    acc.v[27] += dis * dis;
+    acc.n_inl += 1u;
+    return kGateInlier;
+}
+
+// Point-to-point (icp_registration.cpp:62-92).  J = [ R hat(q) / 16 , -I ]  (quirk Q6).
+LR_HD unsigned char icp_point_p2p(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy,
+                                  float sz, Accum& acc, int* nn_out) {
+    if (nn_out) nn_out[0] = -1;
+    if (!finite3(sx, sy, sz)) return kGateSkipped;  // pcl::isFinite (:64)
+    const double qx = sx, qy = sy, qz = sz;
+    double wx, wy, wz;
+    pose_apply(T, qx, qy, qz, wx, wy, wz);
+    KnnResult<1> nn;
+    knn_query<1>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn);
+    if (nn.idx[0] == 0x7fffffff) return kGateSkipped;
+    if (nn_out) nn_out[0] = nn.idx[0];
+    const float4 p = map.pts[nn.pos[0]];
+    const double e[3] = {static_cast<double>(p.x) - wx, static_cast<double>(p.y) - wy, static_cast<double>(p.z) - wz};
+    const double dis2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+    if (dis2 > prm.max_nn_distance) return kGateResidual;  // squared vs unsquared threshold (:75)
+    acc.n_eff += 1u;
+    acc.n_inl += 1u;
+    // rows of J: J_r = [ (R hat(q))_r / 16 , -e_r^T ];  (R hat(q))_r = R_r x q ... as a row: R_r^T hat(q) = (q x R_r)^T * -1
+    // hat(q) columns: R hat(q) (r, c) = sum_k R[r][k] hat(q)[k][c]
+    const double hq[3][3] = {{0.0, -qz, qy}, {qz, 0.0, -qx}, {-qy, qx, 0.0}};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double J[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            J[c] = (T.R[r * 3 + 0] * hq[0][c] + T.R[r * 3 + 1] * hq[1][c] + T.R[r * 3 + 2] * hq[2][c]) / 16;
+        J[3] = r == 0 ? -1.0 : 0.0;
+        J[4] = r == 1 ? -1.0 : 0.0;
+        J[5] = r == 2 ? -1.0 : 0.0;
+        accum_rank1(acc, J, e[r]);
+    }
+    acc.v[27] += dis2;
+    return kGateInlier;
+}
+
+template <int METHOD>
+LR_HD unsigned char icp_point(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy, float sz,
+                              Accum& acc, int* nn_out) {
+    if (METHOD == kIcpP2P) return icp_point_p2p(map, prm, T, sx, sy, sz, acc, nn_out);
+    return icp_point_p2plane(map, prm, T, sx, sy, sz, acc, nn_out);
+}
+
+// One Gauss-Newton update from the reduced accumulator: the tail of AlignP2P / AlignP2Plane
+// (icp_registration.cpp:284-299, 362-375).  Returns 0 = evaluation failed (pose unchanged, quirk Q11),
+// 1 = pose updated, 2 = pose updated and ||dx|| < eps (converged).
+template <int METHOD>
+LR_HD int icp_gn_update(const double* acc28, unsigned int n_eff, const IcpParams& prm, Pose& T) {
+    if (static_cast<long long>(n_eff) < static_cast<long long>(prm.min_effective_pts)) return 0;
+    double dx[6];
+    if (!gn_solve6(acc28, acc28 + 21, dx)) return 0;
+    if (METHOD == kIcpP2P) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dx[i] = dx[i] / 16;  // H.inverse()/16 * err (:287)
+    }
+    pose_update(T, dx);
+    double nrm = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) nrm += dx[i] * dx[i];
+    return sqrt(nrm) < prm.eps ? 2 : 1;
+}
+
+}  // namespace locreg

@@ -1,0 +1,186 @@
+// TEST-ONLY serial harness ("hostsim").  NOT product code, never linked into liblocreg.so.
+//
+// The development container has no GPU, so the per-element bodies of the CUDA kernels
+// (loc_lib_b200/csrc/*.cuh, written as __host__ __device__ inline functions) are compiled here with
+// g++ and driven by plain loops.  The CPU test-suite uses it to check the kernel *logic* (voxel-hash
+// build, exact k-NN termination, plane fit, gates, Gauss-Newton update) against the oracle before
+// GPU time is spent; the `-m gpu` tests then check the real kernels through the C ABI.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../loc_lib_b200/csrc/icp_point.cuh"
+#include "../../loc_lib_b200/csrc/ndt_point.cuh"
+#include "../../loc_lib_b200/csrc/voxel_build.cuh"
+
+using namespace locreg;
+
+struct HsMap {
+    std::vector<VoxelSlot> slots;
+    std::vector<unsigned int> cell_start;
+    std::vector<float4> pts;
+    VoxelMapView view;
+};
+
+static unsigned int next_pow2(unsigned int v) {
+    unsigned int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+extern "C" {
+
+HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsigned int capacity_hint) {
+    auto* m = new HsMap;
+    const float inv_cell = 1.0f / cell;
+    unsigned int cap = capacity_hint ? next_pow2(capacity_hint) : next_pow2(static_cast<unsigned int>(n / 4 + 1024));
+    std::vector<unsigned int> pt_slot(n), pt_pos(n, 0);
+    std::vector<unsigned char> pt_bit(n);
+    unsigned int counters[3];
+    int cmin[3], cmax[3];
+    while (true) {
+        m->slots.assign(cap, VoxelSlot{kEmptyKey, 0ull, 0u, 0u, 0u, 0u});
+        counters[0] = counters[1] = counters[2] = 0;
+        for (int a = 0; a < 3; ++a) { cmin[a] = 0x7fffffff; cmax[a] = -0x7fffffff; }
+        for (size_t i = 0; i < n; ++i) {
+            int f[3];
+            if (build_insert_body<HostAtomics>(i, xyz, stride, inv_cell, m->slots.data(), cap - 1, pt_slot.data(),
+                                               pt_bit.data(), counters, f))
+                for (int a = 0; a < 3; ++a) { cmin[a] = std::min(cmin[a], f[a]); cmax[a] = std::max(cmax[a], f[a]); }
+        }
+        if (counters[1] || counters[0] * 2u > cap) { cap *= 4; continue; }
+        break;
+    }
+    unsigned int ncells = 0;
+    for (unsigned int s = 0; s < cap; ++s) {
+        m->slots[s].cell_base = ncells;
+        if (m->slots[s].key != kEmptyKey) ncells += popc64(m->slots[s].mask);
+    }
+    std::vector<unsigned int> cnt(ncells + 1, 0);
+    for (size_t i = 0; i < n; ++i) build_count_body<HostAtomics>(i, m->slots.data(), pt_slot.data(), pt_bit.data(), cnt.data());
+    m->cell_start.assign(ncells + 1, 0);
+    unsigned int run = 0;
+    for (unsigned int c = 0; c < ncells; ++c) { m->cell_start[c] = run; run += cnt[c]; }
+    m->cell_start[ncells] = run;
+    std::vector<unsigned int> cursor(m->cell_start.begin(), m->cell_start.end());
+    m->pts.assign(run, float4{0, 0, 0, 0});
+    for (size_t i = 0; i < n; ++i) build_scatter_body<HostAtomics>(i, xyz, stride, pt_slot.data(), cursor.data(), m->pts.data(), pt_pos.data());
+    std::vector<unsigned char> dup(n, 0);
+    unsigned int ndup = 0;
+    for (size_t i = 0; i < n; ++i) {
+        dup[i] = build_is_duplicate(i, pt_slot.data(), pt_pos.data(), m->cell_start.data(), m->pts.data());
+        ndup += dup[i];
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (dup[i]) m->pts[pt_pos[i]].x = NAN;
+    VoxelMapView& v = m->view;
+    v.slots = m->slots.data(); v.cell_start = m->cell_start.data(); v.pts = m->pts.data();
+    v.slot_mask = cap - 1; v.n_pts = run; v.n_unique = run - ndup; v.inv_cell = inv_cell; v.cell = cell;
+    for (int a = 0; a < 3; ++a) { v.cmin[a] = cmin[a]; v.cmax[a] = cmax[a]; }
+    return m;
+}
+void hs_map_destroy(HsMap* m) { delete m; }
+void hs_map_stats(const HsMap* m, uint32_t* out) {  // capacity, n_pts, n_unique, n_cells
+    out[0] = m->view.slot_mask + 1; out[1] = m->view.n_pts; out[2] = m->view.n_unique;
+    out[3] = static_cast<uint32_t>(m->cell_start.size() - 1);
+}
+
+void hs_knn(const HsMap* m, const float* q, size_t nq, size_t stride, int k, int32_t* idx_out) {
+    for (size_t i = 0; i < nq; ++i) {
+        const float* p = point_ptr(q, i, stride);
+        if (k == 1) {
+            KnnResult<1> r;
+            knn_query<1>(m->view, p[0], p[1], p[2], r);
+            idx_out[i] = r.idx[0] != 0x7fffffff ? r.idx[0] : -1;
+        } else {
+            KnnResult<5> r;
+            knn_query<5>(m->view, p[0], p[1], p[2], r);
+            for (int j = 0; j < 5; ++j) idx_out[i * 5 + j] = r.idx[j] != 0x7fffffff ? r.idx[j] : -1;
+        }
+    }
+}
+
+}  // extern "C"
+
+// prm: max_nn_distance, max_plane_distance, plane_fit_eps, eps, max_iteration, min_effective_pts
+static IcpParams make_params(const double* prm) {
+    IcpParams p;
+    p.max_nn_distance = prm[0]; p.max_plane_distance = prm[1]; p.plane_fit_eps = prm[2]; p.eps = prm[3];
+    p.max_iteration = static_cast<int>(prm[4]); p.min_effective_pts = static_cast<int>(prm[5]);
+    return p;
+}
+template <int METHOD>
+static void hb_impl(const HsMap* m, const IcpParams& p, const float* src, size_t n, size_t stride, const Pose& T,
+                    Accum& acc, uint8_t* gate, int32_t* nn_out) {
+    accum_zero(acc);
+    const int k = METHOD == kIcpP2P ? 1 : 5;
+    for (size_t i = 0; i < n; ++i) {
+        const float* s = point_ptr(src, i, stride);
+        int nn[5];
+        const unsigned char g = icp_point<METHOD>(m->view, p, T, s[0], s[1], s[2], acc, nn);
+        if (gate) gate[i] = g;
+        if (nn_out) for (int j = 0; j < k; ++j) nn_out[i * k + j] = nn[j];
+    }
+}
+static void unpack(const Accum& acc, double* H36, double* B6) {
+    for (int r = 0; r < 6; ++r)
+        for (int c = r; c < 6; ++c) { H36[c * 6 + r] = acc.v[hidx(r, c)]; H36[r * 6 + c] = acc.v[hidx(r, c)]; }
+    for (int i = 0; i < 6; ++i) B6[i] = acc.v[21 + i];
+}
+
+extern "C" {
+
+void hs_icp_hb(const HsMap* m, int method, const double* prm, const float* src, size_t n, size_t stride,
+               const double* pose7, double* H36, double* B6, int64_t* counts, double* sum_sq, uint8_t* gate,
+               int32_t* nn_out) {
+    const IcpParams p = make_params(prm);
+    Pose T;
+    pose_load(T, pose7);
+    Accum acc;
+    if (method == kIcpP2P) hb_impl<kIcpP2P>(m, p, src, n, stride, T, acc, gate, nn_out);
+    else hb_impl<kIcpP2Plane>(m, p, src, n, stride, T, acc, gate, nn_out);
+    unpack(acc, H36, B6);
+    counts[0] = acc.n_eff; counts[1] = acc.n_inl;
+    *sum_sq = acc.v[27];
+}
+
+// returns iterations executed; status[0]=updates, [1]=converged, [2]=degenerate(last)
+int hs_icp_align(const HsMap* m, int method, const double* prm, const float* src, size_t n, size_t stride,
+                 const double* pose_in, double* pose_out, int32_t* status) {
+    const IcpParams p = make_params(prm);
+    Pose T;
+    pose_load(T, pose_in);
+    int iters = 0;
+    status[0] = status[1] = status[2] = 0;
+    for (int it = 0; it < p.max_iteration; ++it) {
+        Accum acc;
+        int r;
+        if (method == kIcpP2P) {
+            hb_impl<kIcpP2P>(m, p, src, n, stride, T, acc, nullptr, nullptr);
+            r = icp_gn_update<kIcpP2P>(acc.v, acc.n_eff, p, T);
+        } else {
+            hb_impl<kIcpP2Plane>(m, p, src, n, stride, T, acc, nullptr, nullptr);
+            r = icp_gn_update<kIcpP2Plane>(acc.v, acc.n_eff, p, T);
+        }
+        iters = it + 1;
+        status[2] = r == 0;
+        if (r) status[0]++;
+        if (r == 2) { status[1] = 1; break; }
+    }
+    pose_store(T, pose_out);
+    return iters;
+}
+
+void hs_plane_svd5(const double* pts15, double* coef4) {
+    double P[5][3];
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 3; ++j) P[i][j] = pts15[i * 3 + j];
+    double c[4];
+    plane_svd5(P, c);
+    for (int i = 0; i < 4; ++i) coef4[i] = c[i];
+}
+void hs_sym3_eigen(const double* S6, double* lam3, double* Q9) { sym3_eigen(S6, lam3, Q9); }
+int hs_gn_solve6(const double* Hu21, const double* b6, double* dx6) { return gn_solve6(Hu21, b6, dx6) ? 1 : 0; }
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+"""ctypes binding of tests/hostsim (serial, TEST-ONLY build of the CUDA kernels' per-element bodies)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_DIR = os.path.join(_ROOT, "tests", "hostsim")
+_SO = os.path.join(_DIR, "_build", "libhostsim.so")
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-s", "-C", _DIR])
+        L = C.CDLL(_SO)
+        vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+        L.hs_map_create.restype = vp
+        L.hs_map_create.argtypes = [vp, sz, sz, C.c_float, C.c_uint]
+        L.hs_map_destroy.argtypes = [vp]
+        L.hs_map_stats.argtypes = [vp, vp]
+        L.hs_knn.argtypes = [vp, vp, sz, sz, i32, vp]
+        L.hs_icp_hb.argtypes = [vp, i32, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp]
+        L.hs_icp_align.restype = i32
+        L.hs_icp_align.argtypes = [vp, i32, vp, vp, sz, sz, vp, vp, vp]
+        L.hs_plane_svd5.argtypes = [vp, vp]
+        L.hs_sym3_eigen.argtypes = [vp, vp, vp]
+        L.hs_gn_solve6.restype = i32
+        L.hs_gn_solve6.argtypes = [vp, vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def _cloud(a):
+    a = np.ascontiguousarray(a, np.float32)
+    return a, a.shape[0], a.strides[0]
+
+
+def params(max_nn_distance=1.0, max_plane_distance=0.1, plane_fit_eps=1e-2, eps=1e-2, max_iteration=20,
+           min_effective_pts=10):
+    return np.array([max_nn_distance, max_plane_distance, plane_fit_eps, eps, max_iteration, min_effective_pts],
+                    np.float64)
+
+
+class HsMap:
+    def __init__(self, cloud, cell=0.5, capacity_hint=0):
+        a, n, s = _cloud(cloud)
+        self._h = lib().hs_map_create(a.ctypes.data, n, s, cell, capacity_hint)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().hs_map_destroy(self._h)
+            self._h = None
+
+    def stats(self):
+        out = np.zeros(4, np.uint32)
+        lib().hs_map_stats(self._h, out.ctypes.data)
+        return dict(capacity=int(out[0]), n_pts=int(out[1]), n_unique=int(out[2]), n_cells=int(out[3]))
+
+    def knn(self, q, k):
+        a, n, s = _cloud(q)
+        out = np.empty((n, k), np.int32)
+        lib().hs_knn(self._h, a.ctypes.data, n, s, k, out.ctypes.data)
+        return out
+
+    def icp_hb(self, method, prm, src, pose7):
+        a, n, s = _cloud(src)
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        H = np.zeros(36)
+        B = np.zeros(6)
+        counts = np.zeros(2, np.int64)
+        ssq = np.zeros(1)
+        gate = np.zeros(n, np.uint8)
+        k = 1 if method == 0 else 5
+        nn = np.zeros((n, k), np.int32)
+        lib().hs_icp_hb(self._h, method, prm.ctypes.data, a.ctypes.data, n, s, pose7.ctypes.data, H.ctypes.data,
+                        B.ctypes.data, counts.ctypes.data, ssq.ctypes.data, gate.ctypes.data, nn.ctypes.data)
+        return H.reshape(6, 6).T.copy(), B, dict(n_effective=int(counts[0]), n_inlier=int(counts[1]),
+                                                 sum_sq_res=float(ssq[0])), gate, nn
+
+    def icp_align(self, method, prm, src, pose7):
+        a, n, s = _cloud(src)
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        out = np.zeros(7)
+        st = np.zeros(3, np.int32)
+        it = lib().hs_icp_align(self._h, method, prm.ctypes.data, a.ctypes.data, n, s, pose7.ctypes.data,
+                                out.ctypes.data, st.ctypes.data)
+        return out, dict(iters=it, updates=int(st[0]), converged=int(st[1]), degenerate=int(st[2]))
+
+
+def plane_svd5(pts):
+    p = np.ascontiguousarray(pts, np.float64)
+    c = np.zeros(4)
+    lib().hs_plane_svd5(p.ctypes.data, c.ctypes.data)
+    return c
+
+
+def sym3_eigen(S6):
+    s = np.ascontiguousarray(S6, np.float64)
+    lam = np.zeros(3)
+    Q = np.zeros((3, 3))
+    lib().hs_sym3_eigen(s.ctypes.data, lam.ctypes.data, Q.ctypes.data)
+    return lam, Q
