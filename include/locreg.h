@@ -1,0 +1,159 @@
+/* locreg — C ABI of the B200-native scan-to-map registration hot path.
+ *
+ * Drop-in boundary for maotian123/loc_lib's LocUtils::MatchingInterface
+ * (LocUtils/include/LocUtils/model/matching/3d/matching_interface.h:13-54) as implemented by
+ * IcpRegistration (icp_registration.hpp:41-142 / icp_registration.cpp) and NdtRegistration
+ * (ndt_registration.hpp:69-135 / ndt_registration.cpp).  A header-only C++ adapter that derives from
+ * MatchingInterface and forwards to these entry points is in include/locreg_adapter.hpp; the reference
+ * side binding is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   clouds   : pointer to the first float of the first point + point count + stride in bytes between
+ *              points (32 for pcl::PointXYZI, LocUtils point_types.h:18; 16 for float4; >= 12).  x,y,z are
+ *              the first three floats of a point.
+ *   poses    : 7 doubles [qx qy qz qw tx ty tz] = Sophus::SE3d::data() (LocUtils eigen_types.h:66).
+ *   H, B     : 6x6 column-major (Eigen default) and 6x1 doubles, rotation block first, as the reference's
+ *              Mat6d / Vec6d (matching_interface.h:23-26).
+ *   return   : 0 on success, negative LOCREG_E_* on failure; locreg_last_error() describes the last failure
+ *              of the calling thread.  Algorithmic outcomes (too few points, singular H, ...) are NOT
+ *              errors: like the reference's always-true bool they are reported in locreg_result.
+ *   threading: one handle = one CUDA stream; a handle is not thread-safe, distinct handles are independent
+ *              (the reference's classes are not re-entrant either: mutable source_/target_ members).
+ *   there is no CPU fallback: every entry point that computes fails with LOCREG_E_CUDA without a B200.
+ */
+#ifndef LOCREG_H
+#define LOCREG_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOCREG_OK 0
+#define LOCREG_E_ARG (-1)         /* invalid argument */
+#define LOCREG_E_CUDA (-2)        /* CUDA runtime error (no device, out of memory, launch failure) */
+#define LOCREG_E_STATE (-3)       /* call order (e.g. align before set_target) */
+#define LOCREG_E_UNSUPPORTED (-4) /* method not built yet (P2LINE, PCLICP, incremental NDT) */
+
+/* IcpMethod (icp_registration.hpp:15-20) and NdtMethod::DIRECT_NDT (ndt_registration.hpp:21-26) in one enum */
+enum locreg_method {
+    LOCREG_ICP_P2P = 0,
+    LOCREG_ICP_P2LINE = 1, /* not built yet: LOCREG_E_UNSUPPORTED */
+    LOCREG_ICP_P2PLANE = 2,
+    LOCREG_NDT_DIRECT = 3
+};
+/* NdtNearbyType (ndt_registration.hpp:16-20) */
+enum locreg_nearby { LOCREG_NEARBY_CENTER = 0, LOCREG_NEARBY6 = 1 };
+/* how the Gauss-Newton loop is kept on the device */
+enum locreg_loop { LOCREG_LOOP_PERSISTENT = 0, /* one cooperative kernel, grid barrier per iteration */
+                   LOCREG_LOOP_GRAPH = 1 /* one captured CUDA graph of per-iteration kernels */ };
+
+/* POD mirror of IcpOptions (icp_registration.hpp:22-39) + NdtOptions (ndt_registration.hpp:27-42). */
+typedef struct locreg_options {
+    int32_t method;               /* enum locreg_method */
+    int32_t max_iteration;        /* max_iteration_ = 20 */
+    int32_t min_effective_pts;    /* min_effective_pts_ = 10 */
+    int32_t use_ann;              /* IcpOptions::use_ann: accepted and ignored — the search is always exact (deviation Q1) */
+    double eps;                   /* eps_ = 1e-2 */
+    double max_nn_distance;       /* max_nn_distance_ = 1.0 (compared with a squared distance, quirk Q6) */
+    double max_plane_distance;    /* max_plane_distance_ = 0.1 */
+    double max_line_distance;     /* max_line_distance_ = 0.5 (P2LINE, unused) */
+    double voxel_size;            /* NdtOptions::voxel_size_ = 1.0 (inv_voxel_size_ is always recomputed, ndt_registration.cpp:25) */
+    double res_outlier_th;        /* res_outlier_th_ = 20.0 */
+    int32_t min_pts_in_voxel;     /* min_pts_in_voxel_ = 3 */
+    int32_t nearby_type;          /* enum locreg_nearby, default NEARBY6 */
+    /* GPU-side knobs (no reference counterpart) */
+    double knn_cell_size;         /* voxel-hash cell edge in metres for ICP k-NN; <= 0: 0.5 */
+    int32_t loop_mode;            /* enum locreg_loop */
+    int32_t reserved_;
+} locreg_options;
+
+/* Outcome of one registration (what the reference logs or silently drops). */
+typedef struct locreg_result {
+    int32_t iters;        /* Gauss-Newton loop trips executed */
+    int32_t updates;      /* trips whose H/B evaluation succeeded and moved the pose */
+    int32_t converged;    /* 1 if ||dx|| < eps ended the loop */
+    int32_t degenerate;   /* 1 if the LAST evaluation failed (effective_num < min_effective_pts or det(H) == 0) */
+    int64_t n_effective;  /* effective_num of the last evaluation */
+    int64_t n_inlier;     /* residuals that entered H/B in the last evaluation */
+    double sum_sq_res;    /* sum of squared gated residuals of the last evaluation */
+    int32_t pose_written; /* 0 only on direct NDT's det(H)==0 early return, which leaves pose_out untouched (quirk Q11) */
+    int32_t pad_;
+} locreg_result;
+
+typedef struct locreg_handle locreg_handle;
+
+/* Fills *opt with the reference's defaults for `method`. */
+int locreg_default_options(locreg_options* opt, int32_t method);
+
+/* IcpRegistration(IcpOptions) / NdtRegistration(NdtOptions) constructors (icp_registration.hpp:59, ndt_registration.cpp:20). */
+int locreg_create(const locreg_options* opt, int32_t device, locreg_handle** out);
+int locreg_destroy(locreg_handle* h);
+/* Use the caller's CUDA stream (a cudaStream_t) for all work of this handle; NULL = the handle's own stream. */
+int locreg_set_stream(locreg_handle* h, void* cuda_stream);
+
+/* MatchingInterface::SetInputTarget (matching_interface.h:18; icp_registration.cpp:9-29, ndt_registration.cpp:65-148).
+ * Deep-copies the cloud to the device and builds the voxel-hash map (ICP) or the NDT voxel grid. */
+int locreg_set_target(locreg_handle* h, const float* xyz, size_t n, size_t stride_bytes);
+/* Same, cloud already in device memory (stride as above). */
+int locreg_set_target_device(locreg_handle* h, const float* d_xyz, size_t n, size_t stride_bytes);
+
+/* MatchingInterface::ScanMatch (matching_interface.h:30-33; icp_registration.cpp:216-244, ndt_registration.cpp:238-261).
+ * pose_out is IN/OUT: on direct NDT's det(H)==0 early return it is left as the caller passed it.  out_xyz (may be
+ * NULL) receives pcl::transformPointCloud(src, pose_out) with the same stride; bytes 12.. of each point are copied. */
+int locreg_align(locreg_handle* h, const float* src, size_t n, size_t stride_bytes, const double* pose_in,
+                 double* pose_out, float* out_xyz, locreg_result* res);
+
+/* MatchingInterface::CaculateMatrixHAndB (matching_interface.h:23-26; icp_registration.cpp:31-55).
+ * Returns 1/0 in res->degenerate's complement like the reference's bool; NDT's reference body is empty (quirk Q12),
+ * here it returns the loop-body accumulation of AlignNdt (ndt_registration.cpp:399-433). */
+int locreg_compute_hb(locreg_handle* h, const float* src, size_t n, size_t stride_bytes, const double* pose,
+                      double* H36, double* B6, locreg_result* res);
+
+/* Parity probe for SearchPointInterface::FindNearstPoints (search_point_interface.h:9-24; kdtree.cpp:272-283):
+ * exact k-NN (k = 1 or 5) under the total order (float32 dis2, index); idx is nq*k, -1 padded. ICP handles only. */
+int locreg_knn(locreg_handle* h, const float* queries, size_t nq, size_t stride_bytes, int32_t k, int32_t* idx);
+
+/* Parity probe: per-point gate code (0 skipped, 1 plane fit failed, 2 residual gated out, 3 inlier; NDT: number
+ * of gated-in voxels) and, for ICP, neighbour indices (n*k, may be NULL) at `pose`. */
+int locreg_debug_points(locreg_handle* h, const float* src, size_t n, size_t stride_bytes, const double* pose,
+                        uint8_t* gate, int32_t* nn);
+
+/* Batch offline mapping (BASELINE config 4): S independent ScanMatch calls against the current target.
+ * Scan s is points [offsets[s], offsets[s+1]) of `srcs`; poses_in/poses_out are S*7 doubles (poses_out is IN/OUT as
+ * in locreg_align); results is S entries or NULL. */
+int locreg_align_batch(locreg_handle* h, const float* srcs, const int64_t* offsets, size_t stride_bytes,
+                       const double* poses_in, size_t S, double* poses_out, locreg_result* results);
+/* Same with every buffer already on the device: d_srcs is float4 (stride 16). */
+int locreg_align_batch_device(locreg_handle* h, const float* d_srcs, const int64_t* d_offsets, const double* d_poses_in,
+                              size_t S, size_t total_points, double* d_poses_out, locreg_result* d_results);
+
+/* Global relocalisation (BASELINE config 5): n_hyp ScanMatch calls of ONE scan from different initial poses.
+ * score = sum_sq_res / n_inlier at the final pose (+inf when the last evaluation is degenerate or has no inlier);
+ * best = argmin with lowest index winning ties.  scores / poses_out may be NULL.  The cross-GPU argmin is one
+ * min-allreduce of locreg_pack_score(score, global index) (see loc_lib_b200/dist.py). */
+int locreg_relocalise(locreg_handle* h, const float* src, size_t n, size_t stride_bytes, const double* poses_in,
+                      size_t n_hyp, double* best_pose, int64_t* best_idx, double* best_score, double* scores,
+                      double* poses_out);
+/* (float32 score bits << 32) | index: unsigned order = (score, index) order for score >= 0. */
+uint64_t locreg_pack_score(double score, uint32_t index);
+
+/* pcl::transformPointCloud (icp_registration.cpp:241) on its own. */
+int locreg_transform_cloud(locreg_handle* h, const float* src, size_t n, size_t stride_bytes, const double* pose,
+                           float* out_xyz);
+
+/* NDT parity probe: voxel count and, sorted by (kx,ky,kz), keys (nv*3), mu (nv*3), info (nv*9 row-major), npts (nv). */
+int locreg_ndt_num_voxels(locreg_handle* h, size_t* nv);
+int locreg_ndt_get_voxels(locreg_handle* h, int32_t* keys, double* mu, double* info, int32_t* npts);
+
+/* Device time in milliseconds of the last align / align_batch / relocalise / set_target call's kernels
+ * (CUDA events on the handle's stream), and how many kernels that call launched. */
+int locreg_last_timing(locreg_handle* h, double* kernel_ms, int64_t* launches);
+
+const char* locreg_last_error(void);
+const char* locreg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,35 @@
+// Device-resident voxel-hash map: owner of the arrays a VoxelMapView points at, and the host side of
+// the build pipeline described in voxel_build.cuh.
+#pragma once
+#include "device_utils.cuh"
+#include "voxel_map.cuh"
+
+namespace locreg {
+
+class DeviceVoxelMap {
+   public:
+    DeviceVoxelMap() = default;
+    ~DeviceVoxelMap();
+    DeviceVoxelMap(const DeviceVoxelMap&) = delete;
+    DeviceVoxelMap& operator=(const DeviceVoxelMap&) = delete;
+
+    // d_xyz: device pointer to n points, `stride` bytes apart.  Synchronises the stream (the slot
+    // table is sized from the number of occupied blocks, read back once).
+    void build(const void* d_xyz, size_t n, size_t stride, float cell, cudaStream_t stream);
+    const VoxelMapView& view() const { return view_; }
+    bool empty() const { return view_.n_pts == 0; }
+    size_t bytes() const { return bytes_; }
+    unsigned int n_cells() const { return n_cells_; }
+    unsigned int n_blocks() const { return n_blocks_; }
+
+   private:
+    void release();
+    VoxelSlot* slots_ = nullptr;
+    unsigned int* cell_start_ = nullptr;
+    float4* pts_ = nullptr;
+    VoxelMapView view_{};
+    size_t bytes_ = 0;
+    unsigned int n_cells_ = 0, n_blocks_ = 0;
+};
+
+}  // namespace locreg

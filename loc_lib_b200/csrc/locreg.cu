@@ -1,0 +1,626 @@
+// C ABI of the registration hot path (include/locreg.h): handle management, host<->device staging,
+// kernel launches.  No CPU fallback: without a CUDA device every computing entry point fails.
+#include "../../include/locreg.h"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "align_kernels.cuh"
+#include "device_map.cuh"
+#include "device_ndt.cuh"
+
+using namespace locreg;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        LR_CUDA(cudaMalloc(&p, want));
+        cap = want;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        LR_CUDA(cudaMallocHost(&p, want));
+        cap = want;
+    }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+bool is_pinned_or_device(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct locreg_handle {
+    locreg_options opt{};
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DeviceVoxelMap icp_map;
+    DeviceNdtMap ndt_map;
+    bool has_target = false;
+    DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
+        d_scores, d_misc, d_target;
+    PinBuf h_in, h_out, h_small;
+    double last_ms = 0;
+    long long last_launches = 0;
+
+    IcpParams icp_params() const {
+        IcpParams p;
+        p.max_nn_distance = opt.max_nn_distance;
+        p.max_plane_distance = opt.max_plane_distance;
+        p.plane_fit_eps = 1e-2;
+        p.eps = opt.eps;
+        p.max_iteration = opt.max_iteration;
+        p.min_effective_pts = opt.min_effective_pts;
+        return p;
+    }
+    NdtParams ndt_params() const {
+        NdtParams p;
+        p.res_outlier_th = opt.res_outlier_th;
+        p.eps = opt.eps;
+        p.max_iteration = opt.max_iteration;
+        p.min_effective_pts = opt.min_effective_pts;
+        p.min_pts_in_voxel = opt.min_pts_in_voxel;
+        p.n_nearby = opt.nearby_type == LOCREG_NEARBY6 ? 7 : 1;
+        return p;
+    }
+    void begin_timing() {
+        g_launch_count = 0;
+        LR_CUDA(cudaEventRecord(ev0, stream));
+    }
+    void end_timing() {
+        LR_CUDA(cudaEventRecord(ev1, stream));
+        LR_CUDA(cudaEventSynchronize(ev1));
+        float ms = 0;
+        LR_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        last_ms = ms;
+        last_launches = g_launch_count;
+    }
+};
+
+namespace {
+
+// Copies a host (or device) cloud into h->d_raw as-is and produces the float4 view kernels read.
+// Returns the float4 device pointer.
+const float4* stage_cloud(locreg_handle* h, const float* src, size_t n, size_t stride, bool src_on_device) {
+    const size_t bytes = n * stride;
+    if (n == 0) return nullptr;
+    h->d_raw.reserve(bytes);
+    if (src_on_device) {
+        LR_CUDA(cudaMemcpyAsync(h->d_raw.p, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    } else if (is_pinned_or_device(src)) {
+        LR_CUDA(cudaMemcpyAsync(h->d_raw.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        h->h_in.reserve(bytes);
+        std::memcpy(h->h_in.p, src, bytes);
+        LR_CUDA(cudaMemcpyAsync(h->d_raw.p, h->h_in.p, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (stride == 16) return h->d_raw.as<float4>();
+    h->d_src4.reserve(n * sizeof(float4));
+    const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((n + 255) / 256, 4096));
+    LR_LAUNCH(k_pack_float4, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>(), n, stride, h->d_src4.as<float4>());
+    return h->d_src4.as<float4>();
+}
+
+void init_state(locreg_handle* h, const double* pose7) {
+    h->d_state.reserve(sizeof(AlignState));
+    h->h_small.reserve(4096);
+    AlignState* s = h->h_small.as<AlignState>();
+    std::memset(s, 0, sizeof(AlignState));
+    std::memcpy(s->pose, pose7, 7 * sizeof(double));
+    s->res.pose_written = 1;
+    LR_CUDA(cudaMemcpyAsync(h->d_state.p, s, sizeof(AlignState), cudaMemcpyHostToDevice, h->stream));
+}
+
+template <class Problem>
+int persist_grid(const locreg_handle* h, unsigned int n) {
+    int per_sm = 0;
+    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_persist<Problem>, 256, 0));
+    if (per_sm < 1) throw std::runtime_error("persistent kernel does not fit on an SM");
+    const long long max_blocks = static_cast<long long>(per_sm) * h->num_sms;
+    const long long want = (static_cast<long long>(n) + 255) / 256;
+    return static_cast<int>(std::max<long long>(1, std::min(max_blocks, want)));
+}
+
+// Runs the whole Gauss-Newton loop on the device, result left in h->d_state.
+template <class Problem>
+void run_align(locreg_handle* h, const Problem& pb, const float4* src, unsigned int n, int final_eval) {
+    AlignState* st = h->d_state.as<AlignState>();
+    if (h->opt.loop_mode == LOCREG_LOOP_PERSISTENT) {
+        const int grid = persist_grid<Problem>(h, n);
+        h->d_partials.reserve(static_cast<size_t>(2) * grid * kPartialDoubles * sizeof(double));
+        double* partials = h->d_partials.as<double>();
+        Problem pb_copy = pb;
+        void* args[] = {&pb_copy, &src, &n, &st, &partials, &final_eval};
+        LR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_align_persist<Problem>), dim3(grid), dim3(256), args, 0, h->stream));
+        ++g_launch_count;
+    } else {
+        const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((n + 255ll) / 256, 4ll * h->num_sms)));
+        h->d_partials.reserve(static_cast<size_t>(grid) * kPartialDoubles * sizeof(double));
+        double* partials = h->d_partials.as<double>();
+        for (int it = 0; it < h->opt.max_iteration; ++it) {
+            LR_LAUNCH(k_eval<Problem>, grid, 256, 0, h->stream, pb, src, n, st, partials, nullptr, nullptr);
+            LR_LAUNCH(k_finalize<Problem>, 1, 256, 0, h->stream, pb, partials, grid, st, 1, nullptr);
+        }
+        (void)final_eval;
+    }
+}
+
+template <class Problem>
+void run_eval(locreg_handle* h, const Problem& pb, const float4* src, unsigned int n, unsigned char* gate, int* nn) {
+    AlignState* st = h->d_state.as<AlignState>();
+    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((n + 255ll) / 256, 4ll * h->num_sms)));
+    h->d_partials.reserve(static_cast<size_t>(grid) * kPartialDoubles * sizeof(double));
+    h->d_acc.reserve(32 * sizeof(double));
+    LR_LAUNCH(k_eval<Problem>, grid, 256, 0, h->stream, pb, src, n, st, h->d_partials.as<double>(), gate, nn);
+    LR_LAUNCH(k_finalize<Problem>, 1, 256, 0, h->stream, pb, h->d_partials.as<double>(), grid, st, 0, h->d_acc.as<double>());
+}
+
+template <class Problem>
+void run_batch(locreg_handle* h, const Problem& pb, const float4* src, const long long* offsets, unsigned int n_single,
+               const double* poses_in, double* poses_out, DevResult* results, unsigned int S, int final_eval) {
+    int per_sm = 0;
+    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_batch<Problem>, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(S, static_cast<long long>(per_sm) * h->num_sms)));
+    h->d_misc.reserve(64);
+    LR_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 64, h->stream));
+    LR_LAUNCH(k_align_batch<Problem>, grid, 256, 0, h->stream, pb, src, offsets, n_single, poses_in, poses_out, results, S,
+              h->d_misc.as<unsigned int>(), final_eval);
+}
+
+#define DISPATCH_METHOD(h, CALL)                                                                     \
+    switch ((h)->opt.method) {                                                                       \
+        case LOCREG_ICP_P2P: { IcpProblem<kIcpP2P> pb{(h)->icp_map.view(), (h)->icp_params()}; CALL; } break;         \
+        case LOCREG_ICP_P2PLANE: { IcpProblem<kIcpP2Plane> pb{(h)->icp_map.view(), (h)->icp_params()}; CALL; } break; \
+        case LOCREG_NDT_DIRECT: { NdtProblem pb{(h)->ndt_map.view(), (h)->ndt_params()}; CALL; } break;               \
+        default: throw std::invalid_argument("unsupported method");                                  \
+    }
+
+template <int K>
+__global__ void k_knn(VoxelMapView map, const float4* __restrict__ q, unsigned int nq, int* __restrict__ idx) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const float4 p = q[i];
+    KnnResult<K> r;
+    knn_init(r);
+    if (finite3(p.x, p.y, p.z)) knn_query<K>(map, p.x, p.y, p.z, r);
+#pragma unroll
+    for (int j = 0; j < K; ++j) idx[static_cast<size_t>(i) * K + j] = r.idx[j] != 0x7fffffff ? r.idx[j] : -1;
+}
+
+int check_cloud_args(const float* p, size_t n, size_t stride) {
+    if ((n > 0 && p == nullptr) || stride < 12 || (stride % 4) != 0) {
+        g_last_error = "invalid cloud arguments (null pointer, stride < 12 or stride not a multiple of 4)";
+        return LOCREG_E_ARG;
+    }
+    if (n >= (1ull << 31)) { g_last_error = "cloud too large"; return LOCREG_E_ARG; }
+    return LOCREG_OK;
+}
+
+void fill_result(locreg_result* out, const DevResult& r) {
+    if (!out) return;
+    static_assert(sizeof(locreg_result) == sizeof(DevResult), "result layout");
+    std::memcpy(out, &r, sizeof(DevResult));
+}
+
+template <class F>
+int guarded(locreg_handle* h, F&& f) {
+    if (!h) { g_last_error = "null handle"; return LOCREG_E_ARG; }
+    try {
+        if (cudaSetDevice(h->device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; cudaGetLastError(); return LOCREG_E_CUDA; }
+        return f();
+    } catch (const CudaError& e) {
+        g_last_error = e.what();
+        cudaGetLastError();
+        return LOCREG_E_CUDA;
+    } catch (const std::invalid_argument& e) {
+        g_last_error = e.what();
+        return LOCREG_E_ARG;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return LOCREG_E_CUDA;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* locreg_last_error(void) { return g_last_error.c_str(); }
+const char* locreg_version(void) { return "locreg-b200 0.1 (sm_100a)"; }
+
+int locreg_default_options(locreg_options* o, int32_t method) {
+    if (!o) return LOCREG_E_ARG;
+    std::memset(o, 0, sizeof(*o));
+    o->method = method;
+    o->max_iteration = 20;
+    o->min_effective_pts = 10;
+    o->use_ann = 0;
+    o->eps = 1e-2;
+    o->max_nn_distance = 1.0;
+    o->max_plane_distance = 0.1;
+    o->max_line_distance = 0.5;
+    o->voxel_size = 1.0;
+    o->res_outlier_th = 20.0;
+    o->min_pts_in_voxel = 3;
+    o->nearby_type = LOCREG_NEARBY6;
+    o->knn_cell_size = 0.5;
+    o->loop_mode = LOCREG_LOOP_PERSISTENT;
+    return LOCREG_OK;
+}
+
+int locreg_create(const locreg_options* opt, int32_t device, locreg_handle** out) {
+    if (!opt || !out) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    if (opt->method == LOCREG_ICP_P2LINE) { g_last_error = "P2LINE is not built yet"; return LOCREG_E_UNSUPPORTED; }
+    if (opt->method != LOCREG_ICP_P2P && opt->method != LOCREG_ICP_P2PLANE && opt->method != LOCREG_NDT_DIRECT) {
+        g_last_error = "unknown method";
+        return LOCREG_E_ARG;
+    }
+    if (opt->method == LOCREG_NDT_DIRECT && !(opt->voxel_size > 0)) { g_last_error = "voxel_size must be > 0"; return LOCREG_E_ARG; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        g_last_error = "no CUDA device: locreg has no CPU fallback";
+        return LOCREG_E_CUDA;
+    }
+    if (device < 0 || device >= count) { g_last_error = "device index out of range"; return LOCREG_E_ARG; }
+    auto* h = new locreg_handle;
+    h->opt = *opt;
+    if (!(h->opt.knn_cell_size > 0)) h->opt.knn_cell_size = 0.5;
+    h->device = device;
+    const int rc = guarded(h, [&]() {
+        cudaDeviceProp prop{};
+        LR_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw std::runtime_error("locreg kernels are built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor));
+        h->num_sms = prop.multiProcessorCount;
+        LR_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        LR_CUDA(cudaEventCreate(&h->ev0));
+        LR_CUDA(cudaEventCreate(&h->ev1));
+        return LOCREG_OK;
+    });
+    if (rc != LOCREG_OK) { delete h; return rc; }
+    *out = h;
+    return LOCREG_OK;
+}
+
+int locreg_destroy(locreg_handle* h) {
+    if (!h) return LOCREG_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    cudaStream_t s = h->own_stream;
+    delete h;
+    if (s) cudaStreamDestroy(s);
+    return LOCREG_OK;
+}
+
+int locreg_set_stream(locreg_handle* h, void* cuda_stream) {
+    return guarded(h, [&]() {
+        LR_CUDA(cudaStreamSynchronize(h->stream));
+        h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+        return LOCREG_OK;
+    });
+}
+
+static int set_target_impl(locreg_handle* h, const float* xyz, size_t n, size_t stride, bool on_device) {
+    const int rc = check_cloud_args(xyz, n, stride);
+    if (rc) return rc;
+    return guarded(h, [&]() {
+        const void* d_xyz = xyz;
+        if (!on_device && n) {
+            h->d_target.reserve(n * stride);
+            if (is_pinned_or_device(xyz)) {
+                LR_CUDA(cudaMemcpyAsync(h->d_target.p, xyz, n * stride, cudaMemcpyHostToDevice, h->stream));
+            } else {
+                LR_CUDA(cudaMemcpy(h->d_target.p, xyz, n * stride, cudaMemcpyHostToDevice));
+            }
+            d_xyz = h->d_target.p;
+        }
+        h->begin_timing();
+        if (h->opt.method == LOCREG_NDT_DIRECT)
+            h->ndt_map.build(d_xyz, n, stride, h->opt.voxel_size, h->opt.min_pts_in_voxel, h->stream);
+        else
+            h->icp_map.build(d_xyz, n, stride, static_cast<float>(h->opt.knn_cell_size), h->stream);
+        h->end_timing();
+        h->has_target = true;
+        return LOCREG_OK;
+    });
+}
+int locreg_set_target(locreg_handle* h, const float* xyz, size_t n, size_t stride) { return set_target_impl(h, xyz, n, stride, false); }
+int locreg_set_target_device(locreg_handle* h, const float* d_xyz, size_t n, size_t stride) { return set_target_impl(h, d_xyz, n, stride, true); }
+
+int locreg_align(locreg_handle* h, const float* src, size_t n, size_t stride, const double* pose_in, double* pose_out,
+                 float* out_xyz, locreg_result* res) {
+    const int rc = check_cloud_args(src, n, stride);
+    if (rc) return rc;
+    if (!pose_in || !pose_out) { g_last_error = "null pose"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
+        const float4* src4 = stage_cloud(h, src, n, stride, false);
+        init_state(h, pose_in);
+        h->begin_timing();
+        DISPATCH_METHOD(h, run_align(h, pb, src4, static_cast<unsigned int>(n), 0));
+        AlignState* st = h->d_state.as<AlignState>();
+        const size_t bytes = n * stride;
+        if (out_xyz && n) {
+            h->d_out.reserve(bytes);
+            const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((n + 255) / 256, 4096));
+            LR_LAUNCH(k_transform, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>(), h->d_out.as<unsigned char>(), n, stride, st->pose);
+        }
+        h->h_small.reserve(4096);
+        AlignState* hs = h->h_small.as<AlignState>() + 1;
+        LR_CUDA(cudaMemcpyAsync(hs, st, sizeof(AlignState), cudaMemcpyDeviceToHost, h->stream));
+        const bool direct_out = out_xyz && n && is_pinned_or_device(out_xyz);
+        if (out_xyz && n) {
+            if (direct_out) {
+                LR_CUDA(cudaMemcpyAsync(out_xyz, h->d_out.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+            } else {
+                h->h_out.reserve(bytes);
+                LR_CUDA(cudaMemcpyAsync(h->h_out.p, h->d_out.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+            }
+        }
+        h->end_timing();  // synchronises the stream
+        if (hs->res.pose_written) {
+            std::memcpy(pose_out, hs->pose, 7 * sizeof(double));
+        } else if (out_xyz && n) {
+            // direct NDT's early return: result_pose keeps the caller's value and the cloud is transformed with it
+            double* dpose = h->d_acc.as<double>();
+            h->d_acc.reserve(32 * sizeof(double));
+            dpose = h->d_acc.as<double>();
+            LR_CUDA(cudaMemcpyAsync(dpose, pose_out, 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((n + 255) / 256, 4096));
+            LR_LAUNCH(k_transform, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>(), h->d_out.as<unsigned char>(), n, stride, dpose);
+            LR_CUDA(cudaMemcpyAsync(direct_out ? static_cast<void*>(out_xyz) : h->h_out.p, h->d_out.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+            LR_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        if (out_xyz && n && !direct_out) std::memcpy(out_xyz, h->h_out.p, bytes);
+        fill_result(res, hs->res);
+        return LOCREG_OK;
+    });
+}
+
+int locreg_compute_hb(locreg_handle* h, const float* src, size_t n, size_t stride, const double* pose, double* H36,
+                      double* B6, locreg_result* res) {
+    const int rc = check_cloud_args(src, n, stride);
+    if (rc) return rc;
+    if (!pose || !H36 || !B6) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
+        const float4* src4 = stage_cloud(h, src, n, stride, false);
+        init_state(h, pose);
+        h->begin_timing();
+        DISPATCH_METHOD(h, run_eval(h, pb, src4, static_cast<unsigned int>(n), nullptr, nullptr));
+        h->h_small.reserve(4096);
+        double* acc = h->h_small.as<double>() + 64;
+        LR_CUDA(cudaMemcpyAsync(acc, h->d_acc.p, 30 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        h->end_timing();
+        for (int r = 0; r < 6; ++r)
+            for (int c = r; c < 6; ++c) { H36[c * 6 + r] = acc[hidx(r, c)]; H36[r * 6 + c] = acc[hidx(r, c)]; }
+        for (int i = 0; i < 6; ++i) B6[i] = acc[21 + i];
+        DevResult r{};
+        r.n_effective = static_cast<long long>(acc[28]);
+        r.n_inlier = static_cast<long long>(acc[29]);
+        r.sum_sq_res = acc[27];
+        r.pose_written = 1;
+        double dx[6];
+        const bool solvable = gn_solve6(acc, acc + 21, dx);
+        const bool few = r.n_effective < h->opt.min_effective_pts;
+        r.degenerate = (!solvable || (few && h->opt.method != LOCREG_NDT_DIRECT)) ? 1 : 0;
+        fill_result(res, r);
+        return LOCREG_OK;
+    });
+}
+
+int locreg_knn(locreg_handle* h, const float* queries, size_t nq, size_t stride, int32_t k, int32_t* idx) {
+    const int rc = check_cloud_args(queries, nq, stride);
+    if (rc) return rc;
+    if ((k != 1 && k != 5) || !idx) { g_last_error = "k must be 1 or 5"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        if (h->opt.method == LOCREG_NDT_DIRECT) { g_last_error = "k-NN probe needs an ICP handle"; return LOCREG_E_STATE; }
+        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
+        if (nq == 0) return LOCREG_OK;
+        const float4* q4 = stage_cloud(h, queries, nq, stride, false);
+        h->d_nn.reserve(nq * k * sizeof(int));
+        h->begin_timing();
+        const unsigned int grid = static_cast<unsigned int>((nq + 127) / 128);
+        if (k == 1) LR_LAUNCH(k_knn<1>, grid, 128, 0, h->stream, h->icp_map.view(), q4, static_cast<unsigned int>(nq), h->d_nn.as<int>());
+        else LR_LAUNCH(k_knn<5>, grid, 128, 0, h->stream, h->icp_map.view(), q4, static_cast<unsigned int>(nq), h->d_nn.as<int>());
+        h->end_timing();
+        LR_CUDA(cudaMemcpy(idx, h->d_nn.p, nq * k * sizeof(int), cudaMemcpyDeviceToHost));
+        return LOCREG_OK;
+    });
+}
+
+int locreg_debug_points(locreg_handle* h, const float* src, size_t n, size_t stride, const double* pose, uint8_t* gate,
+                        int32_t* nn) {
+    const int rc = check_cloud_args(src, n, stride);
+    if (rc) return rc;
+    if (!pose || !gate) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
+        if (n == 0) return LOCREG_OK;
+        const float4* src4 = stage_cloud(h, src, n, stride, false);
+        init_state(h, pose);
+        const int k = h->opt.method == LOCREG_ICP_P2P ? 1 : (h->opt.method == LOCREG_ICP_P2PLANE ? 5 : 0);
+        h->d_gate.reserve(n);
+        int* d_nn = nullptr;
+        if (nn && k) { h->d_nn.reserve(n * k * sizeof(int)); d_nn = h->d_nn.as<int>(); }
+        h->begin_timing();
+        DISPATCH_METHOD(h, run_eval(h, pb, src4, static_cast<unsigned int>(n), h->d_gate.as<unsigned char>(), d_nn));
+        h->end_timing();
+        LR_CUDA(cudaMemcpy(gate, h->d_gate.p, n, cudaMemcpyDeviceToHost));
+        if (d_nn) LR_CUDA(cudaMemcpy(nn, d_nn, n * k * sizeof(int), cudaMemcpyDeviceToHost));
+        return LOCREG_OK;
+    });
+}
+
+int locreg_align_batch_device(locreg_handle* h, const float* d_srcs, const int64_t* d_offsets, const double* d_poses_in,
+                              size_t S, size_t total_points, double* d_poses_out, locreg_result* d_results) {
+    (void)total_points;
+    if (!d_srcs || !d_offsets || !d_poses_in || !d_poses_out) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    if (S >= (1ull << 31)) { g_last_error = "too many scans"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
+        if (S == 0) return LOCREG_OK;
+        h->begin_timing();
+        DISPATCH_METHOD(h, run_batch(h, pb, reinterpret_cast<const float4*>(d_srcs), reinterpret_cast<const long long*>(d_offsets), 0u,
+                                     d_poses_in, d_poses_out, reinterpret_cast<DevResult*>(d_results), static_cast<unsigned int>(S), 0));
+        h->end_timing();
+        return LOCREG_OK;
+    });
+}
+
+int locreg_align_batch(locreg_handle* h, const float* srcs, const int64_t* offsets, size_t stride, const double* poses_in,
+                       size_t S, double* poses_out, locreg_result* results) {
+    if (!offsets || !poses_in || !poses_out) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    if (S >= (1ull << 31)) { g_last_error = "too many scans"; return LOCREG_E_ARG; }
+    if (S == 0) return LOCREG_OK;
+    for (size_t s = 0; s < S; ++s)
+        if (offsets[s + 1] < offsets[s] || offsets[s] < 0) { g_last_error = "offsets must be non-decreasing"; return LOCREG_E_ARG; }
+    const size_t total = static_cast<size_t>(offsets[S]);
+    const float* first = reinterpret_cast<const float*>(reinterpret_cast<const char*>(srcs) + static_cast<size_t>(offsets[0]) * stride);
+    const int rc = check_cloud_args(first, total - static_cast<size_t>(offsets[0]), stride);
+    if (rc) return rc;
+    return guarded(h, [&]() {
+        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
+        const size_t base = static_cast<size_t>(offsets[0]);
+        const float4* src4 = stage_cloud(h, first, total - base, stride, false);
+        h->d_offsets.reserve((S + 1) * sizeof(long long));
+        h->d_poses_in.reserve(S * 7 * sizeof(double));
+        h->d_poses_out.reserve(S * 7 * sizeof(double));
+        h->d_results.reserve(S * sizeof(DevResult));
+        h->h_in.reserve(0);
+        std::vector<long long> rel(S + 1);
+        for (size_t s = 0; s <= S; ++s) rel[s] = offsets[s] - static_cast<long long>(base);
+        LR_CUDA(cudaMemcpyAsync(h->d_offsets.p, rel.data(), (S + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+        LR_CUDA(cudaMemcpyAsync(h->d_poses_in.p, poses_in, S * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        LR_CUDA(cudaMemcpyAsync(h->d_poses_out.p, poses_out, S * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        LR_CUDA(cudaStreamSynchronize(h->stream));  // rel[] is pageable
+        h->begin_timing();
+        DISPATCH_METHOD(h, run_batch(h, pb, src4, h->d_offsets.as<long long>(), 0u, h->d_poses_in.as<double>(), h->d_poses_out.as<double>(),
+                                     h->d_results.as<DevResult>(), static_cast<unsigned int>(S), 0));
+        h->end_timing();
+        LR_CUDA(cudaMemcpy(poses_out, h->d_poses_out.p, S * 7 * sizeof(double), cudaMemcpyDeviceToHost));
+        if (results) LR_CUDA(cudaMemcpy(results, h->d_results.p, S * sizeof(DevResult), cudaMemcpyDeviceToHost));
+        return LOCREG_OK;
+    });
+}
+
+uint64_t locreg_pack_score(double score, uint32_t index) {
+    float f = static_cast<float>(score);
+    if (!(f == f) || f < 0) f = INFINITY;
+    uint32_t bits;
+    std::memcpy(&bits, &f, 4);
+    return (static_cast<uint64_t>(bits) << 32) | index;
+}
+
+int locreg_relocalise(locreg_handle* h, const float* src, size_t n, size_t stride, const double* poses_in, size_t n_hyp,
+                      double* best_pose, int64_t* best_idx, double* best_score, double* scores, double* poses_out) {
+    const int rc = check_cloud_args(src, n, stride);
+    if (rc) return rc;
+    if (!poses_in || n_hyp == 0 || n_hyp >= (1ull << 31)) { g_last_error = "invalid hypotheses"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
+        const float4* src4 = stage_cloud(h, src, n, stride, false);
+        h->d_poses_in.reserve(n_hyp * 7 * sizeof(double));
+        h->d_poses_out.reserve(n_hyp * 7 * sizeof(double));
+        h->d_results.reserve(n_hyp * sizeof(DevResult));
+        h->d_scores.reserve(n_hyp * sizeof(double));
+        h->d_misc.reserve(64);
+        LR_CUDA(cudaMemcpyAsync(h->d_poses_in.p, poses_in, n_hyp * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        LR_CUDA(cudaMemcpyAsync(h->d_poses_out.p, poses_in, n_hyp * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        LR_CUDA(cudaStreamSynchronize(h->stream));
+        h->begin_timing();
+        DISPATCH_METHOD(h, run_batch(h, pb, src4, nullptr, static_cast<unsigned int>(n), h->d_poses_in.as<double>(), h->d_poses_out.as<double>(),
+                                     h->d_results.as<DevResult>(), static_cast<unsigned int>(n_hyp), 1));
+        unsigned long long* d_key = reinterpret_cast<unsigned long long*>(h->d_misc.as<unsigned char>() + 32);
+        LR_CUDA(cudaMemsetAsync(d_key, 0xFF, sizeof(unsigned long long), h->stream));
+        LR_LAUNCH(k_score_argmin, static_cast<unsigned int>((n_hyp + 255) / 256), 256, 0, h->stream, h->d_results.as<DevResult>(),
+                  static_cast<unsigned int>(n_hyp), 0u, h->d_scores.as<double>(), d_key);
+        h->end_timing();
+        unsigned long long key = 0;
+        LR_CUDA(cudaMemcpy(&key, d_key, sizeof(key), cudaMemcpyDeviceToHost));
+        const uint32_t bi = static_cast<uint32_t>(key & 0xFFFFFFFFull);
+        if (best_idx) *best_idx = bi;
+        if (best_score) LR_CUDA(cudaMemcpy(best_score, h->d_scores.as<double>() + bi, sizeof(double), cudaMemcpyDeviceToHost));
+        if (best_pose) LR_CUDA(cudaMemcpy(best_pose, h->d_poses_out.as<double>() + static_cast<size_t>(bi) * 7, 7 * sizeof(double), cudaMemcpyDeviceToHost));
+        if (scores) LR_CUDA(cudaMemcpy(scores, h->d_scores.p, n_hyp * sizeof(double), cudaMemcpyDeviceToHost));
+        if (poses_out) LR_CUDA(cudaMemcpy(poses_out, h->d_poses_out.p, n_hyp * 7 * sizeof(double), cudaMemcpyDeviceToHost));
+        return LOCREG_OK;
+    });
+}
+
+int locreg_transform_cloud(locreg_handle* h, const float* src, size_t n, size_t stride, const double* pose, float* out_xyz) {
+    const int rc = check_cloud_args(src, n, stride);
+    if (rc) return rc;
+    if (!pose || !out_xyz) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        if (n == 0) return LOCREG_OK;
+        stage_cloud(h, src, n, stride, false);
+        h->d_out.reserve(n * stride);
+        h->d_acc.reserve(32 * sizeof(double));
+        LR_CUDA(cudaMemcpyAsync(h->d_acc.p, pose, 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        LR_CUDA(cudaStreamSynchronize(h->stream));
+        h->begin_timing();
+        const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((n + 255) / 256, 4096));
+        LR_LAUNCH(k_transform, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>(), h->d_out.as<unsigned char>(), n, stride, h->d_acc.as<double>());
+        h->end_timing();
+        LR_CUDA(cudaMemcpy(out_xyz, h->d_out.p, n * stride, cudaMemcpyDeviceToHost));
+        return LOCREG_OK;
+    });
+}
+
+int locreg_ndt_num_voxels(locreg_handle* h, size_t* nv) {
+    if (!h || !nv) return LOCREG_E_ARG;
+    *nv = h->ndt_map.view().n_voxels;
+    return LOCREG_OK;
+}
+int locreg_ndt_get_voxels(locreg_handle* h, int32_t* keys, double* mu, double* info, int32_t* npts) {
+    return guarded(h, [&]() {
+        std::vector<int> k, c;
+        std::vector<double> m, f;
+        h->ndt_map.download(k, m, f, c, h->stream);
+        if (keys) std::memcpy(keys, k.data(), k.size() * sizeof(int));
+        if (mu) std::memcpy(mu, m.data(), m.size() * sizeof(double));
+        if (info) std::memcpy(info, f.data(), f.size() * sizeof(double));
+        if (npts) std::memcpy(npts, c.data(), c.size() * sizeof(int));
+        return LOCREG_OK;
+    });
+}
+
+int locreg_last_timing(locreg_handle* h, double* kernel_ms, int64_t* launches) {
+    if (!h) return LOCREG_E_ARG;
+    if (kernel_ms) *kernel_ms = h->last_ms;
+    if (launches) *launches = h->last_launches;
+    return LOCREG_OK;
+}
+
+}  // extern "C"

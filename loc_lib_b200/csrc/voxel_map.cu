@@ -1,0 +1,275 @@
+// Voxel-hash map build kernels (K1) and the scan primitive.  See voxel_build.cuh for the pipeline.
+#include <algorithm>
+#include <vector>
+
+#include "device_map.cuh"
+#include "voxel_build.cuh"
+
+namespace locreg {
+
+thread_local long long g_launch_count = 0;
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* warp_sums, unsigned int& block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0u;
+        unsigned int winc = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, winc, off);
+            if (lane >= off) winc += t;
+        }
+        warp_sums[lane] = winc - w;  // exclusive warp offsets
+        if (lane == 31) warp_sums[32] = winc;
+    }
+    __syncthreads();
+    block_total = warp_sums[32];
+    return inc - v + warp_sums[warp];
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const unsigned int* __restrict__ in, size_t n,
+                                                                 unsigned int* __restrict__ tile_sums) {
+    __shared__ unsigned int warp_sums[33];
+    const size_t base = static_cast<size_t>(blockIdx.x) * kScanTile + static_cast<size_t>(threadIdx.x) * kScanItems;
+    unsigned int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (base + k < n) s += in[base + k];
+    unsigned int total;
+    block_exclusive_scan(s, warp_sums, total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const unsigned int* __restrict__ in, unsigned int* out, size_t n,
+                                                             const unsigned int* __restrict__ tile_offsets) {
+    __shared__ unsigned int warp_sums[33];
+    const size_t base = static_cast<size_t>(blockIdx.x) * kScanTile + static_cast<size_t>(threadIdx.x) * kScanItems;
+    unsigned int v[kScanItems];
+    unsigned int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0u;
+        s += v[k];
+    }
+    unsigned int total;
+    unsigned int run = block_exclusive_scan(s, warp_sums, total) + (tile_offsets ? tile_offsets[blockIdx.x] : 0u);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+}
+
+__global__ void k_scan_total(const unsigned int* tile_sums, const unsigned int* tile_offsets, size_t last_tile, unsigned int* total) {
+    *total = tile_sums[last_tile] + (tile_offsets ? tile_offsets[last_tile] : 0u);
+}
+
+void exclusive_scan_u32(const unsigned int* in, unsigned int* out, size_t n, unsigned int* total, cudaStream_t stream) {
+    if (n == 0) {
+        if (total) LR_CUDA(cudaMemsetAsync(total, 0, sizeof(unsigned int), stream));
+        return;
+    }
+    const size_t tiles = (n + kScanTile - 1) / kScanTile;
+    unsigned int* sums = nullptr;
+    unsigned int* offs = nullptr;
+    LR_CUDA(cudaMallocAsync(&sums, tiles * sizeof(unsigned int), stream));
+    LR_LAUNCH(k_scan_tile_sums, static_cast<unsigned int>(tiles), kScanThreads, 0, stream, in, n, sums);
+    if (tiles > 1) {
+        LR_CUDA(cudaMallocAsync(&offs, tiles * sizeof(unsigned int), stream));
+        exclusive_scan_u32(sums, offs, tiles, nullptr, stream);
+    }
+    if (total) LR_LAUNCH(k_scan_total, 1, 1, 0, stream, sums, offs, tiles - 1, total);
+    LR_LAUNCH(k_scan_tiles, static_cast<unsigned int>(tiles), kScanThreads, 0, stream, in, out, n, offs);
+    LR_CUDA(cudaFreeAsync(sums, stream));
+    if (offs) LR_CUDA(cudaFreeAsync(offs, stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// build kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_slots_clear(VoxelSlot* slots, unsigned int cap) {
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap) slots[s] = VoxelSlot{kEmptyKey, 0ull, 0u, 0u, 0u, 0u};
+}
+
+// bounds: [0..2] min cell coord, [3..5] max cell coord
+__global__ void k_build_insert(const void* __restrict__ xyz, size_t n, size_t stride, float inv_cell, VoxelSlot* slots,
+                               unsigned int slot_mask, unsigned int* pt_slot, unsigned char* pt_bit,
+                               unsigned int* counters, int* bounds) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int f[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+    int g[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
+    if (i < n) {
+        int c[3];
+        if (build_insert_body<DeviceAtomics>(i, xyz, stride, inv_cell, slots, slot_mask, pt_slot, pt_bit, counters, c)) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { f[a] = c[a]; g[a] = c[a]; }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int lo = __reduce_min_sync(0xffffffffu, f[a]);
+        const int hi = __reduce_max_sync(0xffffffffu, g[a]);
+        if ((threadIdx.x & 31) == 0) {
+            if (lo != 0x7fffffff) atomicMin(&bounds[a], lo);
+            if (hi != -0x7fffffff) atomicMax(&bounds[3 + a], hi);
+        }
+    }
+}
+
+__global__ void k_slot_popc(const VoxelSlot* __restrict__ slots, unsigned int cap, unsigned int* out) {
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap) out[s] = slots[s].key != kEmptyKey ? static_cast<unsigned int>(__popcll(slots[s].mask)) : 0u;
+}
+__global__ void k_slot_set_base(VoxelSlot* slots, unsigned int cap, const unsigned int* __restrict__ base) {
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap) slots[s].cell_base = base[s];
+}
+__global__ void k_build_count(size_t n, const VoxelSlot* __restrict__ slots, unsigned int* pt_slot,
+                              const unsigned char* __restrict__ pt_bit, unsigned int* cell_count) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) build_count_body<DeviceAtomics>(i, slots, pt_slot, pt_bit, cell_count);
+}
+__global__ void k_build_scatter(const void* __restrict__ xyz, size_t n, size_t stride, const unsigned int* __restrict__ pt_cell,
+                                unsigned int* cursor, float4* pts, unsigned int* pt_pos) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) build_scatter_body<DeviceAtomics>(i, xyz, stride, pt_cell, cursor, pts, pt_pos);
+}
+__global__ void k_build_dup_flag(size_t n, const unsigned int* __restrict__ pt_cell, const unsigned int* __restrict__ pt_pos,
+                                 const unsigned int* __restrict__ cell_start, const float4* __restrict__ pts,
+                                 unsigned char* dup, unsigned int* n_dup) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool d = false;
+    if (i < n) {
+        d = build_is_duplicate(i, pt_cell, pt_pos, cell_start, pts);
+        dup[i] = d ? 1 : 0;
+    }
+    const unsigned int c = __popc(__ballot_sync(0xffffffffu, d));
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_dup, c);
+}
+__global__ void k_build_dup_apply(size_t n, const unsigned char* __restrict__ dup, const unsigned int* __restrict__ pt_pos, float4* pts) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n && dup[i]) pts[pt_pos[i]].x = __int_as_float(0x7fc00000);
+}
+
+// ------------------------------------------------------------------------------------------------
+DeviceVoxelMap::~DeviceVoxelMap() { release(); }
+void DeviceVoxelMap::release() {
+    if (slots_) cudaFree(slots_);
+    if (cell_start_) cudaFree(cell_start_);
+    if (pts_) cudaFree(pts_);
+    slots_ = nullptr; cell_start_ = nullptr; pts_ = nullptr;
+    view_ = VoxelMapView{};
+    bytes_ = 0; n_cells_ = 0; n_blocks_ = 0;
+}
+
+static unsigned int next_pow2(size_t v) {
+    unsigned int p = 1024;
+    while (p < v && p < (1u << 31)) p <<= 1;
+    return p;
+}
+
+void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cell, cudaStream_t stream) {
+    release();
+    if (n == 0) return;
+    if (n >= (1ull << 31)) throw std::invalid_argument("target cloud too large (>= 2^31 points)");
+    const float inv_cell = 1.0f / cell;
+    const unsigned int T = 256;
+    const unsigned int gridN = static_cast<unsigned int>((n + T - 1) / T);
+    unsigned int *pt_slot = nullptr, *pt_pos = nullptr, *counters = nullptr, *tmp = nullptr, *cursor = nullptr;
+    unsigned char *pt_bit = nullptr, *dup = nullptr;
+    int* bounds = nullptr;
+    LR_CUDA(cudaMallocAsync(&pt_slot, n * sizeof(unsigned int), stream));
+    LR_CUDA(cudaMallocAsync(&pt_pos, n * sizeof(unsigned int), stream));
+    LR_CUDA(cudaMallocAsync(&pt_bit, n, stream));
+    LR_CUDA(cudaMallocAsync(&dup, n, stream));
+    LR_CUDA(cudaMallocAsync(&counters, 8 * sizeof(unsigned int), stream));
+    LR_CUDA(cudaMallocAsync(&bounds, 6 * sizeof(int), stream));
+    unsigned int cap = next_pow2(n / 4 + 1024);
+    unsigned int h_counters[8];
+    int h_bounds[6];
+    while (true) {
+        LR_CUDA(cudaMalloc(&slots_, static_cast<size_t>(cap) * sizeof(VoxelSlot)));
+        LR_LAUNCH(k_slots_clear, (cap + T - 1) / T, T, 0, stream, slots_, cap);
+        LR_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned int), stream));
+        const int init_bounds[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, -0x7fffffff, -0x7fffffff, -0x7fffffff};
+        LR_CUDA(cudaMemcpyAsync(bounds, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice, stream));
+        LR_LAUNCH(k_build_insert, gridN, T, 0, stream, d_xyz, n, stride, inv_cell, slots_, cap - 1, pt_slot, pt_bit,
+                  counters, bounds);
+        LR_CUDA(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, stream));
+        LR_CUDA(cudaMemcpyAsync(h_bounds, bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, stream));
+        LR_CUDA(cudaStreamSynchronize(stream));
+        if (h_counters[1] || static_cast<size_t>(h_counters[0]) * 2 > cap) {  // too loaded: grow and redo
+            cudaFree(slots_);
+            slots_ = nullptr;
+            if (cap >= (1u << 31)) throw std::runtime_error("voxel hash table overflow");
+            cap = cap << 2 ? cap << 2 : (1u << 31);
+            continue;
+        }
+        break;
+    }
+    n_blocks_ = h_counters[0];
+    const unsigned int n_kept = h_counters[2];
+    if (n_kept == 0) {  // every point was non-finite
+        cudaFree(slots_); slots_ = nullptr;
+        cudaFreeAsync(pt_slot, stream); cudaFreeAsync(pt_pos, stream); cudaFreeAsync(pt_bit, stream);
+        cudaFreeAsync(dup, stream); cudaFreeAsync(counters, stream); cudaFreeAsync(bounds, stream);
+        return;
+    }
+    // 2 rank: slot.cell_base = exclusive scan of popcount(mask)
+    LR_CUDA(cudaMallocAsync(&tmp, static_cast<size_t>(cap) * sizeof(unsigned int), stream));
+    LR_LAUNCH(k_slot_popc, (cap + T - 1) / T, T, 0, stream, slots_, cap, tmp);
+    exclusive_scan_u32(tmp, tmp, cap, counters + 4, stream);
+    LR_LAUNCH(k_slot_set_base, (cap + T - 1) / T, T, 0, stream, slots_, cap, tmp);
+    LR_CUDA(cudaMemcpyAsync(&n_cells_, counters + 4, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    LR_CUDA(cudaStreamSynchronize(stream));
+    LR_CUDA(cudaFreeAsync(tmp, stream));
+    // 3-4 histogram + scan -> cell_start
+    LR_CUDA(cudaMalloc(&cell_start_, (static_cast<size_t>(n_cells_) + 1) * sizeof(unsigned int)));
+    LR_CUDA(cudaMemsetAsync(cell_start_, 0, (static_cast<size_t>(n_cells_) + 1) * sizeof(unsigned int), stream));
+    LR_LAUNCH(k_build_count, gridN, T, 0, stream, n, slots_, pt_slot, pt_bit, cell_start_);
+    exclusive_scan_u32(cell_start_, cell_start_, static_cast<size_t>(n_cells_) + 1, nullptr, stream);
+    // 5 scatter
+    LR_CUDA(cudaMallocAsync(&cursor, static_cast<size_t>(n_cells_) * sizeof(unsigned int), stream));
+    LR_CUDA(cudaMemcpyAsync(cursor, cell_start_, static_cast<size_t>(n_cells_) * sizeof(unsigned int),
+                            cudaMemcpyDeviceToDevice, stream));
+    LR_CUDA(cudaMalloc(&pts_, static_cast<size_t>(n_kept) * sizeof(float4)));
+    LR_LAUNCH(k_build_scatter, gridN, T, 0, stream, d_xyz, n, stride, pt_slot, cursor, pts_, pt_pos);
+    // 6 dedupe (quirk Q3)
+    LR_CUDA(cudaMemsetAsync(counters + 5, 0, sizeof(unsigned int), stream));
+    LR_LAUNCH(k_build_dup_flag, gridN, T, 0, stream, n, pt_slot, pt_pos, cell_start_, pts_, dup, counters + 5);
+    LR_LAUNCH(k_build_dup_apply, gridN, T, 0, stream, n, dup, pt_pos, pts_);
+    unsigned int n_dup = 0;
+    LR_CUDA(cudaMemcpyAsync(&n_dup, counters + 5, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    LR_CUDA(cudaStreamSynchronize(stream));
+    LR_CUDA(cudaFreeAsync(cursor, stream));
+    LR_CUDA(cudaFreeAsync(pt_slot, stream));
+    LR_CUDA(cudaFreeAsync(pt_pos, stream));
+    LR_CUDA(cudaFreeAsync(pt_bit, stream));
+    LR_CUDA(cudaFreeAsync(dup, stream));
+    LR_CUDA(cudaFreeAsync(counters, stream));
+    LR_CUDA(cudaFreeAsync(bounds, stream));
+    view_.slots = slots_; view_.cell_start = cell_start_; view_.pts = pts_;
+    view_.slot_mask = cap - 1; view_.n_pts = n_kept; view_.n_unique = n_kept - n_dup;
+    view_.inv_cell = inv_cell; view_.cell = cell;
+    for (int a = 0; a < 3; ++a) { view_.cmin[a] = h_bounds[a]; view_.cmax[a] = h_bounds[3 + a]; }
+    bytes_ = static_cast<size_t>(cap) * sizeof(VoxelSlot) + (static_cast<size_t>(n_cells_) + 1) * 4 +
+             static_cast<size_t>(n_kept) * sizeof(float4);
+}
+
+}  // namespace locreg

@@ -1,0 +1,239 @@
+"""Host-side mirror of the reference's registration interface over the C ABI.
+
+Same names, argument meaning and return behaviour as LocUtils::MatchingInterface
+(LocUtils/include/LocUtils/model/matching/3d/matching_interface.h:13-54) and its two implementations
+IcpRegistration (icp_registration.hpp:41-142) and NdtRegistration (ndt_registration.hpp:69-135):
+    SetInputTarget(cloud) -> bool
+    ScanMatch(cloud, predict_pose) -> (True, result_cloud, result_pose)      # ScanMatch always returns true
+    CaculateMatrixHAndB(cloud, predict_pose) -> (bool, H, B)
+    GetFitnessScore() -> 0.0                                                  # always 0 in the reference
+Clouds are (n, >=3) float32 numpy arrays (row stride = point stride, e.g. (n, 8) for pcl::PointXYZI's 32 B);
+poses are 7 doubles [qx qy qz qw tx ty tz] (Sophus::SE3d::data()).  All computation happens in the CUDA
+kernels behind liblocreg.so; there is no CPU path.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import ICP_P2P, ICP_P2LINE, ICP_P2PLANE, NDT_DIRECT, NEARBY6, NEARBY_CENTER, LOOP_PERSISTENT, LOOP_GRAPH
+
+
+class IcpMethod:  # icp_registration.hpp:15-20
+    P2P, P2LINE, P2PLANE, PCLICP = 0, 1, 2, 3
+
+
+class NdtNearbyType:  # ndt_registration.hpp:16-20
+    CENTER, NEARBY6 = 0, 1
+
+
+@dataclass
+class IcpOptions:  # icp_registration.hpp:22-39
+    max_iteration_: int = 20
+    max_nn_distance_: float = 1.0
+    max_plane_distance_: float = 0.1
+    max_line_distance_: float = 0.5
+    min_effective_pts_: int = 10
+    eps_: float = 1e-2
+    euc_fitness_eps_: float = 0.36
+    use_initial_translation_: bool = True
+    use_ann: bool = False
+    method_: int = IcpMethod.P2P
+    # GPU-side knobs
+    knn_cell_size: float = 0.5
+    loop_mode: int = LOOP_PERSISTENT
+
+
+@dataclass
+class NdtOptions:  # ndt_registration.hpp:27-42
+    max_iteration_: int = 20
+    voxel_size_: float = 1.0
+    inv_voxel_size_: float = 1.0  # ignored: recomputed from voxel_size_ (ndt_registration.cpp:25)
+    min_effective_pts_: int = 10
+    min_pts_in_voxel_: int = 3
+    max_pts_in_voxel_: int = 50
+    eps_: float = 1e-2
+    res_outlier_th_: float = 20.0
+    remove_centroid_: bool = False
+    capacity_: int = 100000
+    nearby_type_: int = NdtNearbyType.NEARBY6
+    loop_mode: int = LOOP_PERSISTENT
+
+
+def _cloud(a):
+    a = np.asarray(a)
+    if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] < 3 or a.strides[1] != 4:
+        a = np.ascontiguousarray(a, np.float32)
+        assert a.ndim == 2 and a.shape[1] >= 3, "cloud must be (n, >=3) float32"
+    return a, a.shape[0], a.strides[0] if a.shape[0] else a.shape[1] * 4
+
+
+def _pose(p):
+    p = np.ascontiguousarray(p, np.float64)
+    assert p.shape == (7,), "pose must be 7 doubles [qx qy qz qw tx ty tz]"
+    return p
+
+
+class _Registration:
+    """Common C-ABI plumbing; subclasses only build the options."""
+
+    def __init__(self, copt, device=0):
+        self._h = C.c_void_p()
+        self._opt = copt
+        _lib.check(_lib.lib().locreg_create(C.byref(copt), device, C.byref(self._h)))
+        self.last_result = None
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().locreg_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream):
+        _lib.check(_lib.lib().locreg_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    # ---- MatchingInterface ----
+    def SetInputTarget(self, cloud):
+        a, n, s = _cloud(cloud)
+        _lib.check(_lib.lib().locreg_set_target(self._h, a.ctypes.data, n, s))
+        return True
+
+    def SetInputTargetDevice(self, dev_ptr, n, stride):
+        _lib.check(_lib.lib().locreg_set_target_device(self._h, C.c_void_p(dev_ptr), n, stride))
+        return True
+
+    def ScanMatch(self, cloud, predict_pose, result_pose_init=None, want_cloud=True):
+        a, n, s = _cloud(cloud)
+        pin = _pose(predict_pose)
+        pout = np.array([0, 0, 0, 1, 0, 0, 0], np.float64) if result_pose_init is None else \
+            _pose(result_pose_init).copy()
+        out = np.empty_like(a) if want_cloud else None
+        res = _lib.Result()
+        _lib.check(_lib.lib().locreg_align(self._h, a.ctypes.data, n, s, pin.ctypes.data, pout.ctypes.data,
+                                           out.ctypes.data if want_cloud else None, C.byref(res)))
+        self.last_result = res.as_dict()
+        return True, out, pout
+
+    def CaculateMatrixHAndB(self, cloud, predict_pose):
+        a, n, s = _cloud(cloud)
+        pin = _pose(predict_pose)
+        H = np.zeros(36)
+        B = np.zeros(6)
+        res = _lib.Result()
+        _lib.check(_lib.lib().locreg_compute_hb(self._h, a.ctypes.data, n, s, pin.ctypes.data, H.ctypes.data,
+                                                B.ctypes.data, C.byref(res)))
+        self.last_result = res.as_dict()
+        return res.degenerate == 0, H.reshape(6, 6).T.copy(), B
+
+    def GetFitnessScore(self):
+        return 0.0  # icp_registration.cpp:246-250 / ndt_registration.cpp:466-471
+
+    # ---- batch / relocalisation (new capabilities, BASELINE configs 4 and 5) ----
+    def ScanMatchBatch(self, clouds, offsets, predict_poses, result_poses_init=None):
+        a, n, s = _cloud(clouds)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        S = offsets.shape[0] - 1
+        pin = np.ascontiguousarray(predict_poses, np.float64).reshape(S, 7)
+        pout = pin.copy() if result_poses_init is None else np.ascontiguousarray(result_poses_init, np.float64).copy()
+        res = (_lib.Result * S)()
+        _lib.check(_lib.lib().locreg_align_batch(self._h, a.ctypes.data, offsets.ctypes.data, s, pin.ctypes.data, S,
+                                                 pout.ctypes.data, res))
+        return pout, [r.as_dict() for r in res]
+
+    def Relocalise(self, cloud, hypotheses, want_all=False):
+        a, n, s = _cloud(cloud)
+        hyp = np.ascontiguousarray(hypotheses, np.float64).reshape(-1, 7)
+        nh = hyp.shape[0]
+        best_pose = np.zeros(7)
+        best_idx = C.c_int64(-1)
+        best_score = C.c_double(np.inf)
+        scores = np.zeros(nh) if want_all else None
+        poses = np.zeros((nh, 7)) if want_all else None
+        _lib.check(_lib.lib().locreg_relocalise(self._h, a.ctypes.data, n, s, hyp.ctypes.data, nh,
+                                                best_pose.ctypes.data, C.byref(best_idx), C.byref(best_score),
+                                                scores.ctypes.data if want_all else None,
+                                                poses.ctypes.data if want_all else None))
+        return best_pose, int(best_idx.value), float(best_score.value), scores, poses
+
+    # ---- parity probes ----
+    def Knn(self, queries, k):
+        a, n, s = _cloud(queries)
+        out = np.empty((n, k), np.int32)
+        _lib.check(_lib.lib().locreg_knn(self._h, a.ctypes.data, n, s, k, out.ctypes.data))
+        return out
+
+    def DebugPoints(self, cloud, pose, k):
+        a, n, s = _cloud(cloud)
+        gate = np.zeros(n, np.uint8)
+        nn = np.full((n, k), -1, np.int32) if k else None
+        _lib.check(_lib.lib().locreg_debug_points(self._h, a.ctypes.data, n, s, _pose(pose).ctypes.data,
+                                                  gate.ctypes.data, nn.ctypes.data if k else None))
+        return gate, nn
+
+    def TransformCloud(self, cloud, pose):
+        a, n, s = _cloud(cloud)
+        out = np.empty_like(a)
+        _lib.check(_lib.lib().locreg_transform_cloud(self._h, a.ctypes.data, n, s, _pose(pose).ctypes.data,
+                                                     out.ctypes.data))
+        return out
+
+    def last_timing(self):
+        ms = C.c_double()
+        launches = C.c_int64()
+        _lib.lib().locreg_last_timing(self._h, C.byref(ms), C.byref(launches))
+        return ms.value, launches.value
+
+
+class IcpRegistration(_Registration):
+    """IcpRegistration(IcpOptions) (icp_registration.hpp:59-82)."""
+
+    def __init__(self, options=None, device=0):
+        options = options or IcpOptions()
+        if options.method_ == IcpMethod.PCLICP:
+            raise _lib.LocregError("PCLICP is a passthrough to pcl::IterativeClosestPoint and is out of scope")
+        o = _lib.Options()
+        _lib.lib().locreg_default_options(C.byref(o), options.method_)
+        o.max_iteration = options.max_iteration_
+        o.max_nn_distance = options.max_nn_distance_
+        o.max_plane_distance = options.max_plane_distance_
+        o.max_line_distance = options.max_line_distance_
+        o.min_effective_pts = options.min_effective_pts_
+        o.eps = options.eps_
+        o.use_ann = int(options.use_ann)
+        o.knn_cell_size = options.knn_cell_size
+        o.loop_mode = options.loop_mode
+        self.options_ = options
+        super().__init__(o, device)
+
+
+class NdtRegistration(_Registration):
+    """NdtRegistration(NdtOptions) (ndt_registration.cpp:20-28), DIRECT_NDT only."""
+
+    def __init__(self, options=None, device=0):
+        options = options or NdtOptions()
+        o = _lib.Options()
+        _lib.lib().locreg_default_options(C.byref(o), NDT_DIRECT)
+        o.max_iteration = options.max_iteration_
+        o.voxel_size = options.voxel_size_
+        o.min_effective_pts = options.min_effective_pts_
+        o.min_pts_in_voxel = options.min_pts_in_voxel_
+        o.eps = options.eps_
+        o.res_outlier_th = options.res_outlier_th_
+        o.nearby_type = options.nearby_type_
+        o.loop_mode = options.loop_mode
+        self.options_ = options
+        super().__init__(o, device)
+
+    def Voxels(self):
+        nv = C.c_size_t()
+        _lib.check(_lib.lib().locreg_ndt_num_voxels(self._h, C.byref(nv)))
+        nv = nv.value
+        keys = np.zeros((nv, 3), np.int32)
+        mu = np.zeros((nv, 3))
+        info = np.zeros((nv, 3, 3))
+        npts = np.zeros(nv, np.int32)
+        _lib.check(_lib.lib().locreg_ndt_get_voxels(self._h, keys.ctypes.data, mu.ctypes.data, info.ctypes.data,
+                                                    npts.ctypes.data))
+        return keys, mu, info, npts

@@ -534,6 +534,11 @@ struct Ndt {
                 for (int r = 0; r < 3; ++r)
                     for (int c = 0; c < 3; ++c) A[r * 3 + c] = cov.m[r][c];
                 jacobi_svd(A, 3, 3, sig, V, &U);
+                // a numerically zero singular value has no defined left vector (Eigen returns noise there):
+                // take u = v, i.e. treat the PSD covariance as exactly symmetric
+                for (int j = 0; j < 3; ++j)
+                    if (!(sig[j] > 1e-12 * sig[0]))
+                        for (int r = 0; r < 3; ++r) U[r * 3 + j] = V[r * 3 + j];
                 double lambda[3] = {sig[0], sig[1], sig[2]};
                 if (lambda[1] < lambda[0] * 1e-3) lambda[1] = lambda[0] * 1e-3;
                 if (lambda[2] < lambda[0] * 1e-3) lambda[2] = lambda[0] * 1e-3;

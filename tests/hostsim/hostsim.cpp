@@ -184,3 +184,124 @@ void hs_sym3_eigen(const double* S6, double* lam3, double* Q9) { sym3_eigen(S6, 
 int hs_gn_solve6(const double* Hu21, const double* b6, double* dx6) { return gn_solve6(Hu21, b6, dx6) ? 1 : 0; }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// NDT
+// ---------------------------------------------------------------------------------------------
+#include <algorithm>
+
+struct HsNdt {
+    std::vector<NdtSlot> slots;
+    std::vector<NdtVoxel> voxels;
+    NdtMapView view;
+};
+
+static NdtParams make_ndt_params(const double* prm) {  // res_outlier_th, eps, max_iteration, min_effective_pts, min_pts_in_voxel, n_nearby
+    NdtParams p;
+    p.res_outlier_th = prm[0]; p.eps = prm[1]; p.max_iteration = static_cast<int>(prm[2]);
+    p.min_effective_pts = static_cast<int>(prm[3]); p.min_pts_in_voxel = static_cast<int>(prm[4]);
+    p.n_nearby = static_cast<int>(prm[5]);
+    return p;
+}
+static void ndt_hb_impl(const HsNdt* m, const NdtParams& p, const float* src, size_t n, size_t stride, const Pose& T,
+                        Accum& acc, uint8_t* hits) {
+    accum_zero(acc);
+    for (size_t i = 0; i < n; ++i) {
+        const float* s = point_ptr(src, i, stride);
+        const unsigned char h = ndt_point(m->view, p, T, s[0], s[1], s[2], acc);
+        if (hits) hits[i] = h;
+    }
+}
+
+extern "C" {
+
+HsNdt* hs_ndt_create(const float* xyz, size_t n, size_t stride, double voxel_size, int min_pts) {
+    auto* m = new HsNdt;
+    const double inv = 1.0 / voxel_size;
+    unsigned int cap = 1024;
+    while (cap < n / 4 + 1024) cap <<= 1;
+    std::vector<unsigned int> pt_slot(n);
+    unsigned int counters[2];
+    while (true) {
+        m->slots.assign(cap, NdtSlot{kNdtEmpty, -1, 0u});
+        counters[0] = counters[1] = 0;
+        for (size_t i = 0; i < n; ++i) ndt_insert_body<HostAtomics>(i, xyz, stride, inv, m->slots.data(), cap - 1, pt_slot.data(), counters);
+        if (counters[1] || counters[0] * 2u > cap) { cap <<= 2; continue; }
+        break;
+    }
+    std::vector<unsigned int> start(cap + 1, 0);
+    for (unsigned int s = 0; s < cap; ++s) start[s + 1] = start[s] + m->slots[s].count;
+    std::vector<unsigned int> cursor(start.begin(), start.end() - 1), members(n);
+    for (size_t i = 0; i < n; ++i)
+        if (pt_slot[i] != 0xFFFFFFFFu) members[cursor[pt_slot[i]]++] = static_cast<unsigned int>(i);
+    for (unsigned int s = 0; s < cap; ++s) {
+        const unsigned int cnt = m->slots[s].count;
+        if (m->slots[s].key == kNdtEmpty || !(static_cast<long long>(cnt) > static_cast<long long>(min_pts))) continue;
+        unsigned int* idx = members.data() + start[s];
+        std::sort(idx, idx + cnt);
+        NdtVoxel v;
+        ndt_voxel_stats(idx, cnt, xyz, stride, v);
+        m->slots[s].vid = static_cast<int>(m->voxels.size());
+        m->voxels.push_back(v);
+    }
+    m->view.slots = m->slots.data(); m->view.voxels = m->voxels.data(); m->view.slot_mask = cap - 1;
+    m->view.n_voxels = static_cast<unsigned int>(m->voxels.size()); m->view.inv_voxel = inv;
+    return m;
+}
+void hs_ndt_destroy(HsNdt* m) { delete m; }
+size_t hs_ndt_num_voxels(const HsNdt* m) { return m->voxels.size(); }
+void hs_ndt_get_voxels(const HsNdt* m, int32_t* keys, double* mu, double* info, int32_t* npts) {
+    struct Rec { int k[3]; int vid; int cnt; };
+    std::vector<Rec> recs;
+    for (const NdtSlot& s : m->slots)
+        if (s.key != kNdtEmpty && s.vid >= 0) {
+            Rec r;
+            ndt_unpack(s.key, r.k[0], r.k[1], r.k[2]);
+            r.vid = s.vid; r.cnt = static_cast<int>(s.count);
+            recs.push_back(r);
+        }
+    std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) {
+        if (a.k[0] != b.k[0]) return a.k[0] < b.k[0];
+        if (a.k[1] != b.k[1]) return a.k[1] < b.k[1];
+        return a.k[2] < b.k[2];
+    });
+    for (size_t i = 0; i < recs.size(); ++i) {
+        for (int a = 0; a < 3; ++a) { keys[i * 3 + a] = recs[i].k[a]; mu[i * 3 + a] = m->voxels[recs[i].vid].mu[a]; }
+        for (int a = 0; a < 9; ++a) info[i * 9 + a] = m->voxels[recs[i].vid].info[a];
+        npts[i] = recs[i].cnt;
+    }
+}
+void hs_ndt_hb(const HsNdt* m, const double* prm, const float* src, size_t n, size_t stride, const double* pose7,
+               double* H36, double* B6, int64_t* counts, double* sum_sq, uint8_t* hits) {
+    const NdtParams p = make_ndt_params(prm);
+    Pose T;
+    pose_load(T, pose7);
+    Accum acc;
+    ndt_hb_impl(m, p, src, n, stride, T, acc, hits);
+    unpack(acc, H36, B6);
+    counts[0] = acc.n_eff; counts[1] = acc.n_inl;
+    *sum_sq = acc.v[27];
+}
+// status: [0]=updates [1]=converged [2]=degenerate [3]=pose_written
+int hs_ndt_align(const HsNdt* m, const double* prm, const float* src, size_t n, size_t stride, const double* pose_in,
+                 double* pose_inout, int32_t* status) {
+    const NdtParams p = make_ndt_params(prm);
+    Pose T;
+    pose_load(T, pose_in);
+    int iters = 0;
+    status[0] = status[1] = status[2] = 0; status[3] = 1;
+    for (int it = 0; it < p.max_iteration; ++it) {
+        Accum acc;
+        ndt_hb_impl(m, p, src, n, stride, T, acc, nullptr);
+        const int r = ndt_gn_update(acc.v, acc.n_eff, p, T);
+        iters = it + 1;
+        status[2] = (r == 0 || r == 3);
+        if (r == 1 || r == 2) status[0]++;
+        if (r == 2) { status[1] = 1; break; }
+        if (r == 3) { status[3] = 0; break; }
+    }
+    if (status[3]) pose_store(T, pose_inout);
+    return iters;
+}
+
+}  // extern "C"

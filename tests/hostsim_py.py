@@ -103,3 +103,61 @@ def sym3_eigen(S6):
     Q = np.zeros((3, 3))
     lib().hs_sym3_eigen(s.ctypes.data, lam.ctypes.data, Q.ctypes.data)
     return lam, Q
+
+
+def ndt_params(res_outlier_th=20.0, eps=1e-2, max_iteration=20, min_effective_pts=10, min_pts_in_voxel=3, n_nearby=7):
+    return np.array([res_outlier_th, eps, max_iteration, min_effective_pts, min_pts_in_voxel, n_nearby], np.float64)
+
+
+class HsNdt:
+    def __init__(self, cloud, voxel_size=1.0, min_pts=3):
+        L = lib()
+        vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+        L.hs_ndt_create.restype = vp
+        L.hs_ndt_create.argtypes = [vp, sz, sz, C.c_double, i32]
+        L.hs_ndt_destroy.argtypes = [vp]
+        L.hs_ndt_num_voxels.restype = sz
+        L.hs_ndt_num_voxels.argtypes = [vp]
+        L.hs_ndt_get_voxels.argtypes = [vp, vp, vp, vp, vp]
+        L.hs_ndt_hb.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp]
+        L.hs_ndt_align.restype = i32
+        L.hs_ndt_align.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp]
+        a, n, s = _cloud(cloud)
+        self._h = L.hs_ndt_create(a.ctypes.data, n, s, voxel_size, min_pts)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().hs_ndt_destroy(self._h)
+            self._h = None
+
+    def voxels(self):
+        nv = lib().hs_ndt_num_voxels(self._h)
+        keys = np.zeros((nv, 3), np.int32)
+        mu = np.zeros((nv, 3))
+        info = np.zeros((nv, 3, 3))
+        npts = np.zeros(nv, np.int32)
+        lib().hs_ndt_get_voxels(self._h, keys.ctypes.data, mu.ctypes.data, info.ctypes.data, npts.ctypes.data)
+        return keys, mu, info, npts
+
+    def hb(self, prm, src, pose7):
+        a, n, s = _cloud(src)
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        H = np.zeros(36)
+        B = np.zeros(6)
+        counts = np.zeros(2, np.int64)
+        ssq = np.zeros(1)
+        hits = np.zeros(n, np.uint8)
+        lib().hs_ndt_hb(self._h, prm.ctypes.data, a.ctypes.data, n, s, pose7.ctypes.data, H.ctypes.data,
+                        B.ctypes.data, counts.ctypes.data, ssq.ctypes.data, hits.ctypes.data)
+        return H.reshape(6, 6).T.copy(), B, dict(n_effective=int(counts[0]), n_inlier=int(counts[1]),
+                                                 sum_sq_res=float(ssq[0])), hits
+
+    def align(self, prm, src, pose7, pose_out_init=None):
+        a, n, s = _cloud(src)
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        out = np.array([0, 0, 0, 1, 0, 0, 0], np.float64) if pose_out_init is None else np.array(pose_out_init, np.float64)
+        st = np.zeros(4, np.int32)
+        it = lib().hs_ndt_align(self._h, prm.ctypes.data, a.ctypes.data, n, s, pose7.ctypes.data, out.ctypes.data,
+                                st.ctypes.data)
+        return out, dict(iters=it, updates=int(st[0]), converged=int(st[1]), degenerate=int(st[2]),
+                         pose_written=int(st[3]))

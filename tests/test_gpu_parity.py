@@ -1,0 +1,247 @@
+"""-m gpu parity tests: the CUDA path through the C ABI against the CPU oracle on identical seeded inputs.
+
+Gates (BASELINE.json north_star): NN indices bit-exact under the (float32 dis2, index) order; gate masks identical;
+H and B within 1e-6 relative; final poses within 1e-5 rad / 1e-4 m.
+"""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from conftest import pose_delta
+
+pytestmark = pytest.mark.gpu
+
+H_TOL = 1e-6
+ROT_TOL, TRANS_TOL = 1e-5, 1e-4
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def icp_pair(scene):
+    import loc_lib_b200 as L
+    gpu = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=10, eps_=0.0))
+    gpu.SetInputTarget(scene.map)
+    ref = O.OracleIcp(method=O.P2PLANE, max_iteration=10, eps=0.0, nn_mode=O.NN_EXACT_TIEBREAK, skip_nonfinite=1)
+    ref.set_target(scene.map)
+    return gpu, ref
+
+
+def test_knn_bit_exact(scene, icp_pair):
+    gpu, ref = icp_pair
+    R = O.pose_matrix(scene.init[0])
+    q = (scene.scan[:, :3].astype(np.float64) @ R.T + scene.init[0][4:]).astype(np.float32)
+    rng = np.random.default_rng(7)
+    far = rng.uniform(-60, 60, (4000, 3)).astype(np.float32)
+    far[:, 2] = rng.uniform(-4, 25, 4000)
+    for queries in (q, far):
+        for k in (1, 5):
+            assert np.array_equal(gpu.Knn(queries, k), ref.knn(queries, k))
+
+
+def test_knn_matches_brute_force(scene, icp_pair):
+    gpu, _ = icp_pair
+    rng = np.random.default_rng(11)
+    q = scene.map[rng.integers(0, len(scene.map), 300), :3] + rng.normal(0, 0.3, (300, 3)).astype(np.float32)
+    assert np.array_equal(gpu.Knn(q.astype(np.float32), 5), O.bfnn(scene.map, q.astype(np.float32), 5))
+
+
+@pytest.mark.parametrize("method", ["P2PLANE", "P2P"])
+def test_hb_and_gates(scene, method):
+    import loc_lib_b200 as L
+    m = getattr(L.IcpMethod, method)
+    # tight thresholds so that every gate has points on both sides
+    gpu = L.IcpRegistration(L.IcpOptions(method_=m, max_plane_distance_=0.004, max_nn_distance_=0.08))
+    gpu.SetInputTarget(scene.map)
+    ref = O.OracleIcp(method=getattr(O, method), max_plane_distance=0.004, max_nn_distance=0.08,
+                      nn_mode=O.NN_EXACT_TIEBREAK, skip_nonfinite=1)
+    ref.set_target(scene.map)
+    for pose in (scene.init[0], scene.gt[0]):
+        ok, H, B = gpu.CaculateMatrixHAndB(scene.scan, pose)
+        rok, rH, rB, rres, rgate, rnn = ref.compute_hb(scene.scan, pose)
+        k = 1 if method == "P2P" else 5
+        gate, nn = gpu.DebugPoints(scene.scan, pose, k)
+        assert np.array_equal(nn, rnn)
+        assert np.array_equal(gate, rgate)
+        assert len(set(rgate.tolist())) >= 2
+        assert rel(H, rH) < H_TOL and rel(B, rB) < H_TOL
+        assert bool(ok) == bool(rok)
+        assert gpu.last_result["n_effective"] == rres["n_effective"]
+        assert gpu.last_result["n_inlier"] == rres["n_inlier"]
+
+
+@pytest.mark.parametrize("loop_mode", [0, 1])
+@pytest.mark.parametrize("method", ["P2PLANE", "P2P"])
+def test_scan_match_pose(scene, method, loop_mode):
+    import loc_lib_b200 as L
+    gpu = L.IcpRegistration(L.IcpOptions(method_=getattr(L.IcpMethod, method), max_iteration_=10, eps_=0.0,
+                                         loop_mode=loop_mode))
+    gpu.SetInputTarget(scene.map)
+    ref = O.OracleIcp(method=getattr(O, method), max_iteration=10, eps=0.0, nn_mode=O.NN_EXACT_TIEBREAK,
+                      skip_nonfinite=1)
+    ref.set_target(scene.map)
+    for i in range(2):
+        ok, cloud, pose = gpu.ScanMatch(scene.scans[i], scene.init[i])
+        rpose, rcloud, rres, _ = ref.align(scene.scans[i], scene.init[i])
+        dr, dt = pose_delta(pose, rpose)
+        assert ok and dr < ROT_TOL and dt < TRANS_TOL
+        assert gpu.last_result["iters"] == rres["iters"] and gpu.last_result["updates"] == rres["updates"]
+        assert gpu.last_result["n_inlier"] == rres["n_inlier"]
+        # transformed cloud: float32 transform of the (slightly different) double pose
+        assert np.abs(cloud[:, :3] - rcloud[:, :3]).max() < 2e-4
+        assert np.array_equal(cloud[:, 3], scene.scans[i][:, 3])
+
+
+def test_convergence_break_and_default_options(scene):
+    import loc_lib_b200 as L
+    gpu = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE))  # eps 1e-2, 20 iterations
+    gpu.SetInputTarget(scene.map)
+    ref = O.OracleIcp(method=O.P2PLANE, nn_mode=O.NN_EXACT_TIEBREAK, skip_nonfinite=1)
+    ref.set_target(scene.map)
+    _, _, pose = gpu.ScanMatch(scene.scan, scene.init[0], want_cloud=False)
+    rpose, _, rres, _ = ref.align(scene.scan, scene.init[0], want_cloud=False)
+    assert gpu.last_result["converged"] == rres["converged"] == 1
+    assert gpu.last_result["iters"] == rres["iters"]
+    dr, dt = pose_delta(pose, rpose)
+    assert dr < ROT_TOL and dt < TRANS_TOL
+
+
+def test_transform_cloud_bit_exact(scene, icp_pair):
+    gpu, _ = icp_pair
+    pts = np.zeros((len(scene.scan), 8), np.float32)  # pcl::PointXYZI layout: 32-byte stride
+    pts[:, :3] = scene.scan[:, :3]
+    pts[:, 4] = scene.scan[:, 3]
+    pts[5, 0] = np.nan
+    out = gpu.TransformCloud(pts, scene.gt[0])
+    ref = O.transform_cloud(pts, scene.gt[0])
+    assert np.array_equal(out, ref, equal_nan=True)
+
+
+def test_edge_cases(scene):
+    import loc_lib_b200 as L
+    gpu = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=3))
+    gpu.SetInputTarget(scene.map)
+    # empty scan: every evaluation fails (effective_num < min_effective_pts), pose stays the prediction
+    ok, cloud, pose = gpu.ScanMatch(np.zeros((0, 4), np.float32), scene.init[0])
+    assert ok and np.allclose(pose, scene.init[0]) and gpu.last_result["degenerate"] == 1
+    assert gpu.last_result["iters"] == 3 and gpu.last_result["updates"] == 0
+    # scan with non-finite points: skipped (deviation D1), rest unchanged
+    s = scene.scan.copy()
+    s[::7, 1] = np.nan
+    ref = O.OracleIcp(method=O.P2PLANE, max_iteration=3, nn_mode=O.NN_EXACT_TIEBREAK, skip_nonfinite=1)
+    ref.set_target(scene.map)
+    _, _, pose = gpu.ScanMatch(s, scene.init[0], want_cloud=False)
+    rpose, _, _, _ = ref.align(s, scene.init[0], want_cloud=False)
+    dr, dt = pose_delta(pose, rpose)
+    assert dr < ROT_TOL and dt < TRANS_TOL
+    # duplicates in the map (quirk Q3) and a tiny map (< 5 leaves)
+    dup = np.concatenate([scene.map[:5000], scene.map[:2500]])
+    g2 = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE))
+    g2.SetInputTarget(dup)
+    r2 = O.OracleIcp(method=O.P2PLANE, nn_mode=O.NN_EXACT_TIEBREAK)
+    r2.set_target(dup)
+    q = dup[::50, :3] + np.float32(0.01)
+    assert np.array_equal(g2.Knn(q, 5), r2.knn(q, 5))
+    g2.SetInputTarget(scene.map[:3])
+    assert np.all(g2.Knn(q, 5)[:, 3:] == -1)
+    ok, H, B = g2.CaculateMatrixHAndB(scene.scan, scene.init[0])
+    assert not ok and np.all(H == 0)
+
+
+def test_batch_matches_single(scene):
+    import loc_lib_b200 as L
+    gpu = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=10, eps_=0.0))
+    gpu.SetInputTarget(scene.map)
+    ref = O.OracleIcp(method=O.P2PLANE, max_iteration=10, eps=0.0, nn_mode=O.NN_EXACT_TIEBREAK, skip_nonfinite=1)
+    ref.set_target(scene.map)
+    clouds = np.concatenate(scene.scans)
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in scene.scans])]).astype(np.int64)
+    poses, results = gpu.ScanMatchBatch(clouds, offsets, scene.init)
+    for i in range(len(scene.scans)):
+        rpose, _, rres, _ = ref.align(scene.scans[i], scene.init[i], want_cloud=False)
+        dr, dt = pose_delta(poses[i], rpose)
+        assert dr < ROT_TOL and dt < TRANS_TOL
+        assert results[i]["iters"] == rres["iters"] and results[i]["n_inlier"] == rres["n_inlier"]
+
+
+def test_relocalise(scene):
+    import loc_lib_b200 as L
+    from loc_lib_b200 import synth
+    gpu = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=6, eps_=0.0))
+    gpu.SetInputTarget(scene.map)
+    hyp = np.stack([synth.perturb_pose(scene.gt[0], 1000 + i, 1.5, 6.0) for i in range(48)])
+    hyp[17] = scene.init[0]
+    best_pose, best_idx, best_score, scores, poses = gpu.Relocalise(scene.scan, hyp, want_all=True)
+    ref = O.OracleIcp(method=O.P2PLANE, max_iteration=6, eps=0.0, nn_mode=O.NN_EXACT_TIEBREAK, skip_nonfinite=1)
+    ref.set_target(scene.map)
+    rscores = []
+    for i in (3, 17, 30):
+        rpose, _, _, _ = ref.align(scene.scan, hyp[i], want_cloud=False)
+        _, _, _, rres, _, _ = ref.compute_hb(scene.scan, rpose, False, False)
+        sc = rres["sum_sq_res"] / rres["n_inlier"] if rres["n_inlier"] else np.inf
+        rscores.append(sc)
+        dr, dt = pose_delta(poses[i], rpose)
+        assert dr < 1e-4 and dt < 1e-3  # far hypotheses are ill-conditioned; the contract applies to the winner
+        assert abs(scores[i] - sc) <= 1e-5 * sc
+    assert best_idx == int(np.argmin(np.float32(scores)))
+    assert np.isclose(best_score, scores[best_idx])
+    dr, dt = pose_delta(best_pose, scene.gt[0])
+    assert dr < 5e-3 and dt < 0.05
+
+
+# ---------------------------------------------------------------------------------------------- NDT
+@pytest.fixture(scope="module")
+def ndt_pair(scene):
+    import loc_lib_b200 as L
+    gpu = L.NdtRegistration(L.NdtOptions(max_iteration_=10, eps_=0.0))
+    gpu.SetInputTarget(scene.map)
+    ref = O.OracleNdt(max_iteration=10, eps=0.0, skip_nonfinite=1)
+    ref.set_target(scene.map)
+    return gpu, ref
+
+
+def test_ndt_voxels(ndt_pair):
+    gpu, ref = ndt_pair
+    k, mu, info, npts = gpu.Voxels()
+    rk, rmu, rinfo, rn = ref.voxels()
+    assert np.array_equal(k, rk) and np.array_equal(npts, rn)
+    assert np.array_equal(mu, rmu)  # same summation order, no FMA: bit-exact
+    assert np.abs(info - rinfo).max() <= 1e-9 * np.abs(rinfo).max()
+
+
+@pytest.mark.parametrize("nearby", [0, 1])
+def test_ndt_hb_and_pose(scene, nearby):
+    import loc_lib_b200 as L
+    gpu = L.NdtRegistration(L.NdtOptions(max_iteration_=10, eps_=0.0, nearby_type_=nearby))
+    gpu.SetInputTarget(scene.map)
+    ref = O.OracleNdt(max_iteration=10, eps=0.0, nearby6=nearby, skip_nonfinite=1)
+    ref.set_target(scene.map)
+    ok, H, B = gpu.CaculateMatrixHAndB(scene.scan, scene.init[0])
+    rH, rB, rres, rhits = ref.compute_hb(scene.scan, scene.init[0])
+    hits, _ = gpu.DebugPoints(scene.scan, scene.init[0], 0)
+    assert np.array_equal(hits, rhits)
+    assert rel(H, rH) < H_TOL and rel(B, rB) < H_TOL
+    assert gpu.last_result["n_inlier"] == rres["n_inlier"]
+    for loop_mode in (0, 1):
+        g = L.NdtRegistration(L.NdtOptions(max_iteration_=10, eps_=0.0, nearby_type_=nearby, loop_mode=loop_mode))
+        g.SetInputTarget(scene.map)
+        _, cloud, pose = g.ScanMatch(scene.scan, scene.init[0])
+        rpose, rcloud, rr, _ = ref.align(scene.scan, scene.init[0])
+        dr, dt = pose_delta(pose, rpose)
+        assert dr < ROT_TOL and dt < TRANS_TOL
+        assert g.last_result["iters"] == rr["iters"]
+
+
+def test_ndt_degenerate_early_return(scene, ndt_pair):
+    """det(H)==0 on the first iteration: result_pose keeps the caller's value (quirk Q11)."""
+    gpu, ref = ndt_pair
+    far = scene.scan.copy()
+    far[:, :3] += np.float32(5000.0)  # no voxel anywhere near
+    keep = np.array([0.0, 0.0, 0.70710678, 0.70710678, 1.0, 2.0, 3.0])
+    _, cloud, pose = gpu.ScanMatch(far, scene.init[0], result_pose_init=keep)
+    rpose, rcloud, rres, _ = ref.align(far, scene.init[0], pose_out_init=keep)
+    assert gpu.last_result["pose_written"] == rres["pose_written"] == 0
+    assert np.array_equal(pose, keep) and np.array_equal(rpose, keep)
+    assert np.abs(cloud[:, :3] - rcloud[:, :3]).max() < 1e-2
