@@ -64,8 +64,8 @@ typedef struct locreg_options {
     int32_t nearby_type;          /* enum locreg_nearby, default NEARBY6 */
     /* GPU-side knobs (no reference counterpart) */
     double knn_cell_size;         /* voxel-hash cell edge in metres for ICP k-NN; <= 0: 0.5 */
-    int32_t loop_mode;            /* enum locreg_loop */
-    int32_t reserved_;
+    int32_t loop_mode;            /* enum locreg_loop (NDT; ICP always runs the three-kernel pipeline) */
+    int32_t knn_lists;            /* 1 (default): build per-cell 3x3x3 neighbourhood lists (27x point storage) for the fast k-NN path */
 } locreg_options;
 
 /* Outcome of one registration (what the reference logs or silently drops). */

@@ -1,5 +1,6 @@
-// Registration kernels (K3/K4/K7/K8/K9 of SURVEY.md §2.3), shared by ICP and NDT through a
-// "Problem" policy that supplies the per-point body and the Gauss-Newton update.
+// Fused registration kernels (K4/K6/K7/K8/K9 of SURVEY.md §2.3).  NDT's per-point work is seven independent hash
+// probes, light enough to fuse with the reduction and the Gauss-Newton update; ICP runs the three-kernel
+// pipeline of icp_pipeline.cuh instead.  The "Problem" policy supplies the per-point body and the update.
 //
 //   k_eval            one H/B evaluation over a scan (grid-stride), per-block partial sums
 //   k_finalize        fixed-order sum of the partials + Gauss-Newton update (1 block)
@@ -12,96 +13,66 @@
 #include <cooperative_groups.h>
 
 #include "device_utils.cuh"
-#include "icp_point.cuh"
+#include "icp_pipeline.cuh"
 #include "ndt_point.cuh"
+
+#ifndef LR_MIN_BLOCKS
+#define LR_MIN_BLOCKS 2  // resident 256-thread CTAs per SM the registration kernels are compiled for
+#endif
 
 namespace locreg {
 namespace cg = cooperative_groups;
 
-// Mirrors locreg_result (include/locreg.h) field for field.
-struct DevResult {
-    int iters, updates, converged, degenerate;
-    long long n_effective, n_inlier;
-    double sum_sq_res;
-    int pose_written, pad_;
-};
-static_assert(sizeof(DevResult) == 48, "DevResult must match locreg_result");
-
-struct AlignState {  // lives in global memory for the multi-launch path
-    double pose[7];
-    DevResult res;
-    int stop;
-    int pad;
-};
-
 // ---- problem policies -------------------------------------------------------------------------
-template <int METHOD>
-struct IcpProblem {
-    VoxelMapView map;
-    IcpParams prm;
-    static constexpr bool kIsNdt = false;
-    __device__ __forceinline__ unsigned char point(const Pose& T, float4 s, Accum& acc, int* nn) const {
-        return icp_point<METHOD>(map, prm, T, s.x, s.y, s.z, acc, nn);
-    }
-    __device__ __forceinline__ int nn_per_point() const { return METHOD == kIcpP2P ? 1 : 5; }
-    // 0 failed / 1 updated / 2 converged / 3 abort without writing the pose (NDT only)
-    __device__ __forceinline__ int update(const double* acc30, Pose& T) const {
-        return icp_gn_update<METHOD>(acc30, static_cast<unsigned int>(acc30[28]), prm, T);
-    }
-    __device__ __forceinline__ int max_iteration() const { return prm.max_iteration; }
-};
-
+// A warp processes a chunk of up to 32 consecutive source points: lane j owns point base + j.
+// chunk(): count <= 32 points starting at src[base]; gate / nn_out (debug probe) may be nullptr.
 struct NdtProblem {
     NdtMapView map;
     NdtParams prm;
-    static constexpr bool kIsNdt = true;
-    __device__ __forceinline__ unsigned char point(const Pose& T, float4 s, Accum& acc, int* nn) const {
-        (void)nn;
-        return ndt_point(map, prm, T, s.x, s.y, s.z, acc);
+    __device__ __forceinline__ void chunk(const Pose& T, const float4* __restrict__ src, unsigned int base,
+                                          unsigned int count, SmemAccum& acc, unsigned char* gate, int* nn_out) const {
+        (void)nn_out;
+        const unsigned int lane = threadIdx.x & 31;
+        if (lane < count) {
+            const float4 sp = src[base + lane];
+            const unsigned char h = ndt_point(map, prm, T, sp.x, sp.y, sp.z, acc);
+            if (gate) gate[base + lane] = h;
+        }
     }
-    __device__ __forceinline__ int nn_per_point() const { return 0; }
     __device__ __forceinline__ int update(const double* acc30, Pose& T) const {
         return ndt_gn_update(acc30, static_cast<unsigned int>(acc30[28]), prm, T);
     }
     __device__ __forceinline__ int max_iteration() const { return prm.max_iteration; }
 };
 
-__device__ __forceinline__ void result_from_acc(DevResult& r, const double* acc30) {
-    r.n_effective = static_cast<long long>(acc30[28]);
-    r.n_inlier = static_cast<long long>(acc30[29]);
-    r.sum_sq_res = acc30[27];
-}
-
-// Applies one update outcome to the bookkeeping; returns true if the loop must stop.
-__device__ __forceinline__ bool apply_outcome(int outcome, DevResult& r) {
-    r.degenerate = (outcome == 0 || outcome == 3) ? 1 : 0;
-    if (outcome == 1 || outcome == 2) r.updates += 1;
-    if (outcome == 2) r.converged = 1;
-    if (outcome == 3) r.pose_written = 0;
-    return outcome == 2 || outcome == 3;
+// Walks the chunks of a scan assigned to this warp: chunk c covers points [c*ppw, min(n, (c+1)*ppw)).
+template <class Problem>
+__device__ __forceinline__ void eval_scan(const Problem& pb, const Pose& T, const float4* __restrict__ src, unsigned int n,
+                                          unsigned int ppw, unsigned int first_warp, unsigned int warp_stride, SmemAccum& acc,
+                                          unsigned char* gate, int* nn_out) {
+    const unsigned int n_chunks = (n + ppw - 1) / ppw;
+    for (unsigned int c = first_warp; c < n_chunks; c += warp_stride) {
+        const unsigned int base = c * ppw;
+        const unsigned int count = n - base < ppw ? n - base : ppw;
+        pb.chunk(T, src, base, count, acc, gate, nn_out);
+    }
 }
 
 // ---- single evaluation (compute_hb, debug probe, multi-launch loop) -----------------------------
 template <class Problem>
-__global__ void __launch_bounds__(256, 1) k_eval(Problem pb, const float4* __restrict__ src, unsigned int n,
+__global__ void __launch_bounds__(256, LR_MIN_BLOCKS) k_eval(Problem pb, const float4* __restrict__ src, unsigned int n, unsigned int ppw,
                                               const AlignState* __restrict__ state, double* __restrict__ partials,
                                               unsigned char* gate, int* nn_out) {
+    extern __shared__ double dyn_acc[];
     __shared__ Pose T;
     __shared__ double red[8 * kPartialDoubles];
     if (state->stop) return;
     if (threadIdx.x == 0) pose_load(T, state->pose);
     __syncthreads();
-    Accum acc;
-    accum_zero(acc);
-    const int k = pb.nn_per_point();
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int nn[5];
-        const unsigned char g = pb.point(T, src[i], acc, nn_out ? nn : nullptr);
-        if (gate) gate[i] = g;
-        if (nn_out)
-            for (int j = 0; j < k; ++j) nn_out[static_cast<size_t>(i) * k + j] = nn[j];
-    }
-    block_reduce_accum(acc, red, partials + static_cast<size_t>(blockIdx.x) * kPartialDoubles);
+    SmemAccum acc = smem_accum_init(dyn_acc);
+    eval_scan(pb, T, src, n, ppw, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5), acc, gate,
+              nn_out);
+    block_reduce_accum(acc, dyn_acc, red, partials + static_cast<size_t>(blockIdx.x) * kPartialDoubles);
 }
 
 // Sum of `nblocks` partial rows in a fixed order: 8 groups of rows summed sequentially, then the 8
@@ -149,9 +120,10 @@ __global__ void __launch_bounds__(256) k_finalize(Problem pb, const double* __re
 // partials: 2 * gridDim.x rows (double-buffered by iteration parity so a fast block cannot overwrite
 // rows a slow block is still summing).
 template <class Problem>
-__global__ void __launch_bounds__(256, 1) k_align_persist(Problem pb, const float4* __restrict__ src, unsigned int n,
+__global__ void __launch_bounds__(256, LR_MIN_BLOCKS) k_align_persist(Problem pb, const float4* __restrict__ src, unsigned int n, unsigned int ppw,
                                                        AlignState* state, double* partials, int final_eval) {
     cg::grid_group grid = cg::this_grid();
+    extern __shared__ double dyn_acc[];
     __shared__ Pose T;
     __shared__ double red[8 * kPartialDoubles];
     __shared__ double acc30[32];
@@ -170,12 +142,11 @@ __global__ void __launch_bounds__(256, 1) k_align_persist(Problem pb, const floa
     int it = 0;
     bool final_pass = max_it <= 0;
     while (!(final_pass && !final_eval)) {
-        Accum acc;
-        accum_zero(acc);
-        for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-            pb.point(T, src[i], acc, nullptr);
+        SmemAccum acc = smem_accum_init(dyn_acc);
+        eval_scan(pb, T, src, n, ppw, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5), acc,
+                  nullptr, nullptr);
         double* rows = partials + static_cast<size_t>(it & 1) * gridDim.x * kPartialDoubles;
-        block_reduce_accum(acc, red, rows + static_cast<size_t>(blockIdx.x) * kPartialDoubles);
+        block_reduce_accum(acc, dyn_acc, red, rows + static_cast<size_t>(blockIdx.x) * kPartialDoubles);
         grid.sync();
         reduce_partials(rows, gridDim.x, red, acc30);
         if (threadIdx.x == 0) {
@@ -201,11 +172,12 @@ __global__ void __launch_bounds__(256, 1) k_align_persist(Problem pb, const floa
 // ---- batch: one CTA per scan / hypothesis -------------------------------------------------------
 // offsets == nullptr: every item registers the same scan src[0..n_single) (relocalisation).
 template <class Problem>
-__global__ void __launch_bounds__(256, 1) k_align_batch(Problem pb, const float4* __restrict__ src,
+__global__ void __launch_bounds__(256, LR_MIN_BLOCKS) k_align_batch(Problem pb, const float4* __restrict__ src,
                                                      const long long* __restrict__ offsets, unsigned int n_single,
                                                      const double* __restrict__ poses_in, double* poses_out,
                                                      DevResult* results, unsigned int S, unsigned int* work_counter,
                                                      int final_eval) {
+    extern __shared__ double dyn_acc[];
     __shared__ Pose T;
     __shared__ double red[8 * kPartialDoubles];
     __shared__ double acc30[32];
@@ -231,10 +203,9 @@ __global__ void __launch_bounds__(256, 1) k_align_batch(Problem pb, const float4
         int it = 0;
         bool final_pass = max_it <= 0;
         while (!(final_pass && !final_eval)) {
-            Accum acc;
-            accum_zero(acc);
-            for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) pb.point(T, pts[i], acc, nullptr);
-            block_reduce_accum(acc, red, acc30);
+            SmemAccum acc = smem_accum_init(dyn_acc);
+            eval_scan(pb, T, pts, n, 32u, threadIdx.x >> 5, blockDim.x >> 5, acc, nullptr, nullptr);
+            block_reduce_accum(acc, dyn_acc, red, acc30);
             if (threadIdx.x == 0) {
                 result_from_acc(res, acc30);
                 if (!final_pass) {

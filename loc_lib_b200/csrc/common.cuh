@@ -11,9 +11,11 @@
 
 #if defined(__CUDACC__)
 #define LR_HD __host__ __device__ __forceinline__
+#define LR_HD_NOINLINE __host__ __device__ __noinline__
 #define LR_D __device__ __forceinline__
 #else
 #define LR_HD inline
+#define LR_HD_NOINLINE inline
 #define LR_D inline
 #endif
 
@@ -79,10 +81,13 @@ LR_HD bool finite3(float x, float y, float z) {
 // Per-scan Gauss-Newton accumulator: upper triangle of H (21), B (6), sum of squared gated
 // residuals, and the two counters of the reference loops (effective_num, inliers).
 constexpr int kAccDoubles = 28;  // 21 + 6 + 1
-struct Accum {
+struct Accum {  // register / host flavour
     double v[kAccDoubles];
     unsigned int n_eff;
     unsigned int n_inl;
+    LR_HD void add(int i, double x) { v[i] += x; }
+    LR_HD void inc_eff(unsigned int c = 1u) { n_eff += c; }
+    LR_HD void inc_inl(unsigned int c = 1u) { n_inl += c; }
 };
 LR_HD void accum_zero(Accum& a) {
 #pragma unroll
@@ -90,6 +95,17 @@ LR_HD void accum_zero(Accum& a) {
     a.n_eff = 0;
     a.n_inl = 0;
 }
+// Shared-memory flavour used by the kernels: element i of thread t lives at base[i * stride + t], so the 28
+// running sums cost no registers while the k-NN search is in flight and every access is bank-conflict free.
+struct SmemAccum {
+    double* base;  // already offset by the thread index
+    unsigned int stride;
+    unsigned int n_eff;
+    unsigned int n_inl;
+    LR_HD void add(int i, double x) { base[i * stride] += x; }
+    LR_HD void inc_eff(unsigned int c = 1u) { n_eff += c; }
+    LR_HD void inc_inl(unsigned int c = 1u) { n_inl += c; }
+};
 // index of H(r,c), r <= c, in the packed upper triangle (row-major)
 LR_HD constexpr int hidx(int r, int c) { return r * 6 - (r * (r - 1)) / 2 + (c - r); }
 

@@ -15,21 +15,23 @@ class DeviceVoxelMap {
 
     // d_xyz: device pointer to n points, `stride` bytes apart.  Synchronises the stream (the slot
     // table is sized from the number of occupied blocks, read back once).
-    void build(const void* d_xyz, size_t n, size_t stride, float cell, cudaStream_t stream);
+    void build(const void* d_xyz, size_t n, size_t stride, float cell, bool want_lists, cudaStream_t stream);
     const VoxelMapView& view() const { return view_; }
     bool empty() const { return view_.n_pts == 0; }
     size_t bytes() const { return bytes_; }
     unsigned int n_cells() const { return n_cells_; }
     unsigned int n_blocks() const { return n_blocks_; }
+    unsigned int n_lists() const { return n_lists_; }
 
    private:
     void release();
     VoxelSlot* slots_ = nullptr;
     unsigned int* cell_start_ = nullptr;
     float4* pts_ = nullptr;
+    NbrSlot* nbr_ = nullptr;
     VoxelMapView view_{};
     size_t bytes_ = 0;
-    unsigned int n_cells_ = 0, n_blocks_ = 0;
+    unsigned int n_cells_ = 0, n_blocks_ = 0, n_lists_ = 0;
 };
 
 }  // namespace locreg

@@ -35,30 +35,51 @@ void exclusive_scan_u32(const unsigned int* in, unsigned int* out, size_t n, uns
 
 constexpr int kPartialDoubles = 32;  // 28 accumulator doubles + n_eff + n_inl (+2 pad): one 256 B row per block
 
-// Sum an Accum over the block; the result lands in out[0..29] of thread 0's view (shared memory `red`
-// must hold (blockDim.x/32) * kPartialDoubles doubles).  Fixed order: lanes by shuffle tree, warps
-// sequentially, so results are reproducible for a fixed launch shape.
-__device__ __forceinline__ void block_reduce_accum(const Accum& a, double* red, double* out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double v[30];
+// Per-thread Gauss-Newton accumulators live in dynamic shared memory: row i (i < kAccDoubles) holds element i of
+// every thread of the block, base[i * blockDim.x + threadIdx.x].
+constexpr int kBlockThreads = 256;
+constexpr size_t kAccSmemBytes = static_cast<size_t>(kAccDoubles) * kBlockThreads * sizeof(double);
+
+__device__ __forceinline__ SmemAccum smem_accum_init(double* dyn) {
+    SmemAccum a;
+    a.base = dyn + threadIdx.x;
+    a.stride = kBlockThreads;
+    a.n_eff = 0;
+    a.n_inl = 0;
 #pragma unroll
-    for (int i = 0; i < kAccDoubles; ++i) v[i] = a.v[i];
-    v[28] = static_cast<double>(a.n_eff);
-    v[29] = static_cast<double>(a.n_inl);
+    for (int i = 0; i < kAccDoubles; ++i) a.base[i * kBlockThreads] = 0.0;
+    return a;
+}
+
+// Sum of the block's accumulators -> out[0..29] (28 sums, n_eff, n_inl).  Warp w reduces rows w, w+8, ...: lanes
+// read 32 consecutive threads' values (conflict free), shuffle-reduce, and walk the 8 column groups in order, so
+// the result is reproducible for a fixed launch shape.  `red` needs 8 * 2 doubles for the counters.
+__device__ __forceinline__ void block_reduce_accum(const SmemAccum& a, const double* dyn, double* red, double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double ce = static_cast<double>(a.n_eff), ci = static_cast<double>(a.n_inl);
 #pragma unroll
-    for (int i = 0; i < 30; ++i) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], off);
+    for (int off = 16; off > 0; off >>= 1) {
+        ce += __shfl_down_sync(0xffffffffu, ce, off);
+        ci += __shfl_down_sync(0xffffffffu, ci, off);
     }
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 30; ++i) red[warp * kPartialDoubles + i] = v[i];
-    }
-    __syncthreads();
-    if (threadIdx.x < 30) {
+    if (lane == 0) { red[warp * 2] = ce; red[warp * 2 + 1] = ci; }
+    __syncthreads();  // all threads' accumulators are final
+    for (int row = warp; row < kAccDoubles; row += kBlockThreads / 32) {
         double s = 0;
-        for (int w = 0; w < nwarps; ++w) s += red[w * kPartialDoubles + threadIdx.x];
-        out[threadIdx.x] = s;
+#pragma unroll
+        for (int g = 0; g < kBlockThreads / 32; ++g) {
+            double v = dyn[row * kBlockThreads + g * 32 + lane];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            s += v;
+        }
+        if (lane == 0) out[row] = s;
+    }
+    if (threadIdx.x < 2) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < kBlockThreads / 32; ++w) s += red[w * 2 + threadIdx.x];
+        out[28 + threadIdx.x] = s;
     }
     __syncthreads();
 }

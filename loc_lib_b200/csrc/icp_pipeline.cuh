@@ -1,0 +1,302 @@
+// ICP as a three-kernel pipeline per Gauss-Newton iteration (kernels K2/K3/K4 of SURVEY.md §2.3), for one
+// scan, a batch of scans (BASELINE config 4) or many pose hypotheses of one scan (config 5):
+//
+//   k_icp_nn     one thread per source point: transform with the scan's current pose, exact k-NN in the
+//                voxel-hash map, write the k neighbour positions (4 B each).  Light on registers (<= 64) so that
+//                2048 threads per SM hide the L2 latency of the hash / cell / point loads.
+//   k_icp_post   one thread per source point: gather the neighbours, plane fit, gates, Jacobian row, and a
+//                fixed-order block reduction of the 28+2 Gauss-Newton sums -> one 256 B partial row per tile.
+//   k_icp_solve  one warp per scan: sums the scan's partial rows in tile order, solves the 6x6 system, updates
+//                the pose and the convergence flags kept in device memory (AlignState).
+//
+// Nothing returns to the host between iterations: converged / aborted scans carry a stop flag that makes
+// their tiles exit at once.  A tile is 256 consecutive points of one scan; tile t of scan s is block
+// tile_begin[s] + t (relocalisation: s * tiles_per_item + t).
+#pragma once
+#include "device_utils.cuh"
+#include "icp_point.cuh"
+
+namespace locreg {
+
+// Mirrors locreg_result (include/locreg.h) field for field.
+struct DevResult {
+    int iters, updates, converged, degenerate;
+    long long n_effective, n_inlier;
+    double sum_sq_res;
+    int pose_written, pad_;
+};
+static_assert(sizeof(DevResult) == 48, "DevResult must match locreg_result");
+
+struct AlignState {  // one per scan / hypothesis, device resident for the whole Gauss-Newton loop
+    double pose[7];
+    DevResult res;
+    int stop;
+    int pad;
+};
+
+constexpr int kTile = 256;
+constexpr unsigned int kNoNeighbour = 0xFFFFFFFFu;
+
+struct BatchView {
+    const float4* src;              // all scans' points
+    const long long* offsets;       // S+1 point offsets into src, or nullptr: every item is src[0..n_single)
+    const unsigned int* tile_begin; // S+1 tile offsets, or nullptr: item s owns tiles [s*tiles_per_item, ...)
+    unsigned int n_single;
+    unsigned int tiles_per_item;
+    unsigned int S;
+};
+
+struct TileCoord {
+    unsigned int scan;      // item index
+    unsigned int first;     // index of the tile's first point within its scan
+    unsigned int count;     // points in this tile (<= kTile)
+    long long src_base;     // index of the scan's first point in src
+    long long out_base;     // index of the scan's first point in per-point scratch arrays (nn, gate)
+    bool valid;
+};
+
+__device__ __forceinline__ TileCoord locate_tile(const BatchView& b, unsigned int tile) {
+    TileCoord c{};
+    c.valid = false;
+    unsigned int s, t;
+    if (b.tile_begin) {
+        if (tile >= b.tile_begin[b.S]) return c;
+        unsigned int lo = 0, hi = b.S - 1;  // last s with tile_begin[s] <= tile
+        while (lo < hi) {
+            const unsigned int mid = (lo + hi + 1) >> 1;
+            if (b.tile_begin[mid] <= tile) lo = mid; else hi = mid - 1;
+        }
+        s = lo;
+        t = tile - b.tile_begin[s];
+    } else {
+        s = tile / b.tiles_per_item;
+        t = tile - s * b.tiles_per_item;
+        if (s >= b.S) return c;
+    }
+    const long long beg = b.offsets ? b.offsets[s] : 0;
+    const unsigned int n = b.offsets ? static_cast<unsigned int>(b.offsets[s + 1] - beg) : b.n_single;
+    c.scan = s;
+    c.first = t * kTile;
+    if (c.first >= n) return c;
+    c.count = n - c.first < kTile ? n - c.first : kTile;
+    c.src_base = beg;
+    c.out_base = b.offsets ? beg : static_cast<long long>(s) * b.n_single;
+    c.valid = true;
+    return c;
+}
+
+// tile_begin[s] = sum_{r<s} ceil(n_r / kTile); single block, S is at most a few 1e4.
+__global__ void k_tile_begin(const long long* __restrict__ offsets, unsigned int S, unsigned int* tile_begin) {
+    __shared__ unsigned int carry;
+    __shared__ unsigned int warp_sums[33];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (unsigned int base = 0; base < S; base += blockDim.x) {
+        const unsigned int s = base + threadIdx.x;
+        unsigned int v = 0;
+        if (s < S) v = static_cast<unsigned int>((offsets[s + 1] - offsets[s] + kTile - 1) / kTile);
+        // block exclusive scan
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned int inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int w = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0u, winc = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, winc, off);
+                if (lane >= off) winc += t;
+            }
+            warp_sums[lane] = winc - w;
+            if (lane == 31) warp_sums[32] = winc;
+        }
+        __syncthreads();
+        if (s < S) tile_begin[s] = carry + warp_sums[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sums[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_begin[S] = carry;
+}
+
+// ---- K_A: neighbour search ---------------------------------------------------------------------------------
+#ifndef LR_NN_MIN_BLOCKS
+#define LR_NN_MIN_BLOCKS 4
+#endif
+template <int K>
+__global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView map, BatchView bv,
+                                                                    const AlignState* __restrict__ states, int ignore_stop,
+                                                                    unsigned int* __restrict__ nn_pos) {
+    __shared__ Pose T;
+    const TileCoord tc = locate_tile(bv, blockIdx.x);
+    if (!tc.valid) return;
+    const AlignState* st = states + tc.scan;
+    if (st->stop && !ignore_stop) return;
+    if (threadIdx.x == 0) pose_load(T, st->pose);
+    __syncthreads();
+    if (threadIdx.x >= tc.count) return;
+    const unsigned int p = tc.first + threadIdx.x;
+    const float4 sp = bv.src[tc.src_base + p];
+    unsigned int* out = nn_pos + (tc.out_base + p) * K;
+    // non-finite source points are skipped: P2P as the reference (pcl::isFinite, icp_registration.cpp:64),
+    // P2Plane as deviation D1 (the reference would poison H with NaN)
+    if (!finite3(sp.x, sp.y, sp.z)) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = kNoNeighbour;
+        return;
+    }
+    double wx, wy, wz;
+    pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
+    KnnResult<K> nn;
+    knn_query<K>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn);
+#pragma unroll
+    for (int j = 0; j < K; ++j) out[j] = nn.idx[j] != 0x7fffffff ? nn.pos[j] : kNoNeighbour;
+}
+
+// ---- K_B: fit + gates + accumulate ----------------------------------------------------------------------------
+// Fixed-order block reduction of per-thread register accumulators: shuffle tree inside each warp, then the 8
+// warp rows summed in order.  red: 8 * kPartialDoubles doubles of shared memory; out: 30 doubles.
+__device__ __forceinline__ void block_reduce_regs(const Accum& a, double* red, double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 30; ++i) {
+        double v = i < kAccDoubles ? a.v[i] : (i == 28 ? static_cast<double>(a.n_eff) : static_cast<double>(a.n_inl));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp * kPartialDoubles + i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 30) {
+        double s = 0;
+        for (int w = 0; w < nwarps; ++w) s += red[w * kPartialDoubles + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kTile, 2) k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv,
+                                                       const AlignState* __restrict__ states, int ignore_stop,
+                                                       const unsigned int* __restrict__ nn_pos, double* __restrict__ partials,
+                                                       unsigned char* gate, int* nn_idx) {
+    constexpr int K = METHOD == kIcpP2P ? 1 : 5;
+    __shared__ Pose T;
+    __shared__ double red[8 * kPartialDoubles];
+    const TileCoord tc = locate_tile(bv, blockIdx.x);
+    if (!tc.valid) return;
+    const AlignState* st = states + tc.scan;
+    if (st->stop && !ignore_stop) return;
+    if (threadIdx.x == 0) pose_load(T, st->pose);
+    __syncthreads();
+    Accum acc;
+    accum_zero(acc);
+    if (threadIdx.x < tc.count) {
+        const unsigned int p = tc.first + threadIdx.x;
+        const float4 sp = bv.src[tc.src_base + p];
+        const unsigned int* in = nn_pos + (tc.out_base + p) * K;
+        KnnResult<K> nn;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            nn.pos[j] = in[j];
+            nn.idx[j] = nn.pos[j] != kNoNeighbour ? 0 : 0x7fffffff;  // only validity is needed downstream
+            nn.d2[j] = 0.0f;
+        }
+        unsigned char g = kGateSkipped;
+        if (finite3(sp.x, sp.y, sp.z)) {
+            const double qx = sp.x, qy = sp.y, qz = sp.z;
+            double wx, wy, wz;
+            pose_apply(T, qx, qy, qz, wx, wy, wz);
+            if (METHOD == kIcpP2P) g = icp_p2p_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<1>&>(nn), acc);
+            else g = icp_p2plane_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<5>&>(nn), acc);
+        }
+        if (gate) gate[tc.out_base + p] = g;
+        if (nn_idx) {
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                nn_idx[(tc.out_base + p) * K + j] = nn.pos[j] != kNoNeighbour ? __float_as_int(map.pts[nn.pos[j]].w) : -1;
+        }
+    }
+    block_reduce_regs(acc, red, partials + static_cast<size_t>(blockIdx.x) * kPartialDoubles);
+}
+
+// ---- K_C: per-scan reduction + Gauss-Newton update ------------------------------------------------------------
+__device__ __forceinline__ void result_from_acc(DevResult& r, const double* acc30) {
+    r.n_effective = static_cast<long long>(acc30[28]);
+    r.n_inlier = static_cast<long long>(acc30[29]);
+    r.sum_sq_res = acc30[27];
+}
+// Applies one update outcome (0 failed, 1 updated, 2 converged, 3 abort without writing the pose) to the
+// bookkeeping; returns true if the loop must stop.
+__device__ __forceinline__ bool apply_outcome(int outcome, DevResult& r) {
+    r.degenerate = (outcome == 0 || outcome == 3) ? 1 : 0;
+    if (outcome == 1 || outcome == 2) r.updates += 1;
+    if (outcome == 2) r.converged = 1;
+    if (outcome == 3) r.pose_written = 0;
+    return outcome == 2 || outcome == 3;
+}
+
+// One warp per scan.  mode 1: Gauss-Newton iteration (update the pose; stop on convergence or after
+// max_iteration trips); mode 0: evaluation only (compute_hb, relocalisation's final score pass): record the sums,
+// leave the pose.  acc_out (optional, 32 doubles per scan) receives the raw sums.
+template <int METHOD>
+__global__ void __launch_bounds__(128) k_icp_solve(IcpParams prm, BatchView bv, AlignState* states,
+                                                   const double* __restrict__ partials, int mode, double* acc_out) {
+    __shared__ double sums[4][32];
+    const unsigned int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int s = blockIdx.x * 4 + warp;
+    if (s >= bv.S) return;
+    AlignState* st = states + s;
+    if (mode == 1 && st->stop) return;
+    unsigned int t0, t1;
+    if (bv.tile_begin) { t0 = bv.tile_begin[s]; t1 = bv.tile_begin[s + 1]; }
+    else {
+        t0 = s * bv.tiles_per_item;
+        t1 = t0 + (bv.n_single + kTile - 1) / kTile;
+    }
+    double v = 0;
+    if (lane < 30)
+        for (unsigned int t = t0; t < t1; ++t) v += partials[static_cast<size_t>(t) * kPartialDoubles + lane];
+    sums[warp][lane] = v;
+    __syncwarp();
+    if (lane == 0) {
+        const double* acc30 = sums[warp];
+        result_from_acc(st->res, acc30);
+        if (acc_out)
+            for (int i = 0; i < 30; ++i) acc_out[static_cast<size_t>(s) * 32 + i] = acc30[i];
+        if (mode == 1) {
+            Pose T;
+            pose_load(T, st->pose);
+            st->res.iters += 1;
+            const int outcome = icp_gn_update<METHOD>(acc30, static_cast<unsigned int>(acc30[28]), prm, T);
+            if (apply_outcome(outcome, st->res) || st->res.iters >= prm.max_iteration) st->stop = 1;
+            pose_store(T, st->pose);
+        }
+    }
+}
+
+// poses_in -> fresh states (stop is raised at once when max_iteration <= 0: the reference's loop body never runs)
+__global__ void k_states_init(const double* __restrict__ poses_in, unsigned int S, int max_iteration, AlignState* states) {
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    AlignState st;
+    for (int i = 0; i < 7; ++i) st.pose[i] = poses_in[static_cast<size_t>(s) * 7 + i];
+    st.res = DevResult{0, 0, 0, 0, 0, 0, 0.0, 1, 0};
+    st.stop = max_iteration <= 0 ? 1 : 0;
+    st.pad = 0;
+    states[s] = st;
+}
+// states -> poses_out (only where the reference would have written result_pose) and results
+__global__ void k_states_export(const AlignState* __restrict__ states, unsigned int S, double* poses_out, DevResult* results) {
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const AlignState st = states[s];
+    if (poses_out && st.res.pose_written)
+        for (int i = 0; i < 7; ++i) poses_out[static_cast<size_t>(s) * 7 + i] = st.pose[i];
+    if (results) results[s] = st.res;
+}
+
+}  // namespace locreg

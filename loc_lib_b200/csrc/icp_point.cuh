@@ -23,19 +23,80 @@ struct IcpParams {
 enum Gate : unsigned char { kGateSkipped = 0, kGateFitFailed = 1, kGateResidual = 2, kGateInlier = 3 };
 
 // H += J^T J (upper triangle), B += -J^T r, for a 1x6 Jacobian row
-LR_HD void accum_rank1(Accum& a, const double (&J)[6], double r) {
-    int k = 0;
+template <class Acc>
+LR_HD void accum_rank1(Acc& a, const double (&J)[6], double r) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
-        for (int j = i; j < 6; ++j) a.v[k++] += J[i] * J[j];
+        for (int j = i; j < 6; ++j) a.add(hidx(i, j), J[i] * J[j]);
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) a.v[21 + i] += -J[i] * r;
+    for (int i = 0; i < 6; ++i) a.add(21 + i, -J[i] * r);
 }
 
-// Point-to-plane (icp_registration.cpp:166-202).  Returns the gate code; nn_out (5 ints, may be
-// nullptr) receives the neighbour indices in (dis2, index) order.
+// Point-to-plane, everything after the neighbour search (icp_registration.cpp:171-201): plane fit, gates,
+// Jacobian row, accumulation.  q = source point, w = predict_pose * q, nn = its 5 nearest map points.
+template <class Acc>
+LR_HD unsigned char icp_p2plane_post(const VoxelMapView& map, const IcpParams& prm, const Pose& T, double qx, double qy,
+                                     double qz, double wx, double wy, double wz, const KnnResult<5>& nn, Acc& acc) {
+    // a map with fewer than 5 leaves makes KdTree::GetClosestPoint refuse (kdtree.cpp:149): no neighbours
+    if (knn_count(nn) < 5) return kGateSkipped;
+    double P[5][3];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float4 p = map.pts[nn.pos[j]];
+        P[j][0] = p.x; P[j][1] = p.y; P[j][2] = p.z;
+    }
+    double n[4];
+    if (!plane_fit5_fast(P, n)) plane_svd5(P, n);  // math::FitPlane (:179)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const double err = n[0] * P[j][0] + n[1] * P[j][1] + n[2] * P[j][2] + n[3];
+        if (err * err > prm.plane_fit_eps) return kGateFitFailed;
+    }
+    acc.inc_eff();  // quirk Q4: counted before the distance gate (:184)
+    const double dis = n[0] * wx + n[1] * wy + n[2] * wz + n[3];
+    if (fabs(dis) > prm.max_plane_distance) return kGateResidual;
+    // J = [ -n^T R hat(q) , n^T ]  (:193-195): with m = R^T n, -m^T hat(q) = (q x m)^T
+    const double mx = T.R[0] * n[0] + T.R[3] * n[1] + T.R[6] * n[2];
+    const double my = T.R[1] * n[0] + T.R[4] * n[1] + T.R[7] * n[2];
+    const double mz = T.R[2] * n[0] + T.R[5] * n[1] + T.R[8] * n[2];
+    const double J[6] = {qy * mz - qz * my, qz * mx - qx * mz, qx * my - qy * mx, n[0], n[1], n[2]};
+    accum_rank1(acc, J, dis);
+    acc.add(27, dis * dis);
+    acc.inc_inl();
+    return kGateInlier;
+}
+
+// Point-to-point after the neighbour search (icp_registration.cpp:71-91).  J = [ R hat(q) / 16 , -I ]  (quirk Q6).
+template <class Acc>
+LR_HD unsigned char icp_p2p_post(const VoxelMapView& map, const IcpParams& prm, const Pose& T, double qx, double qy,
+                                 double qz, double wx, double wy, double wz, const KnnResult<1>& nn, Acc& acc) {
+    if (nn.idx[0] == 0x7fffffff) return kGateSkipped;
+    const float4 p = map.pts[nn.pos[0]];
+    const double e[3] = {static_cast<double>(p.x) - wx, static_cast<double>(p.y) - wy, static_cast<double>(p.z) - wz};
+    const double dis2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+    if (dis2 > prm.max_nn_distance) return kGateResidual;  // squared vs unsquared threshold (:75)
+    acc.inc_eff();
+    acc.inc_inl();
+    const double hq[3][3] = {{0.0, -qz, qy}, {qz, 0.0, -qx}, {-qy, qx, 0.0}};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double J[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            J[c] = (T.R[r * 3 + 0] * hq[0][c] + T.R[r * 3 + 1] * hq[1][c] + T.R[r * 3 + 2] * hq[2][c]) / 16;
+        J[3] = r == 0 ? -1.0 : 0.0;
+        J[4] = r == 1 ? -1.0 : 0.0;
+        J[5] = r == 2 ? -1.0 : 0.0;
+        accum_rank1(acc, J, e[r]);
+    }
+    acc.add(27, dis2);
+    return kGateInlier;
+}
+
+// Whole per-point bodies with the serial (one thread per query) search: used by tests/hostsim and kept as the
+// readable statement of the algorithm; the kernels run the warp-cooperative search (knn_warp.cuh) instead.
 LR_HD unsigned char icp_point_p2plane(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy,
                                       float sz, Accum& acc, int* nn_out) {
     if (nn_out) {
@@ -52,36 +113,9 @@ LR_HD unsigned char icp_point_p2plane(const VoxelMapView& map, const IcpParams& 
 #pragma unroll
         for (int j = 0; j < 5; ++j) nn_out[j] = nn.idx[j] != 0x7fffffff ? nn.idx[j] : -1;
     }
-    // a map with fewer than 5 leaves makes KdTree::GetClosestPoint refuse (kdtree.cpp:149): no neighbours
-    if (knn_count(nn) < 5) return kGateSkipped;
-    double P[5][3];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const float4 p = map.pts[nn.pos[j]];
-        P[j][0] = p.x; P[j][1] = p.y; P[j][2] = p.z;
-    }
-    double n[4];
-    plane_svd5(P, n);  // math::FitPlane (:179)
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const double err = n[0] * P[j][0] + n[1] * P[j][1] + n[2] * P[j][2] + n[3];
-        if (err * err > prm.plane_fit_eps) return kGateFitFailed;
-    }
-    acc.n_eff += 1u;  // quirk Q4: counted before the distance gate (:184)
-    const double dis = n[0] * wx + n[1] * wy + n[2] * wz + n[3];
-    if (fabs(dis) > prm.max_plane_distance) return kGateResidual;
-    // J = [ -n^T R hat(q) , n^T ]  (:193-195): with m = R^T n, -m^T hat(q) = (q x m)^T
-    const double mx = T.R[0] * n[0] + T.R[3] * n[1] + T.R[6] * n[2];
-    const double my = T.R[1] * n[0] + T.R[4] * n[1] + T.R[7] * n[2];
-    const double mz = T.R[2] * n[0] + T.R[5] * n[1] + T.R[8] * n[2];
-    const double J[6] = {qy * mz - qz * my, qz * mx - qx * mz, qx * my - qy * mx, n[0], n[1], n[2]};
-    accum_rank1(acc, J, dis);
-    acc.v[27] += dis * dis;
-    acc.n_inl += 1u;
-    return kGateInlier;
+    return icp_p2plane_post(map, prm, T, qx, qy, qz, wx, wy, wz, nn, acc);
 }
 
-// Point-to-point (icp_registration.cpp:62-92).  J = [ R hat(q) / 16 , -I ]  (quirk Q6).
 LR_HD unsigned char icp_point_p2p(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy,
                                   float sz, Accum& acc, int* nn_out) {
     if (nn_out) nn_out[0] = -1;
@@ -91,30 +125,8 @@ LR_HD unsigned char icp_point_p2p(const VoxelMapView& map, const IcpParams& prm,
     pose_apply(T, qx, qy, qz, wx, wy, wz);
     KnnResult<1> nn;
     knn_query<1>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn);
-    if (nn.idx[0] == 0x7fffffff) return kGateSkipped;
-    if (nn_out) nn_out[0] = nn.idx[0];
-    const float4 p = map.pts[nn.pos[0]];
-    const double e[3] = {static_cast<double>(p.x) - wx, static_cast<double>(p.y) - wy, static_cast<double>(p.z) - wz};
-    const double dis2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-    if (dis2 > prm.max_nn_distance) return kGateResidual;  // squared vs unsquared threshold (:75)
-    acc.n_eff += 1u;
-    acc.n_inl += 1u;
-    // rows of J: J_r = [ (R hat(q))_r / 16 , -e_r^T ];  (R hat(q))_r = R_r x q ... as a row: R_r^T hat(q) = (q x R_r)^T * -1
-    // hat(q) columns: R hat(q) (r, c) = sum_k R[r][k] hat(q)[k][c]
-    const double hq[3][3] = {{0.0, -qz, qy}, {qz, 0.0, -qx}, {-qy, qx, 0.0}};
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        double J[6];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            J[c] = (T.R[r * 3 + 0] * hq[0][c] + T.R[r * 3 + 1] * hq[1][c] + T.R[r * 3 + 2] * hq[2][c]) / 16;
-        J[3] = r == 0 ? -1.0 : 0.0;
-        J[4] = r == 1 ? -1.0 : 0.0;
-        J[5] = r == 2 ? -1.0 : 0.0;
-        accum_rank1(acc, J, e[r]);
-    }
-    acc.v[27] += dis2;
-    return kGateInlier;
+    if (nn_out) nn_out[0] = nn.idx[0] != 0x7fffffff ? nn.idx[0] : -1;
+    return icp_p2p_post(map, prm, T, qx, qy, qz, wx, wy, wz, nn, acc);
 }
 
 template <int METHOD>

@@ -82,7 +82,8 @@ LR_HD void pose_update(Pose& T, const double* dx) {
 // of A = [x y z 1] (5 x 4), by one-sided (Hestenes) Jacobi kept entirely in registers.
 // One-sided Jacobi works on A itself, so the 1e4-1e5 condition number of a far-from-origin
 // neighbourhood is not squared.  Returns the unit 4-vector (n, d) (quirk Q5: ||n|| != 1).
-LR_HD void plane_svd5(const double (&P)[5][3], double (&coef)[4]) {
+// (Not inlined on the device: it is the rare fallback of plane_fit5_fast and must not set the kernels' register budget.)
+static LR_HD_NOINLINE void plane_svd5(const double (&P)[5][3], double (&coef)[4]) {
     double A[5][4], V[4][4];
 #pragma unroll
     for (int i = 0; i < 5; ++i) { A[i][0] = P[i][0]; A[i][1] = P[i][1]; A[i][2] = P[i][2]; A[i][3] = 1.0; }
@@ -132,6 +133,96 @@ LR_HD void plane_svd5(const double (&P)[5][3], double (&coef)[4]) {
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) coef[i] = bj == 0 ? V[i][0] : (bj == 1 ? V[i][1] : (bj == 2 ? V[i][2] : V[i][3]));
+}
+
+// Fast path of the plane fit.  The smallest right singular vector x = (n, d) of A = [p 1] minimises
+// ||A x||^2 = n^T S n + 5 (n.c + d)^2 subject to |n|^2 + d^2 = 1, with c the centroid of the five points and
+// S = sum (p-c)(p-c)^T.  Eliminating d through its stationarity condition leaves a 3x3 problem
+//     S n = lambda (I + kappa c c^T) n,   kappa = 5 / (5 - lambda),   d = -kappa (c.n),
+// whose smallest eigenpair is found by Rayleigh-quotient iteration (cubic convergence, 3-4 steps) started from
+// the smallest eigenvector of S.  Each step solves (S - mu B) z = B n through the adjugate, which stays accurate
+// when the matrix is (by design) nearly singular, and the centroid shift keeps every quantity at the scale of
+// the neighbourhood, so the 1e4-1e5 condition number of the unshifted [p 1] is never squared.
+// Returns false — the caller then runs plane_svd5 — if the points are collinear, the iteration has not
+// settled, or it settled on an eigenpair that is not the smallest one (inertia check on S - mu B).
+constexpr int kPlaneFitWarmup = 3;
+LR_HD bool plane_fit5_fast(const double (&P)[5][3], double (&coef)[4]) {
+    const double cx = (P[0][0] + P[1][0] + P[2][0] + P[3][0] + P[4][0]) * 0.2;
+    const double cy = (P[0][1] + P[1][1] + P[2][1] + P[3][1] + P[4][1]) * 0.2;
+    const double cz = (P[0][2] + P[1][2] + P[2][2] + P[3][2] + P[4][2]) * 0.2;
+    double sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const double x = P[i][0] - cx, y = P[i][1] - cy, z = P[i][2] - cz;
+        sxx += x * x; sxy += x * y; sxz += x * z; syy += y * y; syz += y * z; szz += z * z;
+    }
+    // start: column of adj(S) with the largest diagonal = one inverse-iteration step on S
+    double nx, ny, nz;
+    {
+        const double axx = syy * szz - syz * syz, axy = sxz * syz - sxy * szz, axz = sxy * syz - sxz * syy;
+        const double ayy = sxx * szz - sxz * sxz, ayz = sxy * sxz - sxx * syz, azz = sxx * syy - sxy * sxy;
+        if (axx >= ayy && axx >= azz) { nx = axx; ny = axy; nz = axz; }
+        else if (ayy >= azz) { nx = axy; ny = ayy; nz = ayz; }
+        else { nx = axz; ny = ayz; nz = azz; }
+    }
+    double nn = nx * nx + ny * ny + nz * nz;
+    if (!(nn > 0.0)) return false;  // collinear / coincident points (or NaN)
+    double inv = 1.0 / sqrt(nn);
+    nx *= inv; ny *= inv; nz *= inv;
+    // The weight c c^T (|c|^2 ~ 1e4 far from the origin, quirk Q5) can make the pencil's smallest eigenvector very
+    // different from S's, so pull the start into the right basin with a few plain inverse iterations
+    // n <- S^-1 B n (adjugate form, kappa = 1) before switching to Rayleigh-quotient shifts.
+    {
+        const double axx = syy * szz - syz * syz, axy = sxz * syz - sxy * szz, axz = sxy * syz - sxz * syy;
+        const double ayy = sxx * szz - sxz * sxz, ayz = sxy * sxz - sxx * syz, azz = sxx * syy - sxy * sxy;
+#pragma unroll
+        for (int it = 0; it < kPlaneFitWarmup; ++it) {
+            const double cn = cx * nx + cy * ny + cz * nz;
+            const double bx = nx + cn * cx, by = ny + cn * cy, bz = nz + cn * cz;
+            const double zx = axx * bx + axy * by + axz * bz, zy = axy * bx + ayy * by + ayz * bz,
+                         zz = axz * bx + ayz * by + azz * bz;
+            nn = zx * zx + zy * zy + zz * zz;
+            if (!(nn > 0.0)) return false;
+            inv = 1.0 / sqrt(nn);
+            nx = zx * inv; ny = zy * inv; nz = zz * inv;
+        }
+    }
+    double kappa = 1.0, mu = 0.0;
+    bool settled = false;
+    double e2 = 0.0, trk = 0.0;
+    for (int it = 0; it < 8; ++it) {
+        const double cn = cx * nx + cy * ny + cz * nz;
+        const double bx = nx + kappa * cn * cx, by = ny + kappa * cn * cy, bz = nz + kappa * cn * cz;  // B n
+        const double snx = sxx * nx + sxy * ny + sxz * nz, sny = sxy * nx + syy * ny + syz * nz,
+                     snz = sxz * nx + syz * ny + szz * nz;
+        mu = (nx * snx + ny * sny + nz * snz) / (nx * bx + ny * by + nz * bz);  // Rayleigh quotient
+        kappa = 5.0 / (5.0 - mu);
+        const double mk = mu * kappa;
+        const double kxx = sxx - mu - mk * cx * cx, kxy = sxy - mk * cx * cy, kxz = sxz - mk * cx * cz;
+        const double kyy = syy - mu - mk * cy * cy, kyz = syz - mk * cy * cz, kzz = szz - mu - mk * cz * cz;
+        const double axx = kyy * kzz - kyz * kyz, axy = kxz * kyz - kxy * kzz, axz = kxy * kyz - kxz * kyy;
+        const double ayy = kxx * kzz - kxz * kxz, ayz = kxy * kxz - kxx * kyz, azz = kxx * kyy - kxy * kxy;
+        e2 = axx + ayy + azz;   // second elementary symmetric polynomial of eig(K)
+        trk = kxx + kyy + kzz;
+        double zx = axx * bx + axy * by + axz * bz;
+        double zy = axy * bx + ayy * by + ayz * bz;
+        double zz = axz * bx + ayz * by + azz * bz;
+        nn = zx * zx + zy * zy + zz * zz;
+        if (!(nn > 0.0)) return false;
+        inv = 1.0 / sqrt(nn);
+        if (zx * nx + zy * ny + zz * nz < 0) inv = -inv;
+        zx *= inv; zy *= inv; zz *= inv;
+        const double ch = fabs(zx - nx) + fabs(zy - ny) + fabs(zz - nz);
+        nx = zx; ny = zy; nz = zz;
+        if (ch < 1e-9) { settled = true; break; }  // cubic convergence: the step just taken is exact to rounding
+    }
+    // K = S - mu B must be positive semi-definite with a one-dimensional null space for mu to be the SMALLEST
+    // eigenvalue (Sylvester): two positive eigenvalues <=> e2 > 0 and trace > 0.
+    if (!settled || !(e2 > 0.0) || !(trk > 0.0)) return false;
+    const double d = -kappa * (cx * nx + cy * ny + cz * nz);
+    inv = 1.0 / sqrt(1.0 + d * d);
+    coef[0] = nx * inv; coef[1] = ny * inv; coef[2] = nz * inv; coef[3] = d * inv;
+    return true;
 }
 
 // Gauss-Newton step: solves H dx = b by partial-pivot LU (what Matrix6d::inverse()/determinant()

@@ -64,7 +64,7 @@ struct locreg_handle {
     DeviceNdtMap ndt_map;
     bool has_target = false;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
-        d_scores, d_misc, d_target;
+        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_states;
     PinBuf h_in, h_out, h_small;
     double last_ms = 0;
     long long last_launches = 0;
@@ -134,84 +134,163 @@ void init_state(locreg_handle* h, const double* pose7) {
     std::memset(s, 0, sizeof(AlignState));
     std::memcpy(s->pose, pose7, 7 * sizeof(double));
     s->res.pose_written = 1;
+    s->stop = 0;
     LR_CUDA(cudaMemcpyAsync(h->d_state.p, s, sizeof(AlignState), cudaMemcpyHostToDevice, h->stream));
 }
 
-template <class Problem>
-int persist_grid(const locreg_handle* h, unsigned int n) {
+// ---- NDT: fused kernels -------------------------------------------------------------------------------------
+// Launch shape of a whole-GPU evaluation of one scan: as many warps as can be co-resident, each taking
+// chunks of `ppw` consecutive points (ppw = 32 when the scan is large enough to keep every warp busy).
+int ndt_persist_grid(const locreg_handle* h, unsigned int n, unsigned int* ppw) {
     int per_sm = 0;
-    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_persist<Problem>, 256, 0));
+    LR_CUDA(cudaFuncSetAttribute(k_align_persist<NdtProblem>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAccSmemBytes)));
+    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_persist<NdtProblem>, 256, kAccSmemBytes));
     if (per_sm < 1) throw std::runtime_error("persistent kernel does not fit on an SM");
     const long long max_blocks = static_cast<long long>(per_sm) * h->num_sms;
-    const long long want = (static_cast<long long>(n) + 255) / 256;
-    return static_cast<int>(std::max<long long>(1, std::min(max_blocks, want)));
+    const long long max_warps = max_blocks * 8;
+    long long p = (static_cast<long long>(n) + max_warps - 1) / max_warps;
+    p = std::max<long long>(1, std::min<long long>(32, p));
+    *ppw = static_cast<unsigned int>(p);
+    const long long chunks = (static_cast<long long>(n) + p - 1) / p;
+    return static_cast<int>(std::max<long long>(1, std::min(max_blocks, (chunks + 7) / 8)));
+}
+unsigned int ndt_eval_grid(const locreg_handle* h, unsigned int n, unsigned int* ppw) {
+    const long long max_warps = 16ll * h->num_sms * 8;
+    long long p = (static_cast<long long>(n) + max_warps - 1) / max_warps;
+    p = std::max<long long>(1, std::min<long long>(32, p));
+    *ppw = static_cast<unsigned int>(p);
+    const long long chunks = (static_cast<long long>(n) + p - 1) / p;
+    LR_CUDA(cudaFuncSetAttribute(k_eval<NdtProblem>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAccSmemBytes)));
+    return static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((chunks + 7) / 8, 16ll * h->num_sms)));
 }
 
-// Runs the whole Gauss-Newton loop on the device, result left in h->d_state.
-template <class Problem>
-void run_align(locreg_handle* h, const Problem& pb, const float4* src, unsigned int n, int final_eval) {
+// Whole AlignNdt loop on the device, result left in h->d_state.
+void ndt_run_align(locreg_handle* h, const float4* src, unsigned int n) {
+    NdtProblem pb{h->ndt_map.view(), h->ndt_params()};
     AlignState* st = h->d_state.as<AlignState>();
     if (h->opt.loop_mode == LOCREG_LOOP_PERSISTENT) {
-        const int grid = persist_grid<Problem>(h, n);
+        unsigned int ppw = 0;
+        const int grid = ndt_persist_grid(h, n, &ppw);
         h->d_partials.reserve(static_cast<size_t>(2) * grid * kPartialDoubles * sizeof(double));
         double* partials = h->d_partials.as<double>();
-        Problem pb_copy = pb;
-        void* args[] = {&pb_copy, &src, &n, &st, &partials, &final_eval};
-        LR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_align_persist<Problem>), dim3(grid), dim3(256), args, 0, h->stream));
+        int final_eval = 0;
+        void* args[] = {&pb, &src, &n, &ppw, &st, &partials, &final_eval};
+        LR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_align_persist<NdtProblem>), dim3(grid), dim3(256), args, kAccSmemBytes, h->stream));
         ++g_launch_count;
     } else {
-        const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((n + 255ll) / 256, 4ll * h->num_sms)));
+        unsigned int ppw = 0;
+        const unsigned int grid = ndt_eval_grid(h, n, &ppw);
         h->d_partials.reserve(static_cast<size_t>(grid) * kPartialDoubles * sizeof(double));
         double* partials = h->d_partials.as<double>();
         for (int it = 0; it < h->opt.max_iteration; ++it) {
-            LR_LAUNCH(k_eval<Problem>, grid, 256, 0, h->stream, pb, src, n, st, partials, nullptr, nullptr);
-            LR_LAUNCH(k_finalize<Problem>, 1, 256, 0, h->stream, pb, partials, grid, st, 1, nullptr);
+            LR_LAUNCH(k_eval<NdtProblem>, grid, 256, kAccSmemBytes, h->stream, pb, src, n, ppw, st, partials, nullptr, nullptr);
+            LR_LAUNCH(k_finalize<NdtProblem>, 1, 256, 0, h->stream, pb, partials, grid, st, 1, nullptr);
         }
-        (void)final_eval;
     }
 }
-
-template <class Problem>
-void run_eval(locreg_handle* h, const Problem& pb, const float4* src, unsigned int n, unsigned char* gate, int* nn) {
+void ndt_run_eval(locreg_handle* h, const float4* src, unsigned int n, unsigned char* gate) {
+    NdtProblem pb{h->ndt_map.view(), h->ndt_params()};
     AlignState* st = h->d_state.as<AlignState>();
-    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((n + 255ll) / 256, 4ll * h->num_sms)));
+    unsigned int ppw = 0;
+    const unsigned int grid = ndt_eval_grid(h, n, &ppw);
     h->d_partials.reserve(static_cast<size_t>(grid) * kPartialDoubles * sizeof(double));
     h->d_acc.reserve(32 * sizeof(double));
-    LR_LAUNCH(k_eval<Problem>, grid, 256, 0, h->stream, pb, src, n, st, h->d_partials.as<double>(), gate, nn);
-    LR_LAUNCH(k_finalize<Problem>, 1, 256, 0, h->stream, pb, h->d_partials.as<double>(), grid, st, 0, h->d_acc.as<double>());
+    LR_LAUNCH(k_eval<NdtProblem>, grid, 256, kAccSmemBytes, h->stream, pb, src, n, ppw, st, h->d_partials.as<double>(), gate, nullptr);
+    LR_LAUNCH(k_finalize<NdtProblem>, 1, 256, 0, h->stream, pb, h->d_partials.as<double>(), grid, st, 0, h->d_acc.as<double>());
 }
-
-template <class Problem>
-void run_batch(locreg_handle* h, const Problem& pb, const float4* src, const long long* offsets, unsigned int n_single,
-               const double* poses_in, double* poses_out, DevResult* results, unsigned int S, int final_eval) {
+void ndt_run_batch(locreg_handle* h, const float4* src, const long long* offsets, const double* poses_in, double* poses_out,
+                   DevResult* results, unsigned int S) {
+    NdtProblem pb{h->ndt_map.view(), h->ndt_params()};
     int per_sm = 0;
-    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_batch<Problem>, 256, 0));
+    LR_CUDA(cudaFuncSetAttribute(k_align_batch<NdtProblem>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAccSmemBytes)));
+    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_batch<NdtProblem>, 256, kAccSmemBytes));
     if (per_sm < 1) per_sm = 1;
     const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(S, static_cast<long long>(per_sm) * h->num_sms)));
     h->d_misc.reserve(64);
     LR_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 64, h->stream));
-    LR_LAUNCH(k_align_batch<Problem>, grid, 256, 0, h->stream, pb, src, offsets, n_single, poses_in, poses_out, results, S,
-              h->d_misc.as<unsigned int>(), final_eval);
+    LR_LAUNCH(k_align_batch<NdtProblem>, grid, 256, kAccSmemBytes, h->stream, pb, src, offsets, 0u, poses_in, poses_out, results, S,
+              h->d_misc.as<unsigned int>(), 0);
 }
 
-#define DISPATCH_METHOD(h, CALL)                                                                     \
-    switch ((h)->opt.method) {                                                                       \
-        case LOCREG_ICP_P2P: { IcpProblem<kIcpP2P> pb{(h)->icp_map.view(), (h)->icp_params()}; CALL; } break;         \
-        case LOCREG_ICP_P2PLANE: { IcpProblem<kIcpP2Plane> pb{(h)->icp_map.view(), (h)->icp_params()}; CALL; } break; \
-        case LOCREG_NDT_DIRECT: { NdtProblem pb{(h)->ndt_map.view(), (h)->ndt_params()}; CALL; } break;               \
-        default: throw std::invalid_argument("unsupported method");                                  \
+// ---- ICP: three-kernel pipeline (icp_pipeline.cuh) -------------------------------------------------------------
+struct IcpJob {
+    BatchView bv{};
+    AlignState* states = nullptr;
+    unsigned int n_tiles = 0;       // grid of the per-point kernels (an upper bound is fine: surplus tiles exit)
+    size_t n_scratch_points = 0;    // rows of the per-point scratch arrays
+};
+
+template <int METHOD>
+void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, unsigned char* gate, int* nn_idx) {
+    constexpr int K = METHOD == kIcpP2P ? 1 : 5;
+    const VoxelMapView map = h->icp_map.view();
+    h->d_nnpos.reserve(job.n_scratch_points * K * sizeof(unsigned int));
+    h->d_partials.reserve(static_cast<size_t>(job.n_tiles) * kPartialDoubles * sizeof(double));
+    if (job.n_tiles == 0) return;
+    LR_LAUNCH(k_icp_nn<K>, job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, h->d_nnpos.as<unsigned int>());
+    LR_LAUNCH(k_icp_post<METHOD>, job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
+              h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx);
+}
+template <int METHOD>
+void icp_launch_solve(locreg_handle* h, const IcpJob& job, int mode, double* acc_out) {
+    LR_LAUNCH(k_icp_solve<METHOD>, (job.bv.S + 3) / 4, 128, 0, h->stream, h->icp_params(), job.bv, job.states,
+              h->d_partials.as<double>(), mode, acc_out);
+}
+// The whole Gauss-Newton loop, queued on the stream without a host round-trip; stopped scans make their tiles exit.
+template <int METHOD>
+void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
+    for (int it = 0; it < h->opt.max_iteration; ++it) {
+        icp_launch_eval<METHOD>(h, job, 0, nullptr, nullptr);
+        icp_launch_solve<METHOD>(h, job, 1, nullptr);
+    }
+    if (final_eval) {
+        icp_launch_eval<METHOD>(h, job, 1, nullptr, nullptr);
+        icp_launch_solve<METHOD>(h, job, 0, nullptr);
+    }
+}
+#define ICP_DISPATCH(h, CALL)                                              \
+    switch ((h)->opt.method) {                                             \
+        case LOCREG_ICP_P2P: { constexpr int M = kIcpP2P; CALL; } break;   \
+        case LOCREG_ICP_P2PLANE: { constexpr int M = kIcpP2Plane; CALL; } break; \
+        default: throw std::invalid_argument("unsupported method");        \
     }
 
+IcpJob icp_single_job(locreg_handle* h, const float4* src, unsigned int n) {
+    IcpJob job;
+    job.bv.src = src; job.bv.offsets = nullptr; job.bv.tile_begin = nullptr;
+    job.bv.n_single = n; job.bv.tiles_per_item = std::max(1u, (n + kTile - 1) / kTile); job.bv.S = 1;
+    job.states = h->d_state.as<AlignState>();
+    job.n_tiles = (n + kTile - 1) / kTile;
+    job.n_scratch_points = n;
+    return job;
+}
+// offsets on the device; total = number of points covered by the offsets
+IcpJob icp_batch_job(locreg_handle* h, const float4* src, const long long* d_offsets, unsigned int S, size_t total) {
+    IcpJob job;
+    h->d_tile_begin.reserve((static_cast<size_t>(S) + 1) * sizeof(unsigned int));
+    h->d_states.reserve(static_cast<size_t>(S) * sizeof(AlignState));
+    LR_LAUNCH(k_tile_begin, 1, 1024, 0, h->stream, d_offsets, S, h->d_tile_begin.as<unsigned int>());
+    job.bv.src = src; job.bv.offsets = d_offsets; job.bv.tile_begin = h->d_tile_begin.as<unsigned int>();
+    job.bv.n_single = 0; job.bv.tiles_per_item = 0; job.bv.S = S;
+    job.states = h->d_states.as<AlignState>();
+    job.n_tiles = static_cast<unsigned int>(std::min<size_t>(total / kTile + S, 0x7fffffffu));
+    job.n_scratch_points = total;
+    return job;
+}
+
+bool is_ndt(const locreg_handle* h) { return h->opt.method == LOCREG_NDT_DIRECT; }
+
+// Parity probe for the search: the same one-thread-per-query knn_query() the pipeline's k_icp_nn runs.
 template <int K>
-__global__ void k_knn(VoxelMapView map, const float4* __restrict__ q, unsigned int nq, int* __restrict__ idx) {
-    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    const float4 p = q[i];
-    KnnResult<K> r;
-    knn_init(r);
-    if (finite3(p.x, p.y, p.z)) knn_query<K>(map, p.x, p.y, p.z, r);
+__global__ void __launch_bounds__(128) k_knn(VoxelMapView map, const float4* __restrict__ q, unsigned int nq, int* __restrict__ idx) {
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+        const float4 p = q[i];
+        KnnResult<K> r;
+        knn_init(r);
+        if (finite3(p.x, p.y, p.z)) knn_query<K>(map, p.x, p.y, p.z, r);
 #pragma unroll
-    for (int j = 0; j < K; ++j) idx[static_cast<size_t>(i) * K + j] = r.idx[j] != 0x7fffffff ? r.idx[j] : -1;
+        for (int j = 0; j < K; ++j) idx[static_cast<size_t>(i) * K + j] = r.idx[j] != 0x7fffffff ? r.idx[j] : -1;
+    }
 }
 
 int check_cloud_args(const float* p, size_t n, size_t stride) {
@@ -271,6 +350,7 @@ int locreg_default_options(locreg_options* o, int32_t method) {
     o->min_pts_in_voxel = 3;
     o->nearby_type = LOCREG_NEARBY6;
     o->knn_cell_size = 0.5;
+    o->knn_lists = 1;
     o->loop_mode = LOCREG_LOOP_PERSISTENT;
     return LOCREG_OK;
 }
@@ -348,7 +428,7 @@ static int set_target_impl(locreg_handle* h, const float* xyz, size_t n, size_t 
         if (h->opt.method == LOCREG_NDT_DIRECT)
             h->ndt_map.build(d_xyz, n, stride, h->opt.voxel_size, h->opt.min_pts_in_voxel, h->stream);
         else
-            h->icp_map.build(d_xyz, n, stride, static_cast<float>(h->opt.knn_cell_size), h->stream);
+            h->icp_map.build(d_xyz, n, stride, static_cast<float>(h->opt.knn_cell_size), h->opt.knn_lists != 0, h->stream);
         h->end_timing();
         h->has_target = true;
         return LOCREG_OK;
@@ -367,7 +447,12 @@ int locreg_align(locreg_handle* h, const float* src, size_t n, size_t stride, co
         const float4* src4 = stage_cloud(h, src, n, stride, false);
         init_state(h, pose_in);
         h->begin_timing();
-        DISPATCH_METHOD(h, run_align(h, pb, src4, static_cast<unsigned int>(n), 0));
+        if (is_ndt(h)) {
+            ndt_run_align(h, src4, static_cast<unsigned int>(n));
+        } else {
+            const IcpJob job = icp_single_job(h, src4, static_cast<unsigned int>(n));
+            ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
+        }
         AlignState* st = h->d_state.as<AlignState>();
         const size_t bytes = n * stride;
         if (out_xyz && n) {
@@ -417,7 +502,13 @@ int locreg_compute_hb(locreg_handle* h, const float* src, size_t n, size_t strid
         const float4* src4 = stage_cloud(h, src, n, stride, false);
         init_state(h, pose);
         h->begin_timing();
-        DISPATCH_METHOD(h, run_eval(h, pb, src4, static_cast<unsigned int>(n), nullptr, nullptr));
+        h->d_acc.reserve(32 * sizeof(double));
+        if (is_ndt(h)) {
+            ndt_run_eval(h, src4, static_cast<unsigned int>(n), nullptr);
+        } else {
+            const IcpJob job = icp_single_job(h, src4, static_cast<unsigned int>(n));
+            ICP_DISPATCH(h, (icp_launch_eval<M>(h, job, 1, nullptr, nullptr), icp_launch_solve<M>(h, job, 0, h->d_acc.as<double>())));
+        }
         h->h_small.reserve(4096);
         double* acc = h->h_small.as<double>() + 64;
         LR_CUDA(cudaMemcpyAsync(acc, h->d_acc.p, 30 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -450,7 +541,7 @@ int locreg_knn(locreg_handle* h, const float* queries, size_t nq, size_t stride,
         const float4* q4 = stage_cloud(h, queries, nq, stride, false);
         h->d_nn.reserve(nq * k * sizeof(int));
         h->begin_timing();
-        const unsigned int grid = static_cast<unsigned int>((nq + 127) / 128);
+                const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((nq + 127) / 128, 64u * h->num_sms));
         if (k == 1) LR_LAUNCH(k_knn<1>, grid, 128, 0, h->stream, h->icp_map.view(), q4, static_cast<unsigned int>(nq), h->d_nn.as<int>());
         else LR_LAUNCH(k_knn<5>, grid, 128, 0, h->stream, h->icp_map.view(), q4, static_cast<unsigned int>(nq), h->d_nn.as<int>());
         h->end_timing();
@@ -474,7 +565,12 @@ int locreg_debug_points(locreg_handle* h, const float* src, size_t n, size_t str
         int* d_nn = nullptr;
         if (nn && k) { h->d_nn.reserve(n * k * sizeof(int)); d_nn = h->d_nn.as<int>(); }
         h->begin_timing();
-        DISPATCH_METHOD(h, run_eval(h, pb, src4, static_cast<unsigned int>(n), h->d_gate.as<unsigned char>(), d_nn));
+        if (is_ndt(h)) {
+            ndt_run_eval(h, src4, static_cast<unsigned int>(n), h->d_gate.as<unsigned char>());
+        } else {
+            const IcpJob job = icp_single_job(h, src4, static_cast<unsigned int>(n));
+            ICP_DISPATCH(h, icp_launch_eval<M>(h, job, 1, h->d_gate.as<unsigned char>(), d_nn));
+        }
         h->end_timing();
         LR_CUDA(cudaMemcpy(gate, h->d_gate.p, n, cudaMemcpyDeviceToHost));
         if (d_nn) LR_CUDA(cudaMemcpy(nn, d_nn, n * k * sizeof(int), cudaMemcpyDeviceToHost));
@@ -484,15 +580,24 @@ int locreg_debug_points(locreg_handle* h, const float* src, size_t n, size_t str
 
 int locreg_align_batch_device(locreg_handle* h, const float* d_srcs, const int64_t* d_offsets, const double* d_poses_in,
                               size_t S, size_t total_points, double* d_poses_out, locreg_result* d_results) {
-    (void)total_points;
     if (!d_srcs || !d_offsets || !d_poses_in || !d_poses_out) { g_last_error = "null argument"; return LOCREG_E_ARG; }
     if (S >= (1ull << 31)) { g_last_error = "too many scans"; return LOCREG_E_ARG; }
     return guarded(h, [&]() {
         if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
         if (S == 0) return LOCREG_OK;
         h->begin_timing();
-        DISPATCH_METHOD(h, run_batch(h, pb, reinterpret_cast<const float4*>(d_srcs), reinterpret_cast<const long long*>(d_offsets), 0u,
-                                     d_poses_in, d_poses_out, reinterpret_cast<DevResult*>(d_results), static_cast<unsigned int>(S), 0));
+        const float4* src4 = reinterpret_cast<const float4*>(d_srcs);
+        const long long* offs = reinterpret_cast<const long long*>(d_offsets);
+        DevResult* results = reinterpret_cast<DevResult*>(d_results);
+        const unsigned int Su = static_cast<unsigned int>(S);
+        if (is_ndt(h)) {
+            ndt_run_batch(h, src4, offs, d_poses_in, d_poses_out, results, Su);
+        } else {
+            const IcpJob job = icp_batch_job(h, src4, offs, Su, total_points);
+            LR_LAUNCH(k_states_init, (Su + 255) / 256, 256, 0, h->stream, d_poses_in, Su, h->opt.max_iteration, job.states);
+            ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
+            LR_LAUNCH(k_states_export, (Su + 255) / 256, 256, 0, h->stream, job.states, Su, d_poses_out, results);
+        }
         h->end_timing();
         return LOCREG_OK;
     });
@@ -525,8 +630,16 @@ int locreg_align_batch(locreg_handle* h, const float* srcs, const int64_t* offse
         LR_CUDA(cudaMemcpyAsync(h->d_poses_out.p, poses_out, S * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         LR_CUDA(cudaStreamSynchronize(h->stream));  // rel[] is pageable
         h->begin_timing();
-        DISPATCH_METHOD(h, run_batch(h, pb, src4, h->d_offsets.as<long long>(), 0u, h->d_poses_in.as<double>(), h->d_poses_out.as<double>(),
-                                     h->d_results.as<DevResult>(), static_cast<unsigned int>(S), 0));
+        const unsigned int Su = static_cast<unsigned int>(S);
+        if (is_ndt(h)) {
+            ndt_run_batch(h, src4, h->d_offsets.as<long long>(), h->d_poses_in.as<double>(), h->d_poses_out.as<double>(),
+                          h->d_results.as<DevResult>(), Su);
+        } else {
+            const IcpJob job = icp_batch_job(h, src4, h->d_offsets.as<long long>(), Su, total - base);
+            LR_LAUNCH(k_states_init, (Su + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>(), Su, h->opt.max_iteration, job.states);
+            ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
+            LR_LAUNCH(k_states_export, (Su + 255) / 256, 256, 0, h->stream, job.states, Su, h->d_poses_out.as<double>(), h->d_results.as<DevResult>());
+        }
         h->end_timing();
         LR_CUDA(cudaMemcpy(poses_out, h->d_poses_out.p, S * 7 * sizeof(double), cudaMemcpyDeviceToHost));
         if (results) LR_CUDA(cudaMemcpy(results, h->d_results.p, S * sizeof(DevResult), cudaMemcpyDeviceToHost));
@@ -559,8 +672,27 @@ int locreg_relocalise(locreg_handle* h, const float* src, size_t n, size_t strid
         LR_CUDA(cudaMemcpyAsync(h->d_poses_out.p, poses_in, n_hyp * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         LR_CUDA(cudaStreamSynchronize(h->stream));
         h->begin_timing();
-        DISPATCH_METHOD(h, run_batch(h, pb, src4, nullptr, static_cast<unsigned int>(n), h->d_poses_in.as<double>(), h->d_poses_out.as<double>(),
-                                     h->d_results.as<DevResult>(), static_cast<unsigned int>(n_hyp), 1));
+        if (is_ndt(h)) { g_last_error = "relocalisation is built for the ICP methods"; return LOCREG_E_UNSUPPORTED; }
+        // hypotheses run in waves so that the per-point neighbour scratch stays below ~1 GiB
+        const int K = h->opt.method == LOCREG_ICP_P2P ? 1 : 5;
+        const size_t per_hyp = std::max<size_t>(n, 1) * K * sizeof(unsigned int);
+        const size_t wave = std::max<size_t>(1, std::min<size_t>(n_hyp, (size_t(1) << 30) / per_hyp));
+        h->d_states.reserve(wave * sizeof(AlignState));
+        for (size_t w0 = 0; w0 < n_hyp; w0 += wave) {
+            const unsigned int W = static_cast<unsigned int>(std::min(wave, n_hyp - w0));
+            IcpJob job;
+            job.bv.src = src4; job.bv.offsets = nullptr; job.bv.tile_begin = nullptr;
+            job.bv.n_single = static_cast<unsigned int>(n);
+            job.bv.tiles_per_item = std::max<unsigned int>(1u, (static_cast<unsigned int>(n) + kTile - 1) / kTile);
+            job.bv.S = W;
+            job.states = h->d_states.as<AlignState>();
+            job.n_tiles = static_cast<unsigned int>(n ? static_cast<size_t>(job.bv.tiles_per_item) * W : 0);
+            job.n_scratch_points = static_cast<size_t>(n) * W;
+            LR_LAUNCH(k_states_init, (W + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>() + w0 * 7, W, h->opt.max_iteration, job.states);
+            ICP_DISPATCH(h, icp_run_loop<M>(h, job, 1));
+            LR_LAUNCH(k_states_export, (W + 255) / 256, 256, 0, h->stream, job.states, W, h->d_poses_out.as<double>() + w0 * 7,
+                      h->d_results.as<DevResult>() + w0);
+        }
         unsigned long long* d_key = reinterpret_cast<unsigned long long*>(h->d_misc.as<unsigned char>() + 32);
         LR_CUDA(cudaMemsetAsync(d_key, 0xFF, sizeof(unsigned long long), h->stream));
         LR_LAUNCH(k_score_argmin, static_cast<unsigned int>((n_hyp + 255) / 256), 256, 0, h->stream, h->d_results.as<DevResult>(),

@@ -155,15 +155,16 @@ LR_HD void ndt_voxel_stats(const unsigned int* idx, unsigned int cnt, const void
 // Returns the number of voxels that passed the chi-square gate.  J = [ -R hat(q) , I ] is the same for
 // every hit of the point, so H += hits * J^T J and err += -J^T (sum of e) — the information matrix
 // only gates (quirk Q8).
+template <class Acc>
 LR_HD unsigned char ndt_point(const NdtMapView& map, const NdtParams& prm, const Pose& T, float sx, float sy, float sz,
-                              Accum& acc) {
+                              Acc& acc) {
     if (!finite3(sx, sy, sz)) return 0;  // deviation D1
     const double qx = sx, qy = sy, qz = sz;
     double wx, wy, wz;
     pose_apply(T, qx, qy, qz, wx, wy, wz);
     const int kx = ndt_trunc(LR_DMUL(wx, map.inv_voxel)), ky = ndt_trunc(LR_DMUL(wy, map.inv_voxel)),
               kz = ndt_trunc(LR_DMUL(wz, map.inv_voxel));
-    acc.n_eff += 1u;  // effective_num++ per point, unconditionally (:432)
+    acc.inc_eff();  // effective_num++ per point, unconditionally (:432)
     int hits = 0;
     double ex = 0, ey = 0, ez = 0, ss = 0;
     for (int o = 0; o < prm.n_nearby; ++o) {
@@ -208,17 +209,17 @@ LR_HD unsigned char ndt_point(const NdtMapView& map, const NdtParams& prm, const
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
         for (int j = i; j < 3; ++j)
-            acc.v[hidx(i, j)] += w * (A[0][i] * A[0][j] + A[1][i] * A[1][j] + A[2][i] * A[2][j]);
+            acc.add(hidx(i, j), w * (A[0][i] * A[0][j] + A[1][i] * A[1][j] + A[2][i] * A[2][j]));
 #pragma unroll
-        for (int j = 0; j < 3; ++j) acc.v[hidx(i, 3 + j)] += w * A[j][i];
+        for (int j = 0; j < 3; ++j) acc.add(hidx(i, 3 + j), w * A[j][i]);
     }
-    acc.v[hidx(3, 3)] += w; acc.v[hidx(4, 4)] += w; acc.v[hidx(5, 5)] += w;
+    acc.add(hidx(3, 3), w); acc.add(hidx(4, 4), w); acc.add(hidx(5, 5), w);
     // err = -J^T sum(e)
 #pragma unroll
-    for (int i = 0; i < 3; ++i) acc.v[21 + i] += -(A[0][i] * ex + A[1][i] * ey + A[2][i] * ez);
-    acc.v[24] += -ex; acc.v[25] += -ey; acc.v[26] += -ez;
-    acc.v[27] += ss;
-    acc.n_inl += static_cast<unsigned int>(hits);
+    for (int i = 0; i < 3; ++i) acc.add(21 + i, -(A[0][i] * ex + A[1][i] * ey + A[2][i] * ez));
+    acc.add(24, -ex); acc.add(25, -ey); acc.add(26, -ez);
+    acc.add(27, ss);
+    acc.inc_inl(static_cast<unsigned int>(hits));
     return static_cast<unsigned char>(hits);
 }
 

@@ -9,6 +9,8 @@
 //   5 scatter  counting-sort points into pts[] as float4 (x, y, z, original index)
 //   6 dedupe   quirk Q3: a point that coincides exactly with a lower-index point of its cell is masked
 //              (x := NaN), which makes every dis2 against it NaN and therefore never selected
+//   7 lists    neighbourhood lists: every surviving point is inserted into the lists of the 27 cells around
+//              its own (count pass, scan, scatter pass) - see voxel_map.cuh
 // The order of points inside a cell depends on atomic arrival order, but no result does: the k-NN
 // total order (dis2, original index) is independent of storage order.
 #pragma once
@@ -107,6 +109,43 @@ LR_HD bool build_is_duplicate(size_t i, const unsigned int* pt_cell, const unsig
         if (float_as_int(o.w) < static_cast<int>(i) && o.x == me.x && o.y == me.y && o.z == me.z) return true;
     }
     return false;
+}
+
+// Step 7a/7c.  The 27 cells whose neighbourhood contains point i each get the point.  pass 0: create the cell's
+// slot if needed and count; pass 1: append the point to the cell's list (cursor[] starts at 0 per slot).
+// counters: [0] lists created, [1] overflow flag
+template <class A>
+LR_HD void build_nbr_body(size_t i, int pass, const void* xyz, size_t stride, float inv_cell, const unsigned int* pt_cell,
+                          const unsigned char* dup, NbrSlot* nbr, unsigned int nbr_mask, unsigned int* cursor,
+                          float4* pts, unsigned int* counters) {
+    if (pt_cell[i] == kDropped || dup[i]) return;
+    const float* p = point_ptr(xyz, i, stride);
+    const int fx = cell_of(cell_coord_f(p[0], inv_cell)), fy = cell_of(cell_coord_f(p[1], inv_cell)),
+              fz = cell_of(cell_coord_f(p[2], inv_cell));
+    for (int o = 0; o < 27; ++o) {
+        const unsigned long long key = pack_cell(fx + (o % 3) - 1, fy + ((o / 3) % 3) - 1, fz + (o / 9) - 1);
+        unsigned int h = hash_block(key) & nbr_mask;
+        unsigned int probes = 0;
+        bool ok = true;
+        while (true) {
+            if (pass == 0) {
+                const unsigned long long k = A::cas64(&nbr[h].key, kEmptyKey, key);
+                if (k == kEmptyKey) { A::add32(&counters[0], 1u); break; }
+                if (k == key) break;
+            } else if (nbr[h].key == key) {
+                break;
+            }
+            h = (h + 1) & nbr_mask;
+            if (++probes > nbr_mask) { counters[1] = 1u; ok = false; break; }
+        }
+        if (!ok) return;
+        if (pass == 0) {
+            A::add32(&nbr[h].count, 1u);
+        } else {
+            const unsigned int pos = nbr[h].start + A::add32(&cursor[h], 1u);
+            pts[pos] = make_float4(p[0], p[1], p[2], int_as_float(static_cast<int>(i)));
+        }
+    }
 }
 
 }  // namespace locreg

@@ -167,15 +167,35 @@ __global__ void k_build_dup_apply(size_t n, const unsigned char* __restrict__ du
     if (i < n && dup[i]) pts[pt_pos[i]].x = __int_as_float(0x7fc00000);
 }
 
+__global__ void k_nbr_clear(NbrSlot* nbr, unsigned int cap) {
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap) nbr[s] = NbrSlot{kEmptyKey, 0u, 0u};
+}
+__global__ void k_nbr_pass(size_t n, int pass, const void* __restrict__ xyz, size_t stride, float inv_cell,
+                           const unsigned int* __restrict__ pt_cell, const unsigned char* __restrict__ dup, NbrSlot* nbr,
+                           unsigned int nbr_mask, unsigned int* cursor, float4* pts, unsigned int* counters) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) build_nbr_body<DeviceAtomics>(i, pass, xyz, stride, inv_cell, pt_cell, dup, nbr, nbr_mask, cursor, pts, counters);
+}
+__global__ void k_nbr_counts(const NbrSlot* __restrict__ nbr, unsigned int cap, unsigned int* out) {
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap) out[s] = nbr[s].count;
+}
+__global__ void k_nbr_set_start(NbrSlot* nbr, unsigned int cap, const unsigned int* __restrict__ start, unsigned int base) {
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap) nbr[s].start = base + start[s];
+}
+
 // ------------------------------------------------------------------------------------------------
 DeviceVoxelMap::~DeviceVoxelMap() { release(); }
 void DeviceVoxelMap::release() {
     if (slots_) cudaFree(slots_);
     if (cell_start_) cudaFree(cell_start_);
     if (pts_) cudaFree(pts_);
-    slots_ = nullptr; cell_start_ = nullptr; pts_ = nullptr;
+    if (nbr_) cudaFree(nbr_);
+    slots_ = nullptr; cell_start_ = nullptr; pts_ = nullptr; nbr_ = nullptr;
     view_ = VoxelMapView{};
-    bytes_ = 0; n_cells_ = 0; n_blocks_ = 0;
+    bytes_ = 0; n_cells_ = 0; n_blocks_ = 0; n_lists_ = 0;
 }
 
 static unsigned int next_pow2(size_t v) {
@@ -184,7 +204,7 @@ static unsigned int next_pow2(size_t v) {
     return p;
 }
 
-void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cell, cudaStream_t stream) {
+void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cell, bool want_lists, cudaStream_t stream) {
     release();
     if (n == 0) return;
     if (n >= (1ull << 31)) throw std::invalid_argument("target cloud too large (>= 2^31 points)");
@@ -248,7 +268,14 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     LR_CUDA(cudaMallocAsync(&cursor, static_cast<size_t>(n_cells_) * sizeof(unsigned int), stream));
     LR_CUDA(cudaMemcpyAsync(cursor, cell_start_, static_cast<size_t>(n_cells_) * sizeof(unsigned int),
                             cudaMemcpyDeviceToDevice, stream));
-    LR_CUDA(cudaMalloc(&pts_, static_cast<size_t>(n_kept) * sizeof(float4)));
+    // neighbourhood lists live behind the sorted points in the same array (28 float4 per point in total);
+    // they are skipped when they would not fit comfortably (the search then always takes the block path)
+    size_t free_b = 0, total_b = 0;
+    LR_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t list_entries = static_cast<size_t>(n_kept) * 27;
+    const bool lists = want_lists && (static_cast<size_t>(n_kept) + list_entries) < 0xF0000000ull &&
+                       (list_entries + n_kept) * sizeof(float4) < free_b / 2;
+    LR_CUDA(cudaMalloc(&pts_, (static_cast<size_t>(n_kept) + (lists ? list_entries : 0)) * sizeof(float4)));
     LR_LAUNCH(k_build_scatter, gridN, T, 0, stream, d_xyz, n, stride, pt_slot, cursor, pts_, pt_pos);
     // 6 dedupe (quirk Q3)
     LR_CUDA(cudaMemsetAsync(counters + 5, 0, sizeof(unsigned int), stream));
@@ -257,6 +284,41 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     unsigned int n_dup = 0;
     LR_CUDA(cudaMemcpyAsync(&n_dup, counters + 5, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     LR_CUDA(cudaStreamSynchronize(stream));
+    // 7 neighbourhood lists
+    unsigned int nbr_cap = 0;
+    if (lists) {
+        nbr_cap = next_pow2(static_cast<size_t>(n_cells_) * 8);
+        unsigned int* ncursor = nullptr;
+        while (true) {
+            LR_CUDA(cudaMalloc(&nbr_, static_cast<size_t>(nbr_cap) * sizeof(NbrSlot)));
+            LR_LAUNCH(k_nbr_clear, (nbr_cap + T - 1) / T, T, 0, stream, nbr_, nbr_cap);
+            LR_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream));
+            LR_LAUNCH(k_nbr_pass, gridN, T, 0, stream, n, 0, d_xyz, stride, inv_cell, pt_slot, dup, nbr_, nbr_cap - 1,
+                      static_cast<unsigned int*>(nullptr), pts_, counters);
+            LR_CUDA(cudaMemcpyAsync(h_counters, counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+            LR_CUDA(cudaStreamSynchronize(stream));
+            if (h_counters[1] || static_cast<size_t>(h_counters[0]) * 2 > nbr_cap) {
+                cudaFree(nbr_);
+                nbr_ = nullptr;
+                if (nbr_cap >= (1u << 30)) throw std::runtime_error("neighbourhood table overflow");
+                nbr_cap <<= 2;
+                continue;
+            }
+            break;
+        }
+        n_lists_ = h_counters[0];
+        LR_CUDA(cudaMallocAsync(&tmp, static_cast<size_t>(nbr_cap) * sizeof(unsigned int), stream));
+        LR_CUDA(cudaMallocAsync(&ncursor, static_cast<size_t>(nbr_cap) * sizeof(unsigned int), stream));
+        LR_LAUNCH(k_nbr_counts, (nbr_cap + T - 1) / T, T, 0, stream, nbr_, nbr_cap, tmp);
+        exclusive_scan_u32(tmp, tmp, nbr_cap, nullptr, stream);
+        LR_LAUNCH(k_nbr_set_start, (nbr_cap + T - 1) / T, T, 0, stream, nbr_, nbr_cap, tmp, n_kept);
+        LR_CUDA(cudaMemsetAsync(ncursor, 0, static_cast<size_t>(nbr_cap) * sizeof(unsigned int), stream));
+        LR_LAUNCH(k_nbr_pass, gridN, T, 0, stream, n, 1, d_xyz, stride, inv_cell, pt_slot, dup, nbr_, nbr_cap - 1, ncursor, pts_,
+                  counters);
+        LR_CUDA(cudaStreamSynchronize(stream));
+        LR_CUDA(cudaFreeAsync(tmp, stream));
+        LR_CUDA(cudaFreeAsync(ncursor, stream));
+    }
     LR_CUDA(cudaFreeAsync(cursor, stream));
     LR_CUDA(cudaFreeAsync(pt_slot, stream));
     LR_CUDA(cudaFreeAsync(pt_pos, stream));
@@ -265,11 +327,12 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     LR_CUDA(cudaFreeAsync(counters, stream));
     LR_CUDA(cudaFreeAsync(bounds, stream));
     view_.slots = slots_; view_.cell_start = cell_start_; view_.pts = pts_;
+    view_.nbr_slots = nbr_; view_.nbr_mask = nbr_cap ? nbr_cap - 1 : 0;
     view_.slot_mask = cap - 1; view_.n_pts = n_kept; view_.n_unique = n_kept - n_dup;
     view_.inv_cell = inv_cell; view_.cell = cell;
     for (int a = 0; a < 3; ++a) { view_.cmin[a] = h_bounds[a]; view_.cmax[a] = h_bounds[3 + a]; }
     bytes_ = static_cast<size_t>(cap) * sizeof(VoxelSlot) + (static_cast<size_t>(n_cells_) + 1) * 4 +
-             static_cast<size_t>(n_kept) * sizeof(float4);
+             static_cast<size_t>(n_kept) * sizeof(float4) * (lists ? 28 : 1) + static_cast<size_t>(nbr_cap) * sizeof(NbrSlot);
 }
 
 }  // namespace locreg

@@ -5,10 +5,17 @@
 // voxel (w carries the caller's original index), grouped into 4x4x4-cell blocks.  A block is one
 // 32-byte open-addressing hash slot {key, 64-bit cell-occupancy mask, first cell id}, so a query
 // touches one 32 B sector per block, skips empty cells with bit tricks instead of probes, and reads
-// candidate points as contiguous 16 B vectors.  Layout in HBM (1 M-point map, cell 0.5 m):
-//   slots       32 B x capacity (power of two, load <= 0.5)      ~ 2 MB
+// candidate points as contiguous 16 B vectors.  On top of that every cell whose 3x3x3 neighbourhood holds a
+// point owns a NEIGHBOURHOOD LIST: all points of those 27 cells copied contiguously (each map point is stored
+// 27 times).  The common query is then ONE 16 B probe of a cell-keyed table plus ONE contiguous float4 scan
+// (~25 candidates) with no per-cell work and little divergence; the block structure remains the exact fallback
+// for queries whose k-th neighbour lies beyond the guaranteed radius (far-off points of the first iteration).
+// Layout in HBM (1 M-point map, cell 0.5 m; sized for 180 GB, not for the L2):
+//   slots       32 B x capacity (power of two, load <= 0.5)      ~ 2 MB     block table (fallback search)
 //   cell_start  4 B x (occupied cells + 1)                        ~ 1.6 MB
-//   pts         16 B x N                                           16 MB     -> all L2-resident (126 MB)
+//   pts         16 B x N                                           16 MB     sorted by cell; positions [0, N)
+//   nbr_slots   16 B x capacity                                   ~ 64 MB    cell -> (start, count) of its list
+//   lists       16 B x 27 N                                        432 MB    positions [N, 28 N) of the same array
 //
 // NN contract: the k nearest points in float32
 //   dis2 = dx*dx + (dy*dy + dz*dz)   (Eigen 3.3 association, no FMA; kdtree.h:94)
@@ -32,13 +39,22 @@ static_assert(sizeof(VoxelSlot) == 32, "slot must be one 32 B sector");
 
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kCoordBias = 1 << 20;        // block coords are biased into 21 bits
-constexpr float kCellClamp = 4194000.0f;   // |fine cell index| clamp (fits 23 bits, exact in float)
+constexpr float kCellClamp = 1048000.0f;   // |fine cell index| clamp (fits 21 bits, exact in float)
 constexpr int kBruteForceShell = 24;       // beyond this Chebyshev radius fall back to a linear scan
+
+struct __attribute__((aligned(16))) NbrSlot {
+    unsigned long long key;  // packed fine-cell coordinate, kEmptyKey if unused
+    unsigned int start;      // first entry of the cell's neighbourhood list, as a position in pts[]
+    unsigned int count;
+};
+static_assert(sizeof(NbrSlot) == 16, "neighbourhood slot must be 16 B");
 
 struct VoxelMapView {
     const VoxelSlot* slots;
     const unsigned int* cell_start;
-    const float4* pts;
+    const float4* pts;        // [0, n_pts): points sorted by cell; [n_pts, ...): neighbourhood lists
+    const NbrSlot* nbr_slots; // nullptr: no neighbourhood lists (fallback search only)
+    unsigned int nbr_mask;
     unsigned int slot_mask;  // capacity - 1
     unsigned int n_pts;      // points stored (non-finite inputs are dropped)
     unsigned int n_unique;   // points that survive de-duplication (= KdTree::size())
@@ -51,6 +67,11 @@ LR_HD unsigned long long pack_block(int bx, int by, int bz) {
     return (static_cast<unsigned long long>(static_cast<unsigned int>(bx + kCoordBias)) << 42) |
            (static_cast<unsigned long long>(static_cast<unsigned int>(by + kCoordBias)) << 21) |
            static_cast<unsigned long long>(static_cast<unsigned int>(bz + kCoordBias));
+}
+LR_HD unsigned long long pack_cell(int cx, int cy, int cz) {  // |c| <= kCellClamp < 2^20
+    return (static_cast<unsigned long long>(static_cast<unsigned int>(cx + kCoordBias)) << 42) |
+           (static_cast<unsigned long long>(static_cast<unsigned int>(cy + kCoordBias)) << 21) |
+           static_cast<unsigned long long>(static_cast<unsigned int>(cz + kCoordBias));
 }
 LR_HD unsigned int hash_block(unsigned long long k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
@@ -172,6 +193,34 @@ LR_HD void knn_query(const VoxelMapView& m, float qx, float qy, float qz, KnnRes
         if (e > R) R = e;
     }
     bool first = true;
+    if (R == 1 && m.nbr_slots != nullptr) {
+        // fast path: the whole box [f-1, f+1]^3 is one contiguous list
+        const unsigned long long key = pack_cell(fx, fy, fz);
+        unsigned int h = hash_block(key) & m.nbr_mask;
+        unsigned int beg = 0, cnt = 0;
+        while (true) {
+            const NbrSlot s = m.nbr_slots[h];
+            if (s.key == key) { beg = s.start; cnt = s.count; break; }
+            if (s.key == kEmptyKey) break;
+            h = (h + 1) & m.nbr_mask;
+        }
+        for (unsigned int i = beg; i < beg + cnt; ++i) {
+            const float4 p = m.pts[i];
+            knn_offer(res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), float_as_int(p.w), i);
+        }
+        first = false;
+        if (res.idx[K - 1] != 0x7fffffff) {
+            float mf = fminf(frx, 1.0f - frx);
+            mf = fminf(mf, fminf(fry, 1.0f - fry));
+            mf = fminf(mf, fminf(frz, 1.0f - frz));
+            const float g = safe_gap(1.0f + mf, mag + 1.0f, m.cell);
+            if (res.d2[K - 1] < g * g * 0.99999f) return;
+        }
+        if (fx - 1 <= m.cmin[0] && fx + 1 >= m.cmax[0] && fy - 1 <= m.cmin[1] && fy + 1 >= m.cmax[1] &&
+            fz - 1 <= m.cmin[2] && fz + 1 >= m.cmax[2])
+            return;
+        R = 2;
+    }
     while (true) {
         if (R > kBruteForceShell) {
             // pathological query (> kBruteForceShell cells from every candidate seen so far): linear scan

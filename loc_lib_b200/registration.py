@@ -42,6 +42,7 @@ class IcpOptions:  # icp_registration.hpp:22-39
     method_: int = IcpMethod.P2P
     # GPU-side knobs
     knn_cell_size: float = 0.5
+    knn_lists: bool = True
     loop_mode: int = LOOP_PERSISTENT
 
 
@@ -203,6 +204,7 @@ class IcpRegistration(_Registration):
         o.eps = options.eps_
         o.use_ann = int(options.use_ann)
         o.knn_cell_size = options.knn_cell_size
+        o.knn_lists = int(options.knn_lists)
         o.loop_mode = options.loop_mode
         self.options_ = options
         super().__init__(o, device)

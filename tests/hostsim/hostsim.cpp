@@ -17,6 +17,7 @@
 using namespace locreg;
 
 struct HsMap {
+    std::vector<NbrSlot> nbr;
     std::vector<VoxelSlot> slots;
     std::vector<unsigned int> cell_start;
     std::vector<float4> pts;
@@ -34,7 +35,7 @@ extern "C" {
 HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsigned int capacity_hint) {
     auto* m = new HsMap;
     const float inv_cell = 1.0f / cell;
-    unsigned int cap = capacity_hint ? next_pow2(capacity_hint) : next_pow2(static_cast<unsigned int>(n / 4 + 1024));
+    unsigned int cap = (capacity_hint && capacity_hint != 0xFFFFFFFFu) ? next_pow2(capacity_hint) : next_pow2(static_cast<unsigned int>(n / 4 + 1024));
     std::vector<unsigned int> pt_slot(n), pt_pos(n, 0);
     std::vector<unsigned char> pt_bit(n);
     unsigned int counters[3];
@@ -74,8 +75,27 @@ HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsi
     }
     for (size_t i = 0; i < n; ++i)
         if (dup[i]) m->pts[pt_pos[i]].x = NAN;
+    unsigned int nbr_cap = 0;
+    if (capacity_hint != 0xFFFFFFFFu) {  // neighbourhood lists (capacity_hint == ~0 disables them)
+        nbr_cap = next_pow2(ncells * 8 + 1024);
+        while (true) {
+            m->nbr.assign(nbr_cap, NbrSlot{kEmptyKey, 0u, 0u});
+            counters[0] = counters[1] = 0;
+            for (size_t i = 0; i < n; ++i)
+                build_nbr_body<HostAtomics>(i, 0, xyz, stride, inv_cell, pt_slot.data(), dup.data(), m->nbr.data(), nbr_cap - 1, nullptr, nullptr, counters);
+            if (counters[1] || counters[0] * 2u > nbr_cap) { nbr_cap *= 4; continue; }
+            break;
+        }
+        unsigned int acc = run;
+        for (unsigned int s = 0; s < nbr_cap; ++s) { m->nbr[s].start = acc; acc += m->nbr[s].count; }
+        m->pts.resize(acc, float4{0, 0, 0, 0});
+        std::vector<unsigned int> ncur(nbr_cap, 0);
+        for (size_t i = 0; i < n; ++i)
+            build_nbr_body<HostAtomics>(i, 1, xyz, stride, inv_cell, pt_slot.data(), dup.data(), m->nbr.data(), nbr_cap - 1, ncur.data(), m->pts.data(), counters);
+    }
     VoxelMapView& v = m->view;
     v.slots = m->slots.data(); v.cell_start = m->cell_start.data(); v.pts = m->pts.data();
+    v.nbr_slots = nbr_cap ? m->nbr.data() : nullptr; v.nbr_mask = nbr_cap ? nbr_cap - 1 : 0;
     v.slot_mask = cap - 1; v.n_pts = run; v.n_unique = run - ndup; v.inv_cell = inv_cell; v.cell = cell;
     for (int a = 0; a < 3; ++a) { v.cmin[a] = cmin[a]; v.cmax[a] = cmax[a]; }
     return m;
@@ -179,6 +199,15 @@ void hs_plane_svd5(const double* pts15, double* coef4) {
     double c[4];
     plane_svd5(P, c);
     for (int i = 0; i < 4; ++i) coef4[i] = c[i];
+}
+int hs_plane_fit5_fast(const double* pts15, double* coef4) {
+    double P[5][3];
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 3; ++j) P[i][j] = pts15[i * 3 + j];
+    double c[4] = {0, 0, 0, 0};
+    const bool ok = plane_fit5_fast(P, c);
+    for (int i = 0; i < 4; ++i) coef4[i] = c[i];
+    return ok ? 1 : 0;
 }
 void hs_sym3_eigen(const double* S6, double* lam3, double* Q9) { sym3_eigen(S6, lam3, Q9); }
 int hs_gn_solve6(const double* Hu21, const double* b6, double* dx6) { return gn_solve6(Hu21, b6, dx6) ? 1 : 0; }
