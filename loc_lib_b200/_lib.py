@@ -16,7 +16,7 @@ SYMBOLS = [
     "locreg_set_target_device", "locreg_align", "locreg_compute_hb", "locreg_knn", "locreg_debug_points",
     "locreg_align_batch", "locreg_align_batch_device", "locreg_relocalise", "locreg_pack_score",
     "locreg_transform_cloud", "locreg_ndt_num_voxels", "locreg_ndt_get_voxels", "locreg_last_timing",
-    "locreg_last_error", "locreg_version",
+    "locreg_profile", "locreg_last_error", "locreg_version",
 ]
 
 
@@ -67,6 +67,7 @@ def lib():
         L.locreg_ndt_num_voxels.argtypes = [vp, C.POINTER(sz)]
         L.locreg_ndt_get_voxels.argtypes = [vp, vp, vp, vp, vp]
         L.locreg_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+        L.locreg_profile.argtypes = [vp, i32, vp, vp]
         L.locreg_last_error.restype = C.c_char_p
         L.locreg_version.restype = C.c_char_p
         _LIB = L

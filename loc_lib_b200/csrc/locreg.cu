@@ -68,6 +68,12 @@ struct locreg_handle {
     PinBuf h_in, h_out, h_small;
     double last_ms = 0;
     long long last_launches = 0;
+    // optional per-kernel-class timing (locreg_profile): events around every search / fit / solve launch
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;  // pairs
+    std::vector<int> prof_class;
+    double prof_ms[3] = {0, 0, 0};
+    long long prof_launches[3] = {0, 0, 0};
 
     IcpParams icp_params() const {
         IcpParams p;
@@ -102,6 +108,7 @@ struct locreg_handle {
         last_launches = g_launch_count;
     }
 };
+namespace { void prof_collect(locreg_handle* h); }
 
 namespace {
 
@@ -212,6 +219,30 @@ void ndt_run_batch(locreg_handle* h, const float4* src, const long long* offsets
               h->d_misc.as<unsigned int>(), 0);
 }
 
+// Event pair around one launch of kernel class cls (0 search, 1 fit+reduce, 2 solve) when profiling is on.
+void prof_mark(locreg_handle* h, int cls, bool begin) {
+    if (!h->profile) return;
+    cudaEvent_t e;
+    LR_CUDA(cudaEventCreate(&e));
+    LR_CUDA(cudaEventRecord(e, h->stream));
+    h->prof_events.push_back(e);
+    if (begin) h->prof_class.push_back(cls);
+}
+void prof_collect(locreg_handle* h) {
+    if (!h->profile) return;
+    LR_CUDA(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i + 1 < h->prof_events.size(); i += 2) {
+        float ms = 0;
+        LR_CUDA(cudaEventElapsedTime(&ms, h->prof_events[i], h->prof_events[i + 1]));
+        const int c = h->prof_class[i / 2];
+        h->prof_ms[c] += ms;
+        h->prof_launches[c] += 1;
+    }
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    h->prof_events.clear();
+    h->prof_class.clear();
+}
+
 // ---- ICP: three-kernel pipeline (icp_pipeline.cuh) -------------------------------------------------------------
 struct IcpJob {
     BatchView bv{};
@@ -227,14 +258,20 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, unsig
     h->d_nnpos.reserve(job.n_scratch_points * K * sizeof(unsigned int));
     h->d_partials.reserve(static_cast<size_t>(job.n_tiles) * kPartialDoubles * sizeof(double));
     if (job.n_tiles == 0) return;
+    prof_mark(h, 0, true);
     LR_LAUNCH(k_icp_nn<K>, job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, h->d_nnpos.as<unsigned int>());
+    prof_mark(h, 0, false);
+    prof_mark(h, 1, true);
     LR_LAUNCH(k_icp_post<METHOD>, job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
               h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx);
+    prof_mark(h, 1, false);
 }
 template <int METHOD>
 void icp_launch_solve(locreg_handle* h, const IcpJob& job, int mode, double* acc_out) {
+    prof_mark(h, 2, true);
     LR_LAUNCH(k_icp_solve<METHOD>, (job.bv.S + 3) / 4, 128, 0, h->stream, h->icp_params(), job.bv, job.states,
               h->d_partials.as<double>(), mode, acc_out);
+    prof_mark(h, 2, false);
 }
 // The whole Gauss-Newton loop, queued on the stream without a host round-trip; stopped scans make their tiles exit.
 template <int METHOD>
@@ -744,6 +781,17 @@ int locreg_ndt_get_voxels(locreg_handle* h, int32_t* keys, double* mu, double* i
         if (mu) std::memcpy(mu, m.data(), m.size() * sizeof(double));
         if (info) std::memcpy(info, f.data(), f.size() * sizeof(double));
         if (npts) std::memcpy(npts, c.data(), c.size() * sizeof(int));
+        return LOCREG_OK;
+    });
+}
+
+int locreg_profile(locreg_handle* h, int32_t enable, double* ms3, int64_t* launches3) {
+    return guarded(h, [&]() {
+        prof_collect(h);
+        if (ms3) for (int i = 0; i < 3; ++i) ms3[i] = h->prof_ms[i];
+        if (launches3) for (int i = 0; i < 3; ++i) launches3[i] = h->prof_launches[i];
+        for (int i = 0; i < 3; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+        h->profile = enable != 0;
         return LOCREG_OK;
     });
 }

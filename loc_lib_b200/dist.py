@@ -1,0 +1,85 @@
+"""Multi-GPU plumbing for the two workloads that shard: one process per GPU, torch.distributed.
+
+* batch offline mapping: scans are block-partitioned over ranks, every rank holds a replica of the map, and there
+  is NO collective on the data path (only the gather of the S x 7 poses at the end);
+* global relocalisation: pose hypotheses are block-partitioned, each rank finds its local best, and ONE
+  min-all-reduce of a packed (float32 score bits << 32 | global hypothesis index) key picks the winner
+  (lowest index wins ties), followed by a broadcast of the winning pose from its owner.
+torch is used for process-group plumbing only; all registration work goes through liblocreg.so.
+"""
+import struct
+
+import numpy as np
+
+
+def shard_range(n_items, rank, world):
+    """Block partition [lo, hi) of n_items over world ranks (remainder spread over the first ranks)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_score(score, index):
+    """(float32 bits of score) << 32 | index, as a Python int; NaN / negative scores map to +inf."""
+    f = np.float32(score)
+    if not (f == f) or f < 0:
+        f = np.float32(np.inf)
+    bits = struct.unpack("<I", struct.pack("<f", float(f)))[0]
+    return (bits << 32) | (int(index) & 0xFFFFFFFF)
+
+
+def unpack_score(key):
+    bits = (key >> 32) & 0xFFFFFFFF
+    return struct.unpack("<f", struct.pack("<I", bits))[0], key & 0xFFFFFFFF
+
+
+def allreduce_argmin(local_score, local_global_index, device=None):
+    """Global (score, index) minimum over all ranks with one MIN all-reduce.
+
+    float32 score bits of a non-negative float are < 2^31, so the packed key fits a signed int64 and integer order
+    equals (score, index) order."""
+    import torch
+    import torch.distributed as dist
+    key = pack_score(local_score, local_global_index)
+    t = torch.tensor([key], dtype=torch.int64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return unpack_score(int(t.item()))
+
+
+def broadcast_pose(pose7, owner_rank, device=None):
+    import torch
+    import torch.distributed as dist
+    t = torch.as_tensor(np.asarray(pose7, np.float64), device=device).clone()
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(t, src=owner_rank)
+    return t.cpu().numpy()
+
+
+def relocalise_sharded(reg, scan, hypotheses, rank=0, world=1, device=None):
+    """Global relocalisation over `world` ranks; `reg` is this rank's IcpRegistration with the map set.
+    Returns (best_pose, best_global_index, best_score), identical on every rank."""
+    hyp = np.ascontiguousarray(hypotheses, np.float64).reshape(-1, 7)
+    lo, hi = shard_range(len(hyp), rank, world)
+    if hi > lo:
+        pose, idx, score, _, _ = reg.Relocalise(scan, hyp[lo:hi])
+        gidx = lo + idx
+    else:
+        pose, gidx, score = np.zeros(7), 0xFFFFFFFF, np.inf
+    best_score, best_idx = allreduce_argmin(score, gidx, device)
+    owner = next(r for r in range(world) if shard_range(len(hyp), r, world)[0] <= best_idx < shard_range(len(hyp), r, world)[1]) \
+        if best_idx != 0xFFFFFFFF else 0
+    best_pose = broadcast_pose(pose if owner == rank else np.zeros(7), owner, device)
+    return best_pose, int(best_idx), float(best_score)
+
+
+def gather_poses(local_poses, device=None):
+    """All-gather of per-rank pose blocks (equal block sizes) -> (world * S_local, 7)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.as_tensor(np.ascontiguousarray(local_poses, np.float64), device=device)
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return t.cpu().numpy()
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return torch.cat(out).cpu().numpy()

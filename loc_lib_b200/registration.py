@@ -180,6 +180,19 @@ class _Registration:
                                                      out.ctypes.data))
         return out
 
+    def profile(self, enable):
+        """Returns ({'search','fit','solve'} -> (ms, launches)) accumulated so far, then switches instrumentation."""
+        ms = np.zeros(3)
+        ln = np.zeros(3, np.int64)
+        _lib.check(_lib.lib().locreg_profile(self._h, int(enable), ms.ctypes.data, ln.ctypes.data))
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(("search", "fit", "solve"))}
+
+    def ScanMatchBatchDevice(self, d_srcs, d_offsets, d_poses_in, S, total_points, d_poses_out, d_results=0):
+        """Batch ScanMatch with every buffer already in device memory (raw device pointers; clouds are float4)."""
+        _lib.check(_lib.lib().locreg_align_batch_device(self._h, C.c_void_p(d_srcs), C.c_void_p(d_offsets),
+                                                        C.c_void_p(d_poses_in), S, total_points,
+                                                        C.c_void_p(d_poses_out), C.c_void_p(d_results)))
+
     def last_timing(self):
         ms = C.c_double()
         launches = C.c_int64()

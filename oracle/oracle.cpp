@@ -699,6 +699,29 @@ int oracle_icp_align(oracle_icp* h, const float* src, size_t n, size_t stride, c
     if (res) *res = r;
     return 1;  // ScanMatch always returns true (icp_registration.cpp:243)
 }
+// S independent ScanMatch calls spread over `threads` host threads.  Each call is the reference's own
+// single-threaded loop (the reference has no parallel path); the kd-tree is shared read-only.
+int oracle_icp_align_batch(oracle_icp* h, const float* srcs, const int64_t* offsets, size_t stride, const double* poses_in,
+                           size_t S, double* poses_out, oracle_result* results, int threads) {
+    if (h->impl.opt.method == ORACLE_ICP_P2LINE) return -2;
+    if (threads <= 0) threads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+    threads = static_cast<int>(std::min<size_t>(threads, std::max<size_t>(S, 1)));
+    auto work = [&](int tid) {
+        for (size_t s = tid; s < S; s += threads) {
+            const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(srcs) + offsets[s] * stride);
+            SE3 result;
+            oracle_result r{};
+            h->impl.Align(src, static_cast<size_t>(offsets[s + 1] - offsets[s]), stride, SE3::from7(poses_in + s * 7), result, r, nullptr);
+            result.to7(poses_out + s * 7);
+            if (results) results[s] = r;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& t : pool) t.join();
+    return threads;
+}
 int oracle_fit_plane(const double* pts, int n, double* coeffs4, double eps) {
     std::vector<Vec3> d;
     for (int i = 0; i < n; ++i) d.emplace_back(pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]);

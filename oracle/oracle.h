@@ -82,6 +82,11 @@ int oracle_icp_compute_hb(oracle_icp* h, const float* src, size_t n, size_t stri
 int oracle_icp_align(oracle_icp* h, const float* src, size_t n, size_t stride_bytes, const double* pose_in,
                      double* pose_out, float* out_xyz, oracle_result* res, double* pose_trace);
 
+/* S independent ScanMatch calls (scan s = points [offsets[s], offsets[s+1]) of srcs) on `threads` host threads
+ * (<= 0: all hardware threads); each call is the single-threaded reference loop.  Returns the threads used. */
+int oracle_icp_align_batch(oracle_icp* h, const float* srcs, const int64_t* offsets, size_t stride_bytes,
+                           const double* poses_in, size_t S, double* poses_out, oracle_result* results, int threads);
+
 /* math::FitPlane (math_utils.h:112-136): pts = n*3 doubles; returns 1 on success */
 int oracle_fit_plane(const double* pts, int n, double* coeffs4, double eps);
 /* brute-force k-NN without a handle (for kd-tree cross checks) */

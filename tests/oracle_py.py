@@ -57,6 +57,7 @@ def lib():
         L.oracle_icp_knn.argtypes = [vp, vp, sz, sz, i32, i32, vp]
         L.oracle_icp_compute_hb.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(Result), vp, vp]
         L.oracle_icp_align.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(Result), vp]
+        L.oracle_icp_align_batch.argtypes = [vp, vp, vp, sz, vp, sz, vp, vp, i32]
         L.oracle_fit_plane.argtypes = [vp, i32, vp, dbl]
         L.oracle_bfnn.argtypes = [vp, sz, sz, vp, sz, sz, i32, vp]
         L.oracle_ndt_create.restype = vp
@@ -147,6 +148,18 @@ class OracleIcp:
         lib().oracle_icp_align(self._h, a.ctypes.data, n, s, pose7.ctypes.data, out_pose.ctypes.data,
                                out.ctypes.data if want_cloud else None, C.byref(res), trace.ctypes.data)
         return out_pose, out, res.as_dict(), trace
+
+
+    def align_batch(self, clouds, offsets, poses, threads=0):
+        a, n, s = _cloud(clouds)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        S = len(offsets) - 1
+        pin = np.ascontiguousarray(poses, np.float64).reshape(S, 7)
+        pout = np.zeros((S, 7))
+        res = (Result * S)()
+        used = lib().oracle_icp_align_batch(self._h, a.ctypes.data, offsets.ctypes.data, s, pin.ctypes.data, S,
+                                            pout.ctypes.data, res, threads)
+        return pout, [r.as_dict() for r in res], used
 
 
 class OracleNdt:
