@@ -245,3 +245,38 @@ def test_ndt_degenerate_early_return(scene, ndt_pair):
     assert gpu.last_result["pose_written"] == rres["pose_written"] == 0
     assert np.array_equal(pose, keep) and np.array_equal(rpose, keep)
     assert np.abs(cloud[:, :3] - rcloud[:, :3]).max() < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------- golden fixture
+def test_gpu_matches_golden_fixture():
+    """tests/golden/registration_small.npz (frozen oracle outputs, tests/golden/make_golden.py) vs the CUDA path."""
+    import os
+    import golden_cases as G
+    import loc_lib_b200 as L
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "registration_small.npz"))
+    m, scan, init = g["map"], g["scan"], g["init"]
+    q = G.queries(scan, init)
+    for name, method, k in (("p2plane", L.IcpMethod.P2PLANE, 5), ("p2p", L.IcpMethod.P2P, 1)):
+        gpu = L.IcpRegistration(L.IcpOptions(method_=method, max_iteration_=G.ITERS, eps_=0.0, max_plane_distance_=0.05,
+                                             max_nn_distance_=0.3))
+        gpu.SetInputTarget(m)
+        assert np.array_equal(gpu.Knn(q, k), g["knn%d" % k])
+        ok, H, B = gpu.CaculateMatrixHAndB(scan, init)
+        gate, nn = gpu.DebugPoints(scan, init, k)
+        assert np.array_equal(gate, g[name + "_gate"]) and np.array_equal(nn, g["knn%d" % k])
+        assert rel(H, g[name + "_H"]) < H_TOL and rel(B, g[name + "_B"]) < H_TOL
+        assert [gpu.last_result["n_effective"], gpu.last_result["n_inlier"]] == g[name + "_counts"].tolist()
+        _, _, pose = gpu.ScanMatch(scan, init, want_cloud=False)
+        dr, dt = pose_delta(pose, g[name + "_trace"][-1])
+        assert dr < ROT_TOL and dt < TRANS_TOL
+    ndt = L.NdtRegistration(L.NdtOptions(max_iteration_=G.ITERS, eps_=0.0))
+    ndt.SetInputTarget(m)
+    k_, mu, info, npts = ndt.Voxels()
+    assert np.array_equal(k_, g["ndt_keys"]) and np.array_equal(npts, g["ndt_npts"]) and np.array_equal(mu, g["ndt_mu"])
+    ok, H, B = ndt.CaculateMatrixHAndB(scan, init)
+    hits, _ = ndt.DebugPoints(scan, init, 0)
+    assert np.array_equal(hits, g["ndt_hits"])
+    assert rel(H, g["ndt_H"]) < H_TOL and rel(B, g["ndt_B"]) < H_TOL
+    _, _, pose = ndt.ScanMatch(scan, init, want_cloud=False)
+    dr, dt = pose_delta(pose, g["ndt_trace"][-1])
+    assert dr < ROT_TOL and dt < TRANS_TOL
