@@ -150,10 +150,11 @@ int locreg_ndt_get_voxels(locreg_handle* h, int32_t* keys, double* mu, double* i
  * (CUDA events on the handle's stream), and how many kernels that call launched. */
 int locreg_last_timing(locreg_handle* h, double* kernel_ms, int64_t* launches);
 
-/* Per-kernel-class device timing for the ICP pipeline (0 neighbour search, 1 fit + reduce, 2 solve): returns and
- * clears the milliseconds / launch counts accumulated since the last call, then switches the instrumentation
- * (a CUDA event pair around every launch) on or off.  Off by default; meant for bench.py's roofline pass. */
-int locreg_profile(locreg_handle* h, int32_t enable, double* ms3, int64_t* launches3);
+/* Per-kernel-class device timing for the ICP pipeline (0 neighbour search stage 1, 1 fit + reduce, 2 solve,
+ * 3 neighbour search stage 2): returns and clears the milliseconds / launch counts (4 entries each) accumulated
+ * since the last call, then switches the instrumentation (a CUDA event pair around every launch) on or off.
+ * Off by default; meant for bench.py's roofline pass. */
+int locreg_profile(locreg_handle* h, int32_t enable, double* ms4, int64_t* launches4);
 
 const char* locreg_last_error(void);
 const char* locreg_version(void);

@@ -88,6 +88,18 @@ struct Accum {  // register / host flavour
     LR_HD void add(int i, double x) { v[i] += x; }
     LR_HD void inc_eff(unsigned int c = 1u) { n_eff += c; }
     LR_HD void inc_inl(unsigned int c = 1u) { n_inl += c; }
+    // one residual row: H += J^T J (upper triangle), B += -J^T r, sum of squares += r^2
+    LR_HD void row(const double (&J)[6], double r) {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = i; j < 6; ++j) v[k++] += J[i] * J[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[21 + i] += -J[i] * r;
+        v[27] += r * r;
+    }
 };
 LR_HD void accum_zero(Accum& a) {
 #pragma unroll

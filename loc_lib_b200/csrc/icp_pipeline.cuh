@@ -35,7 +35,7 @@ struct AlignState {  // one per scan / hypothesis, device resident for the whole
 };
 
 constexpr int kTile = 256;
-constexpr unsigned int kNoNeighbour = 0xFFFFFFFFu;
+constexpr unsigned int kNoNeighbour = kNoPos;
 
 struct BatchView {
     const float4* src;              // all scans' points
@@ -128,10 +128,23 @@ __global__ void k_tile_begin(const long long* __restrict__ offsets, unsigned int
 #ifndef LR_NN_MIN_BLOCKS
 #define LR_NN_MIN_BLOCKS 4
 #endif
+// Stage 1 (k_icp_nn): one thread per source point: transform, seeds + one-list fast path (knn_query_fast).  The few
+// queries whose k-th neighbour may lie outside the visited box - 13 % at a 0.3 m / 2 deg initial error, 0.1 % once the
+// pose has settled - are NOT finished here, where each of them would hold 31 idle lanes hostage for the length of a
+// shell search: they are appended to a queue and finished by k_icp_nn_rings, one queued query per thread.
+// mode bit 0 (kNnSeeds):   nn_pos still holds this job's neighbours of the previous Gauss-Newton iteration; they
+//                          start each query's k-best set, so that almost no candidate passes the acceptance test.
+// mode bit 1 (kNnTwoPass): threshold pre-pass of knn_scan_list (first iterations: no or poor seeds).
+constexpr int kNnSeeds = 1, kNnTwoPass = 2;
+struct RingQueue {
+    unsigned int* count;   // entries appended so far (reset by k_icp_post)
+    uint2* entries;        // (scratch row of the point, scan index)
+};
+
 template <int K>
 __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView map, BatchView bv,
                                                                     const AlignState* __restrict__ states, int ignore_stop,
-                                                                    unsigned int* __restrict__ nn_pos) {
+                                                                    int mode, unsigned int* __restrict__ nn_pos, RingQueue queue) {
     __shared__ Pose T;
     const TileCoord tc = locate_tile(bv, blockIdx.x);
     if (!tc.valid) return;
@@ -139,61 +152,121 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
     if (st->stop && !ignore_stop) return;
     if (threadIdx.x == 0) pose_load(T, st->pose);
     __syncthreads();
-    if (threadIdx.x >= tc.count) return;
-    const unsigned int p = tc.first + threadIdx.x;
+    __shared__ unsigned int blk_pending, blk_base;
+    if (threadIdx.x == 0) blk_pending = 0u;
+    const bool in_tile = threadIdx.x < tc.count;
+    const unsigned int p = tc.first + (in_tile ? threadIdx.x : 0u);
     const float4 sp = bv.src[tc.src_base + p];
-    unsigned int* out = nn_pos + (tc.out_base + p) * K;
+    const size_t row = static_cast<size_t>(tc.out_base + p);
+    unsigned int* out = nn_pos + row * K;
     // non-finite source points are skipped: P2P as the reference (pcl::isFinite, icp_registration.cpp:64),
     // P2Plane as deviation D1 (the reference would poison H with NaN)
-    if (!finite3(sp.x, sp.y, sp.z)) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) out[j] = kNoNeighbour;
-        return;
-    }
-    double wx, wy, wz;
-    pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
+    const bool valid = in_tile && finite3(sp.x, sp.y, sp.z) && map.n_pts != 0;
+    bool done = true;
     KnnResult<K> nn;
-    knn_query<K>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn);
+    knn_init(nn);
+    __syncthreads();
+    if (valid) {
+        unsigned int seeds[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) out[j] = nn.idx[j] != 0x7fffffff ? nn.pos[j] : kNoNeighbour;
+        for (int j = 0; j < K; ++j) seeds[j] = (mode & kNnSeeds) ? out[j] : kNoPos;
+        double wx, wy, wz;
+        pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
+        done = knn_query_fast<K>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, seeds,
+                                 (mode & kNnTwoPass) != 0);
+    }
+    if (in_tile) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+    }
+    // one global atomic per tile: unfinished queries take a slot in shared memory first
+    unsigned int slot = 0;
+    if (!done) slot = atomicAdd(&blk_pending, 1u);
+    __syncthreads();
+    if (blk_pending == 0u) return;
+    if (threadIdx.x == 0) blk_base = atomicAdd(queue.count, blk_pending);
+    __syncthreads();
+    if (!done) queue.entries[blk_base + slot] = make_uint2(static_cast<unsigned int>(row), tc.scan);
+}
+
+// Stage 2: finishes the queued queries (knn_query_finish seeded with what stage 1 found).  Persistent grid-stride
+// launch: the queue length is only known on the device.
+template <int K>
+__global__ void __launch_bounds__(128) k_icp_nn_rings(VoxelMapView map, BatchView bv, const AlignState* __restrict__ states,
+                                                      unsigned int* __restrict__ nn_pos, RingQueue queue) {
+    const unsigned int n = *queue.count;
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint2 q = queue.entries[e];
+        // scratch rows and source points coincide for a batch; hypotheses of one scan share its points
+        const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
+        const float4 sp = bv.src[src_idx];
+        Pose T;
+        pose_load(T, states[q.y].pose);
+        double wx, wy, wz;
+        pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
+        const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
+        unsigned int* out = nn_pos + static_cast<size_t>(q.x) * K;
+        KnnResult<K> nn;
+        knn_init(nn);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const unsigned int sp_j = out[j];
+            if (sp_j < map.n_pts) {
+                const float4 c = map.pts[sp_j];
+                knn_offer(map.pts, nn, dis2_f32(qx, qy, qz, c.x, c.y, c.z), sp_j);
+            }
+        }
+        knn_query_finish<K>(map, qx, qy, qz, nn);
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+    }
 }
 
 // ---- K_B: fit + gates + accumulate ----------------------------------------------------------------------------
-// Fixed-order block reduction of per-thread register accumulators: shuffle tree inside each warp, then the 8
-// warp rows summed in order.  red: 8 * kPartialDoubles doubles of shared memory; out: 30 doubles.
-__device__ __forceinline__ void block_reduce_regs(const Accum& a, double* red, double* out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 30; ++i) {
-        double v = i < kAccDoubles ? a.v[i] : (i == 28 ? static_cast<double>(a.n_eff) : static_cast<double>(a.n_inl));
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-        if (lane == 0) red[warp * kPartialDoubles + i] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 30) {
-        double s = 0;
-        for (int w = 0; w < nwarps; ++w) s += red[w * kPartialDoubles + threadIdx.x];
-        out[threadIdx.x] = s;
-    }
-}
+// A thread handles ONE point, so there is nothing to accumulate per thread: it stages its residual row(s)
+// (J[0..5], r) in shared memory, and each warp then forms the 28 sums of products over its own 32 points with lane l
+// owning one entry of (H upper triangle | B | sum_sq) - 2 LDS + 1 DFMA per point and entry, instead of 28 products
+// per thread followed by 30 five-step shuffle trees.  The sums run in point order inside a warp, then over the 8
+// warps in order: reproducible for a fixed launch shape.
+constexpr int kRowStride = 7;  // J[6] + r
 
+template <int ROWS>
+struct RowSink {
+    double* rows;  // this thread's ROWS staged rows
+    int n_rows;
+    bool eff, inl;
+    __device__ __forceinline__ void row(const double (&J)[6], double r) {
+        double* o = rows + n_rows * kRowStride;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) o[i] = J[i];
+        o[6] = r;
+        ++n_rows;
+    }
+    __device__ __forceinline__ void inc_eff() { eff = true; }
+    __device__ __forceinline__ void inc_inl() { inl = true; }
+};
+
+#ifndef LR_POST_MIN_BLOCKS
+#define LR_POST_MIN_BLOCKS 4
+#endif
 template <int METHOD>
-__global__ void __launch_bounds__(kTile, 2) k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv,
-                                                       const AlignState* __restrict__ states, int ignore_stop,
-                                                       const unsigned int* __restrict__ nn_pos, double* __restrict__ partials,
-                                                       unsigned char* gate, int* nn_idx) {
+__global__ void __launch_bounds__(kTile, METHOD == kIcpP2P ? 2 : LR_POST_MIN_BLOCKS)
+k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
+           const unsigned int* __restrict__ nn_pos, double* __restrict__ partials, unsigned char* gate, int* nn_idx,
+           unsigned int* ring_count) {
     constexpr int K = METHOD == kIcpP2P ? 1 : 5;
+    constexpr int ROWS = METHOD == kIcpP2P ? 3 : 1;  // residual rows per inlier
     __shared__ Pose T;
-    __shared__ double red[8 * kPartialDoubles];
+    __shared__ double rows[kTile * ROWS * kRowStride];
+    __shared__ double wsum[kTile / 32][32];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ring_count = 0u;  // both search stages of this evaluation are done
     const TileCoord tc = locate_tile(bv, blockIdx.x);
     if (!tc.valid) return;
     const AlignState* st = states + tc.scan;
     if (st->stop && !ignore_stop) return;
     if (threadIdx.x == 0) pose_load(T, st->pose);
     __syncthreads();
-    Accum acc;
-    accum_zero(acc);
+    RowSink<ROWS> sink{rows + threadIdx.x * ROWS * kRowStride, 0, false, false};
     if (threadIdx.x < tc.count) {
         const unsigned int p = tc.first + threadIdx.x;
         const float4 sp = bv.src[tc.src_base + p];
@@ -202,16 +275,15 @@ __global__ void __launch_bounds__(kTile, 2) k_icp_post(VoxelMapView map, IcpPara
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             nn.pos[j] = in[j];
-            nn.idx[j] = nn.pos[j] != kNoNeighbour ? 0 : 0x7fffffff;  // only validity is needed downstream
-            nn.d2[j] = 0.0f;
+            nn.d2[j] = 0.0f;  // not needed downstream
         }
         unsigned char g = kGateSkipped;
         if (finite3(sp.x, sp.y, sp.z)) {
             const double qx = sp.x, qy = sp.y, qz = sp.z;
             double wx, wy, wz;
             pose_apply(T, qx, qy, qz, wx, wy, wz);
-            if (METHOD == kIcpP2P) g = icp_p2p_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<1>&>(nn), acc);
-            else g = icp_p2plane_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<5>&>(nn), acc);
+            if (METHOD == kIcpP2P) g = icp_p2p_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<1>&>(nn), sink);
+            else g = icp_p2plane_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<5>&>(nn), sink);
         }
         if (gate) gate[tc.out_base + p] = g;
         if (nn_idx) {
@@ -220,7 +292,47 @@ __global__ void __launch_bounds__(kTile, 2) k_icp_post(VoxelMapView map, IcpPara
                 nn_idx[(tc.out_base + p) * K + j] = nn.pos[j] != kNoNeighbour ? __float_as_int(map.pts[nn.pos[j]].w) : -1;
         }
     }
-    block_reduce_regs(acc, red, partials + static_cast<size_t>(blockIdx.x) * kPartialDoubles);
+    // per-warp sums of products over the warp's own rows
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int eff_mask = __ballot_sync(0xffffffffu, sink.eff);
+    unsigned int todo = __ballot_sync(0xffffffffu, sink.inl);  // also orders the row stores before the loads below
+    // lane -> (a, b): entries 0..20 = H(a, b) upper triangle, 21..26 = B[a] = -sum J[a] r (b = 6), 27 = sum r r
+    int ea = 6, eb = 6;
+    if (lane < 21) {
+        int k = lane;
+        ea = 0;
+        while (k >= 6 - ea) { k -= 6 - ea; ++ea; }
+        eb = ea + k;
+    } else if (lane < 27) {
+        ea = lane - 21;
+    }
+    double s = 0.0;
+    const double* wrows = rows + warp * 32 * ROWS * kRowStride;
+    const unsigned int n_inl = __popc(todo);
+    if (lane < 28) {
+        while (todo) {
+            const int i = __ffs(todo) - 1;
+            todo &= todo - 1;
+#pragma unroll
+            for (int k = 0; k < ROWS; ++k) {
+                const double* r = wrows + (i * ROWS + k) * kRowStride;
+                s = fma(r[ea], r[eb], s);
+            }
+        }
+        if (lane >= 21 && lane < 27) s = -s;
+    } else if (lane == 28) {
+        s = static_cast<double>(__popc(eff_mask));
+    } else if (lane == 29) {
+        s = static_cast<double>(n_inl);
+    }
+    wsum[warp][lane] = s;
+    __syncthreads();
+    if (threadIdx.x < 30) {
+        double t = 0;
+#pragma unroll
+        for (int w = 0; w < kTile / 32; ++w) t += wsum[w][threadIdx.x];
+        partials[static_cast<size_t>(blockIdx.x) * kPartialDoubles + threadIdx.x] = t;
+    }
 }
 
 // ---- K_C: per-scan reduction + Gauss-Newton update ------------------------------------------------------------

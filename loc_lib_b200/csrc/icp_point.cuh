@@ -22,18 +22,10 @@ struct IcpParams {
 // gate codes written by the debug probe (same meaning as oracle_icp_compute_hb's gate[])
 enum Gate : unsigned char { kGateSkipped = 0, kGateFitFailed = 1, kGateResidual = 2, kGateInlier = 3 };
 
-// H += J^T J (upper triangle), B += -J^T r, for a 1x6 Jacobian row
-template <class Acc>
-LR_HD void accum_rank1(Acc& a, const double (&J)[6], double r) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int j = i; j < 6; ++j) a.add(hidx(i, j), J[i] * J[j]);
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) a.add(21 + i, -J[i] * r);
-}
-
+// The accumulator policy `Acc` of the per-point bodies provides row(J, r) - one residual row, meaning
+// H += J^T J, B += -J^T r, sum_sq += r^2 - and the two counters inc_eff() / inc_inl().  On the host (oracle-style
+// serial loop, tests/hostsim) it is `Accum`; in k_icp_post it stages the row in shared memory (RowSink) and the
+// block forms the products cooperatively.
 // Point-to-plane, everything after the neighbour search (icp_registration.cpp:171-201): plane fit, gates,
 // Jacobian row, accumulation.  q = source point, w = predict_pose * q, nn = its 5 nearest map points.
 template <class Acc>
@@ -62,8 +54,7 @@ LR_HD unsigned char icp_p2plane_post(const VoxelMapView& map, const IcpParams& p
     const double my = T.R[1] * n[0] + T.R[4] * n[1] + T.R[7] * n[2];
     const double mz = T.R[2] * n[0] + T.R[5] * n[1] + T.R[8] * n[2];
     const double J[6] = {qy * mz - qz * my, qz * mx - qx * mz, qx * my - qy * mx, n[0], n[1], n[2]};
-    accum_rank1(acc, J, dis);
-    acc.add(27, dis * dis);
+    acc.row(J, dis);
     acc.inc_inl();
     return kGateInlier;
 }
@@ -72,7 +63,7 @@ LR_HD unsigned char icp_p2plane_post(const VoxelMapView& map, const IcpParams& p
 template <class Acc>
 LR_HD unsigned char icp_p2p_post(const VoxelMapView& map, const IcpParams& prm, const Pose& T, double qx, double qy,
                                  double qz, double wx, double wy, double wz, const KnnResult<1>& nn, Acc& acc) {
-    if (nn.idx[0] == 0x7fffffff) return kGateSkipped;
+    if (nn.pos[0] == kNoPos) return kGateSkipped;
     const float4 p = map.pts[nn.pos[0]];
     const double e[3] = {static_cast<double>(p.x) - wx, static_cast<double>(p.y) - wy, static_cast<double>(p.z) - wz};
     const double dis2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
@@ -89,16 +80,17 @@ LR_HD unsigned char icp_p2p_post(const VoxelMapView& map, const IcpParams& prm, 
         J[3] = r == 0 ? -1.0 : 0.0;
         J[4] = r == 1 ? -1.0 : 0.0;
         J[5] = r == 2 ? -1.0 : 0.0;
-        accum_rank1(acc, J, e[r]);
+        acc.row(J, e[r]);  // sum_sq accumulates e[0]^2 + e[1]^2 + e[2]^2 = dis2
     }
-    acc.add(27, dis2);
     return kGateInlier;
 }
 
-// Whole per-point bodies with the serial (one thread per query) search: used by tests/hostsim and kept as the
-// readable statement of the algorithm; the kernels run the warp-cooperative search (knn_warp.cuh) instead.
+// Whole per-point bodies with the serial (one query at a time) search: used by tests/hostsim and kept as the
+// readable statement of the algorithm; the kernels split the same steps over k_icp_nn / k_icp_post.
+// nn_pos (optional, K entries, in/out): seeds from the previous iteration on entry, this iteration's neighbour
+// positions on exit.
 LR_HD unsigned char icp_point_p2plane(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy,
-                                      float sz, Accum& acc, int* nn_out) {
+                                      float sz, Accum& acc, int* nn_out, unsigned int* nn_pos = nullptr) {
     if (nn_out) {
 #pragma unroll
         for (int j = 0; j < 5; ++j) nn_out[j] = -1;
@@ -108,32 +100,34 @@ LR_HD unsigned char icp_point_p2plane(const VoxelMapView& map, const IcpParams& 
     double wx, wy, wz;
     pose_apply(T, qx, qy, qz, wx, wy, wz);  // qs = predict_pose * q  (:169)
     KnnResult<5> nn;
-    knn_query<5>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn);  // (:170)
-    if (nn_out) {
+    knn_query<5>(map, true, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, nn_pos);  // (:170)
 #pragma unroll
-        for (int j = 0; j < 5; ++j) nn_out[j] = nn.idx[j] != 0x7fffffff ? nn.idx[j] : -1;
+    for (int j = 0; j < 5; ++j) {
+        if (nn_out) nn_out[j] = nn.pos[j] != kNoPos ? knn_index_of(map.pts, nn.pos[j]) : -1;
+        if (nn_pos) nn_pos[j] = nn.pos[j];
     }
     return icp_p2plane_post(map, prm, T, qx, qy, qz, wx, wy, wz, nn, acc);
 }
 
 LR_HD unsigned char icp_point_p2p(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy,
-                                  float sz, Accum& acc, int* nn_out) {
+                                  float sz, Accum& acc, int* nn_out, unsigned int* nn_pos = nullptr) {
     if (nn_out) nn_out[0] = -1;
     if (!finite3(sx, sy, sz)) return kGateSkipped;  // pcl::isFinite (:64)
     const double qx = sx, qy = sy, qz = sz;
     double wx, wy, wz;
     pose_apply(T, qx, qy, qz, wx, wy, wz);
     KnnResult<1> nn;
-    knn_query<1>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn);
-    if (nn_out) nn_out[0] = nn.idx[0] != 0x7fffffff ? nn.idx[0] : -1;
+    knn_query<1>(map, true, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, nn_pos);
+    if (nn_out) nn_out[0] = nn.pos[0] != kNoPos ? knn_index_of(map.pts, nn.pos[0]) : -1;
+    if (nn_pos) nn_pos[0] = nn.pos[0];
     return icp_p2p_post(map, prm, T, qx, qy, qz, wx, wy, wz, nn, acc);
 }
 
 template <int METHOD>
 LR_HD unsigned char icp_point(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy, float sz,
-                              Accum& acc, int* nn_out) {
-    if (METHOD == kIcpP2P) return icp_point_p2p(map, prm, T, sx, sy, sz, acc, nn_out);
-    return icp_point_p2plane(map, prm, T, sx, sy, sz, acc, nn_out);
+                              Accum& acc, int* nn_out, unsigned int* nn_pos = nullptr) {
+    if (METHOD == kIcpP2P) return icp_point_p2p(map, prm, T, sx, sy, sz, acc, nn_out, nn_pos);
+    return icp_point_p2plane(map, prm, T, sx, sy, sz, acc, nn_out, nn_pos);
 }
 
 // One Gauss-Newton update from the reduced accumulator: the tail of AlignP2P / AlignP2Plane

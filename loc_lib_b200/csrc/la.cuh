@@ -135,17 +135,22 @@ static LR_HD_NOINLINE void plane_svd5(const double (&P)[5][3], double (&coef)[4]
     for (int i = 0; i < 4; ++i) coef[i] = bj == 0 ? V[i][0] : (bj == 1 ? V[i][1] : (bj == 2 ? V[i][2] : V[i][3]));
 }
 
-// Fast path of the plane fit.  The smallest right singular vector x = (n, d) of A = [p 1] minimises
+// Plane fit without an SVD.  The smallest right singular vector x = (n, d) of A = [p 1] minimises
 // ||A x||^2 = n^T S n + 5 (n.c + d)^2 subject to |n|^2 + d^2 = 1, with c the centroid of the five points and
-// S = sum (p-c)(p-c)^T.  Eliminating d through its stationarity condition leaves a 3x3 problem
-//     S n = lambda (I + kappa c c^T) n,   kappa = 5 / (5 - lambda),   d = -kappa (c.n),
-// whose smallest eigenpair is found by Rayleigh-quotient iteration (cubic convergence, 3-4 steps) started from
-// the smallest eigenvector of S.  Each step solves (S - mu B) z = B n through the adjugate, which stays accurate
-// when the matrix is (by design) nearly singular, and the centroid shift keeps every quantity at the scale of
-// the neighbourhood, so the 1e4-1e5 condition number of the unshifted [p 1] is never squared.
-// Returns false — the caller then runs plane_svd5 — if the points are collinear, the iteration has not
-// settled, or it settled on an eigenpair that is not the smallest one (inertia check on S - mu B).
-constexpr int kPlaneFitWarmup = 3;
+// S = sum (p-c)(p-c)^T.  Eliminating d through its stationarity condition leaves the 3x3 problem
+//     (S - lambda I - lambda kappa c c^T) n = 0,   kappa = 5 / (5 - lambda),   d = -kappa (c.n),
+// and lambda = sigma_min^2 is the smallest root of the quartic (matrix determinant lemma, adj(S - lambda I) =
+// adj(S) - lambda (tr(S) I - S) + lambda^2 I)
+//     f(lambda) = lambda^4 - (5 + t + 5 a2) lambda^3 + (5 t + e + 5 a1) lambda^2 - (5 e + D + 5 a0) lambda + 5 D
+// with t = tr S, e = sum of the principal 2x2 minors, D = det S, a0 = c^T adj(S) c, a1 = t |c|^2 - c^T S c,
+// a2 = |c|^2: every coefficient is a sum of non-negative terms, so the centroid shift keeps the 1e4-1e5 condition
+// number of the unshifted [p 1] out of the arithmetic.  f has four real non-negative roots (the squared singular
+// values); Laguerre's iteration started at 0 increases monotonically to the SMALLEST one with cubic convergence,
+// so - unlike a Rayleigh-quotient iteration - it cannot settle on a neighbouring singular value when two of them
+// are close (common far from the origin, where quirk Q5 makes an in-plane direction compete with the normal).
+// n is then the null vector of K = S - lambda I - lambda kappa c c^T, read off the adjugate column with the
+// largest diagonal.  Returns false - the caller then runs plane_svd5 - only when the points are collinear /
+// coincident (adj(K) vanishes) or a NaN got in.
 LR_HD bool plane_fit5_fast(const double (&P)[5][3], double (&coef)[4]) {
     const double cx = (P[0][0] + P[1][0] + P[2][0] + P[3][0] + P[4][0]) * 0.2;
     const double cy = (P[0][1] + P[1][1] + P[2][1] + P[3][1] + P[4][1]) * 0.2;
@@ -156,71 +161,56 @@ LR_HD bool plane_fit5_fast(const double (&P)[5][3], double (&coef)[4]) {
         const double x = P[i][0] - cx, y = P[i][1] - cy, z = P[i][2] - cz;
         sxx += x * x; sxy += x * y; sxz += x * z; syy += y * y; syz += y * z; szz += z * z;
     }
-    // start: column of adj(S) with the largest diagonal = one inverse-iteration step on S
+    // adj(S), the invariants of S and the three quadratic forms in c
+    const double axx = syy * szz - syz * syz, axy = sxz * syz - sxy * szz, axz = sxy * syz - sxz * syy;
+    const double ayy = sxx * szz - sxz * sxz, ayz = sxy * sxz - sxx * syz, azz = sxx * syy - sxy * sxy;
+    const double t = sxx + syy + szz;
+    const double e = axx + ayy + azz;
+    double D = sxx * axx + sxy * axy + sxz * axz;
+    if (D < 0.0) D = 0.0;  // rounding on an exactly planar set
+    const double cc = cx * cx + cy * cy + cz * cz;
+    const double cSc = cx * (sxx * cx + sxy * cy + sxz * cz) + cy * (sxy * cx + syy * cy + syz * cz) +
+                       cz * (sxz * cx + syz * cy + szz * cz);
+    double a0 = cx * (axx * cx + axy * cy + axz * cz) + cy * (axy * cx + ayy * cy + ayz * cz) +
+                cz * (axz * cx + ayz * cy + azz * cz);
+    if (a0 < 0.0) a0 = 0.0;
+    const double a1 = t * cc - cSc;
+    const double k3 = 5.0 + t + 5.0 * cc, k2 = 5.0 * t + e + 5.0 * a1, k1 = 5.0 * e + D + 5.0 * a0, k0 = 5.0 * D;
+    // Laguerre from 0 (degree 4): monotone from below towards the smallest root
+    double lam = 0.0;
+    for (int it = 0; it < 12; ++it) {
+        const double f = (((lam - k3) * lam + k2) * lam - k1) * lam + k0;
+        if (!(f > 0.0)) break;  // on the root (or past it by rounding)
+        const double f1 = ((4.0 * lam - 3.0 * k3) * lam + 2.0 * k2) * lam - k1;
+        const double f2 = (12.0 * lam - 6.0 * k3) * lam + 2.0 * k2;
+        // Laguerre step for degree n = 4, written without dividing by f:  -n f / (f' - sqrt((n-1)^2 f'^2 - n (n-1) f f''))
+        double disc = 9.0 * f1 * f1 - 12.0 * f * f2;
+        if (disc < 0.0) disc = 0.0;
+        const double den = f1 - sqrt(disc);  // f' < 0 left of the smallest root: the larger magnitude denominator
+        const double step = -4.0 * f / den;
+        if (!(step > 0.0)) break;
+        const double nl = lam + step;
+        if (!(nl > lam)) break;              // step below one ulp
+        const bool done = step <= 1e-15 * nl;
+        lam = nl;
+        if (done) break;
+    }
+    const double kappa = 5.0 / (5.0 - lam);
+    const double mk = lam * kappa;
+    const double kxx = sxx - lam - mk * cx * cx, kxy = sxy - mk * cx * cy, kxz = sxz - mk * cx * cz;
+    const double kyy = syy - lam - mk * cy * cy, kyz = syz - mk * cy * cz, kzz = szz - lam - mk * cz * cz;
+    const double bxx = kyy * kzz - kyz * kyz, bxy = kxz * kyz - kxy * kzz, bxz = kxy * kyz - kxz * kyy;
+    const double byy = kxx * kzz - kxz * kxz, byz = kxy * kxz - kxx * kyz, bzz = kxx * kyy - kxy * kxy;
     double nx, ny, nz;
-    {
-        const double axx = syy * szz - syz * syz, axy = sxz * syz - sxy * szz, axz = sxy * syz - sxz * syy;
-        const double ayy = sxx * szz - sxz * sxz, ayz = sxy * sxz - sxx * syz, azz = sxx * syy - sxy * sxy;
-        if (axx >= ayy && axx >= azz) { nx = axx; ny = axy; nz = axz; }
-        else if (ayy >= azz) { nx = axy; ny = ayy; nz = ayz; }
-        else { nx = axz; ny = ayz; nz = azz; }
-    }
-    double nn = nx * nx + ny * ny + nz * nz;
-    if (!(nn > 0.0)) return false;  // collinear / coincident points (or NaN)
-    double inv = 1.0 / sqrt(nn);
-    nx *= inv; ny *= inv; nz *= inv;
-    // The weight c c^T (|c|^2 ~ 1e4 far from the origin, quirk Q5) can make the pencil's smallest eigenvector very
-    // different from S's, so pull the start into the right basin with a few plain inverse iterations
-    // n <- S^-1 B n (adjugate form, kappa = 1) before switching to Rayleigh-quotient shifts.
-    {
-        const double axx = syy * szz - syz * syz, axy = sxz * syz - sxy * szz, axz = sxy * syz - sxz * syy;
-        const double ayy = sxx * szz - sxz * sxz, ayz = sxy * sxz - sxx * syz, azz = sxx * syy - sxy * sxy;
-#pragma unroll
-        for (int it = 0; it < kPlaneFitWarmup; ++it) {
-            const double cn = cx * nx + cy * ny + cz * nz;
-            const double bx = nx + cn * cx, by = ny + cn * cy, bz = nz + cn * cz;
-            const double zx = axx * bx + axy * by + axz * bz, zy = axy * bx + ayy * by + ayz * bz,
-                         zz = axz * bx + ayz * by + azz * bz;
-            nn = zx * zx + zy * zy + zz * zz;
-            if (!(nn > 0.0)) return false;
-            inv = 1.0 / sqrt(nn);
-            nx = zx * inv; ny = zy * inv; nz = zz * inv;
-        }
-    }
-    double kappa = 1.0, mu = 0.0;
-    bool settled = false;
-    double e2 = 0.0, trk = 0.0;
-    for (int it = 0; it < 8; ++it) {
-        const double cn = cx * nx + cy * ny + cz * nz;
-        const double bx = nx + kappa * cn * cx, by = ny + kappa * cn * cy, bz = nz + kappa * cn * cz;  // B n
-        const double snx = sxx * nx + sxy * ny + sxz * nz, sny = sxy * nx + syy * ny + syz * nz,
-                     snz = sxz * nx + syz * ny + szz * nz;
-        mu = (nx * snx + ny * sny + nz * snz) / (nx * bx + ny * by + nz * bz);  // Rayleigh quotient
-        kappa = 5.0 / (5.0 - mu);
-        const double mk = mu * kappa;
-        const double kxx = sxx - mu - mk * cx * cx, kxy = sxy - mk * cx * cy, kxz = sxz - mk * cx * cz;
-        const double kyy = syy - mu - mk * cy * cy, kyz = syz - mk * cy * cz, kzz = szz - mu - mk * cz * cz;
-        const double axx = kyy * kzz - kyz * kyz, axy = kxz * kyz - kxy * kzz, axz = kxy * kyz - kxz * kyy;
-        const double ayy = kxx * kzz - kxz * kxz, ayz = kxy * kxz - kxx * kyz, azz = kxx * kyy - kxy * kxy;
-        e2 = axx + ayy + azz;   // second elementary symmetric polynomial of eig(K)
-        trk = kxx + kyy + kzz;
-        double zx = axx * bx + axy * by + axz * bz;
-        double zy = axy * bx + ayy * by + ayz * bz;
-        double zz = axz * bx + ayz * by + azz * bz;
-        nn = zx * zx + zy * zy + zz * zz;
-        if (!(nn > 0.0)) return false;
-        inv = 1.0 / sqrt(nn);
-        if (zx * nx + zy * ny + zz * nz < 0) inv = -inv;
-        zx *= inv; zy *= inv; zz *= inv;
-        const double ch = fabs(zx - nx) + fabs(zy - ny) + fabs(zz - nz);
-        nx = zx; ny = zy; nz = zz;
-        if (ch < 1e-9) { settled = true; break; }  // cubic convergence: the step just taken is exact to rounding
-    }
-    // K = S - mu B must be positive semi-definite with a one-dimensional null space for mu to be the SMALLEST
-    // eigenvalue (Sylvester): two positive eigenvalues <=> e2 > 0 and trace > 0.
-    if (!settled || !(e2 > 0.0) || !(trk > 0.0)) return false;
+    if (bxx >= byy && bxx >= bzz) { nx = bxx; ny = bxy; nz = bxz; }
+    else if (byy >= bzz) { nx = bxy; ny = byy; nz = byz; }
+    else { nx = bxz; ny = byz; nz = bzz; }
+    const double nn = nx * nx + ny * ny + nz * nz;
+    // adj(K) = (product of K's two non-zero eigenvalues) n n^T: it vanishes when the null space is not
+    // one-dimensional (collinear / coincident points, or a double smallest singular value)
+    if (!(nn > 1e-30 * (t * t * t * t + 1e-300))) return false;
     const double d = -kappa * (cx * nx + cy * ny + cz * nz);
-    inv = 1.0 / sqrt(1.0 + d * d);
+    const double inv = 1.0 / sqrt(nn + d * d);
     coef[0] = nx * inv; coef[1] = ny * inv; coef[2] = nz * inv; coef[3] = d * inv;
     return true;
 }

@@ -2,6 +2,8 @@
 // kernel launches.  No CPU fallback: without a CUDA device every computing entry point fails.
 #include "../../include/locreg.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,7 +66,7 @@ struct locreg_handle {
     DeviceNdtMap ndt_map;
     bool has_target = false;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
-        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_states;
+        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_states, d_ringq, d_ringc;
     PinBuf h_in, h_out, h_small;
     double last_ms = 0;
     long long last_launches = 0;
@@ -72,8 +74,9 @@ struct locreg_handle {
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;  // pairs
     std::vector<int> prof_class;
-    double prof_ms[3] = {0, 0, 0};
-    long long prof_launches[3] = {0, 0, 0};
+    double prof_ms[4] = {0, 0, 0, 0};
+    long long prof_launches[4] = {0, 0, 0, 0};
+    std::vector<float> prof_trace;  // per launch: class, ms (LOCREG_PROFILE_TRACE=1 prints it)
 
     IcpParams icp_params() const {
         IcpParams p;
@@ -219,7 +222,8 @@ void ndt_run_batch(locreg_handle* h, const float4* src, const long long* offsets
               h->d_misc.as<unsigned int>(), 0);
 }
 
-// Event pair around one launch of kernel class cls (0 search, 1 fit+reduce, 2 solve) when profiling is on.
+// Event pair around one launch of kernel class cls (0 search stage 1, 1 fit+reduce, 2 solve, 3 search stage 2) when
+// profiling is on.
 void prof_mark(locreg_handle* h, int cls, bool begin) {
     if (!h->profile) return;
     cudaEvent_t e;
@@ -237,6 +241,7 @@ void prof_collect(locreg_handle* h) {
         const int c = h->prof_class[i / 2];
         h->prof_ms[c] += ms;
         h->prof_launches[c] += 1;
+        if (getenv("LOCREG_PROFILE_TRACE")) fprintf(stderr, "locreg-trace class %d %.4f ms\n", c, ms);
     }
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     h->prof_events.clear();
@@ -251,19 +256,30 @@ struct IcpJob {
     size_t n_scratch_points = 0;    // rows of the per-point scratch arrays
 };
 
+// nn_mode: kNnSeeds when the per-point neighbour scratch still holds THIS job's previous iteration, kNnTwoPass for the
+// first iterations (see k_icp_nn)
 template <int METHOD>
-void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, unsigned char* gate, int* nn_idx) {
+void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int nn_mode, unsigned char* gate, int* nn_idx) {
     constexpr int K = METHOD == kIcpP2P ? 1 : 5;
     const VoxelMapView map = h->icp_map.view();
     h->d_nnpos.reserve(job.n_scratch_points * K * sizeof(unsigned int));
     h->d_partials.reserve(static_cast<size_t>(job.n_tiles) * kPartialDoubles * sizeof(double));
+    h->d_ringq.reserve(job.n_scratch_points * sizeof(uint2));
+    h->d_ringc.reserve(sizeof(unsigned int));
+    // k_icp_post re-zeroes the counter after every use; the first evaluation of a job starts from a known state
+    if (!(nn_mode & kNnSeeds)) LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, sizeof(unsigned int), h->stream));
     if (job.n_tiles == 0) return;
+    const RingQueue queue{h->d_ringc.as<unsigned int>(), h->d_ringq.as<uint2>()};
     prof_mark(h, 0, true);
-    LR_LAUNCH(k_icp_nn<K>, job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, h->d_nnpos.as<unsigned int>());
+    LR_LAUNCH(k_icp_nn<K>, job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, nn_mode, h->d_nnpos.as<unsigned int>(), queue);
     prof_mark(h, 0, false);
+    prof_mark(h, 3, true);
+    LR_LAUNCH(k_icp_nn_rings<K>, static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * 8)),
+              128, 0, h->stream, map, job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue);
+    prof_mark(h, 3, false);
     prof_mark(h, 1, true);
     LR_LAUNCH(k_icp_post<METHOD>, job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
-              h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx);
+              h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx, h->d_ringc.as<unsigned int>());
     prof_mark(h, 1, false);
 }
 template <int METHOD>
@@ -277,11 +293,11 @@ void icp_launch_solve(locreg_handle* h, const IcpJob& job, int mode, double* acc
 template <int METHOD>
 void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
     for (int it = 0; it < h->opt.max_iteration; ++it) {
-        icp_launch_eval<METHOD>(h, job, 0, nullptr, nullptr);
+        icp_launch_eval<METHOD>(h, job, 0, it == 0 ? kNnTwoPass : (it == 1 ? (kNnSeeds | kNnTwoPass) : kNnSeeds), nullptr, nullptr);
         icp_launch_solve<METHOD>(h, job, 1, nullptr);
     }
     if (final_eval) {
-        icp_launch_eval<METHOD>(h, job, 1, nullptr, nullptr);
+        icp_launch_eval<METHOD>(h, job, 1, h->opt.max_iteration > 0 ? kNnSeeds : kNnTwoPass, nullptr, nullptr);
         icp_launch_solve<METHOD>(h, job, 0, nullptr);
     }
 }
@@ -317,16 +333,21 @@ IcpJob icp_batch_job(locreg_handle* h, const float4* src, const long long* d_off
 
 bool is_ndt(const locreg_handle* h) { return h->opt.method == LOCREG_NDT_DIRECT; }
 
-// Parity probe for the search: the same one-thread-per-query knn_query() the pipeline's k_icp_nn runs.
+// Parity probe for the search: the same warp-synchronous knn_query() the pipeline's k_icp_nn runs, unseeded.
 template <int K>
 __global__ void __launch_bounds__(128) k_knn(VoxelMapView map, const float4* __restrict__ q, unsigned int nq, int* __restrict__ idx) {
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
-        const float4 p = q[i];
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int base = warp * 32; base < nq; base += n_warps * 32) {  // warp-uniform trip count
+        const unsigned int i = base + lane;
+        const bool in_range = i < nq;
+        const float4 p = q[in_range ? i : base];
         KnnResult<K> r;
-        knn_init(r);
-        if (finite3(p.x, p.y, p.z)) knn_query<K>(map, p.x, p.y, p.z, r);
+        knn_query<K>(map, in_range && finite3(p.x, p.y, p.z), p.x, p.y, p.z, r);
+        if (in_range) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) idx[static_cast<size_t>(i) * K + j] = r.idx[j] != 0x7fffffff ? r.idx[j] : -1;
+            for (int j = 0; j < K; ++j) idx[static_cast<size_t>(i) * K + j] = r.pos[j] != kNoPos ? knn_index_of(map.pts, r.pos[j]) : -1;
+        }
     }
 }
 
@@ -544,7 +565,7 @@ int locreg_compute_hb(locreg_handle* h, const float* src, size_t n, size_t strid
             ndt_run_eval(h, src4, static_cast<unsigned int>(n), nullptr);
         } else {
             const IcpJob job = icp_single_job(h, src4, static_cast<unsigned int>(n));
-            ICP_DISPATCH(h, (icp_launch_eval<M>(h, job, 1, nullptr, nullptr), icp_launch_solve<M>(h, job, 0, h->d_acc.as<double>())));
+            ICP_DISPATCH(h, (icp_launch_eval<M>(h, job, 1, kNnTwoPass, nullptr, nullptr), icp_launch_solve<M>(h, job, 0, h->d_acc.as<double>())));
         }
         h->h_small.reserve(4096);
         double* acc = h->h_small.as<double>() + 64;
@@ -606,7 +627,7 @@ int locreg_debug_points(locreg_handle* h, const float* src, size_t n, size_t str
             ndt_run_eval(h, src4, static_cast<unsigned int>(n), h->d_gate.as<unsigned char>());
         } else {
             const IcpJob job = icp_single_job(h, src4, static_cast<unsigned int>(n));
-            ICP_DISPATCH(h, icp_launch_eval<M>(h, job, 1, h->d_gate.as<unsigned char>(), d_nn));
+            ICP_DISPATCH(h, icp_launch_eval<M>(h, job, 1, kNnTwoPass, h->d_gate.as<unsigned char>(), d_nn));
         }
         h->end_timing();
         LR_CUDA(cudaMemcpy(gate, h->d_gate.p, n, cudaMemcpyDeviceToHost));
@@ -785,12 +806,12 @@ int locreg_ndt_get_voxels(locreg_handle* h, int32_t* keys, double* mu, double* i
     });
 }
 
-int locreg_profile(locreg_handle* h, int32_t enable, double* ms3, int64_t* launches3) {
+int locreg_profile(locreg_handle* h, int32_t enable, double* ms4, int64_t* launches4) {
     return guarded(h, [&]() {
         prof_collect(h);
-        if (ms3) for (int i = 0; i < 3; ++i) ms3[i] = h->prof_ms[i];
-        if (launches3) for (int i = 0; i < 3; ++i) launches3[i] = h->prof_launches[i];
-        for (int i = 0; i < 3; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+        if (ms4) for (int i = 0; i < 4; ++i) ms4[i] = h->prof_ms[i];
+        if (launches4) for (int i = 0; i < 4; ++i) launches4[i] = h->prof_launches[i];
+        for (int i = 0; i < 4; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
         h->profile = enable != 0;
         return LOCREG_OK;
     });

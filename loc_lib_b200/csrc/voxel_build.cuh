@@ -111,13 +111,14 @@ LR_HD bool build_is_duplicate(size_t i, const unsigned int* pt_cell, const unsig
     return false;
 }
 
-// Step 7a/7c.  The 27 cells whose neighbourhood contains point i each get the point.  pass 0: create the cell's
+// Step 7a/7c.  The 27 cells whose neighbourhood contains point i each get the point (a copy of its coordinates
+// with w = the point's canonical position pt_pos[i] in the sorted array, which is what the search reports).  pass 0: create the cell's
 // slot if needed and count; pass 1: append the point to the cell's list (cursor[] starts at 0 per slot).
 // counters: [0] lists created, [1] overflow flag
 template <class A>
 LR_HD void build_nbr_body(size_t i, int pass, const void* xyz, size_t stride, float inv_cell, const unsigned int* pt_cell,
-                          const unsigned char* dup, NbrSlot* nbr, unsigned int nbr_mask, unsigned int* cursor,
-                          float4* pts, unsigned int* counters) {
+                          const unsigned int* pt_pos, const unsigned char* dup, NbrSlot* nbr, unsigned int nbr_mask,
+                          unsigned int* cursor, float4* pts, unsigned int* counters) {
     if (pt_cell[i] == kDropped || dup[i]) return;
     const float* p = point_ptr(xyz, i, stride);
     const int fx = cell_of(cell_coord_f(p[0], inv_cell)), fy = cell_of(cell_coord_f(p[1], inv_cell)),
@@ -143,7 +144,7 @@ LR_HD void build_nbr_body(size_t i, int pass, const void* xyz, size_t stride, fl
             A::add32(&nbr[h].count, 1u);
         } else {
             const unsigned int pos = nbr[h].start + A::add32(&cursor[h], 1u);
-            pts[pos] = make_float4(p[0], p[1], p[2], int_as_float(static_cast<int>(i)));
+            pts[pos] = make_float4(p[0], p[1], p[2], int_as_float(static_cast<int>(pt_pos[i])));  // w = canonical position
         }
     }
 }

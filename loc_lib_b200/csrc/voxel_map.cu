@@ -172,10 +172,11 @@ __global__ void k_nbr_clear(NbrSlot* nbr, unsigned int cap) {
     if (s < cap) nbr[s] = NbrSlot{kEmptyKey, 0u, 0u};
 }
 __global__ void k_nbr_pass(size_t n, int pass, const void* __restrict__ xyz, size_t stride, float inv_cell,
-                           const unsigned int* __restrict__ pt_cell, const unsigned char* __restrict__ dup, NbrSlot* nbr,
-                           unsigned int nbr_mask, unsigned int* cursor, float4* pts, unsigned int* counters) {
+                           const unsigned int* __restrict__ pt_cell, const unsigned int* __restrict__ pt_pos,
+                           const unsigned char* __restrict__ dup, NbrSlot* nbr, unsigned int nbr_mask, unsigned int* cursor,
+                           float4* pts, unsigned int* counters) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) build_nbr_body<DeviceAtomics>(i, pass, xyz, stride, inv_cell, pt_cell, dup, nbr, nbr_mask, cursor, pts, counters);
+    if (i < n) build_nbr_body<DeviceAtomics>(i, pass, xyz, stride, inv_cell, pt_cell, pt_pos, dup, nbr, nbr_mask, cursor, pts, counters);
 }
 __global__ void k_nbr_counts(const NbrSlot* __restrict__ nbr, unsigned int cap, unsigned int* out) {
     const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,7 +294,7 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
             LR_CUDA(cudaMalloc(&nbr_, static_cast<size_t>(nbr_cap) * sizeof(NbrSlot)));
             LR_LAUNCH(k_nbr_clear, (nbr_cap + T - 1) / T, T, 0, stream, nbr_, nbr_cap);
             LR_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream));
-            LR_LAUNCH(k_nbr_pass, gridN, T, 0, stream, n, 0, d_xyz, stride, inv_cell, pt_slot, dup, nbr_, nbr_cap - 1,
+            LR_LAUNCH(k_nbr_pass, gridN, T, 0, stream, n, 0, d_xyz, stride, inv_cell, pt_slot, pt_pos, dup, nbr_, nbr_cap - 1,
                       static_cast<unsigned int*>(nullptr), pts_, counters);
             LR_CUDA(cudaMemcpyAsync(h_counters, counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
             LR_CUDA(cudaStreamSynchronize(stream));
@@ -313,7 +314,7 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
         exclusive_scan_u32(tmp, tmp, nbr_cap, nullptr, stream);
         LR_LAUNCH(k_nbr_set_start, (nbr_cap + T - 1) / T, T, 0, stream, nbr_, nbr_cap, tmp, n_kept);
         LR_CUDA(cudaMemsetAsync(ncursor, 0, static_cast<size_t>(nbr_cap) * sizeof(unsigned int), stream));
-        LR_LAUNCH(k_nbr_pass, gridN, T, 0, stream, n, 1, d_xyz, stride, inv_cell, pt_slot, dup, nbr_, nbr_cap - 1, ncursor, pts_,
+        LR_LAUNCH(k_nbr_pass, gridN, T, 0, stream, n, 1, d_xyz, stride, inv_cell, pt_slot, pt_pos, dup, nbr_, nbr_cap - 1, ncursor, pts_,
                   counters);
         LR_CUDA(cudaStreamSynchronize(stream));
         LR_CUDA(cudaFreeAsync(tmp, stream));

@@ -27,6 +27,14 @@
 #pragma once
 #include "common.cuh"
 
+// test-only instrumentation of the search stages (tests/hostsim built with -DLR_STATS); nothing in the product build
+#if defined(LR_STATS) && !defined(__CUDA_ARCH__)
+extern unsigned long long g_knn_stats[16];
+#define LR_STAT(i, v) (g_knn_stats[i] += (v))
+#else
+#define LR_STAT(i, v) ((void)0)
+#endif
+
 namespace locreg {
 
 struct __attribute__((aligned(32))) VoxelSlot {
@@ -124,41 +132,71 @@ LR_HD unsigned int axis_edge_mask(int o, int lo, int hi) {
     return m;
 }
 
+constexpr unsigned int kNoPos = 0xFFFFFFFFu;  // empty result slot / "no neighbour"
+
+// Running k-best set of one query, sorted ascending by (dis2, original index).  Only the position of a point in
+// the cell-sorted array pts[0, n_pts) is kept: its original index sits in pts[pos].w and is fetched on the rare
+// exact distance ties only, which keeps the state at 2K registers and the insertion at ~5 instructions per slot.
 template <int K>
 struct KnnResult {
     float d2[K];
-    int idx[K];           // caller's original index, 0x7fffffff = empty
-    unsigned int pos[K];  // position in the sorted pts[] (to re-read coordinates)
+    unsigned int pos[K];  // canonical position in pts[0, n_pts), kNoPos = empty
 };
 
 template <int K>
 LR_HD void knn_init(KnnResult<K>& r) {
 #pragma unroll
-    for (int j = 0; j < K; ++j) { r.d2[j] = INFINITY; r.idx[j] = 0x7fffffff; r.pos[j] = 0u; }
-}
-template <int K>
-LR_HD void knn_offer(KnnResult<K>& r, float d2, int idx, unsigned int pos) {
-    if (d2 < r.d2[K - 1] || (d2 == r.d2[K - 1] && idx < r.idx[K - 1])) {
-        r.d2[K - 1] = d2;
-        r.idx[K - 1] = idx;
-        r.pos[K - 1] = pos;
-#pragma unroll
-        for (int j = K - 1; j > 0; --j) {
-            const bool sw = r.d2[j] < r.d2[j - 1] || (r.d2[j] == r.d2[j - 1] && r.idx[j] < r.idx[j - 1]);
-            if (sw) {
-                const float td = r.d2[j]; r.d2[j] = r.d2[j - 1]; r.d2[j - 1] = td;
-                const int ti = r.idx[j]; r.idx[j] = r.idx[j - 1]; r.idx[j - 1] = ti;
-                const unsigned int tp = r.pos[j]; r.pos[j] = r.pos[j - 1]; r.pos[j - 1] = tp;
-            }
-        }
-    }
+    for (int j = 0; j < K; ++j) { r.d2[j] = INFINITY; r.pos[j] = kNoPos; }
 }
 template <int K>
 LR_HD int knn_count(const KnnResult<K>& r) {
     int c = 0;
 #pragma unroll
-    for (int j = 0; j < K; ++j) c += (r.idx[j] != 0x7fffffff) ? 1 : 0;
+    for (int j = 0; j < K; ++j) c += (r.pos[j] != kNoPos) ? 1 : 0;
     return c;
+}
+// original (caller's) index of the point at canonical position pos; an empty slot sorts after every point
+LR_HD int knn_index_of(const float4* pts, unsigned int pos) {
+    return pos == kNoPos ? 0x7fffffff : float_as_int(pts[pos].w);
+}
+// strict total order (dis2, original index)
+LR_HD bool knn_less(const float4* pts, float d2a, unsigned int pa, float d2b, unsigned int pb) {
+    if (d2a < d2b) return true;
+    if (d2a == d2b) return knn_index_of(pts, pa) < knn_index_of(pts, pb);
+    return false;
+}
+// Does candidate (d2, pos) belong into the set?  Not if it is no better than the current k-th, and not if it is
+// already a member (seeds from the previous Gauss-Newton iteration are met again in the lists; a point can also
+// sit in several lists).  NaN distances (masked duplicates, quirk Q3) are rejected by the first comparison.
+template <int K>
+LR_HD bool knn_accepts(const float4* pts, const KnnResult<K>& r, float d2, unsigned int pos) {
+    if (!(d2 <= r.d2[K - 1])) return false;
+    bool member = false;
+#pragma unroll
+    for (int j = 0; j < K; ++j) member = member || (r.pos[j] == pos);
+    if (member) return false;
+    if (d2 == r.d2[K - 1]) return knn_index_of(pts, pos) < knn_index_of(pts, r.pos[K - 1]);
+    return true;
+}
+// Sorted insertion of an accepted candidate (precondition: it precedes r[K-1]); straight-line selects, no branches
+// besides the tie lookups.
+template <int K>
+LR_HD void knn_insert(const float4* pts, KnnResult<K>& r, float d2, unsigned int pos) {
+    bool before_old = true;  // candidate precedes the element that sat in slot j before this insertion
+#pragma unroll
+    for (int j = K - 1; j >= 1; --j) {
+        const bool before_prev = knn_less(pts, d2, pos, r.d2[j - 1], r.pos[j - 1]);
+        const float nd = before_prev ? r.d2[j - 1] : (before_old ? d2 : r.d2[j]);
+        const unsigned int np = before_prev ? r.pos[j - 1] : (before_old ? pos : r.pos[j]);
+        r.d2[j] = nd;
+        r.pos[j] = np;
+        before_old = before_prev;
+    }
+    if (before_old) { r.d2[0] = d2; r.pos[0] = pos; }
+}
+template <int K>
+LR_HD void knn_offer(const float4* pts, KnnResult<K>& r, float d2, unsigned int pos) {
+    if (knn_accepts(pts, r, d2, pos)) knn_insert(pts, r, d2, pos);
 }
 
 LR_HD float dis2_f32(float qx, float qy, float qz, float px, float py, float pz) {
@@ -174,28 +212,177 @@ LR_HD float safe_gap(float g, float mag, float cell) {
     return e > 0.0f ? e * cell * 0.99999f : 0.0f;
 }
 
-// Exact k-NN of (qx,qy,qz).  The query must be finite.
+// Scan of one contiguous neighbourhood list pts[beg, beg + cnt) (entries carry the canonical position in w).
+// The search is latency bound (one query per thread, every candidate a dependent L1/L2 access), so the device loop
+// fetches kScanBatch candidates with independent 16 B loads before it looks at any of them; a short last batch
+// re-reads the list's final entry, which the membership test of knn_accepts turns into a no-op.
+// two_pass (device only; same result): when the set starts empty or from poor seeds - the first Gauss-Newton
+// iterations - a third of the candidates would pass the acceptance test at 32 different moments per warp and the
+// (long, divergent) sorted insertion dominates.  A branch-free first pass therefore finds the K-th smallest dis2 of
+// the list with a min/max network on the distances alone, and the second pass offers only the <= K (+ ties)
+// candidates at or below that threshold.
+constexpr int kScanBatch = 4;
 template <int K>
-LR_HD void knn_query(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res) {
-    knn_init(res);
-    if (m.n_pts == 0) return;
-    const float ux = cell_coord_f(qx, m.inv_cell), uy = cell_coord_f(qy, m.inv_cell), uz = cell_coord_f(qz, m.inv_cell);
-    const int fx = cell_of(ux), fy = cell_of(uy), fz = cell_of(uz);
-    const float frx = ux - static_cast<float>(fx), fry = uy - static_cast<float>(fy), frz = uz - static_cast<float>(fz);
-    const float mag = fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz));
-    // smallest Chebyshev radius whose box touches the occupied bounds
-    int R = 1;
-    {
-        const int ex = fx < m.cmin[0] ? m.cmin[0] - fx : (fx > m.cmax[0] ? fx - m.cmax[0] : 0);
-        const int ey = fy < m.cmin[1] ? m.cmin[1] - fy : (fy > m.cmax[1] ? fy - m.cmax[1] : 0);
-        const int ez = fz < m.cmin[2] ? m.cmin[2] - fz : (fz > m.cmax[2] ? fz - m.cmax[2] : 0);
-        const int e = ex > ey ? (ex > ez ? ex : ez) : (ey > ez ? ey : ez);
-        if (e > R) R = e;
+LR_HD void knn_scan_list(const float4* __restrict__ pts, KnnResult<K>& res, float qx, float qy, float qz, unsigned int beg,
+                         unsigned int cnt, bool two_pass) {
+#if defined(__CUDA_ARCH__)
+    if (cnt == 0) return;
+    const unsigned int last = beg + cnt - 1;
+    float thr = INFINITY;
+    if (two_pass) {
+        float t[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) t[j] = INFINITY;
+        for (unsigned int i = beg; i <= last; i += kScanBatch) {
+            float4 p[kScanBatch];
+#pragma unroll
+            for (int u = 0; u < kScanBatch; ++u) p[u] = pts[min(i + u, last)];
+#pragma unroll
+            for (int u = 0; u < kScanBatch; ++u) {
+                // a re-read final entry must not enter twice: the network counts multiplicity
+                float v = (i + u <= last) ? dis2_f32(qx, qy, qz, p[u].x, p[u].y, p[u].z) : INFINITY;
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const float lo = fminf(t[j], v);
+                    v = fmaxf(t[j], v);
+                    t[j] = lo;
+                }
+            }
+        }
+        thr = t[K - 1];
     }
-    bool first = true;
-    if (R == 1 && m.nbr_slots != nullptr) {
-        // fast path: the whole box [f-1, f+1]^3 is one contiguous list
-        const unsigned long long key = pack_cell(fx, fy, fz);
+    for (unsigned int i = beg; i <= last; i += kScanBatch) {
+        float4 p[kScanBatch];
+#pragma unroll
+        for (int u = 0; u < kScanBatch; ++u) p[u] = pts[min(i + u, last)];
+        float d2[kScanBatch];
+#pragma unroll
+        for (int u = 0; u < kScanBatch; ++u) d2[u] = dis2_f32(qx, qy, qz, p[u].x, p[u].y, p[u].z);
+#pragma unroll
+        for (int u = 0; u < kScanBatch; ++u)
+            if (d2[u] <= thr) knn_offer(pts, res, d2[u], static_cast<unsigned int>(float_as_int(p[u].w)));
+    }
+#else
+    (void)two_pass;
+    for (unsigned int i = beg; i < beg + cnt; ++i) {
+        const float4 p = pts[i];
+        knn_offer(pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), static_cast<unsigned int>(float_as_int(p.w)));
+    }
+#endif
+}
+
+// Geometry of a query relative to the cell grid (shared by the two stages of the search).
+struct KnnCellFrame {
+    int fx, fy, fz;        // the query's cell
+    float frx, fry, frz;   // position inside the cell, in cell units
+    float mag;             // largest |coordinate| in cell units (rounding allowance of the bounds)
+    int R0;                // smallest Chebyshev radius whose box touches the occupied bounds (>= 1)
+};
+LR_HD KnnCellFrame knn_frame(const VoxelMapView& m, float qx, float qy, float qz) {
+    KnnCellFrame c;
+    const float ux = cell_coord_f(qx, m.inv_cell), uy = cell_coord_f(qy, m.inv_cell), uz = cell_coord_f(qz, m.inv_cell);
+    c.fx = cell_of(ux); c.fy = cell_of(uy); c.fz = cell_of(uz);
+    c.frx = ux - static_cast<float>(c.fx); c.fry = uy - static_cast<float>(c.fy); c.frz = uz - static_cast<float>(c.fz);
+    c.mag = fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz));
+    const int ex = c.fx < m.cmin[0] ? m.cmin[0] - c.fx : (c.fx > m.cmax[0] ? c.fx - m.cmax[0] : 0);
+    const int ey = c.fy < m.cmin[1] ? m.cmin[1] - c.fy : (c.fy > m.cmax[1] ? c.fy - m.cmax[1] : 0);
+    const int ez = c.fz < m.cmin[2] ? m.cmin[2] - c.fz : (c.fz > m.cmax[2] ? c.fz - m.cmax[2] : 0);
+    const int e = ex > ey ? (ex > ez ? ex : ez) : (ey > ez ? ey : ez);
+    c.R0 = e > 1 ? e : 1;
+    return c;
+}
+// true when the list scan applies to this query: lists exist and the 3x3x3 box around its cell touches the map
+LR_HD bool knn_uses_list(const VoxelMapView& m, const KnnCellFrame& c) { return m.nbr_slots != nullptr && c.R0 == 1; }
+
+// Stage 1 of the exact k-NN of a FINITE query against a NON-EMPTY map: seeds, then the one-list fast path.
+//   seeds    optional K canonical positions (kNoPos = none) that start the k-best set - the neighbours found in the
+//            previous Gauss-Newton iteration.  Any real, distinct points are valid seeds: they only tighten the
+//            acceptance threshold early; the result is still the exact k-NN.
+// Returns true when `res` is final; false when the k-th neighbour may lie outside the visited box and stage 2
+// (knn_query_rings, seeded with `res`) has to continue.
+template <int K>
+LR_HD bool knn_query_fast(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res,
+                          const unsigned int* seeds, bool two_pass) {
+    knn_init(res);
+    const KnnCellFrame c = knn_frame(m, qx, qy, qz);
+    if (seeds != nullptr) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const unsigned int sp = seeds[j];
+            if (sp < m.n_pts) {
+                const float4 p = m.pts[sp];
+                knn_offer(m.pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), sp);
+            }
+        }
+    }
+    if (!knn_uses_list(m, c)) return false;
+    // the whole box [f-1, f+1]^3 is one contiguous list
+    const unsigned long long key = pack_cell(c.fx, c.fy, c.fz);
+    unsigned int h = hash_block(key) & m.nbr_mask;
+    unsigned int beg = 0, cnt = 0;
+    while (true) {
+        const NbrSlot s = m.nbr_slots[h];
+        if (s.key == key) { beg = s.start; cnt = s.count; break; }
+        if (s.key == kEmptyKey) break;
+        h = (h + 1) & m.nbr_mask;
+    }
+    LR_STAT(0, 1); LR_STAT(1, cnt);  // fast-path queries, candidates
+    knn_scan_list<K>(m.pts, res, qx, qy, qz, beg, cnt, two_pass);
+    if (res.pos[K - 1] != kNoPos) {
+        float mf = fminf(c.frx, 1.0f - c.frx);
+        mf = fminf(mf, fminf(c.fry, 1.0f - c.fry));
+        mf = fminf(mf, fminf(c.frz, 1.0f - c.frz));
+        const float g = safe_gap(1.0f + mf, c.mag + 1.0f, m.cell);
+        if (res.d2[K - 1] < g * g * 0.99999f) return true;
+    }
+    return c.fx - 1 <= m.cmin[0] && c.fx + 1 >= m.cmax[0] && c.fy - 1 <= m.cmin[1] && c.fy + 1 >= m.cmax[1] &&
+           c.fz - 1 <= m.cmin[2] && c.fz + 1 >= m.cmax[2];
+}
+
+// Stage 2a: the 5x5x5 box through neighbourhood lists.  The list of the cell f + (sx, sy, sz), s = +-1, covers the
+// cells f + [s-1, s+1] per axis, so the eight "corner" lists together cover [f-2, f+2]^3.  Only the cells the ball of
+// the current k-th distance touches matter (every other unvisited point is farther than that distance and cannot
+// belong to the result), and they are found face by face: where the ball crosses an outer face of the visited
+// 3x3x3 box, its cap has radius rho = sqrt(w^2 - depth^2) and reaches the cell offsets floor(fr -+ rho) on the two
+// other axes, which fixes the corner signs that are needed there - typically one or two lists instead of a walk
+// over up to 98 shell cells.  All quantities are in cell units and inflated by the rounding allowance of the cell
+// assignment.  Needs a full set (a finite k-th distance) from stage 1.
+// Returns true when `res` is final, false when shells R >= 3 must follow (knn_query_rings with boxes_done = 2).
+template <int K>
+LR_HD bool knn_query_corners(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res) {
+    const KnnCellFrame c = knn_frame(m, qx, qy, qz);
+    LR_STAT(2, 1);  // queries entering stage 2a
+    const float slack = 1e-6f * (c.mag + 4.0f);
+    const float wc = sqrtf(res.d2[K - 1]) * m.inv_cell * 1.0001f + slack;  // k-th distance, cell units, rounded up
+    const float fr[3] = {c.frx, c.fry, c.frz};
+    unsigned int need = 0;  // bit (sx > 0) | (sy > 0) << 1 | (sz > 0) << 2
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int b1 = (a + 1) % 3, b2 = (a + 2) % 3;
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            const float depth = dir ? 2.0f - fr[a] : 1.0f + fr[a];  // to the outer face of the visited box
+            if (wc < depth - slack) continue;
+            const float rho = sqrtf(fmaxf(wc * wc - depth * depth, 0.0f)) + 2.0f * slack + 1e-5f;
+            bool p1 = floorf(fr[b1] + rho) >= 1.0f, m1 = floorf(fr[b1] - rho) <= -1.0f;
+            bool p2 = floorf(fr[b2] + rho) >= 1.0f, m2 = floorf(fr[b2] - rho) <= -1.0f;
+            if (!p1 && !m1) m1 = true;
+            if (!p2 && !m2) m2 = true;
+#pragma unroll
+            for (int s1 = 0; s1 < 2; ++s1) {
+                if (!(s1 ? p1 : m1)) continue;
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    if (!(s2 ? p2 : m2)) continue;
+                    need |= 1u << ((dir << a) | (s1 << b1) | (s2 << b2));
+                }
+            }
+        }
+    }
+    for (int o = 0; o < 8; ++o) {
+        if (!((need >> o) & 1u)) continue;
+        const int sx = (o & 1) ? 1 : -1, sy = (o & 2) ? 1 : -1, sz = (o & 4) ? 1 : -1;
+        const unsigned long long key = pack_cell(c.fx + sx, c.fy + sy, c.fz + sz);
         unsigned int h = hash_block(key) & m.nbr_mask;
         unsigned int beg = 0, cnt = 0;
         while (true) {
@@ -204,30 +391,36 @@ LR_HD void knn_query(const VoxelMapView& m, float qx, float qy, float qz, KnnRes
             if (s.key == kEmptyKey) break;
             h = (h + 1) & m.nbr_mask;
         }
-        for (unsigned int i = beg; i < beg + cnt; ++i) {
-            const float4 p = m.pts[i];
-            knn_offer(res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), float_as_int(p.w), i);
-        }
-        first = false;
-        if (res.idx[K - 1] != 0x7fffffff) {
-            float mf = fminf(frx, 1.0f - frx);
-            mf = fminf(mf, fminf(fry, 1.0f - fry));
-            mf = fminf(mf, fminf(frz, 1.0f - frz));
-            const float g = safe_gap(1.0f + mf, mag + 1.0f, m.cell);
-            if (res.d2[K - 1] < g * g * 0.99999f) return;
-        }
-        if (fx - 1 <= m.cmin[0] && fx + 1 >= m.cmax[0] && fy - 1 <= m.cmin[1] && fy + 1 >= m.cmax[1] &&
-            fz - 1 <= m.cmin[2] && fz + 1 >= m.cmax[2])
-            return;
-        R = 2;
+        LR_STAT(3, 1); LR_STAT(4, cnt);  // corner lists scanned, candidates
+        knn_scan_list<K>(m.pts, res, qx, qy, qz, beg, cnt, false);
     }
+    float mf = fminf(c.frx, 1.0f - c.frx);
+    mf = fminf(mf, fminf(c.fry, 1.0f - c.fry));
+    mf = fminf(mf, fminf(c.frz, 1.0f - c.frz));
+    const float g = safe_gap(2.0f + mf, c.mag + 2.0f, m.cell);
+    if (res.d2[K - 1] < g * g * 0.99999f) return true;
+    return c.fx - 2 <= m.cmin[0] && c.fx + 2 >= m.cmax[0] && c.fy - 2 <= m.cmin[1] && c.fy + 2 >= m.cmax[1] &&
+           c.fz - 2 <= m.cmin[2] && c.fz + 2 >= m.cmax[2];
+}
+
+// Stage 2b: Chebyshev shells of cells through the block table until the k-th best is provably final.  `res` holds
+// what the earlier stages found (it may be partly or wholly empty); boxes_done = Chebyshev radius of the box they
+// have dealt with (0: nothing, 1: stage 1's list, 2: stage 2a).
+template <int K>
+LR_HD void knn_query_rings(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res, int boxes_done) {
+    const KnnCellFrame c = knn_frame(m, qx, qy, qz);
+    const int fx = c.fx, fy = c.fy, fz = c.fz;
+    const float frx = c.frx, fry = c.fry, frz = c.frz, mag = c.mag;
+    LR_STAT(5, 1);  // queries entering stage 2b
+    bool first = boxes_done == 0;  // nothing visited yet: the first shell is the full box
+    int R = first ? c.R0 : boxes_done + 1;
     while (true) {
         if (R > kBruteForceShell) {
             // pathological query (> kBruteForceShell cells from every candidate seen so far): linear scan
             knn_init(res);
             for (unsigned int i = 0; i < m.n_pts; ++i) {
                 const float4 p = m.pts[i];
-                knn_offer(res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), float_as_int(p.w), i);
+                knn_offer(m.pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), i);
             }
             return;
         }
@@ -250,6 +443,7 @@ LR_HD void knn_query(const VoxelMapView& m, float qx, float qy, float qz, KnnRes
                     const unsigned int ix = first ? 0u : (rx & ~axis_edge_mask(ox, lox, hix));
                     // cells of this block inside the box but not strictly interior (= the new shell)
                     if (!first && ix == rx && iy == ry && iz == rz) continue;  // block entirely interior
+                    LR_STAT(6, 1);  // block probes
                     const VoxelSlot* s = find_block(m, bx, by, bz);
                     if (s == nullptr) continue;
                     unsigned long long want = spread_x(rx) & spread_y(ry) & spread_z(rz);
@@ -261,7 +455,7 @@ LR_HD void knn_query(const VoxelMapView& m, float qx, float qy, float qz, KnnRes
                         const int bit = ffs64(todo) - 1;
                         todo &= todo - 1;
                         const int cx = ox + (bit & 3), cy = oy + ((bit >> 2) & 3), cz = oz + (bit >> 4);
-                        if (res.idx[K - 1] != 0x7fffffff) {
+                        if (res.pos[K - 1] != kNoPos) {
                             // prune: conservative min distance from the query to this cell
                             const float gx = cx > fx ? static_cast<float>(cx - fx) - frx
                                                      : (cx < fx ? static_cast<float>(fx - cx - 1) + frx : 0.0f);
@@ -276,9 +470,10 @@ LR_HD void knn_query(const VoxelMapView& m, float qx, float qy, float qz, KnnRes
                         }
                         const unsigned int cid = base + popc64(occ & ((1ull << bit) - 1ull));
                         const unsigned int beg = m.cell_start[cid], end = m.cell_start[cid + 1];
+                        LR_STAT(7, end - beg);  // shell candidates
                         for (unsigned int i = beg; i < end; ++i) {
                             const float4 p = m.pts[i];
-                            knn_offer(res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), float_as_int(p.w), i);
+                            knn_offer(m.pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), i);
                         }
                     }
                 }
@@ -287,7 +482,7 @@ LR_HD void knn_query(const VoxelMapView& m, float qx, float qy, float qz, KnnRes
         first = false;
         // every unvisited point lies outside the box [f-R, f+R]: at least R + min(frac, 1-frac) cell
         // units away along some axis
-        if (res.idx[K - 1] != 0x7fffffff) {
+        if (res.pos[K - 1] != kNoPos) {
             float mf = fminf(frx, 1.0f - frx);
             mf = fminf(mf, fminf(fry, 1.0f - fry));
             mf = fminf(mf, fminf(frz, 1.0f - frz));
@@ -299,6 +494,26 @@ LR_HD void knn_query(const VoxelMapView& m, float qx, float qy, float qz, KnnRes
             return;  // the whole map has been visited
         ++R;
     }
+}
+
+// Everything after stage 1 for one query (the body of k_icp_nn_rings).
+template <int K>
+LR_HD void knn_query_finish(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res) {
+    const KnnCellFrame c = knn_frame(m, qx, qy, qz);
+    int boxes_done = knn_uses_list(m, c) ? 1 : 0;
+    if (boxes_done == 1 && res.pos[K - 1] != kNoPos) {
+        if (knn_query_corners<K>(m, qx, qy, qz, res)) return;
+        boxes_done = 2;
+    }
+    knn_query_rings<K>(m, qx, qy, qz, res, boxes_done);
+}
+
+// Exact k-NN of (qx,qy,qz) in one call (parity probe, tests/hostsim).  valid = false: no query, empty result.
+template <int K>
+LR_HD void knn_query(const VoxelMapView& m, bool valid, float qx, float qy, float qz, KnnResult<K>& res,
+                     const unsigned int* seeds = nullptr, bool two_pass = false) {
+    if (!valid || m.n_pts == 0) { knn_init(res); return; }
+    if (!knn_query_fast<K>(m, qx, qy, qz, res, seeds, two_pass)) knn_query_finish<K>(m, qx, qy, qz, res);
 }
 
 }  // namespace locreg

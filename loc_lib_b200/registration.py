@@ -181,11 +181,11 @@ class _Registration:
         return out
 
     def profile(self, enable):
-        """Returns ({'search','fit','solve'} -> (ms, launches)) accumulated so far, then switches instrumentation."""
-        ms = np.zeros(3)
-        ln = np.zeros(3, np.int64)
+        """Returns ({'search','fit','solve','rings'} -> (ms, launches)) accumulated so far, then switches instrumentation."""
+        ms = np.zeros(4)
+        ln = np.zeros(4, np.int64)
         _lib.check(_lib.lib().locreg_profile(self._h, int(enable), ms.ctypes.data, ln.ctypes.data))
-        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(("search", "fit", "solve"))}
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(("search", "fit", "solve", "rings"))}
 
     def ScanMatchBatchDevice(self, d_srcs, d_offsets, d_poses_in, S, total_points, d_poses_out, d_results=0):
         """Batch ScanMatch with every buffer already in device memory (raw device pointers; clouds are float4)."""

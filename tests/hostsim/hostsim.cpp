@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 
+unsigned long long g_knn_stats[16] = {0};  // LR_STATS counters (voxel_map.cuh)
 #include "../../loc_lib_b200/csrc/icp_point.cuh"
 #include "../../loc_lib_b200/csrc/ndt_point.cuh"
 #include "../../loc_lib_b200/csrc/voxel_build.cuh"
@@ -82,7 +83,7 @@ HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsi
             m->nbr.assign(nbr_cap, NbrSlot{kEmptyKey, 0u, 0u});
             counters[0] = counters[1] = 0;
             for (size_t i = 0; i < n; ++i)
-                build_nbr_body<HostAtomics>(i, 0, xyz, stride, inv_cell, pt_slot.data(), dup.data(), m->nbr.data(), nbr_cap - 1, nullptr, nullptr, counters);
+                build_nbr_body<HostAtomics>(i, 0, xyz, stride, inv_cell, pt_slot.data(), pt_pos.data(), dup.data(), m->nbr.data(), nbr_cap - 1, nullptr, nullptr, counters);
             if (counters[1] || counters[0] * 2u > nbr_cap) { nbr_cap *= 4; continue; }
             break;
         }
@@ -91,7 +92,7 @@ HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsi
         m->pts.resize(acc, float4{0, 0, 0, 0});
         std::vector<unsigned int> ncur(nbr_cap, 0);
         for (size_t i = 0; i < n; ++i)
-            build_nbr_body<HostAtomics>(i, 1, xyz, stride, inv_cell, pt_slot.data(), dup.data(), m->nbr.data(), nbr_cap - 1, ncur.data(), m->pts.data(), counters);
+            build_nbr_body<HostAtomics>(i, 1, xyz, stride, inv_cell, pt_slot.data(), pt_pos.data(), dup.data(), m->nbr.data(), nbr_cap - 1, ncur.data(), m->pts.data(), counters);
     }
     VoxelMapView& v = m->view;
     v.slots = m->slots.data(); v.cell_start = m->cell_start.data(); v.pts = m->pts.data();
@@ -101,6 +102,10 @@ HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsi
     return m;
 }
 void hs_map_destroy(HsMap* m) { delete m; }
+// search-stage counters since the last call (see LR_STAT in voxel_map.cuh); reading clears them
+void hs_knn_stats(unsigned long long* out16) {
+    for (int i = 0; i < 16; ++i) { out16[i] = g_knn_stats[i]; g_knn_stats[i] = 0; }
+}
 void hs_map_stats(const HsMap* m, uint32_t* out) {  // capacity, n_pts, n_unique, n_cells
     out[0] = m->view.slot_mask + 1; out[1] = m->view.n_pts; out[2] = m->view.n_unique;
     out[3] = static_cast<uint32_t>(m->cell_start.size() - 1);
@@ -109,15 +114,28 @@ void hs_map_stats(const HsMap* m, uint32_t* out) {  // capacity, n_pts, n_unique
 void hs_knn(const HsMap* m, const float* q, size_t nq, size_t stride, int k, int32_t* idx_out) {
     for (size_t i = 0; i < nq; ++i) {
         const float* p = point_ptr(q, i, stride);
+        const bool ok = finite3(p[0], p[1], p[2]);
         if (k == 1) {
             KnnResult<1> r;
-            knn_query<1>(m->view, p[0], p[1], p[2], r);
-            idx_out[i] = r.idx[0] != 0x7fffffff ? r.idx[0] : -1;
+            knn_query<1>(m->view, ok, p[0], p[1], p[2], r);
+            idx_out[i] = r.pos[0] != kNoPos ? knn_index_of(m->view.pts, r.pos[0]) : -1;
         } else {
             KnnResult<5> r;
-            knn_query<5>(m->view, p[0], p[1], p[2], r);
-            for (int j = 0; j < 5; ++j) idx_out[i * 5 + j] = r.idx[j] != 0x7fffffff ? r.idx[j] : -1;
+            knn_query<5>(m->view, ok, p[0], p[1], p[2], r);
+            for (int j = 0; j < 5; ++j) idx_out[i * 5 + j] = r.pos[j] != kNoPos ? knn_index_of(m->view.pts, r.pos[j]) : -1;
         }
+    }
+}
+
+// k-NN of q seeded with the k-NN of seed_q (a nearby but different query): must equal the unseeded result
+void hs_knn_seeded(const HsMap* m, const float* q, const float* seed_q, size_t nq, size_t stride, int32_t* idx_out) {
+    for (size_t i = 0; i < nq; ++i) {
+        const float* p = point_ptr(q, i, stride);
+        const float* sq = point_ptr(seed_q, i, stride);
+        KnnResult<5> s, r;
+        knn_query<5>(m->view, finite3(sq[0], sq[1], sq[2]), sq[0], sq[1], sq[2], s);
+        knn_query<5>(m->view, finite3(p[0], p[1], p[2]), p[0], p[1], p[2], r, s.pos);
+        for (int j = 0; j < 5; ++j) idx_out[i * 5 + j] = r.pos[j] != kNoPos ? knn_index_of(m->view.pts, r.pos[j]) : -1;
     }
 }
 
@@ -130,15 +148,17 @@ static IcpParams make_params(const double* prm) {
     p.max_iteration = static_cast<int>(prm[4]); p.min_effective_pts = static_cast<int>(prm[5]);
     return p;
 }
+// seeds (optional): n * k neighbour positions carried from one Gauss-Newton iteration to the next, exactly as the
+// kernels reuse their nn_pos scratch
 template <int METHOD>
 static void hb_impl(const HsMap* m, const IcpParams& p, const float* src, size_t n, size_t stride, const Pose& T,
-                    Accum& acc, uint8_t* gate, int32_t* nn_out) {
+                    Accum& acc, uint8_t* gate, int32_t* nn_out, unsigned int* seeds = nullptr) {
     accum_zero(acc);
     const int k = METHOD == kIcpP2P ? 1 : 5;
     for (size_t i = 0; i < n; ++i) {
         const float* s = point_ptr(src, i, stride);
         int nn[5];
-        const unsigned char g = icp_point<METHOD>(m->view, p, T, s[0], s[1], s[2], acc, nn);
+        const unsigned char g = icp_point<METHOD>(m->view, p, T, s[0], s[1], s[2], acc, nn, seeds ? seeds + i * k : nullptr);
         if (gate) gate[i] = g;
         if (nn_out) for (int j = 0; j < k; ++j) nn_out[i * k + j] = nn[j];
     }
@@ -173,14 +193,15 @@ int hs_icp_align(const HsMap* m, int method, const double* prm, const float* src
     pose_load(T, pose_in);
     int iters = 0;
     status[0] = status[1] = status[2] = 0;
+    std::vector<unsigned int> seeds(n * 5, kNoPos);  // iteration 0 starts unseeded
     for (int it = 0; it < p.max_iteration; ++it) {
         Accum acc;
         int r;
         if (method == kIcpP2P) {
-            hb_impl<kIcpP2P>(m, p, src, n, stride, T, acc, nullptr, nullptr);
+            hb_impl<kIcpP2P>(m, p, src, n, stride, T, acc, nullptr, nullptr, seeds.data());
             r = icp_gn_update<kIcpP2P>(acc.v, acc.n_eff, p, T);
         } else {
-            hb_impl<kIcpP2Plane>(m, p, src, n, stride, T, acc, nullptr, nullptr);
+            hb_impl<kIcpP2Plane>(m, p, src, n, stride, T, acc, nullptr, nullptr, seeds.data());
             r = icp_gn_update<kIcpP2Plane>(acc.v, acc.n_eff, p, T);
         }
         iters = it + 1;

@@ -22,10 +22,14 @@ def lib():
         L.hs_map_destroy.argtypes = [vp]
         L.hs_map_stats.argtypes = [vp, vp]
         L.hs_knn.argtypes = [vp, vp, sz, sz, i32, vp]
+        L.hs_knn_stats.argtypes = [vp]
+        L.hs_knn_seeded.argtypes = [vp, vp, vp, sz, sz, vp]
         L.hs_icp_hb.argtypes = [vp, i32, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp]
         L.hs_icp_align.restype = i32
         L.hs_icp_align.argtypes = [vp, i32, vp, vp, sz, sz, vp, vp, vp]
         L.hs_plane_svd5.argtypes = [vp, vp]
+        L.hs_plane_fit5_fast.restype = i32
+        L.hs_plane_fit5_fast.argtypes = [vp, vp]
         L.hs_sym3_eigen.argtypes = [vp, vp, vp]
         L.hs_gn_solve6.restype = i32
         L.hs_gn_solve6.argtypes = [vp, vp, vp]
@@ -36,6 +40,17 @@ def lib():
 def _cloud(a):
     a = np.ascontiguousarray(a, np.float32)
     return a, a.shape[0], a.strides[0]
+
+
+STAT_NAMES = ["fast_queries", "fast_candidates", "corner_queries", "corner_lists", "corner_candidates", "ring_queries",
+              "ring_block_probes", "ring_candidates"]
+
+
+def knn_stats():
+    """Search-stage counters accumulated since the last call (hostsim is built with -DLR_STATS)."""
+    out = np.zeros(16, np.uint64)
+    lib().hs_knn_stats(out.ctypes.data)
+    return {k: int(out[i]) for i, k in enumerate(STAT_NAMES)}
 
 
 def params(max_nn_distance=1.0, max_plane_distance=0.1, plane_fit_eps=1e-2, eps=1e-2, max_iteration=20,
@@ -63,6 +78,15 @@ class HsMap:
         a, n, s = _cloud(q)
         out = np.empty((n, k), np.int32)
         lib().hs_knn(self._h, a.ctypes.data, n, s, k, out.ctypes.data)
+        return out
+
+    def knn_seeded(self, q, seed_q):
+        """5-NN of q, the search seeded with the 5-NN of seed_q (same shape)."""
+        a, n, s = _cloud(q)
+        b, nb, sb = _cloud(seed_q)
+        assert (n, s) == (nb, sb)
+        out = np.empty((n, 5), np.int32)
+        lib().hs_knn_seeded(self._h, a.ctypes.data, b.ctypes.data, n, s, out.ctypes.data)
         return out
 
     def icp_hb(self, method, prm, src, pose7):

@@ -45,6 +45,21 @@ def test_knn_bit_exact_near_and_far(scene, ref_icp, cell, lists):
             assert np.array_equal(m.knn(q, k), ref_icp.knn(q, k))
 
 
+def test_knn_seeded_search_is_still_exact(scene, hs_map, ref_icp):
+    """Seeds (the previous Gauss-Newton iteration's neighbours) only tighten the threshold: near, far and useless
+    seeds must all give the exact result, without duplicates."""
+    q = _queries(scene)[:4000]
+    rng = np.random.default_rng(3)
+    exp = ref_icp.knn(q, 5)
+    for sigma in (0.0, 0.02, 0.3, 5.0):
+        seed_q = (q + rng.normal(0, sigma, q.shape)).astype(np.float32)
+        got = hs_map.knn_seeded(q, seed_q)
+        assert np.array_equal(got, exp)
+    seed_q = q.copy()
+    seed_q[::2] = np.nan  # no seeds for every other query
+    assert np.array_equal(hs_map.knn_seeded(q, seed_q), exp)
+
+
 def test_knn_ties_resolved_by_index():
     """Lattice map: many exactly equal float32 distances; the total order (dis2, index) must decide."""
     g = np.arange(-6, 7, dtype=np.float32) * np.float32(0.25)
@@ -56,6 +71,7 @@ def test_knn_ties_resolved_by_index():
     m = HS.HsMap(pts, cell=0.5)
     assert np.array_equal(m.knn(q, 5), NR.knn_f32(pts[:, :3], q, 5))
     assert np.array_equal(m.knn(q, 5), O.bfnn(pts, q, 5))
+    assert np.array_equal(m.knn_seeded(q, q + np.float32(0.25)), O.bfnn(pts, q, 5))
 
 
 def test_map_stats_and_duplicates(scene):
