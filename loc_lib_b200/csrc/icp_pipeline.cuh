@@ -55,7 +55,7 @@ struct TileCoord {
     bool valid;
 };
 
-__device__ __forceinline__ TileCoord locate_tile(const BatchView& b, unsigned int tile) {
+__device__ __forceinline__ TileCoord locate_tile_thread(const BatchView& b, unsigned int tile) {
     TileCoord c{};
     c.valid = false;
     unsigned int s, t;
@@ -83,6 +83,14 @@ __device__ __forceinline__ TileCoord locate_tile(const BatchView& b, unsigned in
     c.out_base = b.offsets ? beg : static_cast<long long>(s) * b.n_single;
     c.valid = true;
     return c;
+}
+
+// Block-wide flavour: thread 0 does the (binary) search, everybody reads the answer from shared memory.
+__device__ __forceinline__ TileCoord locate_tile(const BatchView& b, unsigned int tile) {
+    __shared__ TileCoord tc_shared;
+    if (threadIdx.x == 0) tc_shared = locate_tile_thread(b, tile);
+    __syncthreads();
+    return tc_shared;
 }
 
 // tile_begin[s] = sum_{r<s} ceil(n_r / kTile); single block, S is at most a few 1e4.
@@ -267,6 +275,8 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
     if (threadIdx.x == 0) pose_load(T, st->pose);
     __syncthreads();
     RowSink<ROWS> sink{rows + threadIdx.x * ROWS * kRowStride, 0, false, false};
+#pragma unroll
+    for (int i = 0; i < ROWS * kRowStride; ++i) sink.rows[i] = 0.0;  // points without a residual contribute zero rows
     if (threadIdx.x < tc.count) {
         const unsigned int p = tc.first + threadIdx.x;
         const float4 sp = bv.src[tc.src_base + p];
@@ -295,7 +305,8 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
     // per-warp sums of products over the warp's own rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int eff_mask = __ballot_sync(0xffffffffu, sink.eff);
-    unsigned int todo = __ballot_sync(0xffffffffu, sink.inl);  // also orders the row stores before the loads below
+    __syncwarp();  // the warp's row stores are visible to its loads below
+    const unsigned int inl_mask = __ballot_sync(0xffffffffu, sink.inl);
     // lane -> (a, b): entries 0..20 = H(a, b) upper triangle, 21..26 = B[a] = -sum J[a] r (b = 6), 27 = sum r r
     int ea = 6, eb = 6;
     if (lane < 21) {
@@ -308,23 +319,13 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
     }
     double s = 0.0;
     const double* wrows = rows + warp * 32 * ROWS * kRowStride;
-    const unsigned int n_inl = __popc(todo);
-    if (lane < 28) {
-        while (todo) {
-            const int i = __ffs(todo) - 1;
-            todo &= todo - 1;
+    const double* ra = wrows + ea;
+    const double* rb = wrows + eb;
 #pragma unroll
-            for (int k = 0; k < ROWS; ++k) {
-                const double* r = wrows + (i * ROWS + k) * kRowStride;
-                s = fma(r[ea], r[eb], s);
-            }
-        }
-        if (lane >= 21 && lane < 27) s = -s;
-    } else if (lane == 28) {
-        s = static_cast<double>(__popc(eff_mask));
-    } else if (lane == 29) {
-        s = static_cast<double>(n_inl);
-    }
+    for (int i = 0; i < 32 * ROWS; ++i) s = fma(ra[i * kRowStride], rb[i * kRowStride], s);  // lanes 28..31: discarded
+    if (lane >= 21 && lane < 27) s = -s;
+    if (lane == 28) s = static_cast<double>(__popc(eff_mask));
+    if (lane == 29) s = static_cast<double>(__popc(inl_mask));
     wsum[warp][lane] = s;
     __syncthreads();
     if (threadIdx.x < 30) {
