@@ -40,6 +40,10 @@ def parse():
     ap.add_argument("--map-points", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-scans", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="icp", choices=["icp", "ndt", "reloc"],
+                    help="icp: configs 2/4 (the headline line); ndt: config 3; reloc: config 5 (extra report lines)")
+    ap.add_argument("--hyp", type=int, default=65536, help="reloc: number of pose hypotheses (64x64 xy grid x 16 yaws)")
+    ap.add_argument("--ndt-map-points", type=int, default=20_000_000)
     return ap.parse_args()
 
 
@@ -273,8 +277,11 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         nn_ms, nn_launches = prof["search"]
         fit_ms, fit_launches = prof["fit"]
+        ring_ms, _ = prof["rings"]
+        solve_ms, _ = prof["solve"]
         per_launch_ms = nn_ms / max(nn_launches, 1)
         achieved = BYTES_PER_POINT_ITER * n_pts / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None
+        pipe_ms = (nn_ms + fit_ms + ring_ms + solve_ms) / max(nn_launches, 1)  # one whole Gauss-Newton iteration
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_icp_nn_dram_bytes_per_launch")
@@ -292,12 +299,16 @@ def run_ours(args):
                     "api": "locreg_align_batch (host buffers, pinned)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_icp_nn<5> (neighbour search, %.0f%% of pipeline kernel time)" %
-                         (100 * nn_ms / max(nn_ms + fit_ms + prof["solve"][0], 1e-9)),
+            "roofline": {"bound": "hbm", "kernel": "k_icp_nn<5> (neighbour search stage 1, %.0f%% of pipeline kernel time)" %
+                         (100 * nn_ms / max(nn_ms + fit_ms + ring_ms + solve_ms, 1e-9)),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_POINT_ITER * n_pts, "launch_ms": per_launch_ms,
                          "fit_kernel_launch_ms": fit_ms / max(fit_launches, 1),
+                         "rings_kernel_launch_ms": ring_ms / max(nn_launches, 1),
+                         "iteration_ms": pipe_ms,
+                         "iteration_achieved": BYTES_PER_POINT_ITER * n_pts / (pipe_ms * 1e-3) / 1e9 if pipe_ms > 0 else None,
+                         "iteration_frac": BYTES_PER_POINT_ITER * n_pts / (pipe_ms * 1e-3) / 1e9 / peak if pipe_ms > 0 else None,
                          "note": "96 B per point-iteration (SURVEY 8d) x points per launch; the map (16 MB of points + "
                                  "neighbour lists) is mostly L2/L1 resident, so DRAM traffic is far below this"},
             "track": track,
@@ -311,9 +322,160 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    return rank, local, world_size, torch.device("cuda", local)
+
+
+def _peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def run_ndt(args):
+    """Config 3: direct NDT (NEARBY6, 1 m voxels, 10 iterations) of a 128-beam scan (~250 k points) against a 20 M-point
+    map; one scan in flight, whole AlignNdt loop in one cooperative launch.  Replicas only: every rank runs the same job."""
+    import torch
+    import torch.distributed as dist
+    import loc_lib_b200 as L
+    from loc_lib_b200 import synth
+    rank, local, world_size, dev = _dist_setup()
+    w = synth.World(900.0)
+    t0 = time.perf_counter()
+    m = w.sample_map(args.ndt_map_points)
+    gen_s = time.perf_counter() - t0
+    gts = w.poses(4)
+    scans = [w.scan(g, beams=128, azimuth=1953, seed=synth.SEED_SCAN + i) for i, g in enumerate(gts)]
+    init = synth.perturb_poses(gts)
+    reg = L.NdtRegistration(L.NdtOptions(max_iteration_=MAX_ITER, eps_=0.0), device=local)
+    t0 = time.perf_counter()
+    reg.SetInputTarget(m)
+    build_wall = (time.perf_counter() - t0) * 1e3
+    build_kernel = reg.last_timing()[0]
+    nv = len(reg.Voxels()[3])
+    pinned = [torch.from_numpy(s).pin_memory().numpy() for s in scans]
+    for i in range(max(args.warmup, 3)):
+        reg.ScanMatch(pinned[i % 4], init[i % 4], want_cloud=False)
+    torch.cuda.synchronize(dev)
+    k_ms, w_ms, pts, hits = [], [], 0, []
+    t_all = time.perf_counter()
+    for i in range(args.steps):
+        t0 = time.perf_counter()
+        _, _, pose = reg.ScanMatch(pinned[i % 4], init[i % 4], want_cloud=False)
+        w_ms.append((time.perf_counter() - t0) * 1e3)
+        k_ms.append(reg.last_timing()[0])
+        pts += len(scans[i % 4])
+        hits.append(reg.last_result["n_inlier"] / max(reg.last_result["n_effective"], 1))
+    wall = time.perf_counter() - t_all
+    if rank == 0:
+        peak, peak_src = _peak()
+        h = float(np.mean(hits))
+        bytes_pt = 16 + 7 * 16 + h * 96
+        dev_s = sum(k_ms) * 1e-3
+        line = {"metric": METRIC, "value": pts / dev_s, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "replicas", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C3: direct NDT (NEARBY6, voxel 1.0 m), 128x1953-ray synthetic scan vs %d-pt synthetic map, "
+                                       "10 Gauss-Newton iterations (eps=0), one cooperative launch" % len(m),
+                           "scan_points": int(np.mean([len(s) for s in scans])), "voxels": nv,
+                           "timing": "one scan in flight; the %d-voxel table (%.0f MB) exceeds L2" % (nv, nv * 112 / 1e6)},
+                "e2e": {"value": pts / wall, "unit": UNIT, "h2d_bytes_per_step": int(scans[0].nbytes), "d2h_bytes_per_step": 7 * 8 + 48,
+                        "api": "locreg_align (pinned host scan in, pose out)"},
+                "gpu_launches": int(reg.last_timing()[1]) * args.steps,
+                "roofline": {"bound": "hbm", "kernel": "k_align_persist<NdtProblem> (10 iterations in one launch)",
+                             "achieved": bytes_pt * pts * MAX_ITER / dev_s / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": bytes_pt * pts * MAX_ITER / dev_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "bytes_per_point_iteration": bytes_pt, "hits_per_point": h},
+                "map_build": {"wall_ms": build_wall, "kernel_ms": build_kernel, "points": int(len(m)), "gen_s": gen_s}}
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def reloc_hypotheses(gt, n_hyp):
+    """64 x 64 xy grid (0.5 m pitch, centred on gt) x 16 yaws (22.5 deg), truncated / tiled to n_hyp."""
+    g = (np.arange(64) - 31.5) * 0.5
+    out = []
+    ax, ay, az, aw = gt[:4]
+    for k in range(16):
+        a = k * np.pi / 8
+        bz, bw = np.sin(a / 2), np.cos(a / 2)  # yaw about the sensor's z axis: q = q_gt * (0, 0, bz, bw)
+        q = np.array([ax * bw + ay * bz, ay * bw - ax * bz, az * bw + aw * bz, aw * bw - az * bz])
+        for y in g:
+            for x in g:
+                out.append(np.concatenate([q, [gt[4] + x, gt[5] + y, gt[6]]]))
+    hyp = np.array(out)
+    return hyp[np.resize(np.arange(len(hyp)), n_hyp)] if n_hyp != len(hyp) else hyp
+
+
+def run_reloc(args):
+    """Config 5: global relocalisation, hypotheses sharded over ranks, ONE MIN all-reduce picks the winner."""
+    import torch
+    import torch.distributed as dist
+    import loc_lib_b200 as L
+    from loc_lib_b200 import dist as D
+    from loc_lib_b200 import synth
+    rank, local, world_size, dev = _dist_setup()
+    world, map_cloud = make_world(args)
+    gt = world.poses(3)[2]
+    scan = world.scan(gt)
+    hyp = reloc_hypotheses(gt, args.hyp)
+    reg = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=MAX_ITER, eps_=0.0), device=local)
+    reg.SetInputTarget(map_cloud)
+    warm = hyp[:: max(1, len(hyp) // 256)][:256]
+    for _ in range(2):
+        reg.Relocalise(scan, warm)
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    barrier()
+    times, kernel = [], []
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        pose, idx, score = D.relocalise_sharded(reg, scan, hyp, rank, world_size, dev)
+        barrier()
+        times.append(time.perf_counter() - t0)
+        kernel.append(reg.last_timing()[0])
+    t = torch.tensor([float(np.mean(times)), float(np.mean(kernel))], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        step_s, kern_ms = float(t[0]), float(t[1])
+        err = float(np.linalg.norm(pose[4:] - gt[4:]))
+        line = {"metric": "relocalisation_hypotheses_per_sec", "value": len(hyp) / step_s, "unit": "hypotheses/s",
+                "n_gpus": world_size, "steps": args.steps, "warmup": 2, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C5: global relocalisation, %d pose hypotheses (64x64 xy grid 0.5 m x 16 yaws) of one 32-beam "
+                                       "scan (%d pts) vs 1M-pt map, P2Plane ICP 10 iterations + score pass each, argmin by one "
+                                       "NCCL MIN all-reduce" % (len(hyp), len(scan)), "hypotheses": len(hyp)},
+                "registered_points_per_s": len(hyp) * len(scan) / step_s, "kernel_ms_max_rank": kern_ms,
+                "best": {"index": int(idx), "score": float(score), "translation_error_m": err}}
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "ndt":
+        run_ndt(a)
+    elif a.workload == "reloc":
+        run_reloc(a)
     else:
         run_ours(a)

@@ -1,0 +1,150 @@
+// Drop-in adapters: LocUtils::MatchingInterface implementations backed by liblocreg.so (include/locreg.h).
+//
+//   LocUtils::CudaIcpRegistration(IcpOptions)   replaces LocUtils::IcpRegistration
+//       (LocUtils/include/LocUtils/model/matching/3d/icp/icp_registration.hpp:41-142)
+//   LocUtils::CudaNdtRegistration(NdtOptions)   replaces LocUtils::NdtRegistration, DIRECT_NDT
+//       (LocUtils/include/LocUtils/model/matching/3d/ndt/ndt_registration.hpp:69-135)
+//
+// Same constructors, same virtual methods, same always-true bool results (icp_registration.cpp:243,
+// ndt_registration.cpp:260), so the callers - Loc (LocUtils/src/slam/3d/loc.cpp:41,55), Lio (lio.cpp:30,40),
+// LoamRegistration (loam_registration.cpp:56,66) - change one make_shared<> line each.
+//
+// Header-only and generic over the host types so that it can be compiled both
+//   * inside LocUtils (PCL / Sophus / Eigen present):   #include "LocUtils/model/matching/3d/matching_interface.h"
+//     BEFORE this header; the adapters then derive from the real LocUtils::MatchingInterface, and
+//   * in this repo's container, where those libraries do not exist: tests/cpp/adapter_standin.cpp defines
+//     stand-in CloudPtr / SE3 / Mat6d / Vec6d types with the same members the adapter touches and
+//     LOCREG_ADAPTER_STANDIN, and checks that the marshalling compiles and links against liblocreg.so.
+// What the adapter needs from the host types (all true for PCL 1.8 / Sophus / Eigen):
+//   cloud->points.data(), cloud->points.size(), sizeof(PointType) == point stride, x/y/z the first three floats
+//   (pcl::PointXYZI: 32 B stride, point_types.h:18); cloud->width/height/is_dense; cloud.reset(new PointCloudType);
+//   SE3::data() -> 7 doubles [qx qy qz qw tx ty tz] (Sophus::SE3d; eigen_types.h:66); Mat6d/Vec6d::data() column-major.
+#pragma once
+#include <stdexcept>
+#include <string>
+
+#include "locreg.h"
+
+namespace LocUtils {
+
+namespace locreg_detail {
+inline void check(int rc, const char* what) {
+    // The reference's methods cannot report errors (bool, always true).  A CUDA failure is not an algorithmic outcome,
+    // so it is raised instead of being swallowed: there is no CPU path to fall back to.
+    if (rc != LOCREG_OK) throw std::runtime_error(std::string(what) + ": " + locreg_last_error());
+}
+template <class Cloud>
+inline const float* cloud_xyz(const Cloud& c) {
+    return c.points.empty() ? nullptr : reinterpret_cast<const float*>(c.points.data());
+}
+}  // namespace locreg_detail
+
+class CudaRegistrationBase : public MatchingInterface {
+   public:
+    ~CudaRegistrationBase() override { locreg_destroy(handle_); }
+    CudaRegistrationBase(const CudaRegistrationBase&) = delete;
+    CudaRegistrationBase& operator=(const CudaRegistrationBase&) = delete;
+
+    // MatchingInterface::SetInputTarget (matching_interface.h:18): deep copy + index build, on the device.
+    bool SetInputTarget(const CloudPtr& input_target) override {
+        locreg_detail::check(locreg_set_target(handle_, locreg_detail::cloud_xyz(*input_target), input_target->points.size(),
+                                               sizeof(PointType)),
+                             "locreg_set_target");
+        return true;
+    }
+
+    // MatchingInterface::CaculateMatrixHAndB (matching_interface.h:23-29; sole caller loam_registration.cpp:56,66).
+    bool CaculateMatrixHAndB(const CloudPtr& input_source, const SE3& predict_pose, Mat6d& H, Vec6d& B) override {
+        locreg_result res{};
+        locreg_detail::check(locreg_compute_hb(handle_, locreg_detail::cloud_xyz(*input_source), input_source->points.size(),
+                                               sizeof(PointType), predict_pose.data(), H.data(), B.data(), &res),
+                             "locreg_compute_hb");
+        last_result_ = res;
+        return res.degenerate == 0;  // icp_registration.cpp:100-102,204-212: false when too few points / det(H) == 0
+    }
+
+    // MatchingInterface::ScanMatch (matching_interface.h:30-36).  result_cloud_ptr is overwritten with the
+    // transformed input (pcl::transformPointCloud, icp_registration.cpp:241); result_pose is IN/OUT exactly as in
+    // the reference: direct NDT's det(H) == 0 early return leaves it untouched (ndt_registration.cpp:435-436).
+    bool ScanMatch(const CloudPtr& input_source, const SE3& predict_pose, CloudPtr& result_cloud_ptr, SE3& result_pose) override {
+        const size_t n = input_source->points.size();
+        if (!result_cloud_ptr) result_cloud_ptr.reset(new PointCloudType);
+        if (result_cloud_ptr.get() != input_source.get()) {
+            result_cloud_ptr->header = input_source->header;
+            result_cloud_ptr->is_dense = input_source->is_dense;
+            result_cloud_ptr->width = input_source->width;
+            result_cloud_ptr->height = input_source->height;
+            result_cloud_ptr->points.resize(n);
+        }
+        locreg_result res{};
+        locreg_detail::check(
+            locreg_align(handle_, locreg_detail::cloud_xyz(*input_source), n, sizeof(PointType), predict_pose.data(), result_pose.data(),
+                         n ? reinterpret_cast<float*>(result_cloud_ptr->points.data()) : nullptr, &res),
+            "locreg_align");
+        last_result_ = res;
+        return true;  // icp_registration.cpp:243, ndt_registration.cpp:260
+    }
+
+    float GetFitnessScore() override { return 0.0f; }  // icp_registration.cpp:246-250, ndt_registration.cpp:466-471
+
+    // what the reference logs or drops: iterations, effective points, convergence, degeneracy
+    const locreg_result& LastResult() const { return last_result_; }
+    locreg_handle* Handle() const { return handle_; }
+
+   protected:
+    explicit CudaRegistrationBase(const locreg_options& opt, int device) {
+        locreg_detail::check(locreg_create(&opt, device, &handle_), "locreg_create");
+    }
+    locreg_handle* handle_ = nullptr;
+    locreg_result last_result_{};
+};
+
+class CudaIcpRegistration : public CudaRegistrationBase {
+   public:
+    explicit CudaIcpRegistration(IcpOptions options, int device = 0) : CudaRegistrationBase(Convert(options), device), options_(options) {}
+
+   private:
+    static locreg_options Convert(const IcpOptions& o) {
+        locreg_options c{};
+        int method = LOCREG_ICP_P2P;
+        switch (o.method_) {
+            case IcpMethod::P2P: method = LOCREG_ICP_P2P; break;
+            case IcpMethod::P2LINE: method = LOCREG_ICP_P2LINE; break;  // locreg_create reports LOCREG_E_UNSUPPORTED
+            case IcpMethod::P2PLANE: method = LOCREG_ICP_P2PLANE; break;
+            case IcpMethod::PCLICP: throw std::runtime_error("PCLICP is a passthrough to pcl::IterativeClosestPoint: keep IcpRegistration for it");
+        }
+        locreg_default_options(&c, method);
+        c.max_iteration = o.max_iteration_;
+        c.max_nn_distance = o.max_nn_distance_;
+        c.max_plane_distance = o.max_plane_distance_;
+        c.max_line_distance = o.max_line_distance_;
+        c.min_effective_pts = o.min_effective_pts_;
+        c.eps = o.eps_;
+        c.use_ann = o.use_ann ? 1 : 0;  // accepted, ignored: the search is exact (deviation Q1)
+        return c;
+    }
+    IcpOptions options_;
+};
+
+class CudaNdtRegistration : public CudaRegistrationBase {
+   public:
+    explicit CudaNdtRegistration(NdtOptions options, int device = 0) : CudaRegistrationBase(Convert(options), device), options_(options) {}
+
+   private:
+    static locreg_options Convert(const NdtOptions& o) {
+        if (o.method_ != NdtMethod::DIRECT_NDT) throw std::runtime_error("only DIRECT_NDT is built (incremental NDT: SURVEY.md 8f)");
+        locreg_options c{};
+        locreg_default_options(&c, LOCREG_NDT_DIRECT);
+        c.max_iteration = o.max_iteration_;
+        c.voxel_size = o.voxel_size_;  // inv_voxel_size_ is recomputed, as in ndt_registration.cpp:25
+        c.min_effective_pts = o.min_effective_pts_;
+        c.min_pts_in_voxel = o.min_pts_in_voxel_;
+        c.eps = o.eps_;
+        c.res_outlier_th = o.res_outlier_th_;
+        c.nearby_type = o.nearby_type_ == NdtNearbyType::NEARBY6 ? LOCREG_NEARBY6 : LOCREG_NEARBY_CENTER;
+        return c;
+    }
+    NdtOptions options_;
+};
+
+}  // namespace LocUtils

@@ -128,3 +128,25 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle_py" not in text and "liboracle" not in text and "hostsim_py" not in text, f
                 assert not re.search(r'#include\s+"[^"]*oracle', text), f
+
+
+def _run_adapter():
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "adapter_standin")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
+    return subprocess.run([exe], capture_output=True, text=True)
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the behaviour of a box WITHOUT a CUDA device")
+def test_cpp_adapter_compiles_and_refuses_without_gpu():
+    """include/locreg_adapter.hpp (the MatchingInterface drop-in) builds against stand-in PCL/Sophus types and,
+    without a GPU, raises instead of computing on the CPU."""
+    r = _run_adapter()
+    assert r.returncode == 3, r.stdout + r.stderr
+    assert "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_adapter_scan_match_on_gpu():
+    """The same binary on the B200: SetInputTarget + ScanMatch through the virtual interface recover a known shift."""
+    r = _run_adapter()
+    assert r.returncode == 0, r.stdout + r.stderr
