@@ -15,7 +15,13 @@ class DeviceVoxelMap {
 
     // d_xyz: device pointer to n points, `stride` bytes apart.  Synchronises the stream (the slot
     // table is sized from the number of occupied blocks, read back once).
-    void build(const void* d_xyz, size_t n, size_t stride, float cell, bool want_lists, cudaStream_t stream);
+    // keep_pos (optional): receives a device array (cudaMallocAsync on `stream`, caller frees) mapping every input
+    // index to its canonical position in pts (undefined for dropped points).
+    void build(const void* d_xyz, size_t n, size_t stride, float cell, bool want_lists, cudaStream_t stream,
+               unsigned int** keep_pos = nullptr);
+    // Turns this map into a coarse level of `fine`: every entry's w (original index) is replaced by the point's
+    // canonical position in fine's pts, which is what the search reports on every level.
+    void attach_to(const VoxelMapView& fine, const unsigned int* fine_pos_of_index, cudaStream_t stream);
     const VoxelMapView& view() const { return view_; }
     bool empty() const { return view_.n_pts == 0; }
     size_t bytes() const { return bytes_; }
@@ -33,5 +39,9 @@ class DeviceVoxelMap {
     size_t bytes_ = 0;
     unsigned int n_cells_ = 0, n_blocks_ = 0, n_lists_ = 0;
 };
+
+// Level 0 (cell, lists) + kCoarseLevels coarser levels (block tables only) of the ICP search index.
+void build_icp_maps(DeviceVoxelMap& fine, DeviceVoxelMap* coarse, const void* d_xyz, size_t n, size_t stride, float cell,
+                    bool want_lists, cudaStream_t stream);
 
 }  // namespace locreg

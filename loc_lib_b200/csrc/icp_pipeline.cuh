@@ -15,6 +15,7 @@
 #pragma once
 #include "device_utils.cuh"
 #include "icp_point.cuh"
+#include "knn_warp.cuh"
 
 namespace locreg {
 
@@ -180,8 +181,8 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
         for (int j = 0; j < K; ++j) seeds[j] = (mode & kNnSeeds) ? out[j] : kNoPos;
         double wx, wy, wz;
         pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
-        done = knn_query_fast<K>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, seeds,
-                                 (mode & kNnTwoPass) != 0);
+        const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
+        done = knn_query_fast<K>(map, qx, qy, qz, nn, seeds, (mode & kNnTwoPass) != 0);
     }
     if (in_tile) {
 #pragma unroll
@@ -197,15 +198,17 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
     if (!done) queue.entries[blk_base + slot] = make_uint2(static_cast<unsigned int>(row), tc.scan);
 }
 
-// Stage 2: finishes the queued queries (knn_query_finish seeded with what stage 1 found).  Persistent grid-stride
-// launch: the queue length is only known on the device.
+// Stage 2 of LARGE jobs (batches, relocalisation), one queued query per thread (knn_query_finish: corner lists, fine
+// shells, coarse levels).  With tens of thousands of queued queries the 32-queries-per-warp form keeps far more
+// memory requests in flight than a warp per query can, and wins on throughput despite its divergence.  Persistent
+// grid-stride launch (the queue length lives on the device).
 template <int K>
-__global__ void __launch_bounds__(128) k_icp_nn_rings(VoxelMapView map, BatchView bv, const AlignState* __restrict__ states,
-                                                      unsigned int* __restrict__ nn_pos, RingQueue queue) {
+__global__ void __launch_bounds__(128) k_icp_nn_finish(VoxelMapView map, CoarseLevels coarse, BatchView bv,
+                                                       const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
+                                                       RingQueue queue) {
     const unsigned int n = *queue.count;
     for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const uint2 q = queue.entries[e];
-        // scratch rows and source points coincide for a batch; hypotheses of one scan share its points
         const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
         const float4 sp = bv.src[src_idx];
         Pose T;
@@ -224,10 +227,134 @@ __global__ void __launch_bounds__(128) k_icp_nn_rings(VoxelMapView map, BatchVie
                 knn_offer(map.pts, nn, dis2_f32(qx, qy, qz, c.x, c.y, c.z), sp_j);
             }
         }
-        knn_query_finish<K>(map, qx, qy, qz, nn);
+        knn_query_finish<K>(map, coarse, qx, qy, qz, nn);
 #pragma unroll
         for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
     }
+}
+
+// Stage 2 of SMALL jobs (one scan): ONE QUERY PER WARP (knn_warp.cuh), seeded with what stage 1 found.  The GPU is
+// mostly idle, so what counts is the latency of the slowest query, and 32 lanes cut that ~10x.
+// Persistent warp-stride launch: the queue length is only known on the device.
+template <int K>
+__global__ void __launch_bounds__(128) k_icp_nn_rings(VoxelMapView map, CoarseLevels coarse, BatchView bv,
+                                                      const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
+                                                      RingQueue queue) {
+    const unsigned int n = *queue.count;
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int e = warp; e < n; e += n_warps) {
+        const uint2 q = queue.entries[e];
+        // scratch rows and source points coincide for a batch; hypotheses of one scan share its points
+        const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
+        const float4 sp = bv.src[src_idx];
+        Pose T;
+        pose_load(T, states[q.y].pose);
+        double wx, wy, wz;
+        pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
+        const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
+        unsigned int* out = nn_pos + static_cast<size_t>(q.x) * K;
+        KnnResult<K> nn;  // replicated: every lane holds the same set
+        knn_init(nn);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const unsigned int sp_j = out[j];
+            if (sp_j < map.n_pts) {
+                const float4 c = map.pts[sp_j];
+                knn_offer(map.pts, nn, dis2_f32(qx, qy, qz, c.x, c.y, c.z), sp_j);
+            }
+        }
+        warp_query_finish<K>(map, coarse, qx, qy, qz, nn);
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+        }
+    }
+}
+
+// ---- the search on its own (locreg_knn parity probe): the same two stages on raw queries ---------------------------
+// Stage 1 for queries that are already in map coordinates: no pose, no seeds; unfinished queries are queued with
+// (row, 0), and k_knn_rings / k_knn_export complete the probe.
+template <int K>
+__global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_knn_stage1(VoxelMapView map, const float4* __restrict__ q, unsigned int nq,
+                                                                        unsigned int* __restrict__ nn_pos, RingQueue queue) {
+    __shared__ unsigned int blk_pending, blk_base;
+    if (threadIdx.x == 0) blk_pending = 0u;
+    __syncthreads();
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool done = true;
+    if (i < nq) {
+        const float4 p = q[i];
+        KnnResult<K> nn;
+        knn_init(nn);
+        if (finite3(p.x, p.y, p.z) && map.n_pts != 0) done = knn_query_fast<K>(map, p.x, p.y, p.z, nn, nullptr, true);
+#pragma unroll
+        for (int j = 0; j < K; ++j) nn_pos[static_cast<size_t>(i) * K + j] = nn.pos[j];
+    }
+    unsigned int slot = 0;
+    if (!done) slot = atomicAdd(&blk_pending, 1u);
+    __syncthreads();
+    if (blk_pending == 0u) return;
+    if (threadIdx.x == 0) blk_base = atomicAdd(queue.count, blk_pending);
+    __syncthreads();
+    if (!done) queue.entries[blk_base + slot] = make_uint2(i, 0u);
+}
+template <int K>
+__global__ void __launch_bounds__(128) k_knn_rings(VoxelMapView map, CoarseLevels coarse, const float4* __restrict__ q,
+                                                   unsigned int* __restrict__ nn_pos, RingQueue queue) {
+    const unsigned int n = *queue.count;
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int e = warp; e < n; e += n_warps) {
+        const unsigned int i = queue.entries[e].x;
+        const float4 p = q[i];
+        unsigned int* out = nn_pos + static_cast<size_t>(i) * K;
+        KnnResult<K> nn;
+        knn_init(nn);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const unsigned int sp_j = out[j];
+            if (sp_j < map.n_pts) {
+                const float4 c = map.pts[sp_j];
+                knn_offer(map.pts, nn, dis2_f32(p.x, p.y, p.z, c.x, c.y, c.z), sp_j);
+            }
+        }
+        warp_query_finish<K>(map, coarse, p.x, p.y, p.z, nn);
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+        }
+    }
+}
+template <int K>
+__global__ void __launch_bounds__(128) k_knn_finish(VoxelMapView map, CoarseLevels coarse, const float4* __restrict__ q,
+                                                    unsigned int* __restrict__ nn_pos, RingQueue queue) {
+    const unsigned int n = *queue.count;
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const unsigned int i = queue.entries[e].x;
+        const float4 p = q[i];
+        unsigned int* out = nn_pos + static_cast<size_t>(i) * K;
+        KnnResult<K> nn;
+        knn_init(nn);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const unsigned int sp_j = out[j];
+            if (sp_j < map.n_pts) {
+                const float4 c = map.pts[sp_j];
+                knn_offer(map.pts, nn, dis2_f32(p.x, p.y, p.z, c.x, c.y, c.z), sp_j);
+            }
+        }
+        knn_query_finish<K>(map, coarse, p.x, p.y, p.z, nn);
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+    }
+}
+// canonical positions -> the caller's original indices (-1 = none)
+__global__ void k_knn_export(VoxelMapView map, const unsigned int* __restrict__ nn_pos, size_t n, int* __restrict__ idx) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = nn_pos[i] != kNoPos ? knn_index_of(map.pts, nn_pos[i]) : -1;
 }
 
 // ---- K_B: fit + gates + accumulate ----------------------------------------------------------------------------
@@ -370,10 +497,20 @@ __global__ void __launch_bounds__(128) k_icp_solve(IcpParams prm, BatchView bv, 
         t0 = s * bv.tiles_per_item;
         t1 = t0 + (bv.n_single + kTile - 1) / kTile;
     }
-    double v = 0;
-    if (lane < 30)
-        for (unsigned int t = t0; t < t1; ++t) v += partials[static_cast<size_t>(t) * kPartialDoubles + lane];
-    sums[warp][lane] = v;
+    // four interleaved running sums keep four loads in flight (the loop is pure latency); fixed order all the same
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if (lane < 30) {
+        const double* col = partials + lane;
+        unsigned int t = t0;
+        for (; t + 4 <= t1; t += 4) {
+            v0 += col[static_cast<size_t>(t) * kPartialDoubles];
+            v1 += col[static_cast<size_t>(t + 1) * kPartialDoubles];
+            v2 += col[static_cast<size_t>(t + 2) * kPartialDoubles];
+            v3 += col[static_cast<size_t>(t + 3) * kPartialDoubles];
+        }
+        for (; t < t1; ++t) v0 += col[static_cast<size_t>(t) * kPartialDoubles];
+    }
+    sums[warp][lane] = (v0 + v1) + (v2 + v3);
     __syncwarp();
     if (lane == 0) {
         const double* acc30 = sums[warp];

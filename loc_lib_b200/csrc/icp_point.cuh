@@ -89,7 +89,7 @@ LR_HD unsigned char icp_p2p_post(const VoxelMapView& map, const IcpParams& prm, 
 // readable statement of the algorithm; the kernels split the same steps over k_icp_nn / k_icp_post.
 // nn_pos (optional, K entries, in/out): seeds from the previous iteration on entry, this iteration's neighbour
 // positions on exit.
-LR_HD unsigned char icp_point_p2plane(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy,
+LR_HD unsigned char icp_point_p2plane(const VoxelMapView& map, const CoarseLevels& coarse, const IcpParams& prm, const Pose& T, float sx, float sy,
                                       float sz, Accum& acc, int* nn_out, unsigned int* nn_pos = nullptr) {
     if (nn_out) {
 #pragma unroll
@@ -100,7 +100,7 @@ LR_HD unsigned char icp_point_p2plane(const VoxelMapView& map, const IcpParams& 
     double wx, wy, wz;
     pose_apply(T, qx, qy, qz, wx, wy, wz);  // qs = predict_pose * q  (:169)
     KnnResult<5> nn;
-    knn_query<5>(map, true, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, nn_pos);  // (:170)
+    knn_query<5>(map, coarse, true, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, nn_pos);  // (:170)
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         if (nn_out) nn_out[j] = nn.pos[j] != kNoPos ? knn_index_of(map.pts, nn.pos[j]) : -1;
@@ -109,7 +109,7 @@ LR_HD unsigned char icp_point_p2plane(const VoxelMapView& map, const IcpParams& 
     return icp_p2plane_post(map, prm, T, qx, qy, qz, wx, wy, wz, nn, acc);
 }
 
-LR_HD unsigned char icp_point_p2p(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy,
+LR_HD unsigned char icp_point_p2p(const VoxelMapView& map, const CoarseLevels& coarse, const IcpParams& prm, const Pose& T, float sx, float sy,
                                   float sz, Accum& acc, int* nn_out, unsigned int* nn_pos = nullptr) {
     if (nn_out) nn_out[0] = -1;
     if (!finite3(sx, sy, sz)) return kGateSkipped;  // pcl::isFinite (:64)
@@ -117,17 +117,17 @@ LR_HD unsigned char icp_point_p2p(const VoxelMapView& map, const IcpParams& prm,
     double wx, wy, wz;
     pose_apply(T, qx, qy, qz, wx, wy, wz);
     KnnResult<1> nn;
-    knn_query<1>(map, true, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, nn_pos);
+    knn_query<1>(map, coarse, true, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, nn_pos);
     if (nn_out) nn_out[0] = nn.pos[0] != kNoPos ? knn_index_of(map.pts, nn.pos[0]) : -1;
     if (nn_pos) nn_pos[0] = nn.pos[0];
     return icp_p2p_post(map, prm, T, qx, qy, qz, wx, wy, wz, nn, acc);
 }
 
 template <int METHOD>
-LR_HD unsigned char icp_point(const VoxelMapView& map, const IcpParams& prm, const Pose& T, float sx, float sy, float sz,
+LR_HD unsigned char icp_point(const VoxelMapView& map, const CoarseLevels& coarse, const IcpParams& prm, const Pose& T, float sx, float sy, float sz,
                               Accum& acc, int* nn_out, unsigned int* nn_pos = nullptr) {
-    if (METHOD == kIcpP2P) return icp_point_p2p(map, prm, T, sx, sy, sz, acc, nn_out, nn_pos);
-    return icp_point_p2plane(map, prm, T, sx, sy, sz, acc, nn_out, nn_pos);
+    if (METHOD == kIcpP2P) return icp_point_p2p(map, coarse, prm, T, sx, sy, sz, acc, nn_out, nn_pos);
+    return icp_point_p2plane(map, coarse, prm, T, sx, sy, sz, acc, nn_out, nn_pos);
 }
 
 // One Gauss-Newton update from the reduced accumulator: the tail of AlignP2P / AlignP2Plane

@@ -62,7 +62,13 @@ struct locreg_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DeviceVoxelMap icp_map;
+    DeviceVoxelMap icp_map;     // level 0: cells of knn_cell_size, neighbourhood lists
+    DeviceVoxelMap icp_coarse[kCoarseLevels];  // cells 4x, 16x larger, block tables only (far queries)
+    CoarseLevels coarse_views() const {
+        CoarseLevels c{};
+        for (int l = 0; l < kCoarseLevels; ++l) c.lv[l] = icp_coarse[l].view();
+        return c;
+    }
     DeviceNdtMap ndt_map;
     bool has_target = false;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
@@ -270,12 +276,20 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     if (!(nn_mode & kNnSeeds)) LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, sizeof(unsigned int), h->stream));
     if (job.n_tiles == 0) return;
     const RingQueue queue{h->d_ringc.as<unsigned int>(), h->d_ringq.as<uint2>()};
+    // Queries stage 1 cannot finish: a small job (one scan) gives each of them a warp (lowest latency, the GPU is idle
+    // anyway); a large job keeps one query per thread (most requests in flight).
+    const bool small = job.n_tiles <= 2u * static_cast<unsigned int>(h->num_sms);
     prof_mark(h, 0, true);
     LR_LAUNCH(k_icp_nn<K>, job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, nn_mode, h->d_nnpos.as<unsigned int>(), queue);
     prof_mark(h, 0, false);
     prof_mark(h, 3, true);
-    LR_LAUNCH(k_icp_nn_rings<K>, static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * 8)),
-              128, 0, h->stream, map, job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue);
+    if (small) {
+        const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 3) / 4, static_cast<size_t>(h->num_sms) * 8));
+        LR_LAUNCH(k_icp_nn_rings<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue);
+    } else {
+        const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * 8));
+        LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue);
+    }
     prof_mark(h, 3, false);
     prof_mark(h, 1, true);
     LR_LAUNCH(k_icp_post<METHOD>, job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
@@ -332,24 +346,6 @@ IcpJob icp_batch_job(locreg_handle* h, const float4* src, const long long* d_off
 }
 
 bool is_ndt(const locreg_handle* h) { return h->opt.method == LOCREG_NDT_DIRECT; }
-
-// Parity probe for the search: the same warp-synchronous knn_query() the pipeline's k_icp_nn runs, unseeded.
-template <int K>
-__global__ void __launch_bounds__(128) k_knn(VoxelMapView map, const float4* __restrict__ q, unsigned int nq, int* __restrict__ idx) {
-    const unsigned int lane = threadIdx.x & 31;
-    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned int base = warp * 32; base < nq; base += n_warps * 32) {  // warp-uniform trip count
-        const unsigned int i = base + lane;
-        const bool in_range = i < nq;
-        const float4 p = q[in_range ? i : base];
-        KnnResult<K> r;
-        knn_query<K>(map, in_range && finite3(p.x, p.y, p.z), p.x, p.y, p.z, r);
-        if (in_range) {
-#pragma unroll
-            for (int j = 0; j < K; ++j) idx[static_cast<size_t>(i) * K + j] = r.pos[j] != kNoPos ? knn_index_of(map.pts, r.pos[j]) : -1;
-        }
-    }
-}
 
 int check_cloud_args(const float* p, size_t n, size_t stride) {
     if ((n > 0 && p == nullptr) || stride < 12 || (stride % 4) != 0) {
@@ -486,7 +482,7 @@ static int set_target_impl(locreg_handle* h, const float* xyz, size_t n, size_t 
         if (h->opt.method == LOCREG_NDT_DIRECT)
             h->ndt_map.build(d_xyz, n, stride, h->opt.voxel_size, h->opt.min_pts_in_voxel, h->stream);
         else
-            h->icp_map.build(d_xyz, n, stride, static_cast<float>(h->opt.knn_cell_size), h->opt.knn_lists != 0, h->stream);
+            build_icp_maps(h->icp_map, h->icp_coarse, d_xyz, n, stride, static_cast<float>(h->opt.knn_cell_size), h->opt.knn_lists != 0, h->stream);
         h->end_timing();
         h->has_target = true;
         return LOCREG_OK;
@@ -598,10 +594,30 @@ int locreg_knn(locreg_handle* h, const float* queries, size_t nq, size_t stride,
         if (nq == 0) return LOCREG_OK;
         const float4* q4 = stage_cloud(h, queries, nq, stride, false);
         h->d_nn.reserve(nq * k * sizeof(int));
+        h->d_nnpos.reserve(nq * k * sizeof(unsigned int));
+        h->d_ringq.reserve(nq * sizeof(uint2));
+        h->d_ringc.reserve(sizeof(unsigned int));
+        LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, sizeof(unsigned int), h->stream));
+        const RingQueue queue{h->d_ringc.as<unsigned int>(), h->d_ringq.as<uint2>()};
         h->begin_timing();
-                const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((nq + 127) / 128, 64u * h->num_sms));
-        if (k == 1) LR_LAUNCH(k_knn<1>, grid, 128, 0, h->stream, h->icp_map.view(), q4, static_cast<unsigned int>(nq), h->d_nn.as<int>());
-        else LR_LAUNCH(k_knn<5>, grid, 128, 0, h->stream, h->icp_map.view(), q4, static_cast<unsigned int>(nq), h->d_nn.as<int>());
+        // the production search: stage 1 per thread, then the queued rest per warp (small: what a single scan runs) or
+        // per thread (large: what batches run) - the probe switches at the same job size as icp_launch_eval
+        const unsigned int n32 = static_cast<unsigned int>(nq);
+        const unsigned int g1 = (n32 + kTile - 1) / kTile;
+        const bool small = g1 <= 2u * static_cast<unsigned int>(h->num_sms);
+        const unsigned int g2 = static_cast<unsigned int>(std::min<size_t>(small ? (nq + 3) / 4 : (nq + 127) / 128, static_cast<size_t>(h->num_sms) * 8));
+        const unsigned int g3 = static_cast<unsigned int>((nq * k + 255) / 256);
+        if (k == 1) {
+            LR_LAUNCH(k_knn_stage1<1>, g1, kTile, 0, h->stream, h->icp_map.view(), q4, n32, h->d_nnpos.as<unsigned int>(), queue);
+            if (small) LR_LAUNCH(k_knn_rings<1>, g2, 128, 0, h->stream, h->icp_map.view(), h->coarse_views(), q4, h->d_nnpos.as<unsigned int>(), queue);
+            else LR_LAUNCH(k_knn_finish<1>, g2, 128, 0, h->stream, h->icp_map.view(), h->coarse_views(), q4, h->d_nnpos.as<unsigned int>(), queue);
+        } else {
+            LR_LAUNCH(k_knn_stage1<5>, g1, kTile, 0, h->stream, h->icp_map.view(), q4, n32, h->d_nnpos.as<unsigned int>(), queue);
+            if (small) LR_LAUNCH(k_knn_rings<5>, g2, 128, 0, h->stream, h->icp_map.view(), h->coarse_views(), q4, h->d_nnpos.as<unsigned int>(), queue);
+            else LR_LAUNCH(k_knn_finish<5>, g2, 128, 0, h->stream, h->icp_map.view(), h->coarse_views(), q4, h->d_nnpos.as<unsigned int>(), queue);
+        }
+        LR_LAUNCH(k_knn_export, g3, 256, 0, h->stream, h->icp_map.view(), h->d_nnpos.as<unsigned int>(), nq * k, h->d_nn.as<int>());
+        LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, sizeof(unsigned int), h->stream));
         h->end_timing();
         LR_CUDA(cudaMemcpy(idx, h->d_nn.p, nq * k * sizeof(int), cudaMemcpyDeviceToHost));
         return LOCREG_OK;

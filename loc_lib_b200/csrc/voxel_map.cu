@@ -205,8 +205,10 @@ static unsigned int next_pow2(size_t v) {
     return p;
 }
 
-void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cell, bool want_lists, cudaStream_t stream) {
+void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cell, bool want_lists, cudaStream_t stream,
+                           unsigned int** keep_pos) {
     release();
+    if (keep_pos) *keep_pos = nullptr;
     if (n == 0) return;
     if (n >= (1ull << 31)) throw std::invalid_argument("target cloud too large (>= 2^31 points)");
     const float inv_cell = 1.0f / cell;
@@ -322,18 +324,43 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     }
     LR_CUDA(cudaFreeAsync(cursor, stream));
     LR_CUDA(cudaFreeAsync(pt_slot, stream));
-    LR_CUDA(cudaFreeAsync(pt_pos, stream));
+    if (keep_pos) *keep_pos = pt_pos; else LR_CUDA(cudaFreeAsync(pt_pos, stream));
     LR_CUDA(cudaFreeAsync(pt_bit, stream));
     LR_CUDA(cudaFreeAsync(dup, stream));
     LR_CUDA(cudaFreeAsync(counters, stream));
     LR_CUDA(cudaFreeAsync(bounds, stream));
     view_.slots = slots_; view_.cell_start = cell_start_; view_.pts = pts_;
+    view_.canon = pts_; view_.w_is_pos = 0;
     view_.nbr_slots = nbr_; view_.nbr_mask = nbr_cap ? nbr_cap - 1 : 0;
     view_.slot_mask = cap - 1; view_.n_pts = n_kept; view_.n_unique = n_kept - n_dup;
     view_.inv_cell = inv_cell; view_.cell = cell;
     for (int a = 0; a < 3; ++a) { view_.cmin[a] = h_bounds[a]; view_.cmax[a] = h_bounds[3 + a]; }
     bytes_ = static_cast<size_t>(cap) * sizeof(VoxelSlot) + (static_cast<size_t>(n_cells_) + 1) * 4 +
              static_cast<size_t>(n_kept) * sizeof(float4) * (lists ? 28 : 1) + static_cast<size_t>(nbr_cap) * sizeof(NbrSlot);
+}
+
+__global__ void k_coarse_remap(float4* pts, unsigned int n, const unsigned int* __restrict__ fine_pos_of_index) {
+    const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) pts[j].w = __int_as_float(static_cast<int>(fine_pos_of_index[__float_as_int(pts[j].w)]));
+}
+void DeviceVoxelMap::attach_to(const VoxelMapView& fine, const unsigned int* fine_pos_of_index, cudaStream_t stream) {
+    if (view_.n_pts == 0) return;
+    LR_LAUNCH(k_coarse_remap, (view_.n_pts + 255) / 256, 256, 0, stream, pts_, view_.n_pts, fine_pos_of_index);
+    view_.canon = fine.pts;
+    view_.w_is_pos = 1;
+}
+
+void build_icp_maps(DeviceVoxelMap& fine, DeviceVoxelMap* coarse, const void* d_xyz, size_t n, size_t stride, float cell,
+                    bool want_lists, cudaStream_t stream) {
+    unsigned int* pos = nullptr;
+    fine.build(d_xyz, n, stride, cell, want_lists, stream, &pos);
+    float c = cell;
+    for (int l = 0; l < kCoarseLevels; ++l) {
+        c *= kCoarseFactor;
+        coarse[l].build(d_xyz, n, stride, c, false, stream);
+        if (pos) coarse[l].attach_to(fine.view(), pos, stream);
+    }
+    if (pos) LR_CUDA(cudaFreeAsync(pos, stream));
 }
 
 }  // namespace locreg

@@ -61,6 +61,8 @@ struct VoxelMapView {
     const VoxelSlot* slots;
     const unsigned int* cell_start;
     const float4* pts;        // [0, n_pts): points sorted by cell; [n_pts, ...): neighbourhood lists
+    const float4* canon;      // array that canonical positions index (= pts on level 0, level 0's pts on a coarse level)
+    int w_is_pos;             // 0: pts[i].w = original index, position = i (level 0); 1: pts[i].w = canonical position
     const NbrSlot* nbr_slots; // nullptr: no neighbourhood lists (fallback search only)
     unsigned int nbr_mask;
     unsigned int slot_mask;  // capacity - 1
@@ -294,6 +296,18 @@ LR_HD KnnCellFrame knn_frame(const VoxelMapView& m, float qx, float qy, float qz
 // true when the list scan applies to this query: lists exist and the 3x3x3 box around its cell touches the map
 LR_HD bool knn_uses_list(const VoxelMapView& m, const KnnCellFrame& c) { return m.nbr_slots != nullptr && c.R0 == 1; }
 
+// (start, count) of the neighbourhood list of cell (cx, cy, cz); count 0 if the cell has none
+LR_HD void knn_find_list(const VoxelMapView& m, int cx, int cy, int cz, unsigned int& beg, unsigned int& cnt) {
+    const unsigned long long key = pack_cell(cx, cy, cz);
+    unsigned int h = hash_block(key) & m.nbr_mask;
+    beg = 0; cnt = 0;
+    while (true) {
+        const NbrSlot s = m.nbr_slots[h];
+        if (s.key == key) { beg = s.start; cnt = s.count; return; }
+        if (s.key == kEmptyKey) return;
+        h = (h + 1) & m.nbr_mask;
+    }
+}
 // Stage 1 of the exact k-NN of a FINITE query against a NON-EMPTY map: seeds, then the one-list fast path.
 //   seeds    optional K canonical positions (kNoPos = none) that start the k-best set - the neighbours found in the
 //            previous Gauss-Newton iteration.  Any real, distinct points are valid seeds: they only tighten the
@@ -317,15 +331,8 @@ LR_HD bool knn_query_fast(const VoxelMapView& m, float qx, float qy, float qz, K
     }
     if (!knn_uses_list(m, c)) return false;
     // the whole box [f-1, f+1]^3 is one contiguous list
-    const unsigned long long key = pack_cell(c.fx, c.fy, c.fz);
-    unsigned int h = hash_block(key) & m.nbr_mask;
     unsigned int beg = 0, cnt = 0;
-    while (true) {
-        const NbrSlot s = m.nbr_slots[h];
-        if (s.key == key) { beg = s.start; cnt = s.count; break; }
-        if (s.key == kEmptyKey) break;
-        h = (h + 1) & m.nbr_mask;
-    }
+    knn_find_list(m, c.fx, c.fy, c.fz, beg, cnt);
     LR_STAT(0, 1); LR_STAT(1, cnt);  // fast-path queries, candidates
     knn_scan_list<K>(m.pts, res, qx, qy, qz, beg, cnt, two_pass);
     if (res.pos[K - 1] != kNoPos) {
@@ -348,14 +355,12 @@ LR_HD bool knn_query_fast(const VoxelMapView& m, float qx, float qy, float qz, K
 // over up to 98 shell cells.  All quantities are in cell units and inflated by the rounding allowance of the cell
 // assignment.  Needs a full set (a finite k-th distance) from stage 1.
 // Returns true when `res` is final, false when shells R >= 3 must follow (knn_query_rings with boxes_done = 2).
-template <int K>
-LR_HD bool knn_query_corners(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res) {
-    const KnnCellFrame c = knn_frame(m, qx, qy, qz);
-    LR_STAT(2, 1);  // queries entering stage 2a
+// Which of the eight corner lists the ball of squared radius worst_d2 needs: bit (sx > 0) | (sy > 0) << 1 | (sz > 0) << 2
+LR_HD unsigned int knn_corner_mask(const VoxelMapView& m, const KnnCellFrame& c, float worst_d2) {
     const float slack = 1e-6f * (c.mag + 4.0f);
-    const float wc = sqrtf(res.d2[K - 1]) * m.inv_cell * 1.0001f + slack;  // k-th distance, cell units, rounded up
+    const float wc = sqrtf(worst_d2) * m.inv_cell * 1.0001f + slack;  // k-th distance, cell units, rounded up
     const float fr[3] = {c.frx, c.fry, c.frz};
-    unsigned int need = 0;  // bit (sx > 0) | (sy > 0) << 1 | (sz > 0) << 2
+    unsigned int need = 0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const int b1 = (a + 1) % 3, b2 = (a + 2) % 3;
@@ -379,21 +384,11 @@ LR_HD bool knn_query_corners(const VoxelMapView& m, float qx, float qy, float qz
             }
         }
     }
-    for (int o = 0; o < 8; ++o) {
-        if (!((need >> o) & 1u)) continue;
-        const int sx = (o & 1) ? 1 : -1, sy = (o & 2) ? 1 : -1, sz = (o & 4) ? 1 : -1;
-        const unsigned long long key = pack_cell(c.fx + sx, c.fy + sy, c.fz + sz);
-        unsigned int h = hash_block(key) & m.nbr_mask;
-        unsigned int beg = 0, cnt = 0;
-        while (true) {
-            const NbrSlot s = m.nbr_slots[h];
-            if (s.key == key) { beg = s.start; cnt = s.count; break; }
-            if (s.key == kEmptyKey) break;
-            h = (h + 1) & m.nbr_mask;
-        }
-        LR_STAT(3, 1); LR_STAT(4, cnt);  // corner lists scanned, candidates
-        knn_scan_list<K>(m.pts, res, qx, qy, qz, beg, cnt, false);
-    }
+    return need;
+}
+// After stage 2a: every unvisited point is outside [f-2, f+2]^3 or farther than the k-th distance the mask used
+template <int K>
+LR_HD bool knn_corners_final(const VoxelMapView& m, const KnnCellFrame& c, const KnnResult<K>& res) {
     float mf = fminf(c.frx, 1.0f - c.frx);
     mf = fminf(mf, fminf(c.fry, 1.0f - c.fry));
     mf = fminf(mf, fminf(c.frz, 1.0f - c.frz));
@@ -402,118 +397,180 @@ LR_HD bool knn_query_corners(const VoxelMapView& m, float qx, float qy, float qz
     return c.fx - 2 <= m.cmin[0] && c.fx + 2 >= m.cmax[0] && c.fy - 2 <= m.cmin[1] && c.fy + 2 >= m.cmax[1] &&
            c.fz - 2 <= m.cmin[2] && c.fz + 2 >= m.cmax[2];
 }
-
-// Stage 2b: Chebyshev shells of cells through the block table until the k-th best is provably final.  `res` holds
-// what the earlier stages found (it may be partly or wholly empty); boxes_done = Chebyshev radius of the box they
-// have dealt with (0: nothing, 1: stage 1's list, 2: stage 2a).
 template <int K>
-LR_HD void knn_query_rings(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res, int boxes_done) {
+LR_HD bool knn_query_corners(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res) {
     const KnnCellFrame c = knn_frame(m, qx, qy, qz);
-    const int fx = c.fx, fy = c.fy, fz = c.fz;
-    const float frx = c.frx, fry = c.fry, frz = c.frz, mag = c.mag;
+    LR_STAT(2, 1);  // queries entering stage 2a
+    const unsigned int need = knn_corner_mask(m, c, res.d2[K - 1]);
+    for (int o = 0; o < 8; ++o) {
+        if (!((need >> o) & 1u)) continue;
+        unsigned int beg = 0, cnt = 0;
+        knn_find_list(m, c.fx + ((o & 1) ? 1 : -1), c.fy + ((o & 2) ? 1 : -1), c.fz + ((o & 4) ? 1 : -1), beg, cnt);
+        LR_STAT(3, 1); LR_STAT(4, cnt);  // corner lists scanned, candidates
+        knn_scan_list<K>(m.pts, res, qx, qy, qz, beg, cnt, false);
+    }
+    return knn_corners_final<K>(m, c, res);
+}
+
+// Geometry of one Chebyshev shell (radius R around the query's cell) clipped to the occupied bounds.
+struct KnnShell {
+    int lox, hix, loy, hiy, loz, hiz;  // the box [f - R, f + R]
+    int clx, chx, cly, chy, clz, chz;  // clipped to the occupied bounds
+    int nbx, nby, nbz;                 // blocks spanned by the clipped box per axis (0: the box misses the bounds)
+    int R;
+    bool first;                        // nothing inside the box has been visited: take the full box, not just the shell
+};
+LR_HD KnnShell knn_shell(const VoxelMapView& m, const KnnCellFrame& c, int R, bool first) {
+    KnnShell s;
+    s.R = R; s.first = first;
+    s.lox = c.fx - R; s.hix = c.fx + R; s.loy = c.fy - R; s.hiy = c.fy + R; s.loz = c.fz - R; s.hiz = c.fz + R;
+    s.clx = s.lox > m.cmin[0] ? s.lox : m.cmin[0]; s.chx = s.hix < m.cmax[0] ? s.hix : m.cmax[0];
+    s.cly = s.loy > m.cmin[1] ? s.loy : m.cmin[1]; s.chy = s.hiy < m.cmax[1] ? s.hiy : m.cmax[1];
+    s.clz = s.loz > m.cmin[2] ? s.loz : m.cmin[2]; s.chz = s.hiz < m.cmax[2] ? s.hiz : m.cmax[2];
+    s.nbx = s.chx >= s.clx ? (s.chx >> 2) - (s.clx >> 2) + 1 : 0;
+    s.nby = s.chy >= s.cly ? (s.chy >> 2) - (s.cly >> 2) + 1 : 0;
+    s.nbz = s.chz >= s.clz ? (s.chz >> 2) - (s.clz >> 2) + 1 : 0;
+    return s;
+}
+// Conservative (never over-estimated) squared distance from the query to cell (cx, cy, cz)
+LR_HD float knn_cell_min_d2(const VoxelMapView& m, const KnnCellFrame& c, int cx, int cy, int cz, float magR) {
+    const float gx = cx > c.fx ? static_cast<float>(cx - c.fx) - c.frx : (cx < c.fx ? static_cast<float>(c.fx - cx - 1) + c.frx : 0.0f);
+    const float gy = cy > c.fy ? static_cast<float>(cy - c.fy) - c.fry : (cy < c.fy ? static_cast<float>(c.fy - cy - 1) + c.fry : 0.0f);
+    const float gz = cz > c.fz ? static_cast<float>(cz - c.fz) - c.frz : (cz < c.fz ? static_cast<float>(c.fz - cz - 1) + c.frz : 0.0f);
+    const float sx = safe_gap(gx, magR, m.cell), sy = safe_gap(gy, magR, m.cell), sz = safe_gap(gz, magR, m.cell);
+    return (sx * sx + sy * sy + sz * sz) * 0.99999f;
+}
+// Occupied cells of block (bx, by, bz) that belong to the shell (bit = z << 4 | y << 2 | x), with the block's
+// occupancy mask and first cell id; 0 if the block is interior, absent or empty there.
+LR_HD unsigned long long knn_shell_block_cells(const VoxelMapView& m, const KnnShell& sh, int bx, int by, int bz,
+                                               unsigned long long& occ, unsigned int& base) {
+    const int ox = bx << 2, oy = by << 2, oz = bz << 2;
+    const unsigned int rx = axis_range_mask(ox, sh.clx, sh.chx), ry = axis_range_mask(oy, sh.cly, sh.chy),
+                       rz = axis_range_mask(oz, sh.clz, sh.chz);
+    const unsigned int ix = sh.first ? 0u : (rx & ~axis_edge_mask(ox, sh.lox, sh.hix));
+    const unsigned int iy = sh.first ? 0u : (ry & ~axis_edge_mask(oy, sh.loy, sh.hiy));
+    const unsigned int iz = sh.first ? 0u : (rz & ~axis_edge_mask(oz, sh.loz, sh.hiz));
+    // cells of this block inside the box but not strictly interior (= the new shell)
+    if (!sh.first && ix == rx && iy == ry && iz == rz) return 0ull;  // block entirely interior
+    LR_STAT(6, 1);  // block probes
+    const VoxelSlot* s = find_block(m, bx, by, bz);
+    if (s == nullptr) return 0ull;
+    unsigned long long want = spread_x(rx) & spread_y(ry) & spread_z(rz);
+    if (!sh.first) want &= ~(spread_x(ix) & spread_y(iy) & spread_z(iz));
+    occ = s->mask;
+    base = s->cell_base;
+    return occ & want;
+}
+// Cells of block (bx, by, bz) that belong to the shell: their points are offered to `res`.  bound (<= INFINITY) is an
+// additional acceptance / pruning bound on dis2 that does not come from `res` itself (the warp-cooperative search
+// passes the replicated global k-th distance while `res` is a lane's private set).
+template <int K>
+LR_HD void knn_shell_block(const VoxelMapView& m, const KnnCellFrame& c, const KnnShell& sh, int bx, int by, int bz,
+                           float qx, float qy, float qz, float bound, KnnResult<K>& res) {
+    unsigned long long occ = 0ull;
+    unsigned int base = 0;
+    unsigned long long todo = knn_shell_block_cells(m, sh, bx, by, bz, occ, base);
+    const int ox = bx << 2, oy = by << 2, oz = bz << 2;
+    const float magR = c.mag + static_cast<float>(sh.R);
+    while (todo) {
+        const int bit = ffs64(todo) - 1;
+        todo &= todo - 1;
+        const float worst = fminf(bound, res.d2[K - 1]);
+        if (worst < INFINITY && knn_cell_min_d2(m, c, ox + (bit & 3), oy + ((bit >> 2) & 3), oz + (bit >> 4), magR) > worst) continue;
+        const unsigned int cid = base + popc64(occ & ((1ull << bit) - 1ull));
+        const unsigned int beg = m.cell_start[cid], end = m.cell_start[cid + 1];
+        LR_STAT(7, end - beg);  // shell candidates
+        for (unsigned int i = beg; i < end; ++i) {
+            const float4 p = m.pts[i];
+            const float d2 = dis2_f32(qx, qy, qz, p.x, p.y, p.z);
+            if (d2 <= bound) knn_offer(m.canon, res, d2, m.w_is_pos ? static_cast<unsigned int>(float_as_int(p.w)) : i);
+        }
+    }
+}
+// After the box [f - R, f + R]^3 has been dealt with: is `res` final?  Every unvisited point lies outside the box,
+// at least R + min(frac, 1 - frac) cell units away along some axis - or the box covers the whole map.
+template <int K>
+LR_HD bool knn_shell_final(const VoxelMapView& m, const KnnCellFrame& c, const KnnShell& sh, const KnnResult<K>& res) {
+    if (res.pos[K - 1] != kNoPos) {
+        float mf = fminf(c.frx, 1.0f - c.frx);
+        mf = fminf(mf, fminf(c.fry, 1.0f - c.fry));
+        mf = fminf(mf, fminf(c.frz, 1.0f - c.frz));
+        const float g = safe_gap(static_cast<float>(sh.R) + mf, c.mag + static_cast<float>(sh.R), m.cell);
+        if (res.d2[K - 1] < g * g * 0.99999f) return true;
+    }
+    return sh.lox <= m.cmin[0] && sh.hix >= m.cmax[0] && sh.loy <= m.cmin[1] && sh.hiy >= m.cmax[1] &&
+           sh.loz <= m.cmin[2] && sh.hiz >= m.cmax[2];
+}
+
+// Stage 2b: Chebyshev shells of cells through the block table of ONE resolution level until the k-th best is
+// provably final (returns true) or the shell radius exceeds max_R (returns false: the caller escalates to a coarser
+// level).  `res` holds what the earlier stages found (it may be partly or wholly empty); boxes_done = Chebyshev
+// radius of the box of THIS level they have dealt with (0: nothing, 1: stage 1's list, 2: stage 2a).
+template <int K>
+LR_HD bool knn_query_rings(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res, int boxes_done, int max_R) {
+    const KnnCellFrame c = knn_frame(m, qx, qy, qz);
     LR_STAT(5, 1);  // queries entering stage 2b
     bool first = boxes_done == 0;  // nothing visited yet: the first shell is the full box
-    int R = first ? c.R0 : boxes_done + 1;
-    while (true) {
-        if (R > kBruteForceShell) {
-            // pathological query (> kBruteForceShell cells from every candidate seen so far): linear scan
-            knn_init(res);
-            for (unsigned int i = 0; i < m.n_pts; ++i) {
-                const float4 p = m.pts[i];
-                knn_offer(m.pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), i);
-            }
-            return;
-        }
-        const int lox = fx - R, hix = fx + R, loy = fy - R, hiy = fy + R, loz = fz - R, hiz = fz + R;
-        // clip enumeration to the occupied bounds
-        const int clx = lox > m.cmin[0] ? lox : m.cmin[0], chx = hix < m.cmax[0] ? hix : m.cmax[0];
-        const int cly = loy > m.cmin[1] ? loy : m.cmin[1], chy = hiy < m.cmax[1] ? hiy : m.cmax[1];
-        const int clz = loz > m.cmin[2] ? loz : m.cmin[2], chz = hiz < m.cmax[2] ? hiz : m.cmax[2];
-        for (int bz = clz >> 2; bz <= (chz >> 2); ++bz) {
-            const int oz = bz << 2;
-            const unsigned int rz = axis_range_mask(oz, clz, chz);
-            const unsigned int iz = first ? 0u : (rz & ~axis_edge_mask(oz, loz, hiz));
-            for (int by = cly >> 2; by <= (chy >> 2); ++by) {
-                const int oy = by << 2;
-                const unsigned int ry = axis_range_mask(oy, cly, chy);
-                const unsigned int iy = first ? 0u : (ry & ~axis_edge_mask(oy, loy, hiy));
-                for (int bx = clx >> 2; bx <= (chx >> 2); ++bx) {
-                    const int ox = bx << 2;
-                    const unsigned int rx = axis_range_mask(ox, clx, chx);
-                    const unsigned int ix = first ? 0u : (rx & ~axis_edge_mask(ox, lox, hix));
-                    // cells of this block inside the box but not strictly interior (= the new shell)
-                    if (!first && ix == rx && iy == ry && iz == rz) continue;  // block entirely interior
-                    LR_STAT(6, 1);  // block probes
-                    const VoxelSlot* s = find_block(m, bx, by, bz);
-                    if (s == nullptr) continue;
-                    unsigned long long want = spread_x(rx) & spread_y(ry) & spread_z(rz);
-                    if (!first) want &= ~(spread_x(ix) & spread_y(iy) & spread_z(iz));
-                    const unsigned long long occ = s->mask;
-                    unsigned long long todo = occ & want;
-                    const unsigned int base = s->cell_base;
-                    while (todo) {
-                        const int bit = ffs64(todo) - 1;
-                        todo &= todo - 1;
-                        const int cx = ox + (bit & 3), cy = oy + ((bit >> 2) & 3), cz = oz + (bit >> 4);
-                        if (res.pos[K - 1] != kNoPos) {
-                            // prune: conservative min distance from the query to this cell
-                            const float gx = cx > fx ? static_cast<float>(cx - fx) - frx
-                                                     : (cx < fx ? static_cast<float>(fx - cx - 1) + frx : 0.0f);
-                            const float gy = cy > fy ? static_cast<float>(cy - fy) - fry
-                                                     : (cy < fy ? static_cast<float>(fy - cy - 1) + fry : 0.0f);
-                            const float gz = cz > fz ? static_cast<float>(cz - fz) - frz
-                                                     : (cz < fz ? static_cast<float>(fz - cz - 1) + frz : 0.0f);
-                            const float sx = safe_gap(gx, mag + R, m.cell), sy = safe_gap(gy, mag + R, m.cell),
-                                        sz = safe_gap(gz, mag + R, m.cell);
-                            const float md2 = (sx * sx + sy * sy + sz * sz) * 0.99999f;
-                            if (md2 > res.d2[K - 1]) continue;
-                        }
-                        const unsigned int cid = base + popc64(occ & ((1ull << bit) - 1ull));
-                        const unsigned int beg = m.cell_start[cid], end = m.cell_start[cid + 1];
-                        LR_STAT(7, end - beg);  // shell candidates
-                        for (unsigned int i = beg; i < end; ++i) {
-                            const float4 p = m.pts[i];
-                            knn_offer(m.pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), i);
-                        }
-                    }
-                }
-            }
-        }
+    for (int R = first ? c.R0 : boxes_done + 1;; ++R) {
+        if (R > max_R) return false;
+        const KnnShell sh = knn_shell(m, c, R, first);
+        for (int jz = 0; jz < sh.nbz; ++jz)
+            for (int jy = 0; jy < sh.nby; ++jy)
+                for (int jx = 0; jx < sh.nbx; ++jx)
+                    knn_shell_block<K>(m, c, sh, (sh.clx >> 2) + jx, (sh.cly >> 2) + jy, (sh.clz >> 2) + jz, qx, qy, qz, INFINITY, res);
         first = false;
-        // every unvisited point lies outside the box [f-R, f+R]: at least R + min(frac, 1-frac) cell
-        // units away along some axis
-        if (res.pos[K - 1] != kNoPos) {
-            float mf = fminf(frx, 1.0f - frx);
-            mf = fminf(mf, fminf(fry, 1.0f - fry));
-            mf = fminf(mf, fminf(frz, 1.0f - frz));
-            const float g = safe_gap(static_cast<float>(R) + mf, mag + R, m.cell);
-            if (res.d2[K - 1] < g * g * 0.99999f) return;
-        }
-        if (lox <= m.cmin[0] && hix >= m.cmax[0] && loy <= m.cmin[1] && hiy >= m.cmax[1] && loz <= m.cmin[2] &&
-            hiz >= m.cmax[2])
-            return;  // the whole map has been visited
-        ++R;
+        if (knn_shell_final<K>(m, c, sh, res)) return true;
     }
 }
 
-// Everything after stage 1 for one query (the body of k_icp_nn_rings).
+// Everything after stage 1 for one query (the body of k_icp_nn_rings).  Escalation: corner lists (5x5x5 fine
+// cells), fine shells up to kFineShells, then the COARSE level (cells kCoarseFactor times larger, same points, no
+// lists) from scratch - its shells reach kBruteForceShell * kCoarseFactor fine cells, which is what keeps far-off
+// queries (global relocalisation hypotheses, points outside the map) from degenerating into a linear scan - and
+// only beyond that the linear scan.  Restarting on another level is sound because the set only ever holds real,
+// distinct points: what a level re-visits is rejected by the membership / threshold tests.
+constexpr int kFineShells = 4;
+constexpr int kCoarseFactor = 4;   // cell edge ratio between consecutive levels
+constexpr int kCoarseLevels = 2;   // 4x and 16x the fine cell: shells reach 24 * 16 fine cells (192 m at 0.5 m)
+constexpr int kCoarseShells = 6;   // shells on a level that has a coarser one behind it
+struct CoarseLevels {
+    VoxelMapView lv[kCoarseLevels];  // n_pts == 0: level absent
+};
 template <int K>
-LR_HD void knn_query_finish(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res) {
+LR_HD void knn_query_finish(const VoxelMapView& m, const CoarseLevels& coarse, float qx, float qy, float qz, KnnResult<K>& res) {
     const KnnCellFrame c = knn_frame(m, qx, qy, qz);
     int boxes_done = knn_uses_list(m, c) ? 1 : 0;
     if (boxes_done == 1 && res.pos[K - 1] != kNoPos) {
         if (knn_query_corners<K>(m, qx, qy, qz, res)) return;
         boxes_done = 2;
     }
-    knn_query_rings<K>(m, qx, qy, qz, res, boxes_done);
+    const bool have_coarse = coarse.lv[0].n_pts != 0;
+    // a query outside the occupied bounds by more than the fine reach goes straight to the coarse levels
+    if (!(have_coarse && c.R0 > kFineShells) &&
+        knn_query_rings<K>(m, qx, qy, qz, res, boxes_done, have_coarse ? kFineShells : kBruteForceShell))
+        return;
+    for (int l = 0; l < kCoarseLevels; ++l) {
+        const VoxelMapView& cl = coarse.lv[l];
+        if (cl.n_pts == 0) break;
+        const bool last = l + 1 == kCoarseLevels || coarse.lv[l + 1].n_pts == 0;
+        // leave a level early (6 shells) when a coarser one can take over, so that far queries climb quickly
+        if (!last && knn_frame(cl, qx, qy, qz).R0 > kCoarseShells) continue;
+        if (knn_query_rings<K>(cl, qx, qy, qz, res, 0, last ? kBruteForceShell : kCoarseShells)) return;
+    }
+    LR_STAT(8, 1);  // linear scans
+    knn_init(res);
+    for (unsigned int i = 0; i < m.n_pts; ++i) {
+        const float4 p = m.pts[i];
+        knn_offer(m.pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), i);
+    }
 }
 
 // Exact k-NN of (qx,qy,qz) in one call (parity probe, tests/hostsim).  valid = false: no query, empty result.
 template <int K>
-LR_HD void knn_query(const VoxelMapView& m, bool valid, float qx, float qy, float qz, KnnResult<K>& res,
-                     const unsigned int* seeds = nullptr, bool two_pass = false) {
+LR_HD void knn_query(const VoxelMapView& m, const CoarseLevels& coarse, bool valid, float qx, float qy, float qz,
+                     KnnResult<K>& res, const unsigned int* seeds = nullptr, bool two_pass = false) {
     if (!valid || m.n_pts == 0) { knn_init(res); return; }
-    if (!knn_query_fast<K>(m, qx, qy, qz, res, seeds, two_pass)) knn_query_finish<K>(m, qx, qy, qz, res);
+    if (!knn_query_fast<K>(m, qx, qy, qz, res, seeds, two_pass)) knn_query_finish<K>(m, coarse, qx, qy, qz, res);
 }
 
 }  // namespace locreg

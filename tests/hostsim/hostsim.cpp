@@ -22,7 +22,11 @@ struct HsMap {
     std::vector<VoxelSlot> slots;
     std::vector<unsigned int> cell_start;
     std::vector<float4> pts;
+    std::vector<unsigned int> pos_of_index;  // input index -> canonical position
     VoxelMapView view;
+    HsMap* coarse_map[kCoarseLevels] = {};   // coarser levels (no lists), or nullptr
+    CoarseLevels coarse{};                   // lv[l].n_pts == 0: level absent
+    ~HsMap() { for (HsMap* c : coarse_map) delete c; }
 };
 
 static unsigned int next_pow2(unsigned int v) {
@@ -33,7 +37,7 @@ static unsigned int next_pow2(unsigned int v) {
 
 extern "C" {
 
-HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsigned int capacity_hint) {
+static HsMap* build_level(const float* xyz, size_t n, size_t stride, float cell, unsigned int capacity_hint) {
     auto* m = new HsMap;
     const float inv_cell = 1.0f / cell;
     unsigned int cap = (capacity_hint && capacity_hint != 0xFFFFFFFFu) ? next_pow2(capacity_hint) : next_pow2(static_cast<unsigned int>(n / 4 + 1024));
@@ -99,6 +103,25 @@ HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsi
     v.nbr_slots = nbr_cap ? m->nbr.data() : nullptr; v.nbr_mask = nbr_cap ? nbr_cap - 1 : 0;
     v.slot_mask = cap - 1; v.n_pts = run; v.n_unique = run - ndup; v.inv_cell = inv_cell; v.cell = cell;
     for (int a = 0; a < 3; ++a) { v.cmin[a] = cmin[a]; v.cmax[a] = cmax[a]; }
+    v.canon = m->pts.data(); v.w_is_pos = 0;
+    m->pos_of_index = pt_pos;
+    return m;
+}
+
+// capacity_hint: 0 = defaults; 0xFFFFFFFF = no neighbourhood lists; 0xFFFFFFFE = no lists and no coarse level
+HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsigned int capacity_hint) {
+    const bool want_coarse = capacity_hint != 0xFFFFFFFEu;
+    HsMap* m = build_level(xyz, n, stride, cell, capacity_hint == 0xFFFFFFFEu ? 0xFFFFFFFFu : capacity_hint);
+    float cc = cell;
+    for (int l = 0; want_coarse && m->view.n_pts && l < kCoarseLevels; ++l) {
+        cc *= kCoarseFactor;
+        HsMap* c = build_level(xyz, n, stride, cc, 0xFFFFFFFFu);
+        for (unsigned int j = 0; j < c->view.n_pts; ++j)  // what DeviceVoxelMap::attach_to does
+            c->pts[j].w = int_as_float(static_cast<int>(m->pos_of_index[float_as_int(c->pts[j].w)]));
+        c->view.canon = m->pts.data(); c->view.w_is_pos = 1;
+        m->coarse_map[l] = c;
+        m->coarse.lv[l] = c->view;
+    }
     return m;
 }
 void hs_map_destroy(HsMap* m) { delete m; }
@@ -117,11 +140,11 @@ void hs_knn(const HsMap* m, const float* q, size_t nq, size_t stride, int k, int
         const bool ok = finite3(p[0], p[1], p[2]);
         if (k == 1) {
             KnnResult<1> r;
-            knn_query<1>(m->view, ok, p[0], p[1], p[2], r);
+            knn_query<1>(m->view, m->coarse, ok, p[0], p[1], p[2], r);
             idx_out[i] = r.pos[0] != kNoPos ? knn_index_of(m->view.pts, r.pos[0]) : -1;
         } else {
             KnnResult<5> r;
-            knn_query<5>(m->view, ok, p[0], p[1], p[2], r);
+            knn_query<5>(m->view, m->coarse, ok, p[0], p[1], p[2], r);
             for (int j = 0; j < 5; ++j) idx_out[i * 5 + j] = r.pos[j] != kNoPos ? knn_index_of(m->view.pts, r.pos[j]) : -1;
         }
     }
@@ -133,8 +156,8 @@ void hs_knn_seeded(const HsMap* m, const float* q, const float* seed_q, size_t n
         const float* p = point_ptr(q, i, stride);
         const float* sq = point_ptr(seed_q, i, stride);
         KnnResult<5> s, r;
-        knn_query<5>(m->view, finite3(sq[0], sq[1], sq[2]), sq[0], sq[1], sq[2], s);
-        knn_query<5>(m->view, finite3(p[0], p[1], p[2]), p[0], p[1], p[2], r, s.pos);
+        knn_query<5>(m->view, m->coarse, finite3(sq[0], sq[1], sq[2]), sq[0], sq[1], sq[2], s);
+        knn_query<5>(m->view, m->coarse, finite3(p[0], p[1], p[2]), p[0], p[1], p[2], r, s.pos);
         for (int j = 0; j < 5; ++j) idx_out[i * 5 + j] = r.pos[j] != kNoPos ? knn_index_of(m->view.pts, r.pos[j]) : -1;
     }
 }
@@ -158,7 +181,7 @@ static void hb_impl(const HsMap* m, const IcpParams& p, const float* src, size_t
     for (size_t i = 0; i < n; ++i) {
         const float* s = point_ptr(src, i, stride);
         int nn[5];
-        const unsigned char g = icp_point<METHOD>(m->view, p, T, s[0], s[1], s[2], acc, nn, seeds ? seeds + i * k : nullptr);
+        const unsigned char g = icp_point<METHOD>(m->view, m->coarse, p, T, s[0], s[1], s[2], acc, nn, seeds ? seeds + i * k : nullptr);
         if (gate) gate[i] = g;
         if (nn_out) for (int j = 0; j < k; ++j) nn_out[i * k + j] = nn[j];
     }

@@ -43,7 +43,7 @@ def _cloud(a):
 
 
 STAT_NAMES = ["fast_queries", "fast_candidates", "corner_queries", "corner_lists", "corner_candidates", "ring_queries",
-              "ring_block_probes", "ring_candidates"]
+              "ring_block_probes", "ring_candidates", "linear_scans"]
 
 
 def knn_stats():

@@ -41,6 +41,26 @@ def test_knn_bit_exact(scene, icp_pair):
             assert np.array_equal(gpu.Knn(queries, k), ref.knn(queries, k))
 
 
+def test_knn_far_and_out_of_bounds_both_job_sizes(scene, icp_pair):
+    """Far-off queries (above the roofs, outside the map, hundreds of metres away) through BOTH stage-2 forms: a small
+    probe runs the warp-per-query kernel (what a single scan uses), a large one the thread-per-query kernel (batches)."""
+    gpu, ref = icp_pair
+    rng = np.random.default_rng(21)
+    above = rng.uniform(-45, 45, (1500, 3)).astype(np.float32)
+    above[:, 2] = rng.uniform(25, 45, 1500)
+    outside = rng.uniform(-120, 120, (1500, 3)).astype(np.float32)
+    way_out = rng.uniform(-900, 900, (24, 3)).astype(np.float32)
+    near = scene.map[rng.integers(0, len(scene.map), 3000), :3] + rng.normal(0, 0.5, (3000, 3)).astype(np.float32)
+    small = np.concatenate([above, outside, way_out, near]).astype(np.float32)
+    for k in (1, 5):
+        assert np.array_equal(gpu.Knn(small, k), ref.knn(small, k))
+    # > 2 * SMs * 256 queries switch the probe (like a batch job) to the thread-per-query kernel
+    more = scene.map[rng.integers(0, len(scene.map), 80_000), :3] + rng.normal(0, 0.4, (80_000, 3)).astype(np.float32)
+    big = np.concatenate([small, more.astype(np.float32)])
+    for k in (1, 5):
+        assert np.array_equal(gpu.Knn(big, k), ref.knn(big, k))
+
+
 def test_knn_matches_brute_force(scene, icp_pair):
     gpu, _ = icp_pair
     rng = np.random.default_rng(11)

@@ -45,6 +45,26 @@ def test_knn_bit_exact_near_and_far(scene, ref_icp, cell, lists):
             assert np.array_equal(m.knn(q, k), ref_icp.knn(q, k))
 
 
+def test_far_queries_use_the_coarse_level_not_a_linear_scan(scene, ref_icp):
+    """Queries metres away from every map point (relocalisation hypotheses, points outside the map) must be answered
+    by the coarse level's shells; the linear scan is only the last resort hundreds of cells away."""
+    rng = np.random.default_rng(5)
+    q = rng.uniform(-45, 45, (600, 3)).astype(np.float32)
+    q[:, 2] = rng.uniform(25, 40, 600)  # 5 - 20 m above the highest roof
+    for hint, expect_linear in ((0, False), (0xFFFFFFFE, True)):
+        m = HS.HsMap(scene.map, capacity_hint=hint)
+        HS.knn_stats()
+        got = m.knn(q, 5)
+        st = HS.knn_stats()
+        assert np.array_equal(got, ref_icp.knn(q, 5))
+        assert (st["linear_scans"] > 0) == expect_linear, st
+    out = np.array([[500, 0, 0], [-300, 700, 10]], np.float32)  # beyond the coarse reach: linear scan, still exact
+    m = HS.HsMap(scene.map)
+    HS.knn_stats()
+    assert np.array_equal(m.knn(out, 5), ref_icp.knn(out, 5))
+    assert HS.knn_stats()["linear_scans"] == 2
+
+
 def test_knn_seeded_search_is_still_exact(scene, hs_map, ref_icp):
     """Seeds (the previous Gauss-Newton iteration's neighbours) only tighten the threshold: near, far and useless
     seeds must all give the exact result, without duplicates."""
