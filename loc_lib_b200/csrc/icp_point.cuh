@@ -33,17 +33,29 @@ LR_HD unsigned char icp_p2plane_post(const VoxelMapView& map, const IcpParams& p
                                      double qz, double wx, double wy, double wz, const KnnResult<5>& nn, Acc& acc) {
     // a map with fewer than 5 leaves makes KdTree::GetClosestPoint refuse (kdtree.cpp:149): no neighbours
     if (knn_count(nn) < 5) return kGateSkipped;
-    double P[5][3];
+    PlaneAcc pa;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const float4 p = map.pts[nn.pos[j]];
-        P[j][0] = p.x; P[j][1] = p.y; P[j][2] = p.z;
+        if (j == 0) pa.start(p.x, p.y, p.z); else pa.add(p.x, p.y, p.z);
     }
     double n[4];
-    if (!plane_fit5_fast(P, n)) plane_svd5(P, n);  // math::FitPlane (:179)
+    if (!plane_fit5_solve(pa, n)) {  // collinear / coincident neighbours only: the SVD of math::FitPlane (:179)
+        // only arrays local to this branch have their address taken (the SVD is not inlined)
+        double Pd[5][3], ns[4];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float4 p = map.pts[nn.pos[j]];
+            Pd[j][0] = p.x; Pd[j][1] = p.y; Pd[j][2] = p.z;
+        }
+        plane_svd5(Pd, ns);
+        n[0] = ns[0]; n[1] = ns[1]; n[2] = ns[2]; n[3] = ns[3];
+    }
+    // FitPlane's own check (math_utils.h:128-133); the neighbours are read again (L1) rather than kept in registers
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-        const double err = n[0] * P[j][0] + n[1] * P[j][1] + n[2] * P[j][2] + n[3];
+        const float4 p = map.pts[nn.pos[j]];
+        const double err = n[0] * static_cast<double>(p.x) + n[1] * static_cast<double>(p.y) + n[2] * static_cast<double>(p.z) + n[3];
         if (err * err > prm.plane_fit_eps) return kGateFitFailed;
     }
     acc.inc_eff();  // quirk Q4: counted before the distance gate (:184)

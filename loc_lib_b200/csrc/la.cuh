@@ -8,6 +8,44 @@
 
 namespace locreg {
 
+// fp64 reciprocal / square roots for the per-point plane fit.  The IEEE-rounded device routines carry slow-path
+// subroutine calls (denormals, exceptional inputs) that force every live register across them to be spilled; here
+// the inputs are ordinary positive numbers, so the hardware seed (rcp/rsqrt.approx.ftz.f64, ~20 bits) plus two
+// Newton steps - accurate to an ulp or two, no calls - is used instead.  Host builds use the plain operators.
+LR_HD double lr_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+LR_HD double lr_rsqrt(double x) {  // x > 0
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = fma(r, fma(-hx * r, r, 0.5), r);
+    r = fma(r, fma(-hx * r, r, 0.5), r);
+    return r;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+LR_HD double lr_sqrt(double x) {  // x >= 0
+#if defined(__CUDA_ARCH__)
+    if (!(x > 0.0)) return 0.0;
+    const double r = lr_rsqrt(x);
+    const double s = x * r;
+    return fma(fma(-s, s, x), 0.5 * r, s);  // one correction step on the root itself
+#else
+    return sqrt(x);
+#endif
+}
+
 // Pose as the kernels use it: unit quaternion + translation (Sophus::SE3d::data() order) and the
 // rotation matrix (row-major) derived from it once per Gauss-Newton iteration.
 struct Pose {
@@ -151,16 +189,30 @@ static LR_HD_NOINLINE void plane_svd5(const double (&P)[5][3], double (&coef)[4]
 // n is then the null vector of K = S - lambda I - lambda kappa c c^T, read off the adjugate column with the
 // largest diagonal.  Returns false - the caller then runs plane_svd5 - only when the points are collinear /
 // coincident (adj(K) vanishes) or a NaN got in.
-LR_HD bool plane_fit5_fast(const double (&P)[5][3], double (&coef)[4]) {
-    const double cx = (P[0][0] + P[1][0] + P[2][0] + P[3][0] + P[4][0]) * 0.2;
-    const double cy = (P[0][1] + P[1][1] + P[2][1] + P[3][1] + P[4][1]) * 0.2;
-    const double cz = (P[0][2] + P[1][2] + P[2][2] + P[3][2] + P[4][2]) * 0.2;
-    double sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const double x = P[i][0] - cx, y = P[i][1] - cy, z = P[i][2] - cz;
-        sxx += x * x; sxy += x * y; sxz += x * z; syy += y * y; syz += y * z; szz += z * z;
+// The five points enter one at a time (PlaneAcc::add) and are not kept: sums are taken relative to the first point
+// (differences of float32 coordinates are exact in double and of the size of the neighbourhood), so one pass gives
+// the centroid and S = sum d d^T - 5 dbar dbar^T without the cancellation a sum of raw p p^T would suffer, and the
+// kernel does not have to hold 15 coordinates in registers across the solve.
+struct PlaneAcc {
+    double ox, oy, oz;                       // first point
+    double sx, sy, sz;                       // sum of d = p - o
+    double sxx, sxy, sxz, syy, syz, szz;     // sum of d d^T
+    LR_HD void start(double x, double y, double z) {
+        ox = x; oy = y; oz = z;
+        sx = sy = sz = 0.0;
+        sxx = sxy = sxz = syy = syz = szz = 0.0;
     }
+    LR_HD void add(double x, double y, double z) {
+        const double dx = x - ox, dy = y - oy, dz = z - oz;
+        sx += dx; sy += dy; sz += dz;
+        sxx += dx * dx; sxy += dx * dy; sxz += dx * dz; syy += dy * dy; syz += dy * dz; szz += dz * dz;
+    }
+};
+LR_HD bool plane_fit5_solve(const PlaneAcc& a, double (&coef)[4]) {
+    const double mx = a.sx * 0.2, my = a.sy * 0.2, mz = a.sz * 0.2;  // centroid relative to the first point
+    const double cx = a.ox + mx, cy = a.oy + my, cz = a.oz + mz;
+    const double sxx = a.sxx - a.sx * mx, sxy = a.sxy - a.sx * my, sxz = a.sxz - a.sx * mz;
+    const double syy = a.syy - a.sy * my, syz = a.syz - a.sy * mz, szz = a.szz - a.sz * mz;
     // adj(S), the invariants of S and the three quadratic forms in c
     const double axx = syy * szz - syz * syz, axy = sxz * syz - sxy * szz, axz = sxy * syz - sxz * syy;
     const double ayy = sxx * szz - sxz * sxz, ayz = sxy * sxz - sxx * syz, azz = sxx * syy - sxy * sxy;
@@ -186,8 +238,8 @@ LR_HD bool plane_fit5_fast(const double (&P)[5][3], double (&coef)[4]) {
         // Laguerre step for degree n = 4, written without dividing by f:  -n f / (f' - sqrt((n-1)^2 f'^2 - n (n-1) f f''))
         double disc = 9.0 * f1 * f1 - 12.0 * f * f2;
         if (disc < 0.0) disc = 0.0;
-        const double den = f1 - sqrt(disc);  // f' < 0 left of the smallest root: the larger magnitude denominator
-        const double step = -4.0 * f / den;
+        const double den = f1 - lr_sqrt(disc);  // f' < 0 left of the smallest root: the larger magnitude denominator
+        const double step = -4.0 * f * lr_rcp(den);
         if (!(step > 0.0)) break;
         const double nl = lam + step;
         if (!(nl > lam)) break;              // step below one ulp
@@ -195,7 +247,7 @@ LR_HD bool plane_fit5_fast(const double (&P)[5][3], double (&coef)[4]) {
         lam = nl;
         if (done) break;
     }
-    const double kappa = 5.0 / (5.0 - lam);
+    const double kappa = 5.0 * lr_rcp(5.0 - lam);
     const double mk = lam * kappa;
     const double kxx = sxx - lam - mk * cx * cx, kxy = sxy - mk * cx * cy, kxz = sxz - mk * cx * cz;
     const double kyy = syy - lam - mk * cy * cy, kyz = syz - mk * cy * cz, kzz = szz - lam - mk * cz * cz;
@@ -210,9 +262,18 @@ LR_HD bool plane_fit5_fast(const double (&P)[5][3], double (&coef)[4]) {
     // one-dimensional (collinear / coincident points, or a double smallest singular value)
     if (!(nn > 1e-30 * (t * t * t * t + 1e-300))) return false;
     const double d = -kappa * (cx * nx + cy * ny + cz * nz);
-    const double inv = 1.0 / sqrt(nn + d * d);
+    const double inv = lr_rsqrt(nn + d * d);
     coef[0] = nx * inv; coef[1] = ny * inv; coef[2] = nz * inv; coef[3] = d * inv;
     return true;
+}
+
+// array flavour (tests/hostsim, readability)
+LR_HD bool plane_fit5_fast(const double (&P)[5][3], double (&coef)[4]) {
+    PlaneAcc a;
+    a.start(P[0][0], P[0][1], P[0][2]);
+#pragma unroll
+    for (int i = 1; i < 5; ++i) a.add(P[i][0], P[i][1], P[i][2]);
+    return plane_fit5_solve(a, coef);
 }
 
 // Gauss-Newton step: solves H dx = b by partial-pivot LU (what Matrix6d::inverse()/determinant()

@@ -165,24 +165,42 @@ LR_HD unsigned char ndt_point(const NdtMapView& map, const NdtParams& prm, const
     const int kx = ndt_trunc(LR_DMUL(wx, map.inv_voxel)), ky = ndt_trunc(LR_DMUL(wy, map.inv_voxel)),
               kz = ndt_trunc(LR_DMUL(wz, map.inv_voxel));
     acc.inc_eff();  // effective_num++ per point, unconditionally (:432)
-    int hits = 0;
-    double ex = 0, ey = 0, ez = 0, ss = 0;
-    for (int o = 0; o < prm.n_nearby; ++o) {
+    // The probes of the (up to seven) voxels are independent: issue all first-slot loads, then all voxel loads, before
+    // anything is consumed - the kernel is bound by the latency of these dependent accesses, not by arithmetic.
+    int vid[7];
+    unsigned int slot_h[7];
+    unsigned long long keys[7];
+    NdtSlot first[7];
+#pragma unroll
+    for (int o = 0; o < 7; ++o) {
         int dx, dy, dz;
         ndt_offset(o, dx, dy, dz);
         const int cx = kx + dx, cy = ky + dy, cz = kz + dz;
-        if (!ndt_key_ok(cx, cy, cz)) continue;
-        const unsigned long long key = ndt_pack(cx, cy, cz);
-        unsigned int h = ndt_hash(key) & map.slot_mask;
-        int vid = -1;
-        while (true) {
-            const NdtSlot s = map.slots[h];
-            if (s.key == key) { vid = s.vid; break; }
+        const bool use = o < prm.n_nearby && ndt_key_ok(cx, cy, cz);
+        keys[o] = use ? ndt_pack(cx, cy, cz) : kNdtEmpty;
+        slot_h[o] = ndt_hash(keys[o]) & map.slot_mask;
+        if (use) first[o] = map.slots[slot_h[o]];
+        else { first[o].key = kNdtEmpty; first[o].vid = -1; first[o].count = 0; }
+    }
+#pragma unroll
+    for (int o = 0; o < 7; ++o) {
+        vid[o] = -1;
+        if (keys[o] == kNdtEmpty) continue;
+        NdtSlot s = first[o];
+        unsigned int h = slot_h[o];
+        while (true) {  // linear probing past the first slot is rare (load factor <= 0.5)
+            if (s.key == keys[o]) { vid[o] = s.vid; break; }
             if (s.key == kNdtEmpty) break;
             h = (h + 1) & map.slot_mask;
+            s = map.slots[h];
         }
-        if (vid < 0) continue;
-        const NdtVoxel& v = map.voxels[vid];
+    }
+    int hits = 0;
+    double ex = 0, ey = 0, ez = 0, ss = 0;
+#pragma unroll
+    for (int o = 0; o < 7; ++o) {  // the reference's order (GenerateNearbyGrids)
+        if (vid[o] < 0) continue;
+        const NdtVoxel& v = map.voxels[vid[o]];
         const double e0 = wx - v.mu[0], e1 = wy - v.mu[1], e2 = wz - v.mu[2];
         const double i0 = v.info[0] * e0 + v.info[1] * e1 + v.info[2] * e2;
         const double i1 = v.info[3] * e0 + v.info[4] * e1 + v.info[5] * e2;

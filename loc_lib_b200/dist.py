@@ -2,7 +2,7 @@
 
 * batch offline mapping: scans are block-partitioned over ranks, every rank holds a replica of the map, and there
   is NO collective on the data path (only the gather of the S x 7 poses at the end);
-* global relocalisation: pose hypotheses are block-partitioned, each rank finds its local best, and ONE
+* global relocalisation: pose hypotheses are dealt out round-robin, each rank finds its local best, and ONE
   min-all-reduce of a packed (float32 score bits << 32 | global hypothesis index) key picks the winner
   (lowest index wins ties), followed by a broadcast of the winning pose from its owner.
 torch is used for process-group plumbing only; all registration work goes through liblocreg.so.
@@ -58,17 +58,20 @@ def broadcast_pose(pose7, owner_rank, device=None):
 
 def relocalise_sharded(reg, scan, hypotheses, rank=0, world=1, device=None):
     """Global relocalisation over `world` ranks; `reg` is this rank's IcpRegistration with the map set.
-    Returns (best_pose, best_global_index, best_score), identical on every rank."""
+
+    Hypotheses are dealt out round-robin (rank r registers hypotheses r, r + world, ...): neighbouring hypotheses of
+    the search grid cost about the same (the far-off ones several times more than those near the truth), so a
+    strided split balances the ranks where a block split would not.  Returns (best_pose, best_global_index,
+    best_score), identical on every rank."""
     hyp = np.ascontiguousarray(hypotheses, np.float64).reshape(-1, 7)
-    lo, hi = shard_range(len(hyp), rank, world)
-    if hi > lo:
-        pose, idx, score, _, _ = reg.Relocalise(scan, hyp[lo:hi])
-        gidx = lo + idx
+    mine = hyp[rank::world]
+    if len(mine):
+        pose, idx, score, _, _ = reg.Relocalise(scan, mine)
+        gidx = rank + idx * world
     else:
         pose, gidx, score = np.zeros(7), 0xFFFFFFFF, np.inf
     best_score, best_idx = allreduce_argmin(score, gidx, device)
-    owner = next(r for r in range(world) if shard_range(len(hyp), r, world)[0] <= best_idx < shard_range(len(hyp), r, world)[1]) \
-        if best_idx != 0xFFFFFFFF else 0
+    owner = best_idx % world if best_idx != 0xFFFFFFFF else 0
     best_pose = broadcast_pose(pose if owner == rank else np.zeros(7), owner, device)
     return best_pose, int(best_idx), float(best_score)
 
