@@ -33,12 +33,12 @@ extern "C" {
 #define LOCREG_E_ARG (-1)         /* invalid argument */
 #define LOCREG_E_CUDA (-2)        /* CUDA runtime error (no device, out of memory, launch failure) */
 #define LOCREG_E_STATE (-3)       /* call order (e.g. align before set_target) */
-#define LOCREG_E_UNSUPPORTED (-4) /* method not built yet (P2LINE, PCLICP, incremental NDT) */
+#define LOCREG_E_UNSUPPORTED (-4) /* not built (PCLICP, incremental NDT; relocalisation with NDT) */
 
 /* IcpMethod (icp_registration.hpp:15-20) and NdtMethod::DIRECT_NDT (ndt_registration.hpp:21-26) in one enum */
 enum locreg_method {
     LOCREG_ICP_P2P = 0,
-    LOCREG_ICP_P2LINE = 1, /* not built yet: LOCREG_E_UNSUPPORTED */
+    LOCREG_ICP_P2LINE = 1,
     LOCREG_ICP_P2PLANE = 2,
     LOCREG_NDT_DIRECT = 3
 };
@@ -57,7 +57,7 @@ typedef struct locreg_options {
     double eps;                   /* eps_ = 1e-2 */
     double max_nn_distance;       /* max_nn_distance_ = 1.0 (compared with a squared distance, quirk Q6) */
     double max_plane_distance;    /* max_plane_distance_ = 0.1 */
-    double max_line_distance;     /* max_line_distance_ = 0.5 (P2LINE, unused) */
+    double max_line_distance;     /* max_line_distance_ = 0.5 (P2LINE: residual gate and FitLine's eps) */
     double voxel_size;            /* NdtOptions::voxel_size_ = 1.0 (inv_voxel_size_ is always recomputed, ndt_registration.cpp:25) */
     double res_outlier_th;        /* res_outlier_th_ = 20.0 */
     int32_t min_pts_in_voxel;     /* min_pts_in_voxel_ = 3 */
@@ -111,7 +111,9 @@ int locreg_compute_hb(locreg_handle* h, const float* src, size_t n, size_t strid
                       double* H36, double* B6, locreg_result* res);
 
 /* Parity probe for SearchPointInterface::FindNearstPoints (search_point_interface.h:9-24; kdtree.cpp:272-283):
- * exact k-NN (k = 1 or 5) under the total order (float32 dis2, index); idx is nq*k, -1 padded. ICP handles only. */
+ * exact k-NN (k = 1 or 5) under the total order (float32 dis2, index); idx is nq*k, -1 padded. ICP handles only.
+ * Runs the production search: stage 1 per thread, then the queued rest per warp (small probes, like one scan) or per
+ * thread (large probes, like a batch). */
 int locreg_knn(locreg_handle* h, const float* queries, size_t nq, size_t stride_bytes, int32_t k, int32_t* idx);
 
 /* Parity probe: per-point gate code (0 skipped, 1 plane fit failed, 2 residual gated out, 3 inlier; NDT: number

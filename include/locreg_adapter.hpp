@@ -109,7 +109,7 @@ class CudaIcpRegistration : public CudaRegistrationBase {
         int method = LOCREG_ICP_P2P;
         switch (o.method_) {
             case IcpMethod::P2P: method = LOCREG_ICP_P2P; break;
-            case IcpMethod::P2LINE: method = LOCREG_ICP_P2LINE; break;  // locreg_create reports LOCREG_E_UNSUPPORTED
+            case IcpMethod::P2LINE: method = LOCREG_ICP_P2LINE; break;
             case IcpMethod::P2PLANE: method = LOCREG_ICP_P2PLANE; break;
             case IcpMethod::PCLICP: throw std::runtime_error("PCLICP is a passthrough to pcl::IterativeClosestPoint: keep IcpRegistration for it");
         }

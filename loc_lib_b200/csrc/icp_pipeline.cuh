@@ -385,12 +385,12 @@ struct RowSink {
 #define LR_POST_MIN_BLOCKS 4
 #endif
 template <int METHOD>
-__global__ void __launch_bounds__(kTile, METHOD == kIcpP2P ? 2 : LR_POST_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTile, METHOD == kIcpP2Plane ? LR_POST_MIN_BLOCKS : 2)
 k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
            const unsigned int* __restrict__ nn_pos, double* __restrict__ partials, unsigned char* gate, int* nn_idx,
            unsigned int* ring_count) {
     constexpr int K = METHOD == kIcpP2P ? 1 : 5;
-    constexpr int ROWS = METHOD == kIcpP2P ? 3 : 1;  // residual rows per inlier
+    constexpr int ROWS = METHOD == kIcpP2Plane ? 1 : 3;  // residual rows per inlier (P2P, P2Line: 3-vector residuals)
     __shared__ Pose T;
     __shared__ double rows[kTile * ROWS * kRowStride];
     __shared__ double wsum[kTile / 32][32];
@@ -420,6 +420,7 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
             double wx, wy, wz;
             pose_apply(T, qx, qy, qz, wx, wy, wz);
             if (METHOD == kIcpP2P) g = icp_p2p_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<1>&>(nn), sink);
+            else if (METHOD == kIcpP2Line) g = icp_p2line_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<5>&>(nn), sink);
             else g = icp_p2plane_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<5>&>(nn), sink);
         }
         if (gate) gate[tc.out_base + p] = g;

@@ -13,6 +13,7 @@ enum Method : int { kIcpP2P = 0, kIcpP2Line = 1, kIcpP2Plane = 2, kNdtDirect = 3
 struct IcpParams {
     double max_nn_distance;     // IcpOptions::max_nn_distance_ (compared against a SQUARED distance, quirk Q6)
     double max_plane_distance;  // IcpOptions::max_plane_distance_
+    double max_line_distance;   // IcpOptions::max_line_distance_ (also FitLine's eps, icp_registration.cpp:123)
     double plane_fit_eps;       // math::FitPlane's eps (1e-2, math_utils.h:113)
     double eps;                 // IcpOptions::eps_
     int max_iteration;
@@ -71,6 +72,60 @@ LR_HD unsigned char icp_p2plane_post(const VoxelMapView& map, const IcpParams& p
     return kGateInlier;
 }
 
+// Point-to-line after the neighbour search (icp_registration.cpp:115-147): line fit through the five neighbours
+// (math::FitLine, math_utils.h:138-163), e = d x (qs - p0), J = [ -hat(d) R hat(q) , hat(d) ] (3 x 6).
+template <class Acc>
+LR_HD unsigned char icp_p2line_post(const VoxelMapView& map, const IcpParams& prm, const Pose& T, double qx, double qy,
+                                    double qz, double wx, double wy, double wz, const KnnResult<5>& nn, Acc& acc) {
+    if (knn_count(nn) != 5) return kGateSkipped;  // nn.size() == 5 (:115)
+    // origin = mean of the five points, summed in neighbour order like std::accumulate (math_utils.h:144)
+    double ox = 0, oy = 0, oz = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float4 p = map.pts[nn.pos[j]];
+        ox += p.x; oy += p.y; oz += p.z;
+    }
+    ox /= 5; oy /= 5; oz /= 5;
+    double S[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float4 p = map.pts[nn.pos[j]];
+        const double x = p.x - ox, y = p.y - oy, z = p.z - oz;
+        S[0] += x * x; S[1] += x * y; S[2] += x * z; S[3] += y * y; S[4] += y * z; S[5] += z * z;
+    }
+    double d[3];
+    line_dir_from_scatter(S, d);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {  // FitLine's eps check: |d x (p - origin)|^2 > eps  (math_utils.h:155-159)
+        const float4 p = map.pts[nn.pos[j]];
+        const double x = p.x - ox, y = p.y - oy, z = p.z - oz;
+        const double cx = d[1] * z - d[2] * y, cy = d[2] * x - d[0] * z, cz = d[0] * y - d[1] * x;
+        if (cx * cx + cy * cy + cz * cz > prm.max_line_distance) return kGateFitFailed;
+    }
+    acc.inc_eff();
+    const double vx = wx - ox, vy = wy - oy, vz = wz - oz;
+    const double e[3] = {d[1] * vz - d[2] * vy, d[2] * vx - d[0] * vz, d[0] * vy - d[1] * vx};
+    if (sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) > prm.max_line_distance) return kGateResidual;
+    acc.inc_inl();
+    // M = R hat(q) (3 x 3); row r of -hat(d) M is -(d x M_col) taken per column, i.e. row r of hat(d) applied to M
+    const double hq[3][3] = {{0.0, -qz, qy}, {qz, 0.0, -qx}, {-qy, qx, 0.0}};
+    double M[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) M[r][c] = T.R[r * 3 + 0] * hq[0][c] + T.R[r * 3 + 1] * hq[1][c] + T.R[r * 3 + 2] * hq[2][c];
+    const double hd[3][3] = {{0.0, -d[2], d[1]}, {d[2], 0.0, -d[0]}, {-d[1], d[0], 0.0}};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double J[6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) J[c] = -(hd[r][0] * M[0][c] + hd[r][1] * M[1][c] + hd[r][2] * M[2][c]);
+        J[3] = hd[r][0]; J[4] = hd[r][1]; J[5] = hd[r][2];
+        acc.row(J, e[r]);
+    }
+    return kGateInlier;
+}
+
 // Point-to-point after the neighbour search (icp_registration.cpp:71-91).  J = [ R hat(q) / 16 , -I ]  (quirk Q6).
 template <class Acc>
 LR_HD unsigned char icp_p2p_post(const VoxelMapView& map, const IcpParams& prm, const Pose& T, double qx, double qy,
@@ -121,6 +176,26 @@ LR_HD unsigned char icp_point_p2plane(const VoxelMapView& map, const CoarseLevel
     return icp_p2plane_post(map, prm, T, qx, qy, qz, wx, wy, wz, nn, acc);
 }
 
+LR_HD unsigned char icp_point_p2line(const VoxelMapView& map, const CoarseLevels& coarse, const IcpParams& prm, const Pose& T,
+                                     float sx, float sy, float sz, Accum& acc, int* nn_out, unsigned int* nn_pos = nullptr) {
+    if (nn_out) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) nn_out[j] = -1;
+    }
+    if (!finite3(sx, sy, sz)) return kGateSkipped;  // deviation D1
+    const double qx = sx, qy = sy, qz = sz;
+    double wx, wy, wz;
+    pose_apply(T, qx, qy, qz, wx, wy, wz);
+    KnnResult<5> nn;
+    knn_query<5>(map, coarse, true, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, nn_pos);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        if (nn_out) nn_out[j] = nn.pos[j] != kNoPos ? knn_index_of(map.pts, nn.pos[j]) : -1;
+        if (nn_pos) nn_pos[j] = nn.pos[j];
+    }
+    return icp_p2line_post(map, prm, T, qx, qy, qz, wx, wy, wz, nn, acc);
+}
+
 LR_HD unsigned char icp_point_p2p(const VoxelMapView& map, const CoarseLevels& coarse, const IcpParams& prm, const Pose& T, float sx, float sy,
                                   float sz, Accum& acc, int* nn_out, unsigned int* nn_pos = nullptr) {
     if (nn_out) nn_out[0] = -1;
@@ -139,6 +214,7 @@ template <int METHOD>
 LR_HD unsigned char icp_point(const VoxelMapView& map, const CoarseLevels& coarse, const IcpParams& prm, const Pose& T, float sx, float sy, float sz,
                               Accum& acc, int* nn_out, unsigned int* nn_pos = nullptr) {
     if (METHOD == kIcpP2P) return icp_point_p2p(map, coarse, prm, T, sx, sy, sz, acc, nn_out, nn_pos);
+    if (METHOD == kIcpP2Line) return icp_point_p2line(map, coarse, prm, T, sx, sy, sz, acc, nn_out, nn_pos);
     return icp_point_p2plane(map, coarse, prm, T, sx, sy, sz, acc, nn_out, nn_pos);
 }
 

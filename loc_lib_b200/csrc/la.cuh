@@ -276,6 +276,18 @@ LR_HD bool plane_fit5_fast(const double (&P)[5][3], double (&coef)[4]) {
     return plane_fit5_solve(a, coef);
 }
 
+// math::FitLine's direction (math_utils.h:138-152): right singular vector of the LARGEST singular value of
+// Y = p - mean (5 x 3), i.e. the principal eigenvector of S = Y^T Y.  Unlike the plane fit's smallest singular vector
+// this one is well conditioned in S (the squared spectrum only widens the gap that separates it), so it is taken
+// from the symmetric 3x3 eigen-decomposition.  Its sign is arbitrary and cancels in J^T J and J^T e.
+// S = {xx, xy, xz, yy, yz, zz} of the centred points.
+LR_HD void sym3_eigen(const double* S, double* lam, double* Q);
+LR_HD void line_dir_from_scatter(const double (&S)[6], double (&dir)[3]) {
+    double lam[3], Q[9];
+    sym3_eigen(S, lam, Q);  // eigenvalues sorted descending, eigenvectors in the columns of Q
+    dir[0] = Q[0]; dir[1] = Q[3]; dir[2] = Q[6];
+}
+
 // Gauss-Newton step: solves H dx = b by partial-pivot LU (what Matrix6d::inverse()/determinant()
 // do in Eigen for size 6).  Hu = packed upper triangle.  Returns false if det(H) == 0
 // (icp_registration.cpp:100,210; ndt_registration.cpp:435).

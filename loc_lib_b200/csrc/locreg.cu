@@ -88,6 +88,7 @@ struct locreg_handle {
         IcpParams p;
         p.max_nn_distance = opt.max_nn_distance;
         p.max_plane_distance = opt.max_plane_distance;
+        p.max_line_distance = opt.max_line_distance;
         p.plane_fit_eps = 1e-2;
         p.eps = opt.eps;
         p.max_iteration = opt.max_iteration;
@@ -318,6 +319,7 @@ void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
 #define ICP_DISPATCH(h, CALL)                                              \
     switch ((h)->opt.method) {                                             \
         case LOCREG_ICP_P2P: { constexpr int M = kIcpP2P; CALL; } break;   \
+        case LOCREG_ICP_P2LINE: { constexpr int M = kIcpP2Line; CALL; } break; \
         case LOCREG_ICP_P2PLANE: { constexpr int M = kIcpP2Plane; CALL; } break; \
         default: throw std::invalid_argument("unsupported method");        \
     }
@@ -411,8 +413,8 @@ int locreg_default_options(locreg_options* o, int32_t method) {
 
 int locreg_create(const locreg_options* opt, int32_t device, locreg_handle** out) {
     if (!opt || !out) { g_last_error = "null argument"; return LOCREG_E_ARG; }
-    if (opt->method == LOCREG_ICP_P2LINE) { g_last_error = "P2LINE is not built yet"; return LOCREG_E_UNSUPPORTED; }
-    if (opt->method != LOCREG_ICP_P2P && opt->method != LOCREG_ICP_P2PLANE && opt->method != LOCREG_NDT_DIRECT) {
+    if (opt->method != LOCREG_ICP_P2P && opt->method != LOCREG_ICP_P2LINE && opt->method != LOCREG_ICP_P2PLANE &&
+        opt->method != LOCREG_NDT_DIRECT) {
         g_last_error = "unknown method";
         return LOCREG_E_ARG;
     }
@@ -634,7 +636,7 @@ int locreg_debug_points(locreg_handle* h, const float* src, size_t n, size_t str
         if (n == 0) return LOCREG_OK;
         const float4* src4 = stage_cloud(h, src, n, stride, false);
         init_state(h, pose);
-        const int k = h->opt.method == LOCREG_ICP_P2P ? 1 : (h->opt.method == LOCREG_ICP_P2PLANE ? 5 : 0);
+        const int k = h->opt.method == LOCREG_ICP_P2P ? 1 : (h->opt.method == LOCREG_NDT_DIRECT ? 0 : 5);
         h->d_gate.reserve(n);
         int* d_nn = nullptr;
         if (nn && k) { h->d_nn.reserve(n * k * sizeof(int)); d_nn = h->d_nn.as<int>(); }

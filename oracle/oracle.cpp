@@ -282,6 +282,34 @@ static bool FitPlane(const std::vector<Vec3>& data, double coeffs[4], double eps
 
 static inline bool finite3(const float* p) { return std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]); }
 
+// math::FitLine (math_utils.h:138-163): origin = mean of the points, dir = right singular vector of the LARGEST
+// singular value of Y = data - origin (JacobiSVD(Y, ComputeFullV), V.col(0)); fails if any point is farther from
+// the line than sqrt(eps) (|dir x (p - origin)|^2 > eps).
+static bool FitLine(const std::vector<Vec3>& data, Vec3& origin, Vec3& dir, double eps) {
+    if (data.size() < 2) return false;
+    const int n = static_cast<int>(data.size());
+    Vec3 sum{0, 0, 0};
+    for (const Vec3& d : data) sum = sum + d;  // std::accumulate, in order
+    origin = Vec3{sum.x / n, sum.y / n, sum.z / n};
+    std::vector<double> Y(static_cast<size_t>(n) * 3);
+    for (int i = 0; i < n; ++i) {
+        Y[i * 3 + 0] = data[i].x - origin.x; Y[i * 3 + 1] = data[i].y - origin.y; Y[i * 3 + 2] = data[i].z - origin.z;
+    }
+    std::vector<double> sigma, V;
+    if (n >= 3) {
+        jacobi_svd(Y, n, 3, sigma, V);
+    } else {
+        Y.resize(9, 0.0);
+        jacobi_svd(Y, 3, 3, sigma, V);
+    }
+    dir = Vec3{V[0 * 3 + 0], V[1 * 3 + 0], V[2 * 3 + 0]};  // singular values are sorted descending
+    for (const Vec3& d : data) {
+        const Vec3 c = cross(dir, d - origin);
+        if (dot(c, c) > eps) return false;
+    }
+    return true;
+}
+
 // pcl::transformPointCloud(in, out, Matrix4f) as PCL 1.8 writes it: per coordinate
 // m(r,0)*x + m(r,1)*y + m(r,2)*z + m(r,3), float32, left to right; non-finite points pass through.
 static void transform_cloud(const float* src, size_t n, size_t stride, const SE3& T, float* out) {
@@ -420,13 +448,62 @@ struct Icp {
         return true;
     }
 
+    // CaculateMatrixHAndBP2Line (icp_registration.cpp:105-159)
+    bool HB_P2Line(const float* src, size_t n, size_t stride, const SE3& pose, Mat6& H, Vec6& B, oracle_result& res,
+                   uint8_t* gate, int32_t* nn_out) const {
+        size_t effective_num = 0, inliers = 0;
+        double total_res = 0;
+        const Mat3 R = pose.matrix();
+        std::vector<int> nn;
+        for (size_t i = 0; i < n; ++i) {
+            const float* sp = pt_at(src, i, stride);
+            if (gate) gate[i] = 0;
+            if (nn_out) for (int j = 0; j < 5; ++j) nn_out[i * 5 + j] = -1;
+            if (opt.skip_nonfinite && !finite3(sp)) continue;  // deviation D1
+            const Vec3 q{sp[0], sp[1], sp[2]};
+            const Vec3 qs = pose * q;
+            FindNearstPoints(Vec3f{static_cast<float>(qs.x), static_cast<float>(qs.y), static_cast<float>(qs.z)}, 5,
+                             opt.nn_mode, nn);
+            if (nn_out) for (size_t j = 0; j < nn.size() && j < 5; ++j) nn_out[i * 5 + j] = nn[j];
+            if (nn.size() != 5) continue;  // (:115)
+            std::vector<Vec3> nn_eigen;
+            for (int j = 0; j < 5; ++j) nn_eigen.emplace_back(target[nn[j]].x, target[nn[j]].y, target[nn[j]].z);
+            Vec3 d, p0;
+            if (!FitLine(nn_eigen, p0, d, opt.max_line_distance)) { if (gate) gate[i] = 1; continue; }  // (:123)
+            effective_num++;
+            const Vec3 e = cross(d, qs - p0);  // SO3::hat(d) * (qs - p0) (:130)
+            if (std::sqrt(dot(e, e)) > opt.max_line_distance) { if (gate) gate[i] = 2; continue; }
+            if (gate) gate[i] = 3;
+            // J = [ -hat(d) R hat(q) , hat(d) ]  (:139-140)
+            const Mat3 hd = hat(d);
+            const Mat3 A = mul(mul(hd, R), hat(q));
+            double J[3][6];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) { J[r][c] = -A.m[r][c]; J[r][3 + c] = hd.m[r][c]; }
+            const double ev[3] = {e.x, e.y, e.z};
+            for (int a = 0; a < 6; ++a) {
+                for (int b = 0; b < 6; ++b) H(a, b) += J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b];
+                B.v[a] += -(J[0][a] * ev[0] + J[1][a] * ev[1] + J[2][a] * ev[2]);
+            }
+            inliers++;
+            total_res += dot(e, e);
+        }
+        res.n_effective = static_cast<int64_t>(effective_num);
+        res.n_inlier = static_cast<int64_t>(inliers);
+        res.sum_sq_res = total_res;
+        if (effective_num < static_cast<size_t>(opt.min_effective_pts)) return false;
+        if (lu6(H, nullptr) == 0) return false;
+        return true;
+    }
+
     bool HB(const float* src, size_t n, size_t stride, const SE3& pose, Mat6& H, Vec6& B, oracle_result& res,
             uint8_t* gate, int32_t* nn_out) const {
         if (opt.method == ORACLE_ICP_P2P) return HB_P2P(src, n, stride, pose, H, B, res, gate, nn_out);
+        if (opt.method == ORACLE_ICP_P2LINE) return HB_P2Line(src, n, stride, pose, H, B, res, gate, nn_out);
         return HB_P2Plane(src, n, stride, pose, H, B, res, gate, nn_out);
     }
 
-    // AlignP2P (icp_registration.cpp:267-303) / AlignP2Plane (:345-381)
+    // AlignP2P (icp_registration.cpp:267-303) / AlignP2Line (:305-343) / AlignP2Plane (:345-381)
     void Align(const float* src, size_t n, size_t stride, const SE3& init, SE3& result, oracle_result& res,
                double* trace) const {
         SE3 pose = init;
@@ -677,7 +754,6 @@ int oracle_icp_knn(oracle_icp* h, const float* q, size_t nq, size_t stride, int 
 }
 int oracle_icp_compute_hb(oracle_icp* h, const float* src, size_t n, size_t stride, const double* pose7, double* H36,
                           double* B6, oracle_result* res, uint8_t* gate, int32_t* nn_out) {
-    if (h->impl.opt.method == ORACLE_ICP_P2LINE) return -2;
     Mat6 H;
     Vec6 B;
     oracle_result r{};
@@ -690,7 +766,6 @@ int oracle_icp_compute_hb(oracle_icp* h, const float* src, size_t n, size_t stri
 }
 int oracle_icp_align(oracle_icp* h, const float* src, size_t n, size_t stride, const double* pose_in, double* pose_out,
                      float* out_xyz, oracle_result* res, double* trace) {
-    if (h->impl.opt.method == ORACLE_ICP_P2LINE) return -2;
     SE3 result;
     oracle_result r{};
     h->impl.Align(src, n, stride, SE3::from7(pose_in), result, r, trace);
@@ -703,7 +778,6 @@ int oracle_icp_align(oracle_icp* h, const float* src, size_t n, size_t stride, c
 // single-threaded loop (the reference has no parallel path); the kd-tree is shared read-only.
 int oracle_icp_align_batch(oracle_icp* h, const float* srcs, const int64_t* offsets, size_t stride, const double* poses_in,
                            size_t S, double* poses_out, oracle_result* results, int threads) {
-    if (h->impl.opt.method == ORACLE_ICP_P2LINE) return -2;
     if (threads <= 0) threads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
     threads = static_cast<int>(std::min<size_t>(threads, std::max<size_t>(S, 1)));
     auto work = [&](int tid) {

@@ -164,9 +164,10 @@ void hs_knn_seeded(const HsMap* m, const float* q, const float* seed_q, size_t n
 
 }  // extern "C"
 
-// prm: max_nn_distance, max_plane_distance, plane_fit_eps, eps, max_iteration, min_effective_pts
+// prm: max_nn_distance, max_plane_distance, plane_fit_eps, eps, max_iteration, min_effective_pts, max_line_distance
 static IcpParams make_params(const double* prm) {
     IcpParams p;
+    p.max_line_distance = prm[6];
     p.max_nn_distance = prm[0]; p.max_plane_distance = prm[1]; p.plane_fit_eps = prm[2]; p.eps = prm[3];
     p.max_iteration = static_cast<int>(prm[4]); p.min_effective_pts = static_cast<int>(prm[5]);
     return p;
@@ -202,6 +203,7 @@ void hs_icp_hb(const HsMap* m, int method, const double* prm, const float* src, 
     pose_load(T, pose7);
     Accum acc;
     if (method == kIcpP2P) hb_impl<kIcpP2P>(m, p, src, n, stride, T, acc, gate, nn_out);
+    else if (method == kIcpP2Line) hb_impl<kIcpP2Line>(m, p, src, n, stride, T, acc, gate, nn_out);
     else hb_impl<kIcpP2Plane>(m, p, src, n, stride, T, acc, gate, nn_out);
     unpack(acc, H36, B6);
     counts[0] = acc.n_eff; counts[1] = acc.n_inl;
@@ -223,6 +225,9 @@ int hs_icp_align(const HsMap* m, int method, const double* prm, const float* src
         if (method == kIcpP2P) {
             hb_impl<kIcpP2P>(m, p, src, n, stride, T, acc, nullptr, nullptr, seeds.data());
             r = icp_gn_update<kIcpP2P>(acc.v, acc.n_eff, p, T);
+        } else if (method == kIcpP2Line) {
+            hb_impl<kIcpP2Line>(m, p, src, n, stride, T, acc, nullptr, nullptr, seeds.data());
+            r = icp_gn_update<kIcpP2Line>(acc.v, acc.n_eff, p, T);
         } else {
             hb_impl<kIcpP2Plane>(m, p, src, n, stride, T, acc, nullptr, nullptr, seeds.data());
             r = icp_gn_update<kIcpP2Plane>(acc.v, acc.n_eff, p, T);

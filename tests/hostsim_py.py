@@ -54,9 +54,9 @@ def knn_stats():
 
 
 def params(max_nn_distance=1.0, max_plane_distance=0.1, plane_fit_eps=1e-2, eps=1e-2, max_iteration=20,
-           min_effective_pts=10):
-    return np.array([max_nn_distance, max_plane_distance, plane_fit_eps, eps, max_iteration, min_effective_pts],
-                    np.float64)
+           min_effective_pts=10, max_line_distance=0.5):
+    return np.array([max_nn_distance, max_plane_distance, plane_fit_eps, eps, max_iteration, min_effective_pts,
+                     max_line_distance], np.float64)
 
 
 class HsMap:

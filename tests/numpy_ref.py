@@ -105,6 +105,49 @@ def p2p_hb(map_xyz, src_xyz, pose, max_nn_distance=1.0):
     return H, B, gates, n_eff
 
 
+def fit_line(pts, eps):
+    pts = np.asarray(pts, float)
+    origin = np.zeros(3)
+    for row in pts:
+        origin = origin + row
+    origin = origin / len(pts)
+    Y = pts - origin
+    _, _, vt = np.linalg.svd(Y, full_matrices=True)
+    d = vt[0]
+    ok = bool(np.all((np.cross(d, Y) ** 2).sum(1) <= eps))
+    return ok, origin, d
+
+
+def p2line_hb(map_xyz, src_xyz, pose, max_line_distance=0.5):
+    """CaculateMatrixHAndBP2Line (icp_registration.cpp:105-159) + math::FitLine (math_utils.h:138-163)."""
+    R, t = quat_R(pose), np.asarray(pose[4:], float)
+    H, B = np.zeros((6, 6)), np.zeros(6)
+    gates = np.zeros(len(src_xyz), np.uint8)
+    n_eff = n_inl = 0
+    m64 = np.asarray(map_xyz, np.float32).astype(np.float64)
+    for i, q32 in enumerate(np.asarray(src_xyz, np.float32)):
+        q = q32.astype(np.float64)
+        qs = R @ q + t
+        nn = knn_f32(map_xyz, qs.astype(np.float32)[None], 5)[0]
+        if (nn >= 0).sum() != 5:
+            continue
+        ok, p0, d = fit_line(m64[nn], max_line_distance)
+        if not ok:
+            gates[i] = 1
+            continue
+        n_eff += 1
+        e = hat(d) @ (qs - p0)
+        if np.linalg.norm(e) > max_line_distance:
+            gates[i] = 2
+            continue
+        J = np.concatenate([-hat(d) @ R @ hat(q), hat(d)], axis=1)
+        H += J.T @ J
+        B += -J.T @ e
+        gates[i] = 3
+        n_inl += 1
+    return H, B, gates, n_eff, n_inl
+
+
 def ndt_voxels(map_xyz, voxel_size=1.0, min_pts=3):
     inv = 1.0 / voxel_size
     m = np.asarray(map_xyz, np.float32).astype(np.float64)

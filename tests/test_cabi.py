@@ -93,8 +93,6 @@ def test_argument_validation_needs_no_gpu():
     o = _lib.Options()
     L.locreg_default_options(C.byref(o), _lib.ICP_P2LINE)
     h = C.c_void_p()
-    assert L.locreg_create(C.byref(o), 0, C.byref(h)) == -4  # LOCREG_E_UNSUPPORTED
-    assert b"P2LINE" in L.locreg_last_error()
     o.method = 17
     assert L.locreg_create(C.byref(o), 0, C.byref(h)) == -1
     assert L.locreg_create(None, 0, C.byref(h)) == -1

@@ -68,14 +68,14 @@ def test_knn_matches_brute_force(scene, icp_pair):
     assert np.array_equal(gpu.Knn(q.astype(np.float32), 5), O.bfnn(scene.map, q.astype(np.float32), 5))
 
 
-@pytest.mark.parametrize("method", ["P2PLANE", "P2P"])
+@pytest.mark.parametrize("method", ["P2PLANE", "P2P", "P2LINE"])
 def test_hb_and_gates(scene, method):
     import loc_lib_b200 as L
     m = getattr(L.IcpMethod, method)
     # tight thresholds so that every gate has points on both sides
-    gpu = L.IcpRegistration(L.IcpOptions(method_=m, max_plane_distance_=0.004, max_nn_distance_=0.08))
+    gpu = L.IcpRegistration(L.IcpOptions(method_=m, max_plane_distance_=0.004, max_nn_distance_=0.08, max_line_distance_=0.05))
     gpu.SetInputTarget(scene.map)
-    ref = O.OracleIcp(method=getattr(O, method), max_plane_distance=0.004, max_nn_distance=0.08,
+    ref = O.OracleIcp(method=getattr(O, method), max_plane_distance=0.004, max_nn_distance=0.08, max_line_distance=0.05,
                       nn_mode=O.NN_EXACT_TIEBREAK, skip_nonfinite=1)
     ref.set_target(scene.map)
     for pose in (scene.init[0], scene.gt[0]):
@@ -93,7 +93,7 @@ def test_hb_and_gates(scene, method):
 
 
 @pytest.mark.parametrize("loop_mode", [0, 1])
-@pytest.mark.parametrize("method", ["P2PLANE", "P2P"])
+@pytest.mark.parametrize("method", ["P2PLANE", "P2P", "P2LINE"])
 def test_scan_match_pose(scene, method, loop_mode):
     import loc_lib_b200 as L
     gpu = L.IcpRegistration(L.IcpOptions(method_=getattr(L.IcpMethod, method), max_iteration_=10, eps_=0.0,

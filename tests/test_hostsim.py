@@ -159,13 +159,13 @@ def test_small_linear_algebra():
     assert HS.lib().hs_gn_solve6(Z.ctypes.data, np.zeros(6).ctypes.data, np.zeros(6).ctypes.data) == 0  # det == 0
 
 
-@pytest.mark.parametrize("method", ["P2PLANE", "P2P"])
+@pytest.mark.parametrize("method", ["P2PLANE", "P2P", "P2LINE"])
 def test_hb_gates_match_oracle(scene, hs_map, method):
     mid = getattr(O, method)
-    ref = O.OracleIcp(method=mid, max_plane_distance=0.004, max_nn_distance=0.08, nn_mode=O.NN_EXACT_TIEBREAK,
-                      skip_nonfinite=1)
+    ref = O.OracleIcp(method=mid, max_plane_distance=0.004, max_nn_distance=0.08, max_line_distance=0.05,
+                      nn_mode=O.NN_EXACT_TIEBREAK, skip_nonfinite=1)
     ref.set_target(scene.map)
-    prm = HS.params(max_nn_distance=0.08, max_plane_distance=0.004)
+    prm = HS.params(max_nn_distance=0.08, max_plane_distance=0.004, max_line_distance=0.05)
     scan = scene.scan.copy()
     scan[::97, 0] = np.nan
     for pose in (scene.init[0], scene.gt[0]):
@@ -178,7 +178,7 @@ def test_hb_gates_match_oracle(scene, hs_map, method):
         assert abs(res["sum_sq_res"] - rres["sum_sq_res"]) <= 1e-9 * rres["sum_sq_res"]
 
 
-@pytest.mark.parametrize("method", ["P2PLANE", "P2P"])
+@pytest.mark.parametrize("method", ["P2PLANE", "P2P", "P2LINE"])
 def test_align_matches_oracle(scene, hs_map, method):
     mid = getattr(O, method)
     for eps, iters in ((0.0, 6), (1e-2, 20)):

@@ -232,6 +232,32 @@ def test_p2p_hb_vs_numpy(small):
     assert rel(H, rH) < 1e-12 and rel(B, rB) < 1e-12
 
 
+def test_p2line_hb_vs_numpy(small):
+    m, scan, gt, init = small
+    ref = O.OracleIcp(method=O.P2LINE, nn_mode=O.NN_EXACT_TIEBREAK, max_line_distance=0.3)
+    ref.set_target(m)
+    ok, H, B, res, gate, nn = ref.compute_hb(scan, init)
+    rH, rB, rgate, n_eff, n_inl = NR.p2line_hb(m[:, :3], scan[:, :3], init, max_line_distance=0.3)
+    assert np.array_equal(gate, rgate) and len(set(gate.tolist())) >= 2, np.bincount(gate)
+    assert res["n_effective"] == n_eff and res["n_inlier"] == n_inl
+    assert rel(H, rH) < 1e-10 and rel(B, rB) < 1e-10
+
+
+def test_p2line_align_on_an_edge_scene():
+    """Points on three mutually orthogonal lines (a wire-frame corner): P2Line pulls a shifted copy back."""
+    t = np.arange(0, 8, 0.05)
+    z = np.zeros_like(t)
+    m = np.concatenate([np.c_[t, z, z], np.c_[z, t, z], np.c_[z, z, t]]).astype(np.float32)
+    m = np.c_[m, np.zeros(len(m))].astype(np.float32)
+    src = m[3::4].copy()
+    src[:, :3] -= np.float32([0.02, -0.015, 0.01])
+    ref = O.OracleIcp(method=O.P2LINE, nn_mode=O.NN_LITERAL_EXACT, max_iteration=5, eps=0.0)
+    ref.set_target(m)
+    pose, _, res, _ = ref.align(src, IDENT, want_cloud=False)
+    assert res["updates"] == 5
+    assert np.abs(pose[4:] - [0.02, -0.015, 0.01]).max() < 2e-3
+
+
 @pytest.mark.parametrize("nearby6", [0, 1])
 def test_ndt_vs_numpy(small, nearby6):
     m, scan, gt, init = small
