@@ -150,6 +150,29 @@ struct RingQueue {
     uint2* entries;        // (scratch row of the point, scan index)
 };
 
+// Block-aggregated queue append without a block barrier (see k_icp_nn).  pending/done/staged live in shared memory
+// and must have been zeroed before a __syncthreads() that every thread of the block has passed.
+__device__ __forceinline__ void tile_queue_append(bool mine, unsigned int row, unsigned int scan, unsigned int* pending,
+                                                  unsigned int* done, unsigned int* staged, const RingQueue& queue) {
+    const unsigned int lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    if (mine) staged[atomicAdd(pending, 1u)] = row;
+    __syncwarp();
+    unsigned int last = 0;
+    if (lane == 0) {
+        __threadfence_block();  // this warp's staged rows before its arrival
+        last = atomicAdd(done, 1u) == n_warps - 1 ? 1u : 0u;
+        __threadfence_block();  // the other warps' staged rows after having seen their arrivals
+    }
+    if (!__shfl_sync(0xffffffffu, last, 0)) return;
+    const unsigned int n = *reinterpret_cast<volatile unsigned int*>(pending);
+    if (n == 0u) return;
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(queue.count, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (unsigned int i = lane; i < n; i += 32)
+        queue.entries[base + i] = make_uint2(reinterpret_cast<volatile unsigned int*>(staged)[i], scan);
+}
+
 template <int K>
 __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView map, BatchView bv,
                                                                     const AlignState* __restrict__ states, int ignore_stop,
@@ -161,8 +184,11 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
     if (st->stop && !ignore_stop) return;
     if (threadIdx.x == 0) pose_load(T, st->pose);
     __syncthreads();
-    __shared__ unsigned int blk_pending, blk_base;
-    if (threadIdx.x == 0) blk_pending = 0u;
+    // Unfinished queries are staged in shared memory; the LAST warp of the tile to finish appends them to the global
+    // queue with one atomic.  No barrier after the search: a warp retires as soon as its own queries are done.
+    __shared__ unsigned int blk_pending, blk_done;
+    __shared__ unsigned int staged[kTile];
+    if (threadIdx.x == 0) { blk_pending = 0u; blk_done = 0u; }
     const bool in_tile = threadIdx.x < tc.count;
     const unsigned int p = tc.first + (in_tile ? threadIdx.x : 0u);
     const float4 sp = bv.src[tc.src_base + p];
@@ -188,14 +214,7 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
 #pragma unroll
         for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
     }
-    // one global atomic per tile: unfinished queries take a slot in shared memory first
-    unsigned int slot = 0;
-    if (!done) slot = atomicAdd(&blk_pending, 1u);
-    __syncthreads();
-    if (blk_pending == 0u) return;
-    if (threadIdx.x == 0) blk_base = atomicAdd(queue.count, blk_pending);
-    __syncthreads();
-    if (!done) queue.entries[blk_base + slot] = make_uint2(static_cast<unsigned int>(row), tc.scan);
+    tile_queue_append(!done, static_cast<unsigned int>(row), tc.scan, &blk_pending, &blk_done, staged, queue);
 }
 
 // Stage 2 of LARGE jobs (batches, relocalisation), one queued query per thread (knn_query_finish: corner lists, fine
@@ -205,8 +224,9 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
 template <int K>
 __global__ void __launch_bounds__(128) k_icp_nn_finish(VoxelMapView map, CoarseLevels coarse, BatchView bv,
                                                        const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
-                                                       RingQueue queue) {
+                                                       RingQueue queue, unsigned int min_count) {
     const unsigned int n = *queue.count;
+    if (n < min_count) return;  // short queues are k_icp_nn_rings' (a warp per query: latency, not throughput)
     for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const uint2 q = queue.entries[e];
         const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
@@ -239,8 +259,9 @@ __global__ void __launch_bounds__(128) k_icp_nn_finish(VoxelMapView map, CoarseL
 template <int K>
 __global__ void __launch_bounds__(128) k_icp_nn_rings(VoxelMapView map, CoarseLevels coarse, BatchView bv,
                                                       const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
-                                                      RingQueue queue) {
+                                                      RingQueue queue, unsigned int max_count) {
     const unsigned int n = *queue.count;
+    if (n >= max_count) return;  // long queues are k_icp_nn_finish's
     const unsigned int lane = threadIdx.x & 31;
     const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int e = warp; e < n; e += n_warps) {
@@ -279,8 +300,9 @@ __global__ void __launch_bounds__(128) k_icp_nn_rings(VoxelMapView map, CoarseLe
 template <int K>
 __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_knn_stage1(VoxelMapView map, const float4* __restrict__ q, unsigned int nq,
                                                                         unsigned int* __restrict__ nn_pos, RingQueue queue) {
-    __shared__ unsigned int blk_pending, blk_base;
-    if (threadIdx.x == 0) blk_pending = 0u;
+    __shared__ unsigned int blk_pending, blk_done;
+    __shared__ unsigned int staged[kTile];
+    if (threadIdx.x == 0) { blk_pending = 0u; blk_done = 0u; }
     __syncthreads();
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool done = true;
@@ -292,13 +314,7 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_knn_stage1(VoxelMap
 #pragma unroll
         for (int j = 0; j < K; ++j) nn_pos[static_cast<size_t>(i) * K + j] = nn.pos[j];
     }
-    unsigned int slot = 0;
-    if (!done) slot = atomicAdd(&blk_pending, 1u);
-    __syncthreads();
-    if (blk_pending == 0u) return;
-    if (threadIdx.x == 0) blk_base = atomicAdd(queue.count, blk_pending);
-    __syncthreads();
-    if (!done) queue.entries[blk_base + slot] = make_uint2(i, 0u);
+    tile_queue_append(!done, i, 0u, &blk_pending, &blk_done, staged, queue);
 }
 template <int K>
 __global__ void __launch_bounds__(128) k_knn_rings(VoxelMapView map, CoarseLevels coarse, const float4* __restrict__ q,

@@ -2,6 +2,7 @@
 // kernel launches.  No CPU fallback: without a CUDA device every computing entry point fails.
 #include "../../include/locreg.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -62,6 +63,8 @@ struct locreg_handle {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;        // host->device copies of later chunks overlap the compute of earlier ones
+    std::vector<cudaEvent_t> chunk_events;     // locreg_align_batch
     DeviceVoxelMap icp_map;     // level 0: cells of knn_cell_size, neighbourhood lists
     DeviceVoxelMap icp_coarse[kCoarseLevels];  // cells 4x, 16x larger, block tables only (far queries)
     CoarseLevels coarse_views() const {
@@ -284,12 +287,19 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     LR_LAUNCH(k_icp_nn<K>, job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, nn_mode, h->d_nnpos.as<unsigned int>(), queue);
     prof_mark(h, 0, false);
     prof_mark(h, 3, true);
-    if (small) {
+    // The queue length is only known on the device, so both forms are launched and each one looks at the count:
+    // below kWarpFinishMax entries the warp-per-query kernel takes the queue (what matters is the latency of the
+    // slowest query), from there on the thread-per-query kernel (throughput).  A small job never gets there.
+    constexpr unsigned int kWarpFinishMax = 16384;
+    {
         const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 3) / 4, static_cast<size_t>(h->num_sms) * 8));
-        LR_LAUNCH(k_icp_nn_rings<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue);
-    } else {
+        LR_LAUNCH(k_icp_nn_rings<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue,
+                  small ? 0xFFFFFFFFu : kWarpFinishMax);
+    }
+    if (!small) {
         const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * 8));
-        LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue);
+        LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue,
+                  kWarpFinishMax);
     }
     prof_mark(h, 3, false);
     prof_mark(h, 1, true);
@@ -452,6 +462,8 @@ int locreg_destroy(locreg_handle* h) {
     cudaStreamSynchronize(h->stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaStream_t s = h->own_stream;
     delete h;
     if (s) cudaStreamDestroy(s);
@@ -693,30 +705,88 @@ int locreg_align_batch(locreg_handle* h, const float* srcs, const int64_t* offse
     return guarded(h, [&]() {
         if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
         const size_t base = static_cast<size_t>(offsets[0]);
-        const float4* src4 = stage_cloud(h, first, total - base, stride, false);
+        const size_t n_pts = total - base;
+        // Large ICP batches from pinned (or device-visible) memory are cut into chunks of whole scans: the copy of
+        // chunk c + 1 runs on a second stream while chunk c is being registered (scans are independent).
+        const bool pipelined = !is_ndt(h) && S >= 16 && n_pts >= (1u << 20) && is_pinned_or_device(first);
+        const float4* src4 = pipelined ? nullptr : stage_cloud(h, first, n_pts, stride, false);
         h->d_offsets.reserve((S + 1) * sizeof(long long));
         h->d_poses_in.reserve(S * 7 * sizeof(double));
         h->d_poses_out.reserve(S * 7 * sizeof(double));
         h->d_results.reserve(S * sizeof(DevResult));
-        h->h_in.reserve(0);
         std::vector<long long> rel(S + 1);
         for (size_t s = 0; s <= S; ++s) rel[s] = offsets[s] - static_cast<long long>(base);
         LR_CUDA(cudaMemcpyAsync(h->d_offsets.p, rel.data(), (S + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
         LR_CUDA(cudaMemcpyAsync(h->d_poses_in.p, poses_in, S * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         LR_CUDA(cudaMemcpyAsync(h->d_poses_out.p, poses_out, S * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         LR_CUDA(cudaStreamSynchronize(h->stream));  // rel[] is pageable
-        h->begin_timing();
         const unsigned int Su = static_cast<unsigned int>(S);
-        if (is_ndt(h)) {
-            ndt_run_batch(h, src4, h->d_offsets.as<long long>(), h->d_poses_in.as<double>(), h->d_poses_out.as<double>(),
-                          h->d_results.as<DevResult>(), Su);
+        if (pipelined) {
+            static const size_t kChunks = getenv("LOCREG_CHUNKS") ? std::max(1, atoi(getenv("LOCREG_CHUNKS"))) : 2;  // 2 measured best on B200 (LOCREG_CHUNKS overrides)
+            if (!h->copy_stream) LR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            while (h->chunk_events.size() < kChunks) {
+                cudaEvent_t e;
+                LR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->chunk_events.push_back(e);
+            }
+            h->d_raw.reserve(n_pts * stride);
+            if (stride != 16) h->d_src4.reserve(n_pts * sizeof(float4));
+            h->d_states.reserve(S * sizeof(AlignState));
+            // chunk boundaries: whole scans, about equal point counts
+            std::vector<size_t> cut{0};
+            for (size_t c = 1; c < kChunks; ++c) {
+                const long long want = static_cast<long long>(n_pts * c / kChunks);
+                size_t s = std::lower_bound(rel.begin(), rel.end(), want) - rel.begin();
+                s = std::min(std::max(s, cut.back()), S);
+                cut.push_back(s);
+            }
+            cut.push_back(S);
+            for (size_t c = 0; c < kChunks; ++c) {
+                const size_t p0 = static_cast<size_t>(rel[cut[c]]), p1 = static_cast<size_t>(rel[cut[c + 1]]);
+                if (p1 > p0)
+                    LR_CUDA(cudaMemcpyAsync(h->d_raw.as<unsigned char>() + p0 * stride, reinterpret_cast<const char*>(first) + p0 * stride,
+                                            (p1 - p0) * stride, cudaMemcpyHostToDevice, h->copy_stream));
+                LR_CUDA(cudaEventRecord(h->chunk_events[c], h->copy_stream));
+            }
+            h->begin_timing();
+            long long launches = 0;
+            for (size_t c = 0; c < kChunks; ++c) {
+                const size_t s0 = cut[c], s1 = cut[c + 1];
+                LR_CUDA(cudaStreamWaitEvent(h->stream, h->chunk_events[c], 0));
+                if (s1 == s0) continue;
+                const size_t p0 = static_cast<size_t>(rel[s0]), p1 = static_cast<size_t>(rel[s1]);
+                const unsigned int Sc = static_cast<unsigned int>(s1 - s0);
+                if (stride != 16 && p1 > p0) {
+                    const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((p1 - p0 + 255) / 256, 4096));
+                    LR_LAUNCH(k_pack_float4, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>() + p0 * stride, p1 - p0, stride,
+                              h->d_src4.as<float4>() + p0);
+                }
+                const float4* all4 = stride == 16 ? h->d_raw.as<float4>() : h->d_src4.as<float4>();
+                // offsets stay absolute (into the whole batch); only the scan range of the job moves
+                IcpJob job = icp_batch_job(h, all4, h->d_offsets.as<long long>() + s0, Sc, p1 - p0);
+                job.states = h->d_states.as<AlignState>() + s0;
+                job.n_scratch_points = n_pts;  // scratch rows are indexed by absolute point number
+                LR_LAUNCH(k_states_init, (Sc + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>() + s0 * 7, Sc, h->opt.max_iteration, job.states);
+                ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
+                LR_LAUNCH(k_states_export, (Sc + 255) / 256, 256, 0, h->stream, job.states, Sc, h->d_poses_out.as<double>() + s0 * 7,
+                          h->d_results.as<DevResult>() + s0);
+                launches = g_launch_count;
+            }
+            (void)launches;
+            h->end_timing();
         } else {
-            const IcpJob job = icp_batch_job(h, src4, h->d_offsets.as<long long>(), Su, total - base);
-            LR_LAUNCH(k_states_init, (Su + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>(), Su, h->opt.max_iteration, job.states);
-            ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
-            LR_LAUNCH(k_states_export, (Su + 255) / 256, 256, 0, h->stream, job.states, Su, h->d_poses_out.as<double>(), h->d_results.as<DevResult>());
+            h->begin_timing();
+            if (is_ndt(h)) {
+                ndt_run_batch(h, src4, h->d_offsets.as<long long>(), h->d_poses_in.as<double>(), h->d_poses_out.as<double>(),
+                              h->d_results.as<DevResult>(), Su);
+            } else {
+                const IcpJob job = icp_batch_job(h, src4, h->d_offsets.as<long long>(), Su, n_pts);
+                LR_LAUNCH(k_states_init, (Su + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>(), Su, h->opt.max_iteration, job.states);
+                ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
+                LR_LAUNCH(k_states_export, (Su + 255) / 256, 256, 0, h->stream, job.states, Su, h->d_poses_out.as<double>(), h->d_results.as<DevResult>());
+            }
+            h->end_timing();
         }
-        h->end_timing();
         LR_CUDA(cudaMemcpy(poses_out, h->d_poses_out.p, S * 7 * sizeof(double), cudaMemcpyDeviceToHost));
         if (results) LR_CUDA(cudaMemcpy(results, h->d_results.p, S * sizeof(DevResult), cudaMemcpyDeviceToHost));
         return LOCREG_OK;

@@ -308,6 +308,46 @@ LR_HD void knn_find_list(const VoxelMapView& m, int cx, int cy, int cz, unsigned
         h = (h + 1) & m.nbr_mask;
     }
 }
+// Starts the k-best set from K seed positions.  The common case - all K present, as after any complete search - loads
+// the K points with independent accesses and orders them with a sorting network (9 compare-exchanges for K = 5)
+// instead of K dependent insertions; seeds are distinct points, so no membership test is needed.
+template <int K>
+LR_HD void knn_seed(const VoxelMapView& m, float qx, float qy, float qz, const unsigned int* seeds, KnnResult<K>& res) {
+    bool all = true;
+#pragma unroll
+    for (int j = 0; j < K; ++j) all = all && seeds[j] < m.n_pts;
+    if (!all) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const unsigned int sp = seeds[j];
+            if (sp < m.n_pts) {
+                const float4 p = m.pts[sp];
+                knn_offer(m.pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), sp);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const float4 p = m.pts[seeds[j]];
+        res.d2[j] = dis2_f32(qx, qy, qz, p.x, p.y, p.z);
+        res.pos[j] = seeds[j];
+    }
+    if (K == 5) {
+        constexpr int net[9][2] = {{0, 1}, {3, 4}, {2, 4}, {2, 3}, {1, 4}, {0, 3}, {0, 2}, {1, 3}, {1, 2}};
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            const int a = net[c][0], b = net[c][1];
+            if (knn_less(m.pts, res.d2[b], res.pos[b], res.d2[a], res.pos[a])) {
+                const float td = res.d2[a]; res.d2[a] = res.d2[b]; res.d2[b] = td;
+                const unsigned int tp = res.pos[a]; res.pos[a] = res.pos[b]; res.pos[b] = tp;
+            }
+        }
+    }
+    // a NaN distance (a seed that is a masked duplicate cannot occur: results never contain one) would break the order;
+    // K == 1 needs no ordering
+}
+
 // Stage 1 of the exact k-NN of a FINITE query against a NON-EMPTY map: seeds, then the one-list fast path.
 //   seeds    optional K canonical positions (kNoPos = none) that start the k-best set - the neighbours found in the
 //            previous Gauss-Newton iteration.  Any real, distinct points are valid seeds: they only tighten the
@@ -319,16 +359,7 @@ LR_HD bool knn_query_fast(const VoxelMapView& m, float qx, float qy, float qz, K
                           const unsigned int* seeds, bool two_pass) {
     knn_init(res);
     const KnnCellFrame c = knn_frame(m, qx, qy, qz);
-    if (seeds != nullptr) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const unsigned int sp = seeds[j];
-            if (sp < m.n_pts) {
-                const float4 p = m.pts[sp];
-                knn_offer(m.pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), sp);
-            }
-        }
-    }
+    if (seeds != nullptr) knn_seed<K>(m, qx, qy, qz, seeds, res);
     if (!knn_uses_list(m, c)) return false;
     // the whole box [f-1, f+1]^3 is one contiguous list
     unsigned int beg = 0, cnt = 0;

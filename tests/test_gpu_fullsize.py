@@ -66,6 +66,25 @@ def test_fullsize_batch_equals_single_and_recovers_ground_truth(full):
     assert np.median([pose_delta(p, g)[1] for p, g in zip(poses, full.gt)]) < 0.006
 
 
+def test_fullsize_pipelined_batch_equals_plain_batch(full):
+    """locreg_align_batch from PINNED host memory overlaps chunked copies with compute; same poses, bit for bit."""
+    import torch
+    reps = 2  # 48 scans, 1.3 M points: above the pipelining threshold
+    clouds = np.concatenate(full.scans * reps)
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in full.scans * reps])]).astype(np.int64)
+    init = np.concatenate([full.init] * reps)
+    plain, res_plain = full.reg.ScanMatchBatch(clouds, offsets, init)
+    pinned = torch.from_numpy(clouds).pin_memory().numpy()
+    piped, res_piped = full.reg.ScanMatchBatch(pinned, offsets, init)
+    assert np.array_equal(plain, piped) and res_plain == res_piped
+    assert np.array_equal(plain[:full.S], plain[full.S:])
+    # 32-byte stride (pcl::PointXYZI layout) through the same path
+    wide = torch.zeros((len(clouds), 8), dtype=torch.float32).pin_memory().numpy()
+    wide[:, :3] = clouds[:, :3]
+    piped32, _ = full.reg.ScanMatchBatch(wide, offsets, init)
+    assert np.array_equal(plain, piped32)
+
+
 def test_fullsize_idempotent_at_convergence_and_oracle_spot_check(full):
     _, _, pose = full.reg.ScanMatch(full.scans[3], full.init[3], want_cloud=False)
     _, _, again = full.reg.ScanMatch(full.scans[3], pose, want_cloud=False)
