@@ -283,8 +283,10 @@ def run_ours(args):
         achieved = BYTES_PER_POINT_ITER * n_pts / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None
         pipe_ms = (nn_ms + fit_ms + ring_ms + solve_ms) / max(nn_launches, 1)  # one whole Gauss-Newton iteration
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_icp_nn_dram_bytes_per_launch")
+        try:  # dram__bytes_read + dram__bytes_write of one k_icp_nn launch of THIS command (tools/profile_remote.sh, ncu --set full)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            cands = [v for k, v in tj.items() if "k_icp_nn<" in k or k.split("@")[0].endswith("k_icp_nn")]
+            traffic = max(cands) if cands else None
         except (OSError, ValueError):
             pass
         value = total_pts * args.steps / (dev_ms * 1e-3)
