@@ -33,14 +33,15 @@ extern "C" {
 #define LOCREG_E_ARG (-1)         /* invalid argument */
 #define LOCREG_E_CUDA (-2)        /* CUDA runtime error (no device, out of memory, launch failure) */
 #define LOCREG_E_STATE (-3)       /* call order (e.g. align before set_target) */
-#define LOCREG_E_UNSUPPORTED (-4) /* not built (PCLICP, incremental NDT; relocalisation with NDT) */
+#define LOCREG_E_UNSUPPORTED (-4) /* not built (PCLICP; relocalisation with NDT) */
 
-/* IcpMethod (icp_registration.hpp:15-20) and NdtMethod::DIRECT_NDT (ndt_registration.hpp:21-26) in one enum */
+/* IcpMethod (icp_registration.hpp:15-20) and NdtMethod (ndt_registration.hpp:21-26) in one enum */
 enum locreg_method {
     LOCREG_ICP_P2P = 0,
     LOCREG_ICP_P2LINE = 1,
     LOCREG_ICP_P2PLANE = 2,
-    LOCREG_NDT_DIRECT = 3
+    LOCREG_NDT_DIRECT = 3,
+    LOCREG_NDT_INCREMENTAL = 4 /* NdtMethod::INCREMENTAL_NDT: locreg_set_target ADDS a cloud to an LRU voxel cache */
 };
 /* NdtNearbyType (ndt_registration.hpp:16-20) */
 enum locreg_nearby { LOCREG_NEARBY_CENTER = 0, LOCREG_NEARBY6 = 1 };
@@ -66,6 +67,8 @@ typedef struct locreg_options {
     double knn_cell_size;         /* voxel-hash cell edge in metres for ICP k-NN; <= 0: 0.5 */
     int32_t loop_mode;            /* enum locreg_loop (NDT; ICP always runs the three-kernel pipeline) */
     int32_t knn_lists;            /* 1 (default): build per-cell 3x3x3 neighbourhood lists (27x point storage) for the fast k-NN path */
+    int32_t ndt_capacity;         /* NdtOptions::capacity_ = 100000: voxels the incremental NDT cache holds (LRU) */
+    int32_t pad_;
 } locreg_options;
 
 /* Outcome of one registration (what the reference logs or silently drops). */
@@ -93,7 +96,8 @@ int locreg_destroy(locreg_handle* h);
 int locreg_set_stream(locreg_handle* h, void* cuda_stream);
 
 /* MatchingInterface::SetInputTarget (matching_interface.h:18; icp_registration.cpp:9-29, ndt_registration.cpp:65-148).
- * Deep-copies the cloud to the device and builds the voxel-hash map (ICP) or the NDT voxel grid. */
+ * Deep-copies the cloud to the device and builds the voxel-hash map (ICP) or the NDT voxel grid.  Incremental NDT:
+ * the cloud is ADDED to the LRU voxel cache (SetIncNdtTargetCloud, ndt_registration.cpp:150-183). */
 int locreg_set_target(locreg_handle* h, const float* xyz, size_t n, size_t stride_bytes);
 /* Same, cloud already in device memory (stride as above). */
 int locreg_set_target_device(locreg_handle* h, const float* d_xyz, size_t n, size_t stride_bytes);

@@ -2,7 +2,7 @@
 //
 //   LocUtils::CudaIcpRegistration(IcpOptions)   replaces LocUtils::IcpRegistration
 //       (LocUtils/include/LocUtils/model/matching/3d/icp/icp_registration.hpp:41-142)
-//   LocUtils::CudaNdtRegistration(NdtOptions)   replaces LocUtils::NdtRegistration, DIRECT_NDT
+//   LocUtils::CudaNdtRegistration(NdtOptions)   replaces LocUtils::NdtRegistration (DIRECT_NDT and INCREMENTAL_NDT)
 //       (LocUtils/include/LocUtils/model/matching/3d/ndt/ndt_registration.hpp:69-135)
 //
 // Same constructors, same virtual methods, same always-true bool results (icp_registration.cpp:243,
@@ -132,9 +132,10 @@ class CudaNdtRegistration : public CudaRegistrationBase {
 
    private:
     static locreg_options Convert(const NdtOptions& o) {
-        if (o.method_ != NdtMethod::DIRECT_NDT) throw std::runtime_error("only DIRECT_NDT is built (incremental NDT: SURVEY.md 8f)");
+        if (o.method_ == NdtMethod::PCL_NDT) throw std::runtime_error("PCL_NDT is an unimplemented stub in the reference");
         locreg_options c{};
-        locreg_default_options(&c, LOCREG_NDT_DIRECT);
+        locreg_default_options(&c, o.method_ == NdtMethod::INCREMENTAL_NDT ? LOCREG_NDT_INCREMENTAL : LOCREG_NDT_DIRECT);
+        c.ndt_capacity = static_cast<int32_t>(o.capacity_);
         c.max_iteration = o.max_iteration_;
         c.voxel_size = o.voxel_size_;  // inv_voxel_size_ is recomputed, as in ndt_registration.cpp:25
         c.min_effective_pts = o.min_effective_pts_;

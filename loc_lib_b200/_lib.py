@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, os.environ.get("LOCREG_SO", "liblocreg.so"))  # LOCREG_SO: experiment builds only
 
-ICP_P2P, ICP_P2LINE, ICP_P2PLANE, NDT_DIRECT = 0, 1, 2, 3
+ICP_P2P, ICP_P2LINE, ICP_P2PLANE, NDT_DIRECT, NDT_INCREMENTAL = 0, 1, 2, 3, 4
 NEARBY_CENTER, NEARBY6 = 0, 1
 LOOP_PERSISTENT, LOOP_GRAPH = 0, 1
 
@@ -25,7 +25,8 @@ class Options(C.Structure):
                 ("use_ann", C.c_int32), ("eps", C.c_double), ("max_nn_distance", C.c_double),
                 ("max_plane_distance", C.c_double), ("max_line_distance", C.c_double), ("voxel_size", C.c_double),
                 ("res_outlier_th", C.c_double), ("min_pts_in_voxel", C.c_int32), ("nearby_type", C.c_int32),
-                ("knn_cell_size", C.c_double), ("loop_mode", C.c_int32), ("knn_lists", C.c_int32)]
+                ("knn_cell_size", C.c_double), ("loop_mode", C.c_int32), ("knn_lists", C.c_int32),
+                ("ndt_capacity", C.c_int32), ("pad_", C.c_int32)]
 
 
 class Result(C.Structure):

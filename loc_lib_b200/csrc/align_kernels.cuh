@@ -45,6 +45,26 @@ struct NdtProblem {
     __device__ __forceinline__ int max_iteration() const { return prm.max_iteration; }
 };
 
+// Incremental NDT (AlignIncNdt): same voxel table layout, information-weighted residuals.
+struct IncNdtProblem {
+    NdtMapView map;
+    NdtParams prm;
+    __device__ __forceinline__ void chunk(const Pose& T, const float4* __restrict__ src, unsigned int base,
+                                          unsigned int count, SmemAccum& acc, unsigned char* gate, int* nn_out) const {
+        (void)nn_out;
+        const unsigned int lane = threadIdx.x & 31;
+        if (lane < count) {
+            const float4 sp = src[base + lane];
+            const unsigned char h = inc_ndt_point(map, prm, T, sp.x, sp.y, sp.z, acc);
+            if (gate) gate[base + lane] = h;
+        }
+    }
+    __device__ __forceinline__ int update(const double* acc30, Pose& T) const {
+        return inc_ndt_gn_update(acc30, static_cast<unsigned int>(acc30[28]), prm, T);
+    }
+    __device__ __forceinline__ int max_iteration() const { return prm.max_iteration; }
+};
+
 // Walks the chunks of a scan assigned to this warp: chunk c covers points [c*ppw, min(n, (c+1)*ppw)).
 template <class Problem>
 __device__ __forceinline__ void eval_scan(const Problem& pb, const Pose& T, const float4* __restrict__ src, unsigned int n,

@@ -486,14 +486,14 @@ __device__ __forceinline__ void result_from_acc(DevResult& r, const double* acc3
     r.n_inlier = static_cast<long long>(acc30[29]);
     r.sum_sq_res = acc30[27];
 }
-// Applies one update outcome (0 failed, 1 updated, 2 converged, 3 abort without writing the pose) to the
-// bookkeeping; returns true if the loop must stop.
+// Applies one update outcome (0 failed, 1 updated, 2 converged, 3 abort without writing the pose, 4 abort with the
+// pose written) to the bookkeeping; returns true if the loop must stop.
 __device__ __forceinline__ bool apply_outcome(int outcome, DevResult& r) {
-    r.degenerate = (outcome == 0 || outcome == 3) ? 1 : 0;
+    r.degenerate = (outcome == 0 || outcome == 3 || outcome == 4) ? 1 : 0;
     if (outcome == 1 || outcome == 2) r.updates += 1;
     if (outcome == 2) r.converged = 1;
     if (outcome == 3) r.pose_written = 0;
-    return outcome == 2 || outcome == 3;
+    return outcome == 2 || outcome == 3 || outcome == 4;
 }
 
 // One warp per scan.  mode 1: Gauss-Newton iteration (update the pose; stop on convergence or after

@@ -11,6 +11,7 @@
 
 #include "align_kernels.cuh"
 #include "device_map.cuh"
+#include "device_inc_ndt.cuh"
 #include "device_ndt.cuh"
 
 using namespace locreg;
@@ -73,6 +74,7 @@ struct locreg_handle {
         return c;
     }
     DeviceNdtMap ndt_map;
+    DeviceIncNdtMap inc_ndt_map;  // LOCREG_NDT_INCREMENTAL
     bool has_target = false;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
         d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_states, d_ringq, d_ringc;
@@ -161,10 +163,11 @@ void init_state(locreg_handle* h, const double* pose7) {
 // ---- NDT: fused kernels -------------------------------------------------------------------------------------
 // Launch shape of a whole-GPU evaluation of one scan: as many warps as can be co-resident, each taking
 // chunks of `ppw` consecutive points (ppw = 32 when the scan is large enough to keep every warp busy).
+template <class PB>
 int ndt_persist_grid(const locreg_handle* h, unsigned int n, unsigned int* ppw) {
     int per_sm = 0;
-    LR_CUDA(cudaFuncSetAttribute(k_align_persist<NdtProblem>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAccSmemBytes)));
-    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_persist<NdtProblem>, 256, kAccSmemBytes));
+    LR_CUDA(cudaFuncSetAttribute(k_align_persist<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAccSmemBytes)));
+    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_persist<PB>, 256, kAccSmemBytes));
     if (per_sm < 1) throw std::runtime_error("persistent kernel does not fit on an SM");
     const long long max_blocks = static_cast<long long>(per_sm) * h->num_sms;
     const long long max_warps = max_blocks * 8;
@@ -174,63 +177,73 @@ int ndt_persist_grid(const locreg_handle* h, unsigned int n, unsigned int* ppw) 
     const long long chunks = (static_cast<long long>(n) + p - 1) / p;
     return static_cast<int>(std::max<long long>(1, std::min(max_blocks, (chunks + 7) / 8)));
 }
+template <class PB>
 unsigned int ndt_eval_grid(const locreg_handle* h, unsigned int n, unsigned int* ppw) {
     const long long max_warps = 16ll * h->num_sms * 8;
     long long p = (static_cast<long long>(n) + max_warps - 1) / max_warps;
     p = std::max<long long>(1, std::min<long long>(32, p));
     *ppw = static_cast<unsigned int>(p);
     const long long chunks = (static_cast<long long>(n) + p - 1) / p;
-    LR_CUDA(cudaFuncSetAttribute(k_eval<NdtProblem>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAccSmemBytes)));
+    LR_CUDA(cudaFuncSetAttribute(k_eval<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAccSmemBytes)));
     return static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((chunks + 7) / 8, 16ll * h->num_sms)));
 }
 
-// Whole AlignNdt loop on the device, result left in h->d_state.
-void ndt_run_align(locreg_handle* h, const float4* src, unsigned int n) {
-    NdtProblem pb{h->ndt_map.view(), h->ndt_params()};
+// Whole AlignNdt / AlignIncNdt loop on the device, result left in h->d_state.
+template <class PB>
+void ndt_run_align(locreg_handle* h, PB pb, const float4* src, unsigned int n) {
     AlignState* st = h->d_state.as<AlignState>();
     if (h->opt.loop_mode == LOCREG_LOOP_PERSISTENT) {
         unsigned int ppw = 0;
-        const int grid = ndt_persist_grid(h, n, &ppw);
+        const int grid = ndt_persist_grid<PB>(h, n, &ppw);
         h->d_partials.reserve(static_cast<size_t>(2) * grid * kPartialDoubles * sizeof(double));
         double* partials = h->d_partials.as<double>();
         int final_eval = 0;
         void* args[] = {&pb, &src, &n, &ppw, &st, &partials, &final_eval};
-        LR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_align_persist<NdtProblem>), dim3(grid), dim3(256), args, kAccSmemBytes, h->stream));
+        LR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_align_persist<PB>), dim3(grid), dim3(256), args, kAccSmemBytes, h->stream));
         ++g_launch_count;
     } else {
         unsigned int ppw = 0;
-        const unsigned int grid = ndt_eval_grid(h, n, &ppw);
+        const unsigned int grid = ndt_eval_grid<PB>(h, n, &ppw);
         h->d_partials.reserve(static_cast<size_t>(grid) * kPartialDoubles * sizeof(double));
         double* partials = h->d_partials.as<double>();
         for (int it = 0; it < h->opt.max_iteration; ++it) {
-            LR_LAUNCH(k_eval<NdtProblem>, grid, 256, kAccSmemBytes, h->stream, pb, src, n, ppw, st, partials, nullptr, nullptr);
-            LR_LAUNCH(k_finalize<NdtProblem>, 1, 256, 0, h->stream, pb, partials, grid, st, 1, nullptr);
+            LR_LAUNCH(k_eval<PB>, grid, 256, kAccSmemBytes, h->stream, pb, src, n, ppw, st, partials, nullptr, nullptr);
+            LR_LAUNCH(k_finalize<PB>, 1, 256, 0, h->stream, pb, partials, grid, st, 1, nullptr);
         }
     }
 }
-void ndt_run_eval(locreg_handle* h, const float4* src, unsigned int n, unsigned char* gate) {
-    NdtProblem pb{h->ndt_map.view(), h->ndt_params()};
+template <class PB>
+void ndt_run_eval(locreg_handle* h, PB pb, const float4* src, unsigned int n, unsigned char* gate) {
     AlignState* st = h->d_state.as<AlignState>();
     unsigned int ppw = 0;
-    const unsigned int grid = ndt_eval_grid(h, n, &ppw);
+    const unsigned int grid = ndt_eval_grid<PB>(h, n, &ppw);
     h->d_partials.reserve(static_cast<size_t>(grid) * kPartialDoubles * sizeof(double));
     h->d_acc.reserve(32 * sizeof(double));
-    LR_LAUNCH(k_eval<NdtProblem>, grid, 256, kAccSmemBytes, h->stream, pb, src, n, ppw, st, h->d_partials.as<double>(), gate, nullptr);
-    LR_LAUNCH(k_finalize<NdtProblem>, 1, 256, 0, h->stream, pb, h->d_partials.as<double>(), grid, st, 0, h->d_acc.as<double>());
+    LR_LAUNCH(k_eval<PB>, grid, 256, kAccSmemBytes, h->stream, pb, src, n, ppw, st, h->d_partials.as<double>(), gate, nullptr);
+    LR_LAUNCH(k_finalize<PB>, 1, 256, 0, h->stream, pb, h->d_partials.as<double>(), grid, st, 0, h->d_acc.as<double>());
 }
-void ndt_run_batch(locreg_handle* h, const float4* src, const long long* offsets, const double* poses_in, double* poses_out,
+template <class PB>
+void ndt_run_batch(locreg_handle* h, PB pb, const float4* src, const long long* offsets, const double* poses_in, double* poses_out,
                    DevResult* results, unsigned int S) {
-    NdtProblem pb{h->ndt_map.view(), h->ndt_params()};
     int per_sm = 0;
-    LR_CUDA(cudaFuncSetAttribute(k_align_batch<NdtProblem>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAccSmemBytes)));
-    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_batch<NdtProblem>, 256, kAccSmemBytes));
+    LR_CUDA(cudaFuncSetAttribute(k_align_batch<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAccSmemBytes)));
+    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_batch<PB>, 256, kAccSmemBytes));
     if (per_sm < 1) per_sm = 1;
     const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(S, static_cast<long long>(per_sm) * h->num_sms)));
     h->d_misc.reserve(64);
     LR_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 64, h->stream));
-    LR_LAUNCH(k_align_batch<NdtProblem>, grid, 256, kAccSmemBytes, h->stream, pb, src, offsets, 0u, poses_in, poses_out, results, S,
+    LR_LAUNCH(k_align_batch<PB>, grid, 256, kAccSmemBytes, h->stream, pb, src, offsets, 0u, poses_in, poses_out, results, S,
               h->d_misc.as<unsigned int>(), 0);
 }
+// direct or incremental NDT problem of this handle -> f(problem)
+#define NDT_DISPATCH(h, CALL)                                                                   \
+    if ((h)->opt.method == LOCREG_NDT_INCREMENTAL) {                                            \
+        const IncNdtProblem PB{(h)->inc_ndt_map.view(), (h)->ndt_params()};                     \
+        CALL;                                                                                   \
+    } else {                                                                                    \
+        const NdtProblem PB{(h)->ndt_map.view(), (h)->ndt_params()};                            \
+        CALL;                                                                                   \
+    }
 
 // Event pair around one launch of kernel class cls (0 search stage 1, 1 fit+reduce, 2 solve, 3 search stage 2) when
 // profiling is on.
@@ -357,7 +370,7 @@ IcpJob icp_batch_job(locreg_handle* h, const float4* src, const long long* d_off
     return job;
 }
 
-bool is_ndt(const locreg_handle* h) { return h->opt.method == LOCREG_NDT_DIRECT; }
+bool is_ndt(const locreg_handle* h) { return h->opt.method == LOCREG_NDT_DIRECT || h->opt.method == LOCREG_NDT_INCREMENTAL; }
 
 int check_cloud_args(const float* p, size_t n, size_t stride) {
     if ((n > 0 && p == nullptr) || stride < 12 || (stride % 4) != 0) {
@@ -418,17 +431,21 @@ int locreg_default_options(locreg_options* o, int32_t method) {
     o->knn_cell_size = 0.5;
     o->knn_lists = 1;
     o->loop_mode = LOCREG_LOOP_PERSISTENT;
+    o->ndt_capacity = 100000;
     return LOCREG_OK;
 }
 
 int locreg_create(const locreg_options* opt, int32_t device, locreg_handle** out) {
     if (!opt || !out) { g_last_error = "null argument"; return LOCREG_E_ARG; }
     if (opt->method != LOCREG_ICP_P2P && opt->method != LOCREG_ICP_P2LINE && opt->method != LOCREG_ICP_P2PLANE &&
-        opt->method != LOCREG_NDT_DIRECT) {
+        opt->method != LOCREG_NDT_DIRECT && opt->method != LOCREG_NDT_INCREMENTAL) {
         g_last_error = "unknown method";
         return LOCREG_E_ARG;
     }
-    if (opt->method == LOCREG_NDT_DIRECT && !(opt->voxel_size > 0)) { g_last_error = "voxel_size must be > 0"; return LOCREG_E_ARG; }
+    if ((opt->method == LOCREG_NDT_DIRECT || opt->method == LOCREG_NDT_INCREMENTAL) && !(opt->voxel_size > 0)) {
+        g_last_error = "voxel_size must be > 0";
+        return LOCREG_E_ARG;
+    }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
         cudaGetLastError();
@@ -449,6 +466,8 @@ int locreg_create(const locreg_options* opt, int32_t device, locreg_handle** out
         h->stream = h->own_stream;
         LR_CUDA(cudaEventCreate(&h->ev0));
         LR_CUDA(cudaEventCreate(&h->ev1));
+        if (h->opt.method == LOCREG_NDT_INCREMENTAL)
+            h->inc_ndt_map.configure(h->opt.voxel_size, h->opt.ndt_capacity > 0 ? static_cast<size_t>(h->opt.ndt_capacity) : 100000);
         return LOCREG_OK;
     });
     if (rc != LOCREG_OK) { delete h; return rc; }
@@ -493,10 +512,22 @@ static int set_target_impl(locreg_handle* h, const float* xyz, size_t n, size_t 
             d_xyz = h->d_target.p;
         }
         h->begin_timing();
-        if (h->opt.method == LOCREG_NDT_DIRECT)
+        if (h->opt.method == LOCREG_NDT_DIRECT) {
             h->ndt_map.build(d_xyz, n, stride, h->opt.voxel_size, h->opt.min_pts_in_voxel, h->stream);
-        else
+        } else if (h->opt.method == LOCREG_NDT_INCREMENTAL) {
+            // SetIncNdtTargetCloud ADDS the cloud to the voxel cache; the LRU bookkeeping needs the cloud on the host
+            std::vector<unsigned char> tmp;
+            const void* h_xyz = xyz;
+            if (on_device && n) {
+                tmp.resize(n * stride);
+                LR_CUDA(cudaMemcpyAsync(tmp.data(), xyz, n * stride, cudaMemcpyDeviceToHost, h->stream));
+                LR_CUDA(cudaStreamSynchronize(h->stream));
+                h_xyz = tmp.data();
+            }
+            h->inc_ndt_map.add_cloud(h_xyz, d_xyz, n, stride, h->stream);
+        } else {
             build_icp_maps(h->icp_map, h->icp_coarse, d_xyz, n, stride, static_cast<float>(h->opt.knn_cell_size), h->opt.knn_lists != 0, h->stream);
+        }
         h->end_timing();
         h->has_target = true;
         return LOCREG_OK;
@@ -516,7 +547,7 @@ int locreg_align(locreg_handle* h, const float* src, size_t n, size_t stride, co
         init_state(h, pose_in);
         h->begin_timing();
         if (is_ndt(h)) {
-            ndt_run_align(h, src4, static_cast<unsigned int>(n));
+            NDT_DISPATCH(h, ndt_run_align(h, PB, src4, static_cast<unsigned int>(n)));
         } else {
             const IcpJob job = icp_single_job(h, src4, static_cast<unsigned int>(n));
             ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
@@ -572,7 +603,7 @@ int locreg_compute_hb(locreg_handle* h, const float* src, size_t n, size_t strid
         h->begin_timing();
         h->d_acc.reserve(32 * sizeof(double));
         if (is_ndt(h)) {
-            ndt_run_eval(h, src4, static_cast<unsigned int>(n), nullptr);
+            NDT_DISPATCH(h, ndt_run_eval(h, PB, src4, static_cast<unsigned int>(n), nullptr));
         } else {
             const IcpJob job = icp_single_job(h, src4, static_cast<unsigned int>(n));
             ICP_DISPATCH(h, (icp_launch_eval<M>(h, job, 1, kNnTwoPass, nullptr, nullptr), icp_launch_solve<M>(h, job, 0, h->d_acc.as<double>())));
@@ -592,7 +623,7 @@ int locreg_compute_hb(locreg_handle* h, const float* src, size_t n, size_t strid
         double dx[6];
         const bool solvable = gn_solve6(acc, acc + 21, dx);
         const bool few = r.n_effective < h->opt.min_effective_pts;
-        r.degenerate = (!solvable || (few && h->opt.method != LOCREG_NDT_DIRECT)) ? 1 : 0;
+        r.degenerate = (!solvable || (few && h->opt.method != LOCREG_NDT_DIRECT)) ? 1 : 0;  // direct NDT only looks at det(H) here
         fill_result(res, r);
         return LOCREG_OK;
     });
@@ -654,7 +685,7 @@ int locreg_debug_points(locreg_handle* h, const float* src, size_t n, size_t str
         if (nn && k) { h->d_nn.reserve(n * k * sizeof(int)); d_nn = h->d_nn.as<int>(); }
         h->begin_timing();
         if (is_ndt(h)) {
-            ndt_run_eval(h, src4, static_cast<unsigned int>(n), h->d_gate.as<unsigned char>());
+            NDT_DISPATCH(h, ndt_run_eval(h, PB, src4, static_cast<unsigned int>(n), h->d_gate.as<unsigned char>()));
         } else {
             const IcpJob job = icp_single_job(h, src4, static_cast<unsigned int>(n));
             ICP_DISPATCH(h, icp_launch_eval<M>(h, job, 1, kNnTwoPass, h->d_gate.as<unsigned char>(), d_nn));
@@ -679,7 +710,7 @@ int locreg_align_batch_device(locreg_handle* h, const float* d_srcs, const int64
         DevResult* results = reinterpret_cast<DevResult*>(d_results);
         const unsigned int Su = static_cast<unsigned int>(S);
         if (is_ndt(h)) {
-            ndt_run_batch(h, src4, offs, d_poses_in, d_poses_out, results, Su);
+            NDT_DISPATCH(h, ndt_run_batch(h, PB, src4, offs, d_poses_in, d_poses_out, results, Su));
         } else {
             const IcpJob job = icp_batch_job(h, src4, offs, Su, total_points);
             LR_LAUNCH(k_states_init, (Su + 255) / 256, 256, 0, h->stream, d_poses_in, Su, h->opt.max_iteration, job.states);
@@ -777,8 +808,8 @@ int locreg_align_batch(locreg_handle* h, const float* srcs, const int64_t* offse
         } else {
             h->begin_timing();
             if (is_ndt(h)) {
-                ndt_run_batch(h, src4, h->d_offsets.as<long long>(), h->d_poses_in.as<double>(), h->d_poses_out.as<double>(),
-                              h->d_results.as<DevResult>(), Su);
+                NDT_DISPATCH(h, ndt_run_batch(h, PB, src4, h->d_offsets.as<long long>(), h->d_poses_in.as<double>(),
+                                              h->d_poses_out.as<double>(), h->d_results.as<DevResult>(), Su));
             } else {
                 const IcpJob job = icp_batch_job(h, src4, h->d_offsets.as<long long>(), Su, n_pts);
                 LR_LAUNCH(k_states_init, (Su + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>(), Su, h->opt.max_iteration, job.states);
@@ -878,14 +909,15 @@ int locreg_transform_cloud(locreg_handle* h, const float* src, size_t n, size_t 
 
 int locreg_ndt_num_voxels(locreg_handle* h, size_t* nv) {
     if (!h || !nv) return LOCREG_E_ARG;
-    *nv = h->ndt_map.view().n_voxels;
+    *nv = h->opt.method == LOCREG_NDT_INCREMENTAL ? h->inc_ndt_map.size() : h->ndt_map.view().n_voxels;
     return LOCREG_OK;
 }
 int locreg_ndt_get_voxels(locreg_handle* h, int32_t* keys, double* mu, double* info, int32_t* npts) {
     return guarded(h, [&]() {
         std::vector<int> k, c;
         std::vector<double> m, f;
-        h->ndt_map.download(k, m, f, c, h->stream);
+        if (h->opt.method == LOCREG_NDT_INCREMENTAL) h->inc_ndt_map.download(k, m, f, c, h->stream);
+        else h->ndt_map.download(k, m, f, c, h->stream);
         if (keys) std::memcpy(keys, k.data(), k.size() * sizeof(int));
         if (mu) std::memcpy(mu, m.data(), m.size() * sizeof(double));
         if (info) std::memcpy(info, f.data(), f.size() * sizeof(double));

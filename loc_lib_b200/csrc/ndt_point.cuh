@@ -241,6 +241,136 @@ LR_HD unsigned char ndt_point(const NdtMapView& map, const NdtParams& prm, const
     return static_cast<unsigned char>(hits);
 }
 
+// ---- incremental NDT (ndt_registration.cpp:150-236, 262-372) ------------------------------------------------------
+// UpdateVoxel as it actually runs: flag_first_scan_ is set back to true after every SetIncNdtTargetCloud
+// (:181), so only its first branch (:186-198) is ever taken.  The statistics of a voxel are those of the points the
+// CURRENT cloud put into it (pts_ is cleared after every update): mean and covariance (/(n-1), math_utils.h:55-72) in
+// arrival order and info = (sigma + 1e-3 I)^-1 for two or more points, mu = the point and info = 100 I for one.
+LR_HD void inc_ndt_voxel_stats(const unsigned int* idx, unsigned int cnt, const void* xyz, size_t stride, NdtVoxel& out) {
+    if (cnt == 1) {
+        const float* p = reinterpret_cast<const float*>(static_cast<const char*>(xyz) + static_cast<size_t>(idx[0]) * stride);
+        out.mu[0] = p[0]; out.mu[1] = p[1]; out.mu[2] = p[2];
+        for (int k = 0; k < 9; ++k) out.info[k] = (k % 4 == 0) ? 1e2 : 0.0;
+        return;
+    }
+    double sx = 0, sy = 0, sz = 0;
+    for (unsigned int j = 0; j < cnt; ++j) {
+        const float* p = reinterpret_cast<const float*>(static_cast<const char*>(xyz) + static_cast<size_t>(idx[j]) * stride);
+        sx = LR_DADD(sx, static_cast<double>(p[0])); sy = LR_DADD(sy, static_cast<double>(p[1])); sz = LR_DADD(sz, static_cast<double>(p[2]));
+    }
+    const double len = static_cast<double>(cnt);
+    const double mx = sx / len, my = sy / len, mz = sz / len;
+    double c[6] = {0, 0, 0, 0, 0, 0};  // xx xy xz yy yz zz
+    for (unsigned int j = 0; j < cnt; ++j) {
+        const float* p = reinterpret_cast<const float*>(static_cast<const char*>(xyz) + static_cast<size_t>(idx[j]) * stride);
+        const double dx = LR_DSUB(static_cast<double>(p[0]), mx), dy = LR_DSUB(static_cast<double>(p[1]), my),
+                     dz = LR_DSUB(static_cast<double>(p[2]), mz);
+        c[0] = LR_DADD(c[0], LR_DMUL(dx, dx)); c[1] = LR_DADD(c[1], LR_DMUL(dx, dy)); c[2] = LR_DADD(c[2], LR_DMUL(dx, dz));
+        c[3] = LR_DADD(c[3], LR_DMUL(dy, dy)); c[4] = LR_DADD(c[4], LR_DMUL(dy, dz)); c[5] = LR_DADD(c[5], LR_DMUL(dz, dz));
+    }
+    const double len1 = static_cast<double>(cnt - 1);
+    // A = sigma + 1e-3 I (symmetric), info = adj(A) / det(A): Eigen's fixed-size 3x3 inverse is the cofactor formula
+    const double a = c[0] / len1 + 1e-3, b = c[1] / len1, cc = c[2] / len1, d = c[3] / len1 + 1e-3, e = c[4] / len1,
+                 f = c[5] / len1 + 1e-3;
+    const double A00 = d * f - e * e, A01 = cc * e - b * f, A02 = b * e - cc * d;
+    const double A11 = a * f - cc * cc, A12 = b * cc - a * e, A22 = a * d - b * b;
+    const double det = a * A00 + b * A01 + cc * A02;
+    const double inv = 1.0 / det;
+    out.mu[0] = mx; out.mu[1] = my; out.mu[2] = mz;
+    out.info[0] = A00 * inv; out.info[1] = A01 * inv; out.info[2] = A02 * inv;
+    out.info[3] = A01 * inv; out.info[4] = A11 * inv; out.info[5] = A12 * inv;
+    out.info[6] = A02 * inv; out.info[7] = A12 * inv; out.info[8] = A22 * inv;
+}
+
+// Per-point body of AlignIncNdt (ndt_registration.cpp:289-324, 334-347): every gated-in voxel is one residual,
+// weighted by its information matrix: H += J^T info J, err += -J^T info e, total_res += e^T info e, with
+// J = [ -R hat(q) , I ] the same for all voxels of the point, so the sums W = sum info_k and g = sum info_k e_k are
+// formed first.  effective_num counts RESIDUALS (:341), not points.
+template <class Acc>
+LR_HD unsigned char inc_ndt_point(const NdtMapView& map, const NdtParams& prm, const Pose& T, float sx, float sy, float sz,
+                                  Acc& acc) {
+    if (!finite3(sx, sy, sz)) return 0;  // deviation D1
+    const double qx = sx, qy = sy, qz = sz;
+    double wx, wy, wz;
+    pose_apply(T, qx, qy, qz, wx, wy, wz);
+    const int kx = ndt_trunc(LR_DMUL(wx, map.inv_voxel)), ky = ndt_trunc(LR_DMUL(wy, map.inv_voxel)),
+              kz = ndt_trunc(LR_DMUL(wz, map.inv_voxel));
+    int hits = 0;
+    double W[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0}, rr = 0;
+    for (int o = 0; o < prm.n_nearby; ++o) {
+        int dx, dy, dz;
+        ndt_offset(o, dx, dy, dz);
+        const int cx = kx + dx, cy = ky + dy, cz = kz + dz;
+        if (!ndt_key_ok(cx, cy, cz)) continue;
+        const unsigned long long key = ndt_pack(cx, cy, cz);
+        unsigned int h = ndt_hash(key) & map.slot_mask;
+        int vid = -1;
+        while (true) {
+            const NdtSlot s = map.slots[h];
+            if (s.key == key) { vid = s.vid; break; }
+            if (s.key == kNdtEmpty) break;
+            h = (h + 1) & map.slot_mask;
+        }
+        if (vid < 0) continue;
+        const NdtVoxel& v = map.voxels[vid];
+        const double e0 = wx - v.mu[0], e1 = wy - v.mu[1], e2 = wz - v.mu[2];
+        const double i0 = v.info[0] * e0 + v.info[1] * e1 + v.info[2] * e2;
+        const double i1 = v.info[3] * e0 + v.info[4] * e1 + v.info[5] * e2;
+        const double i2 = v.info[6] * e0 + v.info[7] * e1 + v.info[8] * e2;
+        const double res = e0 * i0 + e1 * i1 + e2 * i2;
+        if (!(res == res) || res > prm.res_outlier_th) continue;
+        ++hits;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) W[k] += v.info[k];
+        g[0] += i0; g[1] += i1; g[2] += i2;
+        rr += res;
+    }
+    if (hits == 0) return 0;
+    double A[3][3];  // A = -R hat(q)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double r0 = T.R[r * 3], r1 = T.R[r * 3 + 1], r2 = T.R[r * 3 + 2];
+        A[r][0] = -(r1 * qz - r2 * qy);
+        A[r][1] = -(-r0 * qz + r2 * qx);
+        A[r][2] = -(r0 * qy - r1 * qx);
+    }
+    // WA = W A (3 x 3); H = [A^T W A, A^T W; W A, W] (upper triangle kept), err = -[A^T g; g]
+    double WA[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) WA[r][c] = W[r * 3] * A[0][c] + W[r * 3 + 1] * A[1][c] + W[r * 3 + 2] * A[2][c];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = i; j < 3; ++j) acc.add(hidx(i, j), A[0][i] * WA[0][j] + A[1][i] * WA[1][j] + A[2][i] * WA[2][j]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc.add(hidx(i, 3 + j), A[0][i] * W[j] + A[1][i] * W[3 + j] + A[2][i] * W[6 + j]);  // (A^T W)(i, j)
+    }
+    acc.add(hidx(3, 3), W[0]); acc.add(hidx(3, 4), W[1]); acc.add(hidx(3, 5), W[2]);
+    acc.add(hidx(4, 4), W[4]); acc.add(hidx(4, 5), W[5]); acc.add(hidx(5, 5), W[8]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc.add(21 + i, -(A[0][i] * g[0] + A[1][i] * g[1] + A[2][i] * g[2]));
+    acc.add(24, -g[0]); acc.add(25, -g[1]); acc.add(26, -g[2]);
+    acc.add(27, rr);
+    acc.inc_eff(static_cast<unsigned int>(hits));
+    acc.inc_inl(static_cast<unsigned int>(hits));
+    return static_cast<unsigned char>(hits);
+}
+// Tail of one AlignIncNdt iteration (:349-367): too few residuals -> result_pose = pose, return false (4: stop, the
+// pose IS written); otherwise solve, update, converged?  The reference never looks at det(H) here; a singular H
+// (not reachable with >= min_effective_pts_ residuals on real data) stops the loop with the pose unchanged.
+LR_HD int inc_ndt_gn_update(const double* acc28, unsigned int n_eff, const NdtParams& prm, Pose& T) {
+    if (static_cast<long long>(n_eff) < static_cast<long long>(prm.min_effective_pts)) return 4;
+    double dx[6];
+    if (!gn_solve6(acc28, acc28 + 21, dx)) return 4;
+    pose_update(T, dx);
+    double nrm = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) nrm += dx[i] * dx[i];
+    return sqrt(nrm) < prm.eps ? 2 : 1;
+}
+
 // Tail of one AlignNdt iteration (ndt_registration.cpp:435-459).
 // 3 = det(H)==0: return false WITHOUT writing result_pose (quirk Q11); 0 = too few points (`continue`);
 // 1 = updated; 2 = updated and converged.

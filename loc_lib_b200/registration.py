@@ -17,7 +17,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import ICP_P2P, ICP_P2LINE, ICP_P2PLANE, NDT_DIRECT, NEARBY6, NEARBY_CENTER, LOOP_PERSISTENT, LOOP_GRAPH
+from ._lib import (ICP_P2P, ICP_P2LINE, ICP_P2PLANE, NDT_DIRECT, NDT_INCREMENTAL, NEARBY6, NEARBY_CENTER,  # noqa: F401
+                   LOOP_PERSISTENT, LOOP_GRAPH)
 
 
 class IcpMethod:  # icp_registration.hpp:15-20
@@ -26,6 +27,10 @@ class IcpMethod:  # icp_registration.hpp:15-20
 
 class NdtNearbyType:  # ndt_registration.hpp:16-20
     CENTER, NEARBY6 = 0, 1
+
+
+class NdtMethod:  # ndt_registration.hpp:21-26
+    PCL_NDT, DIRECT_NDT, INCREMENTAL_NDT = 0, 1, 2
 
 
 @dataclass
@@ -59,6 +64,7 @@ class NdtOptions:  # ndt_registration.hpp:27-42
     remove_centroid_: bool = False
     capacity_: int = 100000
     nearby_type_: int = NdtNearbyType.NEARBY6
+    method_: int = NdtMethod.DIRECT_NDT
     loop_mode: int = LOOP_PERSISTENT
 
 
@@ -224,12 +230,16 @@ class IcpRegistration(_Registration):
 
 
 class NdtRegistration(_Registration):
-    """NdtRegistration(NdtOptions) (ndt_registration.cpp:20-28), DIRECT_NDT only."""
+    """NdtRegistration(NdtOptions) (ndt_registration.cpp:20-28): DIRECT_NDT, or INCREMENTAL_NDT where every
+    SetInputTarget ADDS its cloud to an LRU cache of capacity_ voxels (ndt_registration.cpp:150-183)."""
 
     def __init__(self, options=None, device=0):
         options = options or NdtOptions()
+        if options.method_ == NdtMethod.PCL_NDT:
+            raise _lib.LocregError("PCL_NDT is an unimplemented stub in the reference (ndt_registration.cpp:69-70)")
         o = _lib.Options()
-        _lib.lib().locreg_default_options(C.byref(o), NDT_DIRECT)
+        _lib.lib().locreg_default_options(C.byref(o), NDT_INCREMENTAL if options.method_ == NdtMethod.INCREMENTAL_NDT else NDT_DIRECT)
+        o.ndt_capacity = int(options.capacity_)
         o.max_iteration = options.max_iteration_
         o.voxel_size = options.voxel_size_
         o.min_effective_pts = options.min_effective_pts_

@@ -16,7 +16,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <list>
 #include <memory>
+#include <set>
 #include <queue>
 #include <thread>
 #include <unordered_map>
@@ -712,12 +714,205 @@ struct Ndt {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// NdtRegistration (incremental): SetIncNdtTargetCloud / UpdateVoxel / AlignIncNdt
+// (ndt_registration.cpp:150-236, 262-372), literally: std::list LRU + unordered_map of list iterators.
+// ---------------------------------------------------------------------------------------------
+struct IncVoxel {  // NdtVoxelData members the incremental path uses (ndt_registration.hpp:46-67)
+    std::vector<Vec3> pts_;
+    bool ndt_estimated_ = false;
+    int num_pts_ = 0;
+    int n_last = 0;  // (oracle only) points of the last update, for the parity probe
+    Vec3 mu_;
+    Mat3 sigma_;
+    Mat3 info_;
+};
+struct IncNdt {
+    oracle_ndt_options opt;
+    size_t capacity = 100000;  // NdtOptions::capacity_
+    double inv_voxel_size = 1.0;
+    using KeyAndData = std::pair<Key3, IncVoxel>;
+    std::list<KeyAndData> data_;
+    std::unordered_map<Key3, std::list<KeyAndData>::iterator, HashKey3> inc_grids_;
+    std::vector<Key3> nearby;
+    bool flag_first_scan_ = true;
+
+    void Init() {
+        inv_voxel_size = 1.0 / opt.voxel_size;
+        nearby.clear();
+        if (!opt.nearby6) nearby.push_back({0, 0, 0});
+        else nearby = {{0, 0, 0}, {-1, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, -1}, {0, 0, 1}};
+    }
+    Key3 KeyOf(const Vec3& p) const {
+        return {static_cast<int>(p.x * inv_voxel_size), static_cast<int>(p.y * inv_voxel_size),
+                static_cast<int>(p.z * inv_voxel_size)};
+    }
+    static Mat3 Inverse3(const Mat3& A) {  // Eigen's fixed-size 3x3 inverse: cofactors / determinant
+        Mat3 C;
+        C.m[0][0] = A.m[1][1] * A.m[2][2] - A.m[1][2] * A.m[2][1];
+        C.m[0][1] = A.m[0][2] * A.m[2][1] - A.m[0][1] * A.m[2][2];
+        C.m[0][2] = A.m[0][1] * A.m[1][2] - A.m[0][2] * A.m[1][1];
+        C.m[1][0] = A.m[1][2] * A.m[2][0] - A.m[1][0] * A.m[2][2];
+        C.m[1][1] = A.m[0][0] * A.m[2][2] - A.m[0][2] * A.m[2][0];
+        C.m[1][2] = A.m[0][2] * A.m[1][0] - A.m[0][0] * A.m[1][2];
+        C.m[2][0] = A.m[1][0] * A.m[2][1] - A.m[1][1] * A.m[2][0];
+        C.m[2][1] = A.m[0][1] * A.m[2][0] - A.m[0][0] * A.m[2][1];
+        C.m[2][2] = A.m[0][0] * A.m[1][1] - A.m[0][1] * A.m[1][0];
+        const double det = A.m[0][0] * C.m[0][0] + A.m[0][1] * C.m[1][0] + A.m[0][2] * C.m[2][0];
+        for (auto& row : C.m) for (double& v : row) v = v / det;
+        return C;
+    }
+    // UpdateVoxel (:185-236).  flag_first_scan_ is true whenever this runs (it is set back to true at :181), so only
+    // the first branch is reachable; the others are kept out rather than restated untested.
+    void UpdateVoxel(IncVoxel& v) {
+        if (flag_first_scan_) {
+            if (v.pts_.size() > 1) {
+                Vec3 sum{0, 0, 0};
+                for (const Vec3& p : v.pts_) sum = sum + p;
+                const double len = static_cast<double>(v.pts_.size());
+                v.mu_ = Vec3{sum.x / len, sum.y / len, sum.z / len};
+                Mat3 cov;
+                for (auto& row : cov.m) for (double& x : row) x = 0;
+                for (const Vec3& p : v.pts_) {
+                    const Vec3 d = p - v.mu_;
+                    const double dv[3] = {d.x, d.y, d.z};
+                    for (int r = 0; r < 3; ++r)
+                        for (int c = 0; c < 3; ++c) cov.m[r][c] = cov.m[r][c] + dv[r] * dv[c];
+                }
+                for (auto& row : cov.m) for (double& x : row) x = x / (len - 1);
+                v.sigma_ = cov;
+                Mat3 A = cov;
+                for (int k = 0; k < 3; ++k) A.m[k][k] += 1e-3;
+                v.info_ = Inverse3(A);  // (:189)
+            } else {
+                v.mu_ = v.pts_[0];
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) v.info_.m[r][c] = (r == c) ? 1e2 : 0.0;
+            }
+            v.ndt_estimated_ = true;
+            v.n_last = static_cast<int>(v.pts_.size());
+            v.pts_.clear();
+            return;
+        }
+    }
+    // SetIncNdtTargetCloud (:150-183)
+    void AddCloud(const float* xyz, size_t n, size_t stride) {
+        auto less3 = [](const Key3& a, const Key3& b) {
+            return a.x < b.x || (a.x == b.x && a.y < b.y) || (a.x == b.x && a.y == b.y && a.z < b.z);
+        };
+        std::set<Key3, decltype(less3)> active_voxels(less3);
+        for (size_t i = 0; i < n; ++i) {
+            const float* p = pt_at(xyz, i, stride);
+            if (opt.skip_nonfinite && !finite3(p)) continue;
+            const Vec3 pt{p[0], p[1], p[2]};
+            const Key3 key = KeyOf(pt);
+            auto iter = inc_grids_.find(key);
+            if (iter == inc_grids_.end()) {
+                IncVoxel v;
+                v.pts_.emplace_back(pt);
+                v.num_pts_ = 1;
+                data_.push_front({key, v});
+                inc_grids_.insert({key, data_.begin()});
+                if (data_.size() >= capacity) {
+                    inc_grids_.erase(data_.back().first);
+                    data_.pop_back();
+                }
+            } else {
+                IncVoxel& v = iter->second->second;
+                v.pts_.emplace_back(pt);
+                if (!v.ndt_estimated_) v.num_pts_++;
+                data_.splice(data_.begin(), data_, iter->second);
+                iter->second = data_.begin();
+            }
+            active_voxels.emplace(key);
+        }
+        for (const Key3& key : active_voxels) {
+            auto it = inc_grids_.find(key);  // the reference's operator[] would insert a null iterator for an evicted key
+            if (it == inc_grids_.end() || it->second->second.pts_.empty()) continue;
+            UpdateVoxel(it->second->second);
+        }
+        flag_first_scan_ = true;
+    }
+    // the two loops of one AlignIncNdt iteration (:289-347); hits[i] = gated-in voxels of point i
+    void HB(const float* src, size_t n, size_t stride, const SE3& pose, Mat6& H, Vec6& err, oracle_result& res, uint8_t* hits) const {
+        int effective_num = 0;
+        double total_res = 0;
+        const Mat3 R = pose.matrix();
+        for (size_t i = 0; i < n; ++i) {
+            const float* sp = pt_at(src, i, stride);
+            if (hits) hits[i] = 0;
+            if (opt.skip_nonfinite && !finite3(sp)) continue;
+            const Vec3 q{sp[0], sp[1], sp[2]};
+            const Vec3 qs = pose * q;
+            const Key3 key = KeyOf(qs);
+            for (const Key3& off : nearby) {
+                const Key3 k{key.x + off.x, key.y + off.y, key.z + off.z};
+                auto it = inc_grids_.find(k);
+                if (it == inc_grids_.end() || !it->second->second.ndt_estimated_) continue;
+                const IncVoxel& v = it->second->second;
+                const Vec3 e = qs - v.mu_;
+                const Vec3 ie = mul(v.info_, e);
+                const double r2 = dot(e, ie);
+                if (std::isnan(r2) || r2 > opt.res_outlier_th) continue;
+                const Mat3 Rh = mul(R, hat(q));
+                double J[3][6];
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) { J[r][c] = -Rh.m[r][c]; J[r][3 + c] = (r == c) ? 1.0 : 0.0; }
+                // H += J^T info J; err += -J^T info e  (:345-346)
+                double IJ[3][6];
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 6; ++c) IJ[r][c] = v.info_.m[r][0] * J[0][c] + v.info_.m[r][1] * J[1][c] + v.info_.m[r][2] * J[2][c];
+                const double iev[3] = {ie.x, ie.y, ie.z};
+                for (int a = 0; a < 6; ++a) {
+                    for (int b = 0; b < 6; ++b) H(a, b) += J[0][a] * IJ[0][b] + J[1][a] * IJ[1][b] + J[2][a] * IJ[2][b];
+                    err.v[a] += -(J[0][a] * iev[0] + J[1][a] * iev[1] + J[2][a] * iev[2]);
+                }
+                total_res += r2;
+                effective_num++;
+                if (hits) hits[i]++;
+            }
+        }
+        res.n_effective = effective_num;
+        res.n_inlier = effective_num;
+        res.sum_sq_res = total_res;
+    }
+    // AlignIncNdt (:262-372)
+    bool Align(const float* src, size_t n, size_t stride, const SE3& init, SE3& result, oracle_result& res, double* trace) const {
+        SE3 pose = init;
+        res = oracle_result{};
+        res.pose_written = 1;
+        if (trace) pose.to7(trace);
+        bool ok = true;
+        for (int iter = 0; iter < opt.max_iteration; ++iter) {
+            Mat6 H;
+            Vec6 err;
+            res.iters = iter + 1;
+            HB(src, n, stride, pose, H, err, res, nullptr);
+            if (res.n_effective < opt.min_effective_pts) { res.degenerate = 1; ok = false; break; }  // result_pose = pose; return false
+            res.degenerate = 0;
+            Mat6 Hinv;
+            lu6(H, &Hinv);
+            const Vec6 dx = mul(Hinv, err);
+            pose.right_mul_exp(Vec3{dx.v[0], dx.v[1], dx.v[2]});
+            pose.t = pose.t + Vec3{dx.v[3], dx.v[4], dx.v[5]};
+            res.updates++;
+            if (trace) pose.to7(trace + (iter + 1) * 7);
+            if (dx.norm() < opt.eps) { res.converged = 1; break; }
+        }
+        if (trace)
+            for (int it = res.iters + (ok && !res.converged ? 1 : 0); it <= opt.max_iteration; ++it) pose.to7(trace + it * 7);
+        result = pose;
+        return ok;
+    }
+};
+
 }  // namespace oracle
 
 using namespace oracle;
 
 struct oracle_icp { Icp impl; };
 struct oracle_ndt { Ndt impl; };
+struct oracle_inc_ndt { IncNdt impl; };
 
 extern "C" {
 
@@ -860,6 +1055,61 @@ int oracle_ndt_align(oracle_ndt* h, const float* src, size_t n, size_t stride, c
     if (out_xyz) transform_cloud(src, n, stride, result, out_xyz);
     if (res) *res = r;
     return 1;  // ScanMatch always returns true (ndt_registration.cpp:260)
+}
+
+/* ---- incremental NDT ---- */
+oracle_inc_ndt* oracle_inc_ndt_create(const oracle_ndt_options* o, size_t capacity) {
+    auto* h = new oracle_inc_ndt;
+    h->impl.opt = *o;
+    h->impl.capacity = capacity;
+    h->impl.Init();
+    return h;
+}
+void oracle_inc_ndt_destroy(oracle_inc_ndt* h) { delete h; }
+int oracle_inc_ndt_add_cloud(oracle_inc_ndt* h, const float* xyz, size_t n, size_t stride) {
+    h->impl.AddCloud(xyz, n, stride);
+    return 0;
+}
+size_t oracle_inc_ndt_num_voxels(const oracle_inc_ndt* h) { return h->impl.data_.size(); }
+int oracle_inc_ndt_get_voxels(const oracle_inc_ndt* h, int32_t* keys, double* mu, double* info, int32_t* npts) {
+    std::vector<const IncNdt::KeyAndData*> v;
+    for (auto& kv : h->impl.data_) v.push_back(&kv);
+    std::sort(v.begin(), v.end(), [](auto* a, auto* b) {
+        if (a->first.x != b->first.x) return a->first.x < b->first.x;
+        if (a->first.y != b->first.y) return a->first.y < b->first.y;
+        return a->first.z < b->first.z;
+    });
+    for (size_t i = 0; i < v.size(); ++i) {
+        keys[i * 3] = v[i]->first.x; keys[i * 3 + 1] = v[i]->first.y; keys[i * 3 + 2] = v[i]->first.z;
+        mu[i * 3] = v[i]->second.mu_.x; mu[i * 3 + 1] = v[i]->second.mu_.y; mu[i * 3 + 2] = v[i]->second.mu_.z;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) info[i * 9 + r * 3 + c] = v[i]->second.info_.m[r][c];
+        if (npts) npts[i] = v[i]->second.n_last;
+    }
+    return 0;
+}
+int oracle_inc_ndt_compute_hb(oracle_inc_ndt* h, const float* src, size_t n, size_t stride, const double* pose7, double* H36,
+                              double* B6, oracle_result* res, uint8_t* hits) {
+    Mat6 H;
+    Vec6 B;
+    oracle_result r{};
+    h->impl.HB(src, n, stride, SE3::from7(pose7), H, B, r, hits);
+    std::memcpy(H36, H.a, sizeof(H.a));
+    std::memcpy(B6, B.v, sizeof(B.v));
+    r.degenerate = r.n_effective < h->impl.opt.min_effective_pts ? 1 : 0;
+    r.pose_written = 1;
+    if (res) *res = r;
+    return 1;
+}
+int oracle_inc_ndt_align(oracle_inc_ndt* h, const float* src, size_t n, size_t stride, const double* pose_in, double* pose_out,
+                         float* out_xyz, oracle_result* res, double* trace) {
+    SE3 result;
+    oracle_result r{};
+    h->impl.Align(src, n, stride, SE3::from7(pose_in), result, r, trace);
+    result.to7(pose_out);
+    if (out_xyz) transform_cloud(src, n, stride, result, out_xyz);
+    if (res) *res = r;
+    return 1;
 }
 
 void oracle_transform_cloud(const float* src, size_t n, size_t stride, const double* pose7, float* out_xyz) {

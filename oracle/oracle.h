@@ -106,6 +106,19 @@ int oracle_ndt_compute_hb(oracle_ndt* h, const float* src, size_t n, size_t stri
 int oracle_ndt_align(oracle_ndt* h, const float* src, size_t n, size_t stride_bytes, const double* pose_in,
                      double* pose_inout, float* out_xyz, oracle_result* res, double* pose_trace);
 
+/* ---- incremental NDT (ndt_registration.cpp:150-236, 262-372): LRU voxel cache of `capacity` voxels; add_cloud =
+ * SetIncNdtTargetCloud; npts of get_voxels = points the last cloud that touched the voxel put into it ---- */
+typedef struct oracle_inc_ndt oracle_inc_ndt;
+oracle_inc_ndt* oracle_inc_ndt_create(const oracle_ndt_options* o, size_t capacity);
+void oracle_inc_ndt_destroy(oracle_inc_ndt* h);
+int oracle_inc_ndt_add_cloud(oracle_inc_ndt* h, const float* xyz, size_t n, size_t stride_bytes);
+size_t oracle_inc_ndt_num_voxels(const oracle_inc_ndt* h);
+int oracle_inc_ndt_get_voxels(const oracle_inc_ndt* h, int32_t* keys, double* mu, double* info, int32_t* npts);
+int oracle_inc_ndt_compute_hb(oracle_inc_ndt* h, const float* src, size_t n, size_t stride_bytes, const double* pose7,
+                              double* H36, double* B6, oracle_result* res, uint8_t* hits);
+int oracle_inc_ndt_align(oracle_inc_ndt* h, const float* src, size_t n, size_t stride_bytes, const double* pose_in,
+                         double* pose_out, float* out_xyz, oracle_result* res, double* pose_trace);
+
 /* pcl::transformPointCloud (icp_registration.cpp:241, ndt_registration.cpp:258) */
 void oracle_transform_cloud(const float* src, size_t n, size_t stride_bytes, const double* pose7, float* out_xyz);
 /* pose helpers for tests: pose7 <- pose7 * (exp(w), +dt) in the reference's split update form */

@@ -327,6 +327,43 @@ HsNdt* hs_ndt_create(const float* xyz, size_t n, size_t stride, double voxel_siz
     return m;
 }
 void hs_ndt_destroy(HsNdt* m) { delete m; }
+
+// Incremental NDT: a voxel table built from a dump (keys nv*3, point lists per voxel as in one SetIncNdtTargetCloud
+// call: member indices + group starts) so that inc_ndt_voxel_stats and inc_ndt_point run on the host.
+HsNdt* hs_inc_ndt_create(const int32_t* keys, const uint32_t* group_start, const uint32_t* members, size_t nv,
+                         const float* xyz, size_t stride, double voxel_size) {
+    auto* m = new HsNdt;
+    unsigned int cap = 1024;
+    while (cap < nv * 4 + 16) cap <<= 1;
+    m->slots.assign(cap, NdtSlot{kNdtEmpty, -1, 0u});
+    m->voxels.resize(nv);
+    for (size_t v = 0; v < nv; ++v) {
+        inc_ndt_voxel_stats(members + group_start[v], group_start[v + 1] - group_start[v], xyz, stride, m->voxels[v]);
+        const unsigned long long key = ndt_pack(keys[v * 3], keys[v * 3 + 1], keys[v * 3 + 2]);
+        unsigned int h = ndt_hash(key) & (cap - 1);
+        while (m->slots[h].key != kNdtEmpty) h = (h + 1) & (cap - 1);
+        m->slots[h] = NdtSlot{key, static_cast<int>(v), group_start[v + 1] - group_start[v]};
+    }
+    m->view.slots = m->slots.data(); m->view.voxels = m->voxels.data(); m->view.slot_mask = cap - 1;
+    m->view.n_voxels = static_cast<unsigned int>(nv); m->view.inv_voxel = 1.0 / voxel_size;
+    return m;
+}
+void hs_inc_ndt_hb(const HsNdt* m, const double* prm, const float* src, size_t n, size_t stride, const double* pose7,
+                   double* H36, double* B6, int64_t* counts, double* sum_sq, uint8_t* hits) {
+    const NdtParams p = make_ndt_params(prm);
+    Pose T;
+    pose_load(T, pose7);
+    Accum acc;
+    accum_zero(acc);
+    for (size_t i = 0; i < n; ++i) {
+        const float* s = point_ptr(src, i, stride);
+        const unsigned char h = inc_ndt_point(m->view, p, T, s[0], s[1], s[2], acc);
+        if (hits) hits[i] = h;
+    }
+    unpack(acc, H36, B6);
+    counts[0] = acc.n_eff; counts[1] = acc.n_inl;
+    *sum_sq = acc.v[27];
+}
 size_t hs_ndt_num_voxels(const HsNdt* m) { return m->voxels.size(); }
 void hs_ndt_get_voxels(const HsNdt* m, int32_t* keys, double* mu, double* info, int32_t* npts) {
     struct Rec { int k[3]; int vid; int cnt; };

@@ -185,3 +185,45 @@ class HsNdt:
                                 st.ctypes.data)
         return out, dict(iters=it, updates=int(st[0]), converged=int(st[1]), degenerate=int(st[2]),
                          pose_written=int(st[3]))
+
+
+class HsIncNdt(HsNdt):
+    """Incremental-NDT voxel table as ONE SetIncNdtTargetCloud call on an empty cache leaves it (no evictions): voxel
+    statistics and the weighted per-point body come from the kernels' host build."""
+
+    def __init__(self, cloud, voxel_size=1.0):
+        L = lib()
+        vp, sz = C.c_void_p, C.c_size_t
+        L.hs_inc_ndt_create.restype = vp
+        L.hs_inc_ndt_create.argtypes = [vp, vp, vp, sz, vp, sz, C.c_double]
+        L.hs_inc_ndt_hb.argtypes = [vp, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp]
+        L.hs_ndt_destroy.argtypes = [vp]
+        L.hs_ndt_num_voxels.restype = sz
+        L.hs_ndt_num_voxels.argtypes = [vp]
+        L.hs_ndt_get_voxels.argtypes = [vp, vp, vp, vp, vp]
+        a, n, s = _cloud(cloud)
+        keys = np.trunc(a[:, :3].astype(np.float64) * (1.0 / voxel_size)).astype(np.int32)
+        order = np.lexsort((np.arange(n), keys[:, 2], keys[:, 1], keys[:, 0]))  # group by key, arrival order inside
+        ks = keys[order]
+        first = np.ones(n, bool)
+        first[1:] = (ks[1:] != ks[:-1]).any(1)
+        starts = np.concatenate([np.flatnonzero(first), [n]]).astype(np.uint32)
+        self._keys = np.ascontiguousarray(ks[first], np.int32)
+        self._members = np.ascontiguousarray(order, np.uint32)
+        self._starts = starts
+        self._cloud = a
+        self._h = L.hs_inc_ndt_create(self._keys.ctypes.data, starts.ctypes.data, self._members.ctypes.data, len(self._keys),
+                                      a.ctypes.data, s, voxel_size)
+
+    def hb(self, prm, src, pose7):
+        a, n, s = _cloud(src)
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        H = np.zeros(36)
+        B = np.zeros(6)
+        counts = np.zeros(2, np.int64)
+        ssq = np.zeros(1)
+        hits = np.zeros(n, np.uint8)
+        lib().hs_inc_ndt_hb(self._h, prm.ctypes.data, a.ctypes.data, n, s, pose7.ctypes.data, H.ctypes.data,
+                            B.ctypes.data, counts.ctypes.data, ssq.ctypes.data, hits.ctypes.data)
+        return H.reshape(6, 6).T.copy(), B, dict(n_effective=int(counts[0]), n_inlier=int(counts[1]),
+                                                 sum_sq_res=float(ssq[0])), hits

@@ -199,3 +199,71 @@ def ndt_hb(vox, src_xyz, pose, voxel_size=1.0, res_outlier_th=20.0, nearby=NEARB
             B += -J.T @ e
             hits[i] += 1
     return H, B, hits
+
+
+class IncNdtRef:
+    """SetIncNdtTargetCloud / UpdateVoxel (first-scan branch, the only reachable one) / AlignIncNdt loop body
+    (ndt_registration.cpp:150-236, 289-347) with an OrderedDict as the LRU list (last = most recent)."""
+
+    def __init__(self, voxel_size=1.0, capacity=100000):
+        from collections import OrderedDict
+        self.inv = 1.0 / voxel_size
+        self.capacity = capacity
+        self.vox = OrderedDict()  # key -> dict(mu, info, pts)
+
+    def add_cloud(self, xyz):
+        m = np.asarray(xyz, np.float32).astype(np.float64)
+        active = []
+        for pt in m:
+            key = tuple(np.trunc(pt * self.inv).astype(np.int64))
+            if key not in self.vox:
+                self.vox[key] = dict(mu=None, info=None, pts=[pt])
+                if len(self.vox) >= self.capacity:
+                    self.vox.popitem(last=False)  # evict the least recently touched voxel
+            else:
+                self.vox[key]["pts"].append(pt)
+                self.vox.move_to_end(key)
+            if key not in active:
+                active.append(key)
+        for key in active:
+            v = self.vox.get(key)
+            if v is None or not v["pts"]:
+                continue
+            p = np.array(v["pts"])
+            if len(p) > 1:
+                mu = np.zeros(3)
+                for row in p:
+                    mu = mu + row
+                mu = mu / len(p)
+                d = p - mu
+                v["mu"] = mu
+                v["info"] = np.linalg.inv(d.T @ d / (len(p) - 1) + 1e-3 * np.eye(3))
+            else:
+                v["mu"] = p[0]
+                v["info"] = 1e2 * np.eye(3)
+            v["n_last"] = len(p)
+            v["pts"] = []
+
+    def hb(self, src_xyz, pose, res_outlier_th=20.0, nearby=NEARBY6):
+        R, t = quat_R(pose), np.asarray(pose[4:], float)
+        H, B = np.zeros((6, 6)), np.zeros(6)
+        hits = np.zeros(len(src_xyz), np.uint8)
+        total = 0.0
+        for i, q32 in enumerate(np.asarray(src_xyz, np.float32)):
+            q = q32.astype(np.float64)
+            qs = R @ q + t
+            key = np.trunc(qs * self.inv).astype(np.int64)
+            J = np.concatenate([-R @ hat(q), np.eye(3)], axis=1)
+            for off in nearby:
+                v = self.vox.get(tuple(key + np.array(off)))
+                if v is None:
+                    continue
+                e = qs - v["mu"]
+                res = e @ v["info"] @ e
+                if np.isnan(res) or res > res_outlier_th:
+                    continue
+                H += J.T @ v["info"] @ J
+                B += -J.T @ v["info"] @ e
+                total += res
+                hits[i] += 1
+        return H, B, hits, total

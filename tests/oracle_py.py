@@ -69,6 +69,15 @@ def lib():
         L.oracle_ndt_get_voxels.argtypes = [vp, vp, vp, vp, vp]
         L.oracle_ndt_compute_hb.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(Result), vp]
         L.oracle_ndt_align.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(Result), vp]
+        L.oracle_inc_ndt_create.restype = vp
+        L.oracle_inc_ndt_create.argtypes = [C.POINTER(NdtOptions), sz]
+        L.oracle_inc_ndt_destroy.argtypes = [vp]
+        L.oracle_inc_ndt_add_cloud.argtypes = [vp, vp, sz, sz]
+        L.oracle_inc_ndt_num_voxels.restype = sz
+        L.oracle_inc_ndt_num_voxels.argtypes = [vp]
+        L.oracle_inc_ndt_get_voxels.argtypes = [vp, vp, vp, vp, vp]
+        L.oracle_inc_ndt_compute_hb.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(Result), vp]
+        L.oracle_inc_ndt_align.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(Result), vp]
         L.oracle_transform_cloud.argtypes = [vp, sz, sz, vp, vp]
         L.oracle_pose_update.argtypes = [vp, vp]
         L.oracle_pose_matrix.argtypes = [vp, vp]
@@ -209,6 +218,53 @@ class OracleNdt:
         lib().oracle_ndt_align(self._h, a.ctypes.data, n, s, pose7.ctypes.data, out_pose.ctypes.data,
                                out.ctypes.data if want_cloud else None, C.byref(res), trace.ctypes.data)
         return out_pose, out, res.as_dict(), trace
+
+
+class OracleIncNdt:
+    """NdtRegistration (INCREMENTAL_NDT) restated: set_target ADDS a cloud to the LRU voxel cache."""
+
+    def __init__(self, capacity=100000, **opts):
+        self.opt = ndt_options(**opts)
+        self._h = lib().oracle_inc_ndt_create(C.byref(self.opt), capacity)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_inc_ndt_destroy(self._h)
+            self._h = None
+
+    def set_target(self, cloud):
+        a, n, s = _cloud(cloud)
+        return lib().oracle_inc_ndt_add_cloud(self._h, a.ctypes.data, n, s)
+
+    def voxels(self):
+        nv = lib().oracle_inc_ndt_num_voxels(self._h)
+        keys = np.zeros((nv, 3), np.int32)
+        mu = np.zeros((nv, 3))
+        info = np.zeros((nv, 3, 3))
+        npts = np.zeros(nv, np.int32)
+        lib().oracle_inc_ndt_get_voxels(self._h, keys.ctypes.data, mu.ctypes.data, info.ctypes.data, npts.ctypes.data)
+        return keys, mu, info, npts
+
+    def compute_hb(self, src, pose7):
+        a, n, s = _cloud(src)
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        H = np.zeros(36)
+        B = np.zeros(6)
+        res = Result()
+        hits = np.zeros(n, np.uint8)
+        lib().oracle_inc_ndt_compute_hb(self._h, a.ctypes.data, n, s, pose7.ctypes.data, H.ctypes.data, B.ctypes.data,
+                                        C.byref(res), hits.ctypes.data)
+        return H.reshape(6, 6).T.copy(), B, res.as_dict(), hits
+
+    def align(self, src, pose7, want_cloud=True):
+        a, n, s = _cloud(src)
+        pose7 = np.ascontiguousarray(pose7, np.float64)
+        out_pose = np.zeros(7)
+        out = np.zeros_like(a) if want_cloud else None
+        res = Result()
+        lib().oracle_inc_ndt_align(self._h, a.ctypes.data, n, s, pose7.ctypes.data, out_pose.ctypes.data,
+                                   out.ctypes.data if want_cloud else None, C.byref(res), None)
+        return out_pose, out, res.as_dict()
 
 
 def fit_plane(pts, eps=1e-2):

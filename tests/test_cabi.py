@@ -44,8 +44,8 @@ def test_library_is_sm100a_and_self_contained():
 
 def test_struct_layouts_match_header():
     from loc_lib_b200 import _lib
-    # locreg_options: 4 x i32, 6 x f64, 2 x i32, f64, 2 x i32 ; locreg_result: 48 bytes (kernels write it verbatim)
-    assert C.sizeof(_lib.Options) == 16 + 48 + 8 + 8 + 8
+    # locreg_options: 4 x i32, 6 x f64, 2 x i32, f64, 4 x i32 ; locreg_result: 48 bytes (kernels write it verbatim)
+    assert C.sizeof(_lib.Options) == 16 + 48 + 8 + 8 + 8 + 8
     assert C.sizeof(_lib.Result) == 48
     assert _lib.Options.eps.offset == 16 and _lib.Options.knn_cell_size.offset == 72
     assert _lib.Result.n_effective.offset == 16 and _lib.Result.pose_written.offset == 40

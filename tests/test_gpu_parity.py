@@ -254,6 +254,47 @@ def test_ndt_hb_and_pose(scene, nearby):
         assert g.last_result["iters"] == rr["iters"]
 
 
+def test_inc_ndt_cache_hb_and_pose(scene):
+    """Incremental NDT: clouds added one by one into a small LRU cache (evictions), voxel dump, weighted H / B, poses."""
+    import loc_lib_b200 as L
+    clouds = [scene.map[:40_000], scene.map[30_000:80_000], scene.map[70_000:]]
+    for nearby in (0, 1):
+        gpu = L.NdtRegistration(L.NdtOptions(method_=L.NdtMethod.INCREMENTAL_NDT, capacity_=2500, max_iteration_=8, eps_=0.0,
+                                             nearby_type_=nearby))
+        ref = O.OracleIncNdt(capacity=2500, max_iteration=8, eps=0.0, nearby6=nearby, skip_nonfinite=1)
+        for c in clouds:
+            gpu.SetInputTarget(c)
+            ref.set_target(c)
+            k, mu, info, npts = gpu.Voxels()
+            rk, rmu, rinfo, rn = ref.voxels()
+            assert len(rk) <= 2499
+            assert np.array_equal(k, rk) and np.array_equal(npts, rn) and np.array_equal(mu, rmu)
+            assert np.abs(info - rinfo).max() <= 1e-9 * np.abs(rinfo).max()
+        ok, H, B = gpu.CaculateMatrixHAndB(scene.scan, scene.init[0])
+        rH, rB, rres, rhits = ref.compute_hb(scene.scan, scene.init[0])
+        hits, _ = gpu.DebugPoints(scene.scan, scene.init[0], 0)
+        assert np.array_equal(hits, rhits)
+        assert rel(H, rH) < H_TOL and rel(B, rB) < H_TOL
+        assert gpu.last_result["n_effective"] == rres["n_effective"]
+        for loop_mode in (0, 1):
+            g = L.NdtRegistration(L.NdtOptions(method_=L.NdtMethod.INCREMENTAL_NDT, max_iteration_=8, eps_=0.0,
+                                               nearby_type_=nearby, loop_mode=loop_mode))
+            r = O.OracleIncNdt(max_iteration=8, eps=0.0, nearby6=nearby, skip_nonfinite=1)
+            g.SetInputTarget(scene.map)
+            r.set_target(scene.map)
+            _, cloud, pose = g.ScanMatch(scene.scan, scene.init[0])
+            rpose, rcloud, rr = r.align(scene.scan, scene.init[0])
+            dr, dt = pose_delta(pose, rpose)
+            assert dr < ROT_TOL and dt < TRANS_TOL and g.last_result["iters"] == rr["iters"]
+            assert np.abs(cloud[:, :3] - rcloud[:, :3]).max() < 2e-4
+    # too few residuals: the loop stops at once, the pose IS written (= the prediction)  (ndt_registration.cpp:349-353)
+    far = scene.scan.copy()
+    far[:, :3] += np.float32(5000.0)
+    _, _, pose = g.ScanMatch(far, scene.init[0], want_cloud=False)
+    assert g.last_result["degenerate"] == 1 and g.last_result["pose_written"] == 1 and g.last_result["iters"] == 1
+    assert np.array_equal(pose, scene.init[0])
+
+
 def test_ndt_degenerate_early_return(scene, ndt_pair):
     """det(H)==0 on the first iteration: result_pose keeps the caller's value (quirk Q11)."""
     gpu, ref = ndt_pair

@@ -218,6 +218,22 @@ def test_ndt_build_and_loop_match_oracle(scene):
     assert st["pose_written"] == 0 and np.array_equal(pose, keep)
 
 
+def test_inc_ndt_bodies_match_oracle(scene):
+    hs = HS.HsIncNdt(scene.map)
+    for nearby in (1, 7):
+        ref = O.OracleIncNdt(nearby6=int(nearby == 7), skip_nonfinite=1)
+        ref.set_target(scene.map)
+        k, mu, info, npts = hs.voxels()
+        rk, rmu, rinfo, rn = ref.voxels()
+        assert np.array_equal(k, rk) and np.array_equal(npts, rn) and np.array_equal(mu, rmu)
+        assert np.abs(info - rinfo).max() <= 1e-9 * np.abs(rinfo).max()
+        H, B, res, hits = hs.hb(HS.ndt_params(n_nearby=nearby), scene.scan, scene.init[0])
+        rH, rB, rres, rhits = ref.compute_hb(scene.scan, scene.init[0])
+        assert np.array_equal(hits, rhits) and rel(H, rH) < 1e-9 and rel(B, rB) < 1e-9
+        assert res["n_effective"] == rres["n_effective"] == int(rhits.sum())
+        assert abs(res["sum_sq_res"] - rres["sum_sq_res"]) <= 1e-9 * rres["sum_sq_res"]
+
+
 def test_hostsim_reproduces_golden():
     import os
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "registration_small.npz"))

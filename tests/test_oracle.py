@@ -277,6 +277,60 @@ def test_ndt_vs_numpy(small, nearby6):
     assert res["n_effective"] == len(scan)  # effective_num++ per point, unconditionally (ndt_registration.cpp:432)
 
 
+def test_inc_ndt_lru_and_stats_vs_numpy(small):
+    """Incremental NDT: three clouds into a small cache (evictions happen), then the weighted H / B."""
+    m, scan, gt, init = small
+    clouds = [m[:2500], m[2000:4500], m[4000:]]
+    ref = O.OracleIncNdt(capacity=600, res_outlier_th=8.0)
+    nr = NR.IncNdtRef(capacity=600)
+    for c in clouds:
+        ref.set_target(c)
+        nr.add_cloud(c[:, :3])
+        keys, mu, info, npts = ref.voxels()
+        assert len(keys) == len(nr.vox) <= 599  # size stays below capacity_ (ndt_registration.cpp:161)
+        assert sorted(nr.vox) == [tuple(k) for k in keys.tolist()]  # same eviction victims
+        for k, mu_k, info_k, n_k in zip(map(tuple, keys.tolist()), mu, info, npts):
+            v = nr.vox[k]
+            assert n_k == v["n_last"]
+            assert np.allclose(mu_k, v["mu"], rtol=0, atol=1e-12)
+            assert np.abs(info_k - v["info"]).max() <= 1e-9 * np.abs(v["info"]).max()
+    H, B, res, hits = ref.compute_hb(scan, init)
+    rH, rB, rhits, total = NR.IncNdtRef.hb(nr, scan[:, :3], init, res_outlier_th=8.0)
+    assert np.array_equal(hits, rhits) and hits.max() >= 1
+    assert rel(H, rH) < 1e-10 and rel(B, rB) < 1e-10
+    assert res["n_effective"] == int(rhits.sum()) == res["n_inlier"]  # residuals, not points (:341)
+    assert abs(res["sum_sq_res"] - total) <= 1e-10 * total
+
+
+def test_inc_ndt_single_point_voxel_and_overwrite_semantics():
+    """One point: mu = the point, info = 100 I (:193-195).  A later cloud REPLACES a voxel's statistics with those
+    of its own points (pts_ is cleared after every update and only the first-scan branch ever runs)."""
+    ref = O.OracleIncNdt(nearby6=0)
+    ref.set_target(np.array([[0.5, 0.5, 0.5, 0]], np.float32))
+    keys, mu, info, npts = ref.voxels()
+    assert keys.tolist() == [[0, 0, 0]] and npts.tolist() == [1]
+    assert np.array_equal(mu[0], [0.5, 0.5, 0.5]) and np.array_equal(info[0], 100 * np.eye(3))
+    pts = np.array([[0.1, 0.1, 0.1], [0.3, 0.2, 0.1], [0.2, 0.4, 0.3]], np.float32)
+    ref.set_target(np.c_[pts, np.zeros(3)].astype(np.float32))
+    keys, mu, info, npts = ref.voxels()
+    p = pts.astype(float)
+    assert npts.tolist() == [3] and np.allclose(mu[0], p.mean(0), atol=1e-15)
+    assert np.allclose(info[0], np.linalg.inv(np.cov(p.T) + 1e-3 * np.eye(3)), rtol=1e-10)
+
+
+def test_inc_ndt_align(scene):
+    ref = O.OracleIncNdt(max_iteration=20, eps=0.0)
+    ref.set_target(scene.map)
+    pose, _, res = ref.align(scene.scan, scene.init[0], want_cloud=False)
+    assert res["iters"] == 20 and res["updates"] == 20
+    d0, d1 = pose_delta(scene.init[0], scene.gt[0]), pose_delta(pose, scene.gt[0])
+    assert d1[1] < 0.1 * d0[1] and d1[0] < 0.1 * d0[0]  # the information-weighted form does converge (unlike direct NDT, Q8)
+    far = scene.scan.copy()
+    far[:, :3] += np.float32(5000)
+    pose, _, res = ref.align(far, scene.init[0], want_cloud=False)
+    assert res["degenerate"] == 1 and res["pose_written"] == 1 and np.array_equal(pose, scene.init[0])  # (:349-353)
+
+
 # ------------------------------------------------------------------------- (iii) kd-tree semantics
 def test_kdtree_exact_equals_brute_force(scene):
     ref = O.OracleIcp(method=O.P2PLANE)
