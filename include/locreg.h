@@ -148,6 +148,19 @@ uint64_t locreg_pack_score(double score, uint32_t index);
 int locreg_transform_cloud(locreg_handle* h, const float* src, size_t n, size_t stride_bytes, const double* pose,
                            float* out_xyz);
 
+/* Cloud pre-filters the reference runs right before SetInputTarget / ScanMatch (CloudFilterInterface:
+ * LocUtils/src/model/cloud_filter/{voxel_filter,box_filter}.cpp; RemoveNanPoint, point_cloud_utils.h:13-20), on the
+ * device.  out_xyz has room for n points of the same stride; *n_out receives the number written.
+ *   remove_nan : pcl::removeNaNFromPointCloud - points with finite x, y, z, order kept
+ *   crop_box   : pcl::CropBox(min, max), identity transform - finite points with min <= p <= max per axis, order kept
+ *   voxel_grid : pcl::VoxelGrid(leaf, leaf, leaf), all fields - per occupied voxel the float32 mean of every float
+ *                word of its points (summed in point order), voxels in ascending PCL voxel index */
+int locreg_filter_remove_nan(locreg_handle* h, const float* xyz, size_t n, size_t stride_bytes, float* out_xyz, size_t* n_out);
+int locreg_filter_crop_box(locreg_handle* h, const float* xyz, size_t n, size_t stride_bytes, const float* min3,
+                           const float* max3, float* out_xyz, size_t* n_out);
+int locreg_filter_voxel_grid(locreg_handle* h, const float* xyz, size_t n, size_t stride_bytes, float leaf_size,
+                             float* out_xyz, size_t* n_out);
+
 /* NDT parity probe: voxel count and, sorted by (kx,ky,kz), keys (nv*3), mu (nv*3), info (nv*9 row-major), npts (nv). */
 int locreg_ndt_num_voxels(locreg_handle* h, size_t* nv);
 int locreg_ndt_get_voxels(locreg_handle* h, int32_t* keys, double* mu, double* info, int32_t* npts);

@@ -13,6 +13,7 @@
 #include "device_map.cuh"
 #include "device_inc_ndt.cuh"
 #include "device_ndt.cuh"
+#include "filters.cuh"
 
 using namespace locreg;
 
@@ -905,6 +906,43 @@ int locreg_transform_cloud(locreg_handle* h, const float* src, size_t n, size_t 
         LR_CUDA(cudaMemcpy(out_xyz, h->d_out.p, n * stride, cudaMemcpyDeviceToHost));
         return LOCREG_OK;
     });
+}
+
+// kind: 0 remove NaN, 1 crop box (a = min3, b = max3), 2 voxel grid (a[0] = leaf)
+static int filter_impl(locreg_handle* h, int kind, const float* xyz, size_t n, size_t stride, const float* a, const float* b,
+                       float* out_xyz, size_t* n_out) {
+    const int rc = check_cloud_args(xyz, n, stride);
+    if (rc) return rc;
+    if (!n_out || (n && !out_xyz)) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    if (kind == 2 && !(a[0] > 0)) { g_last_error = "leaf size must be > 0"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        *n_out = 0;
+        if (n == 0) return LOCREG_OK;
+        stage_cloud(h, xyz, n, stride, false);  // raw copy in d_raw (the float4 view is not needed)
+        h->d_out.reserve(n * stride);
+        h->begin_timing();
+        size_t kept = 0;
+        const unsigned char* in = h->d_raw.as<unsigned char>();
+        unsigned char* out = h->d_out.as<unsigned char>();
+        if (kind == 0) kept = filter_remove_nan(in, n, stride, out, h->stream);
+        else if (kind == 1) kept = filter_crop_box(in, n, stride, a, b, out, h->stream);
+        else kept = filter_voxel_grid(in, n, stride, a[0], out, h->stream);
+        h->end_timing();
+        if (kept) LR_CUDA(cudaMemcpy(out_xyz, out, kept * stride, cudaMemcpyDeviceToHost));
+        *n_out = kept;
+        return LOCREG_OK;
+    });
+}
+int locreg_filter_remove_nan(locreg_handle* h, const float* xyz, size_t n, size_t stride, float* out_xyz, size_t* n_out) {
+    return filter_impl(h, 0, xyz, n, stride, nullptr, nullptr, out_xyz, n_out);
+}
+int locreg_filter_crop_box(locreg_handle* h, const float* xyz, size_t n, size_t stride, const float* min3, const float* max3,
+                           float* out_xyz, size_t* n_out) {
+    if (!min3 || !max3) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    return filter_impl(h, 1, xyz, n, stride, min3, max3, out_xyz, n_out);
+}
+int locreg_filter_voxel_grid(locreg_handle* h, const float* xyz, size_t n, size_t stride, float leaf_size, float* out_xyz, size_t* n_out) {
+    return filter_impl(h, 2, xyz, n, stride, &leaf_size, nullptr, out_xyz, n_out);
 }
 
 int locreg_ndt_num_voxels(locreg_handle* h, size_t* nv) {

@@ -186,6 +186,28 @@ class _Registration:
                                                      out.ctypes.data))
         return out
 
+    # ---- cloud pre-filters (CloudFilterInterface / RemoveNanPoint of the reference), on the device ----
+    def _filter(self, fn, cloud, *args):
+        a, n, s = _cloud(cloud)
+        out = np.empty_like(a)
+        n_out = C.c_size_t(0)
+        _lib.check(fn(self._h, a.ctypes.data, n, s, *args, out.ctypes.data, C.byref(n_out)))
+        return out[:n_out.value]
+
+    def RemoveNanPoint(self, cloud):
+        """pcl::removeNaNFromPointCloud (point_cloud_utils.h:13-20)."""
+        return self._filter(_lib.lib().locreg_filter_remove_nan, cloud)
+
+    def BoxFilter(self, cloud, min3, max3):
+        """BoxFilter::Filter = pcl::CropBox(min, max) (box_filter.cpp:24-32)."""
+        lo = np.ascontiguousarray(min3, np.float32)
+        hi = np.ascontiguousarray(max3, np.float32)
+        return self._filter(_lib.lib().locreg_filter_crop_box, cloud, lo.ctypes.data, hi.ctypes.data)
+
+    def VoxelFilter(self, cloud, voxel_size):
+        """VoxelFilter::Filter = pcl::VoxelGrid with a cubic leaf (voxel_filter.cpp:10-26)."""
+        return self._filter(_lib.lib().locreg_filter_voxel_grid, cloud, C.c_float(voxel_size))
+
     def profile(self, enable):
         """Returns ({'search','fit','solve','rings'} -> (ms, launches)) accumulated so far, then switches instrumentation."""
         ms = np.zeros(4)

@@ -14,6 +14,7 @@
 #include "oracle.h"
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstring>
 #include <list>
@@ -1110,6 +1111,79 @@ int oracle_inc_ndt_align(oracle_inc_ndt* h, const float* src, size_t n, size_t s
     if (out_xyz) transform_cloud(src, n, stride, result, out_xyz);
     if (res) *res = r;
     return 1;
+}
+
+/* ---- cloud pre-filters (PCL 1.8 algorithms restated; PCL is not under /root/reference) ---- */
+/* pcl::removeNaNFromPointCloud (filter.hpp): finite points, order kept */
+size_t oracle_filter_remove_nan(const float* src, size_t n, size_t stride, float* out) {
+    size_t k = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = pt_at(src, i, stride);
+        if (!finite3(p)) continue;
+        std::memcpy(pt_at(out, k++, stride), p, stride);
+    }
+    return k;
+}
+/* pcl::CropBox, identity transform, negative = false (crop_box.hpp): keep min <= p <= max */
+size_t oracle_filter_crop_box(const float* src, size_t n, size_t stride, const float* mn, const float* mx, float* out) {
+    size_t k = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = pt_at(src, i, stride);
+        if (!finite3(p)) continue;
+        if (p[0] < mn[0] || p[1] < mn[1] || p[2] < mn[2] || p[0] > mx[0] || p[1] > mx[1] || p[2] > mx[2]) continue;
+        std::memcpy(pt_at(out, k++, stride), p, stride);
+    }
+    return k;
+}
+/* pcl::VoxelGrid::applyFilter (voxel_grid.hpp), cubic leaf, downsample_all_data: voxel index from float floor(p *
+ * inverse_leaf) - min_b, points sorted by voxel index (stable here: PCL's std::sort leaves the order inside a voxel
+ * unspecified), float32 mean of every float word, voxels in ascending index.  Returns (size_t)-1 if the index space
+ * exceeds 2^28 cells (PCL itself gives up at 2^31). */
+size_t oracle_filter_voxel_grid(const float* src, size_t n, size_t stride, float leaf, float* out) {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool any = false;
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = pt_at(src, i, stride);
+        if (!finite3(p)) continue;
+        any = true;
+        for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], p[a]); mx[a] = std::max(mx[a], p[a]); }
+    }
+    if (!any) return 0;
+    const float inv = 1.0f / leaf;
+    int min_b[3];
+    long long div[3];
+    for (int a = 0; a < 3; ++a) {
+        min_b[a] = static_cast<int>(std::floor(mn[a] * inv));
+        div[a] = static_cast<long long>(static_cast<int>(std::floor(mx[a] * inv))) - min_b[a] + 1;
+    }
+    if (div[0] * div[1] * div[2] > (1ll << 28)) return static_cast<size_t>(-1);
+    const int mul[3] = {1, static_cast<int>(div[0]), static_cast<int>(div[0] * div[1])};
+    std::vector<std::pair<unsigned int, unsigned int>> iv;  // (voxel index, point index)
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = pt_at(src, i, stride);
+        if (!finite3(p)) continue;
+        const int i0 = static_cast<int>(std::floor(p[0] * inv) - static_cast<float>(min_b[0]));
+        const int i1 = static_cast<int>(std::floor(p[1] * inv) - static_cast<float>(min_b[1]));
+        const int i2 = static_cast<int>(std::floor(p[2] * inv) - static_cast<float>(min_b[2]));
+        iv.emplace_back(static_cast<unsigned int>(i0 * mul[0] + i1 * mul[1] + i2 * mul[2]), static_cast<unsigned int>(i));
+    }
+    std::stable_sort(iv.begin(), iv.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    const size_t words = std::min<size_t>(stride / 4, 8);
+    size_t k = 0;
+    for (size_t a = 0; a < iv.size();) {
+        size_t b = a;
+        float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        while (b < iv.size() && iv[b].first == iv[a].first) {
+            const float* p = pt_at(src, iv[b].second, stride);
+            for (size_t w = 0; w < words; ++w) sum[w] = sum[w] + p[w];
+            ++b;
+        }
+        float* o = pt_at(out, k++, stride);
+        const float fn = static_cast<float>(b - a);
+        for (size_t w = 0; w < stride / 4; ++w) o[w] = w < words ? sum[w] / fn : 0.0f;
+        a = b;
+    }
+    return k;
 }
 
 void oracle_transform_cloud(const float* src, size_t n, size_t stride, const double* pose7, float* out_xyz) {

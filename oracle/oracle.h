@@ -119,6 +119,12 @@ int oracle_inc_ndt_compute_hb(oracle_inc_ndt* h, const float* src, size_t n, siz
 int oracle_inc_ndt_align(oracle_inc_ndt* h, const float* src, size_t n, size_t stride_bytes, const double* pose_in,
                          double* pose_out, float* out_xyz, oracle_result* res, double* pose_trace);
 
+/* cloud pre-filters (pcl::removeNaNFromPointCloud, pcl::CropBox, pcl::VoxelGrid as the reference's RemoveNanPoint /
+ * BoxFilter / VoxelFilter use them); out has room for n points of the same stride; return = points written */
+size_t oracle_filter_remove_nan(const float* src, size_t n, size_t stride_bytes, float* out);
+size_t oracle_filter_crop_box(const float* src, size_t n, size_t stride_bytes, const float* min3, const float* max3, float* out);
+size_t oracle_filter_voxel_grid(const float* src, size_t n, size_t stride_bytes, float leaf, float* out);
+
 /* pcl::transformPointCloud (icp_registration.cpp:241, ndt_registration.cpp:258) */
 void oracle_transform_cloud(const float* src, size_t n, size_t stride_bytes, const double* pose7, float* out_xyz);
 /* pose helpers for tests: pose7 <- pose7 * (exp(w), +dt) in the reference's split update form */

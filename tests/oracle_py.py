@@ -78,6 +78,12 @@ def lib():
         L.oracle_inc_ndt_get_voxels.argtypes = [vp, vp, vp, vp, vp]
         L.oracle_inc_ndt_compute_hb.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(Result), vp]
         L.oracle_inc_ndt_align.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(Result), vp]
+        L.oracle_filter_remove_nan.restype = sz
+        L.oracle_filter_remove_nan.argtypes = [vp, sz, sz, vp]
+        L.oracle_filter_crop_box.restype = sz
+        L.oracle_filter_crop_box.argtypes = [vp, sz, sz, vp, vp, vp]
+        L.oracle_filter_voxel_grid.restype = sz
+        L.oracle_filter_voxel_grid.argtypes = [vp, sz, sz, C.c_float, vp]
         L.oracle_transform_cloud.argtypes = [vp, sz, sz, vp, vp]
         L.oracle_pose_update.argtypes = [vp, vp]
         L.oracle_pose_matrix.argtypes = [vp, vp]
@@ -280,6 +286,25 @@ def bfnn(map_cloud, q, k):
     out = np.empty((nq, k), np.int32)
     lib().oracle_bfnn(m.ctypes.data, n, ms, qq.ctypes.data, nq, qs, k, out.ctypes.data)
     return out
+
+
+def filter_remove_nan(cloud):
+    a, n, s = _cloud(cloud)
+    out = np.zeros_like(a)
+    return out[:lib().oracle_filter_remove_nan(a.ctypes.data, n, s, out.ctypes.data)]
+
+
+def filter_crop_box(cloud, min3, max3):
+    a, n, s = _cloud(cloud)
+    out = np.zeros_like(a)
+    lo, hi = np.ascontiguousarray(min3, np.float32), np.ascontiguousarray(max3, np.float32)
+    return out[:lib().oracle_filter_crop_box(a.ctypes.data, n, s, lo.ctypes.data, hi.ctypes.data, out.ctypes.data)]
+
+
+def filter_voxel_grid(cloud, leaf):
+    a, n, s = _cloud(cloud)
+    out = np.zeros_like(a)
+    return out[:lib().oracle_filter_voxel_grid(a.ctypes.data, n, s, leaf, out.ctypes.data)]
 
 
 def transform_cloud(src, pose7):

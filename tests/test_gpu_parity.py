@@ -295,6 +295,28 @@ def test_inc_ndt_cache_hb_and_pose(scene):
     assert np.array_equal(pose, scene.init[0])
 
 
+def test_prefilters_match_oracle(scene, icp_pair):
+    gpu, _ = icp_pair
+    for width in (8, 4):  # pcl::PointXYZI (32 B) and float4
+        pts = np.zeros((len(scene.map), width), np.float32)
+        pts[:, :3] = scene.map[:, :3]
+        pts[:, 3] = np.arange(len(pts)) % 251 if width == 4 else 1.0
+        if width == 8:
+            pts[:, 4] = np.arange(len(pts)) % 251
+        pts[::97, 1] = np.nan
+        pts[5, 0] = np.inf
+        assert np.array_equal(gpu.RemoveNanPoint(pts), O.filter_remove_nan(pts))
+        lo, hi = np.float32([-10, -5, -1]), np.float32([12, 20, 3])
+        box = gpu.BoxFilter(pts, lo, hi)
+        assert np.array_equal(box, O.filter_crop_box(pts, lo, hi)) and 0 < len(box) < len(pts)
+        for leaf in (0.5, 1.0, 2.5):
+            vg = gpu.VoxelFilter(pts, leaf)
+            ref = O.filter_voxel_grid(pts, leaf)
+            assert vg.shape == ref.shape and np.array_equal(vg, ref) and 0 < len(vg) < len(pts)
+    assert len(gpu.VoxelFilter(np.zeros((0, 4), np.float32), 1.0)) == 0
+    assert len(gpu.RemoveNanPoint(np.full((7, 4), np.nan, np.float32))) == 0
+
+
 def test_ndt_degenerate_early_return(scene, ndt_pair):
     """det(H)==0 on the first iteration: result_pose keeps the caller's value (quirk Q11)."""
     gpu, ref = ndt_pair

@@ -331,6 +331,43 @@ def test_inc_ndt_align(scene):
     assert res["degenerate"] == 1 and res["pose_written"] == 1 and np.array_equal(pose, scene.init[0])  # (:349-353)
 
 
+def test_prefilters_vs_numpy(scene):
+    """RemoveNanPoint / BoxFilter / VoxelFilter restated (pcl::removeNaNFromPointCloud, CropBox, VoxelGrid)."""
+    pts = np.zeros((20000, 8), np.float32)  # pcl::PointXYZI layout
+    pts[:, :3] = scene.map[:20000, :3]
+    pts[:, 3] = 1.0
+    pts[:, 4] = np.arange(20000) % 255
+    pts[::97, 1] = np.nan
+    pts[5, 0] = np.inf
+    fin = np.isfinite(pts[:, :3]).all(1)
+    assert np.array_equal(O.filter_remove_nan(pts), pts[fin])
+    lo, hi = np.float32([-10, -5, -1]), np.float32([12, 20, 3])
+    keep = fin & (pts[:, :3] >= lo).all(1) & (pts[:, :3] <= hi).all(1)
+    assert np.array_equal(O.filter_crop_box(pts, lo, hi), pts[keep]) and 0 < keep.sum() < fin.sum()
+    leaf = np.float32(1.0)
+    out = O.filter_voxel_grid(pts, leaf)
+    p = pts[fin]
+    inv = np.float32(1.0) / leaf
+    mb = np.floor(p[:, :3].min(0) * inv).astype(np.int64)
+    div = np.floor(p[:, :3].max(0) * inv).astype(np.int64) - mb + 1
+    ijk = (np.floor(p[:, :3] * inv) - mb.astype(np.float32)).astype(np.int64)
+    idx = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    order = np.argsort(idx, kind="stable")
+    uniq, start = np.unique(idx[order], return_index=True)
+    assert len(out) == len(uniq)
+    bounds = list(start) + [len(order)]
+    for v in (0, len(uniq) // 2, len(uniq) - 1):
+        grp = p[order[bounds[v]:bounds[v + 1]]]
+        acc = np.zeros(8, np.float32)
+        for row in grp:
+            acc = acc + row
+        assert np.array_equal(out[v], acc / np.float32(len(grp)))
+    assert np.allclose(out[:, 3], 1.0) and out[:, 4].max() <= 254  # intensity is averaged like every other field
+    # fewer points than the input, none lost: the count-weighted mean of the centroids is the mean of the cloud
+    counts = np.diff(bounds)
+    assert np.allclose((out[:, :3] * counts[:, None]).sum(0) / counts.sum(), p[:, :3].astype(np.float64).mean(0), atol=1e-3)
+
+
 # ------------------------------------------------------------------------- (iii) kd-tree semantics
 def test_kdtree_exact_equals_brute_force(scene):
     ref = O.OracleIcp(method=O.P2PLANE)
