@@ -146,7 +146,7 @@ __global__ void k_tile_begin(const long long* __restrict__ offsets, unsigned int
 // mode bit 1 (kNnTwoPass): threshold pre-pass of knn_scan_list (first iterations: no or poor seeds).
 constexpr int kNnSeeds = 1, kNnTwoPass = 2;
 struct RingQueue {
-    unsigned int* count;   // entries appended so far (reset by k_icp_post)
+    unsigned int* count;   // entries appended so far (reset by k_icp_post); count[1] = the consumers' work cursor
     uint2* entries;        // (scratch row of the point, scan index)
 };
 
@@ -226,8 +226,17 @@ __global__ void __launch_bounds__(128) k_icp_nn_finish(VoxelMapView map, CoarseL
                                                        const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
                                                        RingQueue queue, unsigned int min_count) {
     const unsigned int n = *queue.count;
-    if (n < min_count) return;  // short queues are k_icp_nn_rings' (a warp per query: latency, not throughput)
-    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    if (n < min_count) return;  // short queues are k_icp_nn_rings'
+    // Queries differ several-fold in cost, so warps do not own a fixed share of the queue: each one takes the next
+    // 32 entries from a shared cursor whenever it has finished its last batch.
+    const unsigned int lane = threadIdx.x & 31;
+    while (true) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(queue.count + 1, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const unsigned int e = base + lane;
+        if (e >= n) continue;
         const uint2 q = queue.entries[e];
         const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
         const float4 sp = bv.src[src_idx];
@@ -410,7 +419,7 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
     __shared__ Pose T;
     __shared__ double rows[kTile * ROWS * kRowStride];
     __shared__ double wsum[kTile / 32][32];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *ring_count = 0u;  // both search stages of this evaluation are done
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ring_count[0] = 0u; ring_count[1] = 0u; }  // both search stages of this evaluation are done
     const TileCoord tc = locate_tile(bv, blockIdx.x);
     if (!tc.valid) return;
     const AlignState* st = states + tc.scan;

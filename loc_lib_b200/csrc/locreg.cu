@@ -289,9 +289,9 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     h->d_nnpos.reserve(job.n_scratch_points * K * sizeof(unsigned int));
     h->d_partials.reserve(static_cast<size_t>(job.n_tiles) * kPartialDoubles * sizeof(double));
     h->d_ringq.reserve(job.n_scratch_points * sizeof(uint2));
-    h->d_ringc.reserve(sizeof(unsigned int));
-    // k_icp_post re-zeroes the counter after every use; the first evaluation of a job starts from a known state
-    if (!(nn_mode & kNnSeeds)) LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, sizeof(unsigned int), h->stream));
+    h->d_ringc.reserve(2 * sizeof(unsigned int));
+    // k_icp_post re-zeroes the counters after every use; the first evaluation of a job starts from a known state
+    if (!(nn_mode & kNnSeeds)) LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, 2 * sizeof(unsigned int), h->stream));
     if (job.n_tiles == 0) return;
     const RingQueue queue{h->d_ringc.as<unsigned int>(), h->d_ringq.as<uint2>()};
     // Queries stage 1 cannot finish: a small job (one scan) gives each of them a warp (lowest latency, the GPU is idle
