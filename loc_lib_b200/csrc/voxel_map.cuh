@@ -253,16 +253,46 @@ LR_HD void knn_scan_list(const float4* __restrict__ pts, KnnResult<K>& res, floa
         }
         thr = t[K - 1];
     }
-    for (unsigned int i = beg; i <= last; i += kScanBatch) {
-        float4 p[kScanBatch];
+    if (!two_pass) {
+        // seeded scan: what passes the bound is almost always a seed met again in the list (rejected by the membership
+        // test), now and then a closer point; handled in place
+        for (unsigned int i = beg; i <= last; i += kScanBatch) {
+            float4 p[kScanBatch];
 #pragma unroll
-        for (int u = 0; u < kScanBatch; ++u) p[u] = pts[min(i + u, last)];
-        float d2[kScanBatch];
+            for (int u = 0; u < kScanBatch; ++u) p[u] = pts[min(i + u, last)];
+            float d2[kScanBatch];
 #pragma unroll
-        for (int u = 0; u < kScanBatch; ++u) d2[u] = dis2_f32(qx, qy, qz, p[u].x, p[u].y, p[u].z);
+            for (int u = 0; u < kScanBatch; ++u) d2[u] = dis2_f32(qx, qy, qz, p[u].x, p[u].y, p[u].z);
 #pragma unroll
-        for (int u = 0; u < kScanBatch; ++u)
-            if (d2[u] <= thr) knn_offer(pts, res, d2[u], static_cast<unsigned int>(float_as_int(p[u].w)));
+            for (int u = 0; u < kScanBatch; ++u) knn_offer(pts, res, d2[u], static_cast<unsigned int>(float_as_int(p[u].w)));
+        }
+        return;
+    }
+    // Second pass of the unseeded scan: the <= K (+ ties) candidates at or below the threshold are only MARKED while
+    // the list streams through again (branch-free: a bit per entry, 64 entries per chunk), then inserted in a loop all
+    // lanes walk together - every lane has about K of them, at different places of its list.
+    for (unsigned int chunk = beg; chunk <= last; chunk += 64) {
+        const unsigned int cend = min(chunk + 63u, last);
+        const float bound = fminf(thr, res.d2[K - 1]);
+        unsigned long long marks = 0ull;
+        for (unsigned int i = chunk; i <= cend; i += kScanBatch) {
+            float4 p[kScanBatch];
+#pragma unroll
+            for (int u = 0; u < kScanBatch; ++u) p[u] = pts[min(i + u, cend)];
+            unsigned int m = 0u;
+#pragma unroll
+            for (int u = 0; u < kScanBatch; ++u) {
+                const float d2 = dis2_f32(qx, qy, qz, p[u].x, p[u].y, p[u].z);
+                m |= (d2 <= bound && i + u <= cend) ? (1u << u) : 0u;
+            }
+            marks |= static_cast<unsigned long long>(m) << (i - chunk);
+        }
+        while (marks) {
+            const int bit = ffs64(marks) - 1;
+            marks &= marks - 1;
+            const float4 p = pts[chunk + bit];
+            knn_offer(pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), static_cast<unsigned int>(float_as_int(p.w)));
+        }
     }
 #else
     (void)two_pass;
