@@ -332,7 +332,8 @@ void icp_launch_solve(locreg_handle* h, const IcpJob& job, int mode, double* acc
 template <int METHOD>
 void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
     for (int it = 0; it < h->opt.max_iteration; ++it) {
-        icp_launch_eval<METHOD>(h, job, 0, it == 0 ? kNnTwoPass : kNnSeeds, nullptr, nullptr);
+        static const int tp_iters = getenv("LOCREG_TWOPASS_ITERS") ? atoi(getenv("LOCREG_TWOPASS_ITERS")) : 2;  // iterations whose scan uses the threshold pre-pass (2 measured best)
+        icp_launch_eval<METHOD>(h, job, 0, it == 0 ? kNnTwoPass : (it < tp_iters ? (kNnSeeds | kNnTwoPass) : kNnSeeds), nullptr, nullptr);
         icp_launch_solve<METHOD>(h, job, 1, nullptr);
     }
     if (final_eval) {
