@@ -161,6 +161,13 @@ int locreg_filter_crop_box(locreg_handle* h, const float* xyz, size_t n, size_t 
 int locreg_filter_voxel_grid(locreg_handle* h, const float* xyz, size_t n, size_t stride_bytes, float leaf_size,
                              float* out_xyz, size_t* n_out);
 
+/* Caller state kept on the device (Loc, LocUtils/src/slam/3d/loc.cpp): the global map is uploaded once
+ * (Loc::InitGlobalMap, loc.cpp:268-283); locreg_reset_local_map is Loc::ResetLocalMap (loc.cpp:187-206) -
+ * BoxFilter::SetOrigin(origin) + Filter (crop to origin +- half_size) + SetInputTarget(local map) - with the crop and
+ * the index build both on the device; *n_local (may be NULL) receives the size of the local map. */
+int locreg_set_global_map(locreg_handle* h, const float* xyz, size_t n, size_t stride_bytes);
+int locreg_reset_local_map(locreg_handle* h, const float* origin3, const float* half_size3, size_t* n_local);
+
 /* NDT parity probe: voxel count and, sorted by (kx,ky,kz), keys (nv*3), mu (nv*3), info (nv*9 row-major), npts (nv). */
 int locreg_ndt_num_voxels(locreg_handle* h, size_t* nv);
 int locreg_ndt_get_voxels(locreg_handle* h, int32_t* keys, double* mu, double* info, int32_t* npts);

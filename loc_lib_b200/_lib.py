@@ -17,7 +17,7 @@ SYMBOLS = [
     "locreg_align_batch", "locreg_align_batch_device", "locreg_relocalise", "locreg_pack_score",
     "locreg_transform_cloud", "locreg_ndt_num_voxels", "locreg_ndt_get_voxels", "locreg_last_timing",
     "locreg_profile", "locreg_last_error", "locreg_version", "locreg_filter_remove_nan", "locreg_filter_crop_box",
-    "locreg_filter_voxel_grid",
+    "locreg_filter_voxel_grid", "locreg_set_global_map", "locreg_reset_local_map",
 ]
 
 
@@ -70,6 +70,8 @@ def lib():
         L.locreg_ndt_get_voxels.argtypes = [vp, vp, vp, vp, vp]
         L.locreg_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
         L.locreg_profile.argtypes = [vp, i32, vp, vp]
+        L.locreg_set_global_map.argtypes = [vp, vp, sz, sz]
+        L.locreg_reset_local_map.argtypes = [vp, vp, vp, C.POINTER(sz)]
         L.locreg_filter_remove_nan.argtypes = [vp, vp, sz, sz, vp, C.POINTER(sz)]
         L.locreg_filter_crop_box.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(sz)]
         L.locreg_filter_voxel_grid.argtypes = [vp, vp, sz, sz, C.c_float, vp, C.POINTER(sz)]

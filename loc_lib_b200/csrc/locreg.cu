@@ -78,7 +78,8 @@ struct locreg_handle {
     DeviceIncNdtMap inc_ndt_map;  // LOCREG_NDT_INCREMENTAL
     bool has_target = false;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
-        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_states, d_ringq, d_ringc;
+        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_states, d_ringq, d_ringc, d_global, d_local;
+    size_t n_global = 0, global_stride = 0;  // Loc's global map kept on the device (locreg_set_global_map)
     PinBuf h_in, h_out, h_small;
     double last_ms = 0;
     long long last_launches = 0;
@@ -906,6 +907,39 @@ int locreg_transform_cloud(locreg_handle* h, const float* src, size_t n, size_t 
         h->end_timing();
         LR_CUDA(cudaMemcpy(out_xyz, h->d_out.p, n * stride, cudaMemcpyDeviceToHost));
         return LOCREG_OK;
+    });
+}
+
+// Loc::InitGlobalMap (loc.cpp:268-283): the global map goes to the device once and stays there.
+int locreg_set_global_map(locreg_handle* h, const float* xyz, size_t n, size_t stride) {
+    const int rc = check_cloud_args(xyz, n, stride);
+    if (rc) return rc;
+    return guarded(h, [&]() {
+        h->d_global.reserve(std::max<size_t>(n * stride, 1));
+        if (n) LR_CUDA(cudaMemcpyAsync(h->d_global.p, xyz, n * stride, cudaMemcpyHostToDevice, h->stream));
+        LR_CUDA(cudaStreamSynchronize(h->stream));
+        h->n_global = n;
+        h->global_stride = stride;
+        return LOCREG_OK;
+    });
+}
+// Loc::ResetLocalMap (loc.cpp:187-206): BoxFilter::SetOrigin + Filter (pcl::CropBox, box_filter.cpp:24-32,46-60) of the
+// global map, then SetInputTarget of the cropped cloud - without the cloud leaving the device.
+int locreg_reset_local_map(locreg_handle* h, const float* origin3, const float* half_size3, size_t* n_local) {
+    if (!origin3 || !half_size3) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        if (h->global_stride == 0) { g_last_error = "locreg_set_global_map has not been called"; return LOCREG_E_STATE; }
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {  // edge = size + origin in float (BoxFilter::CalculateEdge)
+            lo[a] = -half_size3[a] + origin3[a];
+            hi[a] = half_size3[a] + origin3[a];
+        }
+        h->d_local.reserve(std::max<size_t>(h->n_global * h->global_stride, 1));
+        size_t kept = 0;
+        if (h->n_global)
+            kept = filter_crop_box(h->d_global.as<unsigned char>(), h->n_global, h->global_stride, lo, hi, h->d_local.as<unsigned char>(), h->stream);
+        if (n_local) *n_local = kept;
+        return set_target_impl(h, h->d_local.as<float>(), kept, h->global_stride, true);
     });
 }
 

@@ -69,11 +69,14 @@ class NdtOptions:  # ndt_registration.hpp:27-42
 
 
 def _cloud(a):
+    """(array, point count, point stride in bytes) of an (n, >= 3) float32 cloud; anything that is not a C-contiguous
+    float32 matrix (other dtypes, sliced views) is copied first, so that the row stride is always shape[1] * 4 and an
+    output array made with empty_like has the same layout."""
     a = np.asarray(a)
-    if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] < 3 or a.strides[1] != 4:
+    if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] < 3 or not a.flags.c_contiguous:
         a = np.ascontiguousarray(a, np.float32)
         assert a.ndim == 2 and a.shape[1] >= 3, "cloud must be (n, >=3) float32"
-    return a, a.shape[0], a.strides[0] if a.shape[0] else a.shape[1] * 4
+    return a, a.shape[0], a.shape[1] * 4
 
 
 def _pose(p):
@@ -208,6 +211,19 @@ class _Registration:
         """VoxelFilter::Filter = pcl::VoxelGrid with a cubic leaf (voxel_filter.cpp:10-26)."""
         return self._filter(_lib.lib().locreg_filter_voxel_grid, cloud, C.c_float(voxel_size))
 
+    # ---- Loc's map state on the device (loc.cpp:187-206, 268-283) ----
+    def SetGlobalMap(self, cloud):
+        a, n, s = _cloud(cloud)
+        _lib.check(_lib.lib().locreg_set_global_map(self._h, a.ctypes.data, n, s))
+
+    def ResetLocalMap(self, x, y, z, half_size=(150.0, 150.0, 150.0)):
+        """Loc::ResetLocalMap: crop the global map to (x, y, z) +- half_size and make it the target; returns its size."""
+        o = np.ascontiguousarray([x, y, z], np.float32)
+        hs = np.ascontiguousarray(half_size, np.float32)
+        n_local = C.c_size_t(0)
+        _lib.check(_lib.lib().locreg_reset_local_map(self._h, o.ctypes.data, hs.ctypes.data, C.byref(n_local)))
+        return n_local.value
+
     def profile(self, enable):
         """Returns ({'search','fit','solve','rings'} -> (ms, launches)) accumulated so far, then switches instrumentation."""
         ms = np.zeros(4)
@@ -284,3 +300,61 @@ class NdtRegistration(_Registration):
         _lib.check(_lib.lib().locreg_ndt_get_voxels(self._h, keys.ctypes.data, mu.ctypes.data, info.ctypes.data,
                                                     npts.ctypes.data))
         return keys, mu, info, npts
+
+
+# ---- the slice of Loc (LocUtils/src/slam/3d/loc.cpp) that decides what the registration is called with ----------------
+def _q_mul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _q_rot(q, v):
+    x, y, z, w = q
+    u = np.array([x, y, z])
+    t = 2.0 * np.cross(u, v)
+    return v + w * t + np.cross(u, t)
+
+
+def se3_mul(a, b):
+    """Sophus SE3d product of two [qx qy qz qw tx ty tz] poses."""
+    q = _q_mul(a[:4], b[:4])
+    return np.concatenate([q / np.linalg.norm(q), a[4:] + _q_rot(a[:4], b[4:])])
+
+
+def se3_inv(a):
+    qi = np.array([-a[0], -a[1], -a[2], a[3]])
+    return np.concatenate([qi, -_q_rot(qi, a[4:])])
+
+
+class LocTracker:
+    """Loc::Update without the ROS / ESKF parts (loc.cpp:208-246): ScanMatch from the constant-velocity prediction
+    predict = result * last^-1 * result (:232), and a new 150 m local map (ResetLocalMap, on the device) whenever the
+    pose comes within 50 m of the box edge on any axis (:235-246)."""
+
+    def __init__(self, registration, global_map, init_pose, half_size=(150.0, 150.0, 150.0), margin=50.0):
+        self.reg, self.half, self.margin = registration, np.asarray(half_size, np.float32), margin
+        self.reg.SetGlobalMap(global_map)
+        self.last_pose = np.asarray(init_pose, np.float64).copy()
+        self.predict = self.last_pose.copy()
+        self.resets = 0
+        self._reset(self.last_pose[4:])
+
+    def _reset(self, t):
+        self.origin = np.asarray(t, np.float32)
+        self.n_local = self.reg.ResetLocalMap(*self.origin, half_size=self.half)
+        self.edge = np.stack([-self.half + self.origin, self.half + self.origin], 1)  # per axis [lo, hi]
+        self.resets += 1
+
+    def Update(self, scan):
+        _, cloud, result = self.reg.ScanMatch(scan, self.predict)
+        self.predict = se3_mul(se3_mul(result, se3_inv(self.last_pose)), result)
+        self.last_pose = result
+        t = result[4:]
+        for i in range(3):
+            if abs(t[i] - self.edge[i, 0]) > self.margin and abs(t[i] - self.edge[i, 1]) > self.margin:
+                continue
+            self._reset(t)
+            break
+        return result, cloud

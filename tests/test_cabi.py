@@ -148,3 +148,27 @@ def test_cpp_adapter_scan_match_on_gpu():
     """The same binary on the B200: SetInputTarget + ScanMatch through the virtual interface recover a known shift."""
     r = _run_adapter()
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_se3_helpers_of_the_loc_slice():
+    """predict = result * last^-1 * result (loc.cpp:232) on 7-double poses, against 4x4 matrices."""
+    import loc_lib_b200 as L
+    import oracle_py as O
+    rng = np.random.default_rng(0)
+
+    def rand_pose():
+        q = rng.normal(size=4)
+        return np.concatenate([q / np.linalg.norm(q), rng.uniform(-5, 5, 3)])
+
+    def mat(p):
+        T = np.eye(4)
+        T[:3, :3] = O.pose_matrix(p)
+        T[:3, 3] = p[4:]
+        return T
+
+    for _ in range(20):
+        a, b = rand_pose(), rand_pose()
+        assert np.allclose(mat(L.se3_mul(a, b)), mat(a) @ mat(b), atol=1e-13)
+        assert np.allclose(mat(L.se3_inv(a)), np.linalg.inv(mat(a)), atol=1e-13)
+        pred = L.se3_mul(L.se3_mul(a, L.se3_inv(b)), a)
+        assert np.allclose(mat(pred), mat(a) @ np.linalg.inv(mat(b)) @ mat(a), atol=1e-12)

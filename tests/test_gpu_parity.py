@@ -317,6 +317,39 @@ def test_prefilters_match_oracle(scene, icp_pair):
     assert len(gpu.RemoveNanPoint(np.full((7, 4), np.nan, np.float32))) == 0
 
 
+def test_loc_tracker_device_local_map_equals_host_path(scene):
+    """Loc's loop (constant-velocity prediction, re-crop near the box edge) with the global map resident on the device
+    gives exactly the poses of the host path: CropBox on the host, SetInputTarget, ScanMatch."""
+    import loc_lib_b200 as L
+    opts = L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=6, eps_=0.0)
+    half, margin = (25.0, 25.0, 25.0), 12.0
+    dev = L.IcpRegistration(opts)
+    trk = L.LocTracker(dev, scene.map, scene.init[0], half_size=half, margin=margin)
+    host = L.IcpRegistration(opts)
+    origin = np.float32(scene.init[0][4:])
+    hs = np.float32(half)
+    local = O.filter_crop_box(scene.map, -hs + origin, hs + origin)
+    assert trk.n_local == len(local) and 0 < len(local) < len(scene.map)
+    host.SetInputTarget(local)
+    predict, last = scene.init[0].copy(), scene.init[0].copy()
+    resets = 1
+    for step in range(len(scene.scans)):
+        # the scene's scans come from different places: move each into the frame of the first so that the walk is short
+        scan = scene.scans[0] if step % 2 == 0 else scene.scans[0][::2]
+        result, _ = trk.Update(scan)
+        _, _, ref = host.ScanMatch(scan, predict, want_cloud=False)
+        assert np.array_equal(result, ref)
+        predict = L.se3_mul(L.se3_mul(ref, L.se3_inv(last)), ref)
+        last = ref
+        edge = np.stack([-hs + origin, hs + origin], 1)
+        if any(not (abs(ref[4 + i] - edge[i, 0]) > margin and abs(ref[4 + i] - edge[i, 1]) > margin) for i in range(3)):
+            origin = np.float32(ref[4:])
+            host.SetInputTarget(O.filter_crop_box(scene.map, -hs + origin, hs + origin))
+            resets += 1
+        assert np.array_equal(trk.predict, predict)
+    assert trk.resets == resets
+
+
 def test_ndt_degenerate_early_return(scene, ndt_pair):
     """det(H)==0 on the first iteration: result_pose keeps the caller's value (quirk Q11)."""
     gpu, ref = ndt_pair
