@@ -31,6 +31,28 @@ class DeviceVoxelMap {
 
    private:
     void release();
+    // Device arrays keep their capacity across builds: Loc re-crops its local map every few hundred scans, and a
+    // cudaMalloc / cudaFree pair of the 0.4 GB list array costs more than all the build kernels together.
+    template <class T>
+    struct Grow {
+        T* p = nullptr;
+        size_t cap = 0;  // elements
+        T* ensure(size_t count) {
+            if (count > cap) {
+                if (p) cudaFree(p);
+                p = nullptr; cap = 0;
+                const size_t want = count + count / 8 + 64;
+                LR_CUDA(cudaMalloc(&p, want * sizeof(T)));
+                cap = want;
+            }
+            return p;
+        }
+        void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    };
+    Grow<VoxelSlot> slots_buf_;
+    Grow<unsigned int> cell_start_buf_;
+    Grow<float4> pts_buf_;
+    Grow<NbrSlot> nbr_buf_;
     VoxelSlot* slots_ = nullptr;
     unsigned int* cell_start_ = nullptr;
     float4* pts_ = nullptr;

@@ -465,6 +465,14 @@ int locreg_create(const locreg_options* opt, int32_t device, locreg_handle** out
         LR_CUDA(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) throw std::runtime_error("locreg kernels are built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor));
         h->num_sms = prop.multiProcessorCount;
+        // stream-ordered scratch (map builds, filters) comes from the device's default pool: keep what it has handed
+        // out instead of returning it to the driver at every synchronisation point (the default threshold is 0)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
         LR_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
         LR_CUDA(cudaEventCreate(&h->ev0));

@@ -188,12 +188,10 @@ __global__ void k_nbr_set_start(NbrSlot* nbr, unsigned int cap, const unsigned i
 }
 
 // ------------------------------------------------------------------------------------------------
-DeviceVoxelMap::~DeviceVoxelMap() { release(); }
-void DeviceVoxelMap::release() {
-    if (slots_) cudaFree(slots_);
-    if (cell_start_) cudaFree(cell_start_);
-    if (pts_) cudaFree(pts_);
-    if (nbr_) cudaFree(nbr_);
+DeviceVoxelMap::~DeviceVoxelMap() {
+    slots_buf_.free(); cell_start_buf_.free(); pts_buf_.free(); nbr_buf_.free();
+}
+void DeviceVoxelMap::release() {  // forgets the map, keeps the memory
     slots_ = nullptr; cell_start_ = nullptr; pts_ = nullptr; nbr_ = nullptr;
     view_ = VoxelMapView{};
     bytes_ = 0; n_cells_ = 0; n_blocks_ = 0; n_lists_ = 0;
@@ -227,7 +225,7 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     unsigned int h_counters[8];
     int h_bounds[6];
     while (true) {
-        LR_CUDA(cudaMalloc(&slots_, static_cast<size_t>(cap) * sizeof(VoxelSlot)));
+        slots_ = slots_buf_.ensure(cap);
         LR_LAUNCH(k_slots_clear, (cap + T - 1) / T, T, 0, stream, slots_, cap);
         LR_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(unsigned int), stream));
         const int init_bounds[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, -0x7fffffff, -0x7fffffff, -0x7fffffff};
@@ -238,7 +236,6 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
         LR_CUDA(cudaMemcpyAsync(h_bounds, bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, stream));
         LR_CUDA(cudaStreamSynchronize(stream));
         if (h_counters[1] || static_cast<size_t>(h_counters[0]) * 2 > cap) {  // too loaded: grow and redo
-            cudaFree(slots_);
             slots_ = nullptr;
             if (cap >= (1u << 31)) throw std::runtime_error("voxel hash table overflow");
             cap = cap << 2 ? cap << 2 : (1u << 31);
@@ -249,7 +246,7 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     n_blocks_ = h_counters[0];
     const unsigned int n_kept = h_counters[2];
     if (n_kept == 0) {  // every point was non-finite
-        cudaFree(slots_); slots_ = nullptr;
+        slots_ = nullptr;
         cudaFreeAsync(pt_slot, stream); cudaFreeAsync(pt_pos, stream); cudaFreeAsync(pt_bit, stream);
         cudaFreeAsync(dup, stream); cudaFreeAsync(counters, stream); cudaFreeAsync(bounds, stream);
         return;
@@ -263,7 +260,7 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     LR_CUDA(cudaStreamSynchronize(stream));
     LR_CUDA(cudaFreeAsync(tmp, stream));
     // 3-4 histogram + scan -> cell_start
-    LR_CUDA(cudaMalloc(&cell_start_, (static_cast<size_t>(n_cells_) + 1) * sizeof(unsigned int)));
+    cell_start_ = cell_start_buf_.ensure(static_cast<size_t>(n_cells_) + 1);
     LR_CUDA(cudaMemsetAsync(cell_start_, 0, (static_cast<size_t>(n_cells_) + 1) * sizeof(unsigned int), stream));
     LR_LAUNCH(k_build_count, gridN, T, 0, stream, n, slots_, pt_slot, pt_bit, cell_start_);
     exclusive_scan_u32(cell_start_, cell_start_, static_cast<size_t>(n_cells_) + 1, nullptr, stream);
@@ -278,7 +275,7 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     const size_t list_entries = static_cast<size_t>(n_kept) * 27;
     const bool lists = want_lists && (static_cast<size_t>(n_kept) + list_entries) < 0xF0000000ull &&
                        (list_entries + n_kept) * sizeof(float4) < free_b / 2;
-    LR_CUDA(cudaMalloc(&pts_, (static_cast<size_t>(n_kept) + (lists ? list_entries : 0)) * sizeof(float4)));
+    pts_ = pts_buf_.ensure(static_cast<size_t>(n_kept) + (lists ? list_entries : 0));
     LR_LAUNCH(k_build_scatter, gridN, T, 0, stream, d_xyz, n, stride, pt_slot, cursor, pts_, pt_pos);
     // 6 dedupe (quirk Q3)
     LR_CUDA(cudaMemsetAsync(counters + 5, 0, sizeof(unsigned int), stream));
@@ -293,7 +290,7 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
         nbr_cap = next_pow2(static_cast<size_t>(n_cells_) * 8);
         unsigned int* ncursor = nullptr;
         while (true) {
-            LR_CUDA(cudaMalloc(&nbr_, static_cast<size_t>(nbr_cap) * sizeof(NbrSlot)));
+            nbr_ = nbr_buf_.ensure(nbr_cap);
             LR_LAUNCH(k_nbr_clear, (nbr_cap + T - 1) / T, T, 0, stream, nbr_, nbr_cap);
             LR_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream));
             LR_LAUNCH(k_nbr_pass, gridN, T, 0, stream, n, 0, d_xyz, stride, inv_cell, pt_slot, pt_pos, dup, nbr_, nbr_cap - 1,
@@ -301,7 +298,6 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
             LR_CUDA(cudaMemcpyAsync(h_counters, counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
             LR_CUDA(cudaStreamSynchronize(stream));
             if (h_counters[1] || static_cast<size_t>(h_counters[0]) * 2 > nbr_cap) {
-                cudaFree(nbr_);
                 nbr_ = nullptr;
                 if (nbr_cap >= (1u << 30)) throw std::runtime_error("neighbourhood table overflow");
                 nbr_cap <<= 2;
