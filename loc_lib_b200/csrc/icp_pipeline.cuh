@@ -42,9 +42,17 @@ struct BatchView {
     const float4* src;              // all scans' points
     const long long* offsets;       // S+1 point offsets into src, or nullptr: every item is src[0..n_single)
     const unsigned int* tile_begin; // S+1 tile offsets, or nullptr: item s owns tiles [s*tiles_per_item, ...)
+    const struct TileRec* tiles;    // with tile_begin: the per-tile table k_tile_table derived from it (one load, no search)
     unsigned int n_single;
     unsigned int tiles_per_item;
     unsigned int S;
+};
+
+// One tile of a ragged batch, precomputed once per job: a block finds its work with one broadcast load instead of a
+// binary search of dependent loads in front of every kernel of every iteration.
+struct alignas(16) TileRec {
+    unsigned int scan, first, count, valid;
+    long long base, pad;
 };
 
 struct TileCoord {
@@ -60,6 +68,12 @@ __device__ __forceinline__ TileCoord locate_tile_thread(const BatchView& b, unsi
     TileCoord c{};
     c.valid = false;
     unsigned int s, t;
+    if (b.tiles) {
+        const uint4 a = reinterpret_cast<const uint4*>(b.tiles + tile)[0];
+        c.scan = a.x; c.first = a.y; c.count = a.z; c.valid = a.w != 0u;
+        c.src_base = c.out_base = b.tiles[tile].base;
+        return c;
+    }
     if (b.tile_begin) {
         if (tile >= b.tile_begin[b.S]) return c;
         unsigned int lo = 0, hi = b.S - 1;  // last s with tile_begin[s] <= tile
@@ -88,6 +102,7 @@ __device__ __forceinline__ TileCoord locate_tile_thread(const BatchView& b, unsi
 
 // Block-wide flavour: thread 0 does the (binary) search, everybody reads the answer from shared memory.
 __device__ __forceinline__ TileCoord locate_tile(const BatchView& b, unsigned int tile) {
+    if (b.tiles || !b.tile_begin) return locate_tile_thread(b, tile);  // a broadcast load / pure arithmetic: no hand-over needed
     __shared__ TileCoord tc_shared;
     if (threadIdx.x == 0) tc_shared = locate_tile_thread(b, tile);
     __syncthreads();
@@ -133,6 +148,18 @@ __global__ void k_tile_begin(const long long* __restrict__ offsets, unsigned int
     if (threadIdx.x == 0) tile_begin[S] = carry;
 }
 
+// tiles[t] for every tile of the grid (surplus tiles: valid = 0), from tile_begin.
+__global__ void k_tile_table(BatchView bv, unsigned int n_tiles, TileRec* tiles) {
+    const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    bv.tiles = nullptr;
+    const TileCoord c = locate_tile_thread(bv, t);
+    TileRec r;
+    r.scan = c.scan; r.first = c.first; r.count = c.valid ? c.count : 0u; r.valid = c.valid ? 1u : 0u;
+    r.base = c.src_base; r.pad = 0;
+    tiles[t] = r;
+}
+
 // ---- K_A: neighbour search ---------------------------------------------------------------------------------
 #ifndef LR_NN_MIN_BLOCKS
 #define LR_NN_MIN_BLOCKS 6  // 40 registers: 75 % occupancy measured best on B200 (4: +6 % time, 8: +35 %)
@@ -176,7 +203,8 @@ __device__ __forceinline__ void tile_queue_append(bool mine, unsigned int row, u
 template <int K>
 __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView map, BatchView bv,
                                                                     const AlignState* __restrict__ states, int ignore_stop,
-                                                                    int mode, unsigned int* __restrict__ nn_pos, RingQueue queue) {
+                                                                    int mode, unsigned int* __restrict__ nn_pos,
+                                                                    unsigned char* __restrict__ plane_valid, RingQueue queue) {
     __shared__ Pose T;
     const TileCoord tc = locate_tile(bv, blockIdx.x);
     if (!tc.valid) return;
@@ -197,22 +225,28 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
     // non-finite source points are skipped: P2P as the reference (pcl::isFinite, icp_registration.cpp:64),
     // P2Plane as deviation D1 (the reference would poison H with NaN)
     const bool valid = in_tile && finite3(sp.x, sp.y, sp.z) && map.n_pts != 0;
-    bool done = true;
+    bool done = true, same = false;
     KnnResult<K> nn;
     knn_init(nn);
     __syncthreads();
-    if (valid) {
-        unsigned int seeds[K];
+    // (loaded before sp is looked at: one round trip for the point and its seeds instead of two)
+    unsigned int seeds[K];
 #pragma unroll
-        for (int j = 0; j < K; ++j) seeds[j] = (mode & kNnSeeds) ? out[j] : kNoPos;
+    for (int j = 0; j < K; ++j) seeds[j] = (mode & kNnSeeds) && in_tile ? out[j] : kNoPos;
+    if (valid) {
         double wx, wy, wz;
         pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
         const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
         done = knn_query_fast<K>(map, qx, qy, qz, nn, seeds, (mode & kNnTwoPass) != 0);
+        // same neighbours, in the same order, as in the previous iteration: what k_icp_fit derived from them still holds
+        same = done && (mode & kNnSeeds) != 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) same = same && seeds[j] == nn.pos[j] && seeds[j] != kNoPos;
     }
     if (in_tile) {
 #pragma unroll
         for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+        if (plane_valid && !same) plane_valid[row] = 0;  // k_icp_fit sets it again
     }
     tile_queue_append(!done, static_cast<unsigned int>(row), tc.scan, &blk_pending, &blk_done, staged, queue);
 }
@@ -393,6 +427,71 @@ __global__ void k_knn_export(VoxelMapView map, const unsigned int* __restrict__ 
 // warps in order: reproducible for a fixed launch shape.
 constexpr int kRowStride = 7;  // J[6] + r
 
+// ---- K_B1: plane fit (P2Plane) ----------------------------------------------------------------------------------
+// The plane of a point depends on its five neighbours (and their order) only.  Stage 1 clears plane_valid[row] where
+// they changed - every point in the first iteration, 1 % by the tenth - and leaves it alone otherwise: the cached
+// coefficients are then the ones a new fit would reproduce bit for bit.  A fit is ~500 dependent fp64 instructions, so
+// the rows that need one are compacted first: a block gathers them over `group` consecutive tiles and only then fits,
+// every lane busy, instead of one divergent lane holding a warp (and a barrier its whole tile) for the length of a fit.
+constexpr int kFitGroup = 16;
+#ifndef LR_FIT_MIN_BLOCKS
+#define LR_FIT_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kTile, LR_FIT_MIN_BLOCKS)
+k_icp_fit(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
+          const unsigned int* __restrict__ nn_pos, unsigned char* plane_valid, double* plane_cache, unsigned char* plane_stat,
+          unsigned int group) {
+    __shared__ TileCoord tcs[kFitGroup];
+    __shared__ unsigned int list[kFitGroup * kTile];
+    __shared__ unsigned int list_n;
+    if (threadIdx.x < group) {
+        TileCoord c = locate_tile_thread(bv, blockIdx.x * group + threadIdx.x);
+        if (c.valid && states[c.scan].stop && !ignore_stop) c.valid = false;
+        tcs[threadIdx.x] = c;
+    }
+    if (threadIdx.x == 0) list_n = 0u;
+    __syncthreads();
+    const unsigned int lane = threadIdx.x & 31;
+    for (unsigned int g = 0; g < group; ++g) {
+        const TileCoord& c = tcs[g];
+        unsigned int row = 0;
+        bool need = false;
+        if (c.valid && threadIdx.x < c.count) {
+            row = static_cast<unsigned int>(c.out_base + c.first + threadIdx.x);
+            need = plane_valid[row] == 0;
+        }
+        const unsigned int mask = __ballot_sync(0xffffffffu, need);
+        if (mask == 0u) continue;
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(&list_n, static_cast<unsigned int>(__popc(mask)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (need) list[base + __popc(mask & ((1u << lane) - 1u))] = row;
+    }
+    __syncthreads();
+    const unsigned int n = list_n;
+    for (unsigned int i = threadIdx.x; i < n; i += kTile) {
+        const size_t row = list[i];
+        KnnResult<5> nn;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            nn.pos[j] = nn_pos[row * 5 + j];
+            nn.d2[j] = 0.0f;  // not needed by the fit
+        }
+        double pl[4] = {0, 0, 0, 0};
+        plane_stat[row] = icp_fit_plane(map, prm, nn, pl);
+        reinterpret_cast<double4*>(plane_cache)[row] = make_double4(pl[0], pl[1], pl[2], pl[3]);
+        plane_valid[row] = 1;
+    }
+}
+
+// Upper-triangle entry e = 0..20 of a 6x6 matrix -> its row (col = false) or column (col = true), 3 bits per entry.
+constexpr unsigned long long tri_table(bool col) {
+    unsigned long long t = 0;
+    int e = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b, ++e) t |= static_cast<unsigned long long>(col ? b : a) << (3 * e);
+    return t;
+}
 template <int ROWS>
 struct RowSink {
     double* rows;  // this thread's ROWS staged rows
@@ -410,13 +509,15 @@ struct RowSink {
 };
 
 #ifndef LR_POST_MIN_BLOCKS
-#define LR_POST_MIN_BLOCKS 4
+#define LR_POST_MIN_BLOCKS 6  // 40 registers; the fit lives in k_icp_fit, what is left is latency-bound
 #endif
-template <int METHOD>
-__global__ void __launch_bounds__(kTile, METHOD == kIcpP2Plane ? LR_POST_MIN_BLOCKS : 2)
+// FIT_INLINE (P2Plane, single scans): the plane is fitted here, per point, instead of coming from k_icp_fit - one launch
+// less per iteration where launches, not throughput, set the latency.
+template <int METHOD, bool FIT_INLINE>
+__global__ void __launch_bounds__(kTile, METHOD == kIcpP2Plane ? (FIT_INLINE ? 4 : LR_POST_MIN_BLOCKS) : 2)
 k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
            const unsigned int* __restrict__ nn_pos, double* __restrict__ partials, unsigned char* gate, int* nn_idx,
-           unsigned int* ring_count) {
+           unsigned int* ring_count, const double* __restrict__ plane_cache, const unsigned char* __restrict__ plane_stat) {
     constexpr int K = METHOD == kIcpP2P ? 1 : 5;
     constexpr int ROWS = METHOD == kIcpP2Plane ? 1 : 3;  // residual rows per inlier (P2P, P2Line: 3-vector residuals)
     __shared__ Pose T;
@@ -442,6 +543,12 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
             nn.pos[j] = in[j];
             nn.d2[j] = 0.0f;  // not needed downstream
         }
+        double4 pl = make_double4(0, 0, 0, 0);
+        unsigned char pst = kPlaneNone;
+        if (METHOD == kIcpP2Plane && !FIT_INLINE) {  // the plane comes from k_icp_fit; fetched together with the point
+            pl = reinterpret_cast<const double4*>(plane_cache)[tc.out_base + p];
+            pst = plane_stat[tc.out_base + p];
+        }
         unsigned char g = kGateSkipped;
         if (finite3(sp.x, sp.y, sp.z)) {
             const double qx = sp.x, qy = sp.y, qz = sp.z;
@@ -449,7 +556,11 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
             pose_apply(T, qx, qy, qz, wx, wy, wz);
             if (METHOD == kIcpP2P) g = icp_p2p_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<1>&>(nn), sink);
             else if (METHOD == kIcpP2Line) g = icp_p2line_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<5>&>(nn), sink);
-            else g = icp_p2plane_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<5>&>(nn), sink);
+            else {
+                double n[4] = {pl.x, pl.y, pl.z, pl.w};
+                if (FIT_INLINE) pst = icp_fit_plane(map, prm, reinterpret_cast<const KnnResult<5>&>(nn), n);
+                g = icp_p2plane_residual(prm, T, qx, qy, qz, wx, wy, wz, pst, n, sink);
+            }
         }
         if (gate) gate[tc.out_base + p] = g;
         if (nn_idx) {
@@ -464,12 +575,12 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
     __syncwarp();  // the warp's row stores are visible to its loads below
     const unsigned int inl_mask = __ballot_sync(0xffffffffu, sink.inl);
     // lane -> (a, b): entries 0..20 = H(a, b) upper triangle, 21..26 = B[a] = -sum J[a] r (b = 6), 27 = sum r r
+    // (3 bits per lane, packed: rows 0 0 0 0 0 0 1 1 1 1 1 2 2 2 2 3 3 3 4 4 5, columns 0..5 1..5 2..5 3..5 4 5 5)
+    constexpr unsigned long long kTriRow = tri_table(false), kTriCol = tri_table(true);
     int ea = 6, eb = 6;
     if (lane < 21) {
-        int k = lane;
-        ea = 0;
-        while (k >= 6 - ea) { k -= 6 - ea; ++ea; }
-        eb = ea + k;
+        ea = static_cast<int>(kTriRow >> (3 * lane)) & 7;
+        eb = static_cast<int>(kTriCol >> (3 * lane)) & 7;
     } else if (lane < 27) {
         ea = lane - 21;
     }

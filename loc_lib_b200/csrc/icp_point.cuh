@@ -27,20 +27,18 @@ enum Gate : unsigned char { kGateSkipped = 0, kGateFitFailed = 1, kGateResidual 
 // H += J^T J, B += -J^T r, sum_sq += r^2 - and the two counters inc_eff() / inc_inl().  On the host (oracle-style
 // serial loop, tests/hostsim) it is `Accum`; in k_icp_post it stages the row in shared memory (RowSink) and the
 // block forms the products cooperatively.
-// Point-to-plane, everything after the neighbour search (icp_registration.cpp:171-201): plane fit, gates,
-// Jacobian row, accumulation.  q = source point, w = predict_pose * q, nn = its 5 nearest map points.
-template <class Acc>
-LR_HD unsigned char icp_p2plane_post(const VoxelMapView& map, const IcpParams& prm, const Pose& T, double qx, double qy,
-                                     double qz, double wx, double wy, double wz, const KnnResult<5>& nn, Acc& acc) {
+// math::FitPlane on the five neighbours (icp_registration.cpp:171-181): kPlaneOk + coefficients, kPlaneFailed (the eps
+// check rejected the fit) or kPlaneNone (fewer than five neighbours).
+enum PlaneStatus : unsigned char { kPlaneNone = 0, kPlaneOk = 1, kPlaneFailed = 2 };
+LR_HD unsigned char icp_fit_plane(const VoxelMapView& map, const IcpParams& prm, const KnnResult<5>& nn, double (&n)[4]) {
     // a map with fewer than 5 leaves makes KdTree::GetClosestPoint refuse (kdtree.cpp:149): no neighbours
-    if (knn_count(nn) < 5) return kGateSkipped;
+    if (knn_count(nn) < 5) return kPlaneNone;
     PlaneAcc pa;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const float4 p = map.pts[nn.pos[j]];
         if (j == 0) pa.start(p.x, p.y, p.z); else pa.add(p.x, p.y, p.z);
     }
-    double n[4];
     if (!plane_fit5_solve(pa, n)) {  // collinear / coincident neighbours only: the SVD of math::FitPlane (:179)
         // only arrays local to this branch have their address taken (the SVD is not inlined)
         double Pd[5][3], ns[4];
@@ -57,8 +55,16 @@ LR_HD unsigned char icp_p2plane_post(const VoxelMapView& map, const IcpParams& p
     for (int j = 0; j < 5; ++j) {
         const float4 p = map.pts[nn.pos[j]];
         const double err = n[0] * static_cast<double>(p.x) + n[1] * static_cast<double>(p.y) + n[2] * static_cast<double>(p.z) + n[3];
-        if (err * err > prm.plane_fit_eps) return kGateFitFailed;
+        if (err * err > prm.plane_fit_eps) return kPlaneFailed;
     }
+    return kPlaneOk;
+}
+// Point-to-plane residual of one source point against a fitted plane (icp_registration.cpp:183-201).
+template <class Acc>
+LR_HD unsigned char icp_p2plane_residual(const IcpParams& prm, const Pose& T, double qx, double qy, double qz, double wx, double wy,
+                                         double wz, unsigned char plane_status, const double (&n)[4], Acc& acc) {
+    if (plane_status == kPlaneNone) return kGateSkipped;
+    if (plane_status == kPlaneFailed) return kGateFitFailed;
     acc.inc_eff();  // quirk Q4: counted before the distance gate (:184)
     const double dis = n[0] * wx + n[1] * wy + n[2] * wz + n[3];
     if (fabs(dis) > prm.max_plane_distance) return kGateResidual;
@@ -70,6 +76,15 @@ LR_HD unsigned char icp_p2plane_post(const VoxelMapView& map, const IcpParams& p
     acc.row(J, dis);
     acc.inc_inl();
     return kGateInlier;
+}
+// Point-to-plane, everything after the neighbour search (icp_registration.cpp:171-201): plane fit, gates,
+// Jacobian row, accumulation.  q = source point, w = predict_pose * q, nn = its 5 nearest map points.
+template <class Acc>
+LR_HD unsigned char icp_p2plane_post(const VoxelMapView& map, const IcpParams& prm, const Pose& T, double qx, double qy,
+                                     double qz, double wx, double wy, double wz, const KnnResult<5>& nn, Acc& acc) {
+    double n[4] = {0, 0, 0, 0};
+    const unsigned char st = icp_fit_plane(map, prm, nn, n);
+    return icp_p2plane_residual(prm, T, qx, qy, qz, wx, wy, wz, st, n, acc);
 }
 
 // Point-to-line after the neighbour search (icp_registration.cpp:115-147): line fit through the five neighbours

@@ -78,7 +78,7 @@ struct locreg_handle {
     DeviceIncNdtMap inc_ndt_map;  // LOCREG_NDT_INCREMENTAL
     bool has_target = false;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
-        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_states, d_ringq, d_ringc, d_global, d_local;
+        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_global, d_local, d_same, d_plane, d_pstat;
     size_t n_global = 0, global_stride = 0;  // Loc's global map kept on the device (locreg_set_global_map)
     PinBuf h_in, h_out, h_small;
     double last_ms = 0;
@@ -290,6 +290,14 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     h->d_nnpos.reserve(job.n_scratch_points * K * sizeof(unsigned int));
     h->d_partials.reserve(static_cast<size_t>(job.n_tiles) * kPartialDoubles * sizeof(double));
     h->d_ringq.reserve(job.n_scratch_points * sizeof(uint2));
+    // P2Plane: per-point plane (k_icp_fit) and the flag that says it still belongs to the point's current neighbours
+    const bool small = job.n_tiles <= 2u * static_cast<unsigned int>(h->num_sms);
+    const bool cache = METHOD == kIcpP2Plane && !small;
+    if (cache) {
+        h->d_same.reserve(job.n_scratch_points);
+        h->d_plane.reserve(job.n_scratch_points * 4 * sizeof(double));
+        h->d_pstat.reserve(job.n_scratch_points);
+    }
     h->d_ringc.reserve(2 * sizeof(unsigned int));
     // k_icp_post re-zeroes the counters after every use; the first evaluation of a job starts from a known state
     if (!(nn_mode & kNnSeeds)) LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, 2 * sizeof(unsigned int), h->stream));
@@ -297,9 +305,9 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     const RingQueue queue{h->d_ringc.as<unsigned int>(), h->d_ringq.as<uint2>()};
     // Queries stage 1 cannot finish: a small job (one scan) gives each of them a warp (lowest latency, the GPU is idle
     // anyway); a large job keeps one query per thread (most requests in flight).
-    const bool small = job.n_tiles <= 2u * static_cast<unsigned int>(h->num_sms);
     prof_mark(h, 0, true);
-    LR_LAUNCH(k_icp_nn<K>, job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, nn_mode, h->d_nnpos.as<unsigned int>(), queue);
+    LR_LAUNCH(k_icp_nn<K>, job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, nn_mode, h->d_nnpos.as<unsigned int>(),
+              cache ? h->d_same.as<unsigned char>() : nullptr, queue);
     prof_mark(h, 0, false);
     prof_mark(h, 3, true);
     // The queue length is only known on the device, so both forms are launched and each one looks at the count:
@@ -318,8 +326,19 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     }
     prof_mark(h, 3, false);
     prof_mark(h, 1, true);
-    LR_LAUNCH(k_icp_post<METHOD>, job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
-              h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx, h->d_ringc.as<unsigned int>());
+    if (cache && !small) {
+        LR_LAUNCH(k_icp_fit, (job.n_tiles + kFitGroup - 1) / kFitGroup, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
+                  h->d_nnpos.as<unsigned int>(), h->d_same.as<unsigned char>(), h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(),
+                  static_cast<unsigned int>(kFitGroup));
+        LR_LAUNCH((k_icp_post<METHOD, false>), job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
+                  h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx, h->d_ringc.as<unsigned int>(),
+                  h->d_plane.as<double>(), h->d_pstat.as<unsigned char>());
+    } else {
+        // a single scan: launches, not throughput, set the latency - P2Plane fits its planes inside k_icp_post
+        LR_LAUNCH((k_icp_post<METHOD, METHOD == kIcpP2Plane>), job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states,
+                  ignore_stop, h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx, h->d_ringc.as<unsigned int>(),
+                  nullptr, nullptr);
+    }
     prof_mark(h, 1, false);
 }
 template <int METHOD>
@@ -352,7 +371,7 @@ void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
 
 IcpJob icp_single_job(locreg_handle* h, const float4* src, unsigned int n) {
     IcpJob job;
-    job.bv.src = src; job.bv.offsets = nullptr; job.bv.tile_begin = nullptr;
+    job.bv.src = src; job.bv.offsets = nullptr; job.bv.tile_begin = nullptr; job.bv.tiles = nullptr;
     job.bv.n_single = n; job.bv.tiles_per_item = std::max(1u, (n + kTile - 1) / kTile); job.bv.S = 1;
     job.states = h->d_state.as<AlignState>();
     job.n_tiles = (n + kTile - 1) / kTile;
@@ -370,6 +389,12 @@ IcpJob icp_batch_job(locreg_handle* h, const float4* src, const long long* d_off
     job.states = h->d_states.as<AlignState>();
     job.n_tiles = static_cast<unsigned int>(std::min<size_t>(total / kTile + S, 0x7fffffffu));
     job.n_scratch_points = total;
+    job.bv.tiles = nullptr;
+    if (job.n_tiles) {
+        h->d_tiles.reserve(static_cast<size_t>(job.n_tiles) * sizeof(TileRec));
+        LR_LAUNCH(k_tile_table, (job.n_tiles + 255) / 256, 256, 0, h->stream, job.bv, job.n_tiles, h->d_tiles.as<TileRec>());
+        job.bv.tiles = h->d_tiles.as<TileRec>();
+    }
     return job;
 }
 
@@ -869,7 +894,7 @@ int locreg_relocalise(locreg_handle* h, const float* src, size_t n, size_t strid
         for (size_t w0 = 0; w0 < n_hyp; w0 += wave) {
             const unsigned int W = static_cast<unsigned int>(std::min(wave, n_hyp - w0));
             IcpJob job;
-            job.bv.src = src4; job.bv.offsets = nullptr; job.bv.tile_begin = nullptr;
+            job.bv.src = src4; job.bv.offsets = nullptr; job.bv.tile_begin = nullptr; job.bv.tiles = nullptr;
             job.bv.n_single = static_cast<unsigned int>(n);
             job.bv.tiles_per_item = std::max<unsigned int>(1u, (static_cast<unsigned int>(n) + kTile - 1) / kTile);
             job.bv.S = W;
