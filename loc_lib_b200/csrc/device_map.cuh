@@ -24,6 +24,7 @@ class DeviceVoxelMap {
     void attach_to(const VoxelMapView& fine, const unsigned int* fine_pos_of_index, cudaStream_t stream);
     const VoxelMapView& view() const { return view_; }
     bool empty() const { return view_.n_pts == 0; }
+    void clear() { release(); }  // forgets the map, keeps the memory
     size_t bytes() const { return bytes_; }
     unsigned int n_cells() const { return n_cells_; }
     unsigned int n_blocks() const { return n_blocks_; }
@@ -60,10 +61,12 @@ class DeviceVoxelMap {
     VoxelMapView view_{};
     size_t bytes_ = 0;
     unsigned int n_cells_ = 0, n_blocks_ = 0, n_lists_ = 0;
+    size_t n_list_entries_ = 0;
 };
 
-// Level 0 (cell, lists) + kCoarseLevels coarser levels (block tables only) of the ICP search index.
-void build_icp_maps(DeviceVoxelMap& fine, DeviceVoxelMap* coarse, const void* d_xyz, size_t n, size_t stride, float cell,
-                    bool want_lists, cudaStream_t stream);
+// Level 0 (cell, lists) + the mid level (cells kMidFactor times larger, lists; nullptr: none) + kCoarseLevels coarser
+// levels (block tables only) of the ICP search index.
+void build_icp_maps(DeviceVoxelMap& fine, DeviceVoxelMap* coarse, DeviceVoxelMap* mid, const void* d_xyz, size_t n, size_t stride,
+                    float cell, bool want_lists, cudaStream_t stream);
 
 }  // namespace locreg

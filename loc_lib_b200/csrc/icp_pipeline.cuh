@@ -43,6 +43,7 @@ struct BatchView {
     const long long* offsets;       // S+1 point offsets into src, or nullptr: every item is src[0..n_single)
     const unsigned int* tile_begin; // S+1 tile offsets, or nullptr: item s owns tiles [s*tiles_per_item, ...)
     const struct TileRec* tiles;    // with tile_begin: the per-tile table k_tile_table derived from it (one load, no search)
+    unsigned int n_table_tiles;     // entries of tiles[]
     unsigned int n_single;
     unsigned int tiles_per_item;
     unsigned int S;
@@ -69,6 +70,7 @@ __device__ __forceinline__ TileCoord locate_tile_thread(const BatchView& b, unsi
     c.valid = false;
     unsigned int s, t;
     if (b.tiles) {
+        if (tile >= b.n_table_tiles) return c;
         const uint4 a = reinterpret_cast<const uint4*>(b.tiles + tile)[0];
         c.scan = a.x; c.first = a.y; c.count = a.z; c.valid = a.w != 0u;
         c.src_base = c.out_base = b.tiles[tile].base;
@@ -511,10 +513,8 @@ struct RowSink {
 #ifndef LR_POST_MIN_BLOCKS
 #define LR_POST_MIN_BLOCKS 6  // 40 registers; the fit lives in k_icp_fit, what is left is latency-bound
 #endif
-// FIT_INLINE (P2Plane, single scans): the plane is fitted here, per point, instead of coming from k_icp_fit - one launch
-// less per iteration where launches, not throughput, set the latency.
-template <int METHOD, bool FIT_INLINE>
-__global__ void __launch_bounds__(kTile, METHOD == kIcpP2Plane ? (FIT_INLINE ? 4 : LR_POST_MIN_BLOCKS) : 2)
+template <int METHOD>
+__global__ void __launch_bounds__(kTile, METHOD == kIcpP2Plane ? LR_POST_MIN_BLOCKS : 2)
 k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
            const unsigned int* __restrict__ nn_pos, double* __restrict__ partials, unsigned char* gate, int* nn_idx,
            unsigned int* ring_count, const double* __restrict__ plane_cache, const unsigned char* __restrict__ plane_stat) {
@@ -545,7 +545,7 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
         }
         double4 pl = make_double4(0, 0, 0, 0);
         unsigned char pst = kPlaneNone;
-        if (METHOD == kIcpP2Plane && !FIT_INLINE) {  // the plane comes from k_icp_fit; fetched together with the point
+        if (METHOD == kIcpP2Plane) {  // the plane comes from k_icp_fit; fetched together with the point
             pl = reinterpret_cast<const double4*>(plane_cache)[tc.out_base + p];
             pst = plane_stat[tc.out_base + p];
         }
@@ -557,8 +557,7 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
             if (METHOD == kIcpP2P) g = icp_p2p_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<1>&>(nn), sink);
             else if (METHOD == kIcpP2Line) g = icp_p2line_post(map, prm, T, qx, qy, qz, wx, wy, wz, reinterpret_cast<const KnnResult<5>&>(nn), sink);
             else {
-                double n[4] = {pl.x, pl.y, pl.z, pl.w};
-                if (FIT_INLINE) pst = icp_fit_plane(map, prm, reinterpret_cast<const KnnResult<5>&>(nn), n);
+                const double n[4] = {pl.x, pl.y, pl.z, pl.w};
                 g = icp_p2plane_residual(prm, T, qx, qy, qz, wx, wy, wz, pst, n, sink);
             }
         }

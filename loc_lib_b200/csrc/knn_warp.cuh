@@ -51,8 +51,8 @@ __device__ __forceinline__ void warp_merge(const float4* __restrict__ canon, Knn
 
 // One contiguous neighbourhood list (entries carry the canonical position in w), lanes striding over it.
 template <int K>
-__device__ __forceinline__ void warp_scan_list(const float4* __restrict__ pts, KnnResult<K>& res, float qx, float qy, float qz,
-                                               unsigned int beg, unsigned int cnt) {
+__device__ __forceinline__ void warp_scan_list(const float4* __restrict__ pts, const float4* __restrict__ canon, KnnResult<K>& res,
+                                               float qx, float qy, float qz, unsigned int beg, unsigned int cnt) {
     const unsigned int lane = threadIdx.x & 31;
     KnnResult<K> priv;
     knn_init(priv);
@@ -60,9 +60,9 @@ __device__ __forceinline__ void warp_scan_list(const float4* __restrict__ pts, K
     for (unsigned int i = lane; i < cnt; i += 32) {
         const float4 p = pts[beg + i];
         const float d2 = dis2_f32(qx, qy, qz, p.x, p.y, p.z);
-        if (d2 <= bound) knn_offer(pts, priv, d2, static_cast<unsigned int>(float_as_int(p.w)));
+        if (d2 <= bound) knn_offer(canon, priv, d2, static_cast<unsigned int>(float_as_int(p.w)));
     }
-    warp_merge<K>(pts, res, priv);
+    warp_merge<K>(canon, res, priv);
 }
 
 // Stage 2a (see knn_query_corners): same corner selection, lists scanned cooperatively.
@@ -74,7 +74,7 @@ __device__ __forceinline__ bool warp_query_corners(const VoxelMapView& m, float 
         if (!((need >> o) & 1u)) continue;
         unsigned int beg = 0, cnt = 0;
         knn_find_list(m, c.fx + ((o & 1) ? 1 : -1), c.fy + ((o & 2) ? 1 : -1), c.fz + ((o & 4) ? 1 : -1), beg, cnt);
-        warp_scan_list<K>(m.pts, res, qx, qy, qz, beg, cnt);
+        warp_scan_list<K>(m.pts, m.canon, res, qx, qy, qz, beg, cnt);
     }
     return knn_corners_final<K>(m, c, res);
 }
@@ -150,7 +150,24 @@ template <int K>
 __device__ __forceinline__ void warp_query_finish(const VoxelMapView& m, const CoarseLevels& coarse, float qx, float qy, float qz,
                                                   KnnResult<K>& res) {
     const unsigned int lane = threadIdx.x & 31;
-    {
+    const bool have_mid = coarse.mid.n_pts != 0;
+    if (have_mid) {  // knn_query_mid, lists and shells scanned cooperatively
+        const VoxelMapView& md = coarse.mid;
+        const bool have_coarse = coarse.lv[0].n_pts != 0;
+        const KnnCellFrame c = knn_frame(md, qx, qy, qz);
+        int boxes_done = 0;
+        if (knn_uses_list(md, c)) {
+            unsigned int beg = 0, cnt = 0;
+            knn_find_list(md, c.fx, c.fy, c.fz, beg, cnt);
+            warp_scan_list<K>(md.pts, md.canon, res, qx, qy, qz, beg, cnt);
+            if (knn_list_final<K>(md, c, res)) return;
+            boxes_done = 1;
+        }
+        if (!(have_coarse && c.R0 > kMidShells) &&
+            warp_query_rings<K>(md, qx, qy, qz, res, boxes_done, have_coarse ? kMidShells : kBruteForceShell))
+            return;
+    }
+    if (!have_mid) {
         const KnnCellFrame c = knn_frame(m, qx, qy, qz);
         int boxes_done = knn_uses_list(m, c) ? 1 : 0;
         if (boxes_done == 1 && res.pos[K - 1] != kNoPos) {

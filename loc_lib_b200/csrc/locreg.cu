@@ -69,9 +69,11 @@ struct locreg_handle {
     std::vector<cudaEvent_t> chunk_events;     // locreg_align_batch
     DeviceVoxelMap icp_map;     // level 0: cells of knn_cell_size, neighbourhood lists
     DeviceVoxelMap icp_coarse[kCoarseLevels];  // cells 4x, 16x larger, block tables only (far queries)
+    DeviceVoxelMap icp_mid;     // cells 2x larger, neighbourhood lists: stage 2 of the search (LOCREG_MID=0: off)
     CoarseLevels coarse_views() const {
         CoarseLevels c{};
         for (int l = 0; l < kCoarseLevels; ++l) c.lv[l] = icp_coarse[l].view();
+        c.mid = icp_mid.view();
         return c;
     }
     DeviceNdtMap ndt_map;
@@ -292,7 +294,7 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     h->d_ringq.reserve(job.n_scratch_points * sizeof(uint2));
     // P2Plane: per-point plane (k_icp_fit) and the flag that says it still belongs to the point's current neighbours
     const bool small = job.n_tiles <= 2u * static_cast<unsigned int>(h->num_sms);
-    const bool cache = METHOD == kIcpP2Plane && !small;
+    const bool cache = METHOD == kIcpP2Plane;
     if (cache) {
         h->d_same.reserve(job.n_scratch_points);
         h->d_plane.reserve(job.n_scratch_points * 4 * sizeof(double));
@@ -326,19 +328,16 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     }
     prof_mark(h, 3, false);
     prof_mark(h, 1, true);
-    if (cache && !small) {
-        LR_LAUNCH(k_icp_fit, (job.n_tiles + kFitGroup - 1) / kFitGroup, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
-                  h->d_nnpos.as<unsigned int>(), h->d_same.as<unsigned char>(), h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(),
-                  static_cast<unsigned int>(kFitGroup));
-        LR_LAUNCH((k_icp_post<METHOD, false>), job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
-                  h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx, h->d_ringc.as<unsigned int>(),
-                  h->d_plane.as<double>(), h->d_pstat.as<unsigned char>());
-    } else {
-        // a single scan: launches, not throughput, set the latency - P2Plane fits its planes inside k_icp_post
-        LR_LAUNCH((k_icp_post<METHOD, METHOD == kIcpP2Plane>), job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states,
-                  ignore_stop, h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx, h->d_ringc.as<unsigned int>(),
-                  nullptr, nullptr);
+    if (cache) {
+        // a single scan spreads its tiles over the SMs (latency); a batch compacts over 16 tiles per block (throughput).
+        // The same kernel either way: batch results equal those of single ScanMatch calls bit for bit.
+        const unsigned int group = small ? 1u : static_cast<unsigned int>(kFitGroup);
+        LR_LAUNCH(k_icp_fit, (job.n_tiles + group - 1) / group, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
+                  h->d_nnpos.as<unsigned int>(), h->d_same.as<unsigned char>(), h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(), group);
     }
+    LR_LAUNCH(k_icp_post<METHOD>, job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
+              h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx, h->d_ringc.as<unsigned int>(),
+              cache ? h->d_plane.as<double>() : nullptr, cache ? h->d_pstat.as<unsigned char>() : nullptr);
     prof_mark(h, 1, false);
 }
 template <int METHOD>
@@ -394,6 +393,7 @@ IcpJob icp_batch_job(locreg_handle* h, const float4* src, const long long* d_off
         h->d_tiles.reserve(static_cast<size_t>(job.n_tiles) * sizeof(TileRec));
         LR_LAUNCH(k_tile_table, (job.n_tiles + 255) / 256, 256, 0, h->stream, job.bv, job.n_tiles, h->d_tiles.as<TileRec>());
         job.bv.tiles = h->d_tiles.as<TileRec>();
+        job.bv.n_table_tiles = job.n_tiles;
     }
     return job;
 }
@@ -562,7 +562,9 @@ static int set_target_impl(locreg_handle* h, const float* xyz, size_t n, size_t 
             }
             h->inc_ndt_map.add_cloud(h_xyz, d_xyz, n, stride, h->stream);
         } else {
-            build_icp_maps(h->icp_map, h->icp_coarse, d_xyz, n, stride, static_cast<float>(h->opt.knn_cell_size), h->opt.knn_lists != 0, h->stream);
+            static const bool use_mid = !(getenv("LOCREG_MID") && atoi(getenv("LOCREG_MID")) == 0);
+            if (!use_mid) h->icp_mid.clear();
+            build_icp_maps(h->icp_map, h->icp_coarse, use_mid ? &h->icp_mid : nullptr, d_xyz, n, stride, static_cast<float>(h->opt.knn_cell_size), h->opt.knn_lists != 0, h->stream);
         }
         h->end_timing();
         h->has_target = true;

@@ -194,7 +194,7 @@ DeviceVoxelMap::~DeviceVoxelMap() {
 void DeviceVoxelMap::release() {  // forgets the map, keeps the memory
     slots_ = nullptr; cell_start_ = nullptr; pts_ = nullptr; nbr_ = nullptr;
     view_ = VoxelMapView{};
-    bytes_ = 0; n_cells_ = 0; n_blocks_ = 0; n_lists_ = 0;
+    bytes_ = 0; n_cells_ = 0; n_blocks_ = 0; n_lists_ = 0; n_list_entries_ = 0;
 }
 
 static unsigned int next_pow2(size_t v) {
@@ -306,6 +306,7 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
             break;
         }
         n_lists_ = h_counters[0];
+        n_list_entries_ = static_cast<size_t>(n_kept - n_dup) * 27;  // every surviving point, once per cell of its 3x3x3 box
         LR_CUDA(cudaMallocAsync(&tmp, static_cast<size_t>(nbr_cap) * sizeof(unsigned int), stream));
         LR_CUDA(cudaMallocAsync(&ncursor, static_cast<size_t>(nbr_cap) * sizeof(unsigned int), stream));
         LR_LAUNCH(k_nbr_counts, (nbr_cap + T - 1) / T, T, 0, stream, nbr_, nbr_cap, tmp);
@@ -339,17 +340,30 @@ __global__ void k_coarse_remap(float4* pts, unsigned int n, const unsigned int* 
     const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) pts[j].w = __int_as_float(static_cast<int>(fine_pos_of_index[__float_as_int(pts[j].w)]));
 }
+// list entries carry the level's OWN canonical position; after k_coarse_remap that point's w is its fine position
+__global__ void k_coarse_remap_lists(float4* pts, unsigned int n_pts, size_t n_entries) {
+    const size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j < n_entries) pts[n_pts + j].w = pts[__float_as_int(pts[n_pts + j].w)].w;
+}
 void DeviceVoxelMap::attach_to(const VoxelMapView& fine, const unsigned int* fine_pos_of_index, cudaStream_t stream) {
     if (view_.n_pts == 0) return;
     LR_LAUNCH(k_coarse_remap, (view_.n_pts + 255) / 256, 256, 0, stream, pts_, view_.n_pts, fine_pos_of_index);
+    if (nbr_ != nullptr && n_list_entries_ != 0)
+        LR_LAUNCH(k_coarse_remap_lists, static_cast<unsigned int>((n_list_entries_ + 255) / 256), 256, 0, stream, pts_, view_.n_pts,
+                  n_list_entries_);
     view_.canon = fine.pts;
     view_.w_is_pos = 1;
 }
 
-void build_icp_maps(DeviceVoxelMap& fine, DeviceVoxelMap* coarse, const void* d_xyz, size_t n, size_t stride, float cell,
-                    bool want_lists, cudaStream_t stream) {
+void build_icp_maps(DeviceVoxelMap& fine, DeviceVoxelMap* coarse, DeviceVoxelMap* mid, const void* d_xyz, size_t n, size_t stride,
+                    float cell, bool want_lists, cudaStream_t stream) {
     unsigned int* pos = nullptr;
     fine.build(d_xyz, n, stride, cell, want_lists, stream, &pos);
+    if (mid) {
+        mid->build(d_xyz, n, stride, cell * kMidFactor, want_lists, stream);
+        if (pos && mid->view().nbr_slots != nullptr) mid->attach_to(fine.view(), pos, stream);
+        else mid->clear();  // no lists (memory): stage 2 takes the corner-list path
+    }
     float c = cell;
     for (int l = 0; l < kCoarseLevels; ++l) {
         c *= kCoarseFactor;

@@ -224,9 +224,10 @@ LR_HD float safe_gap(float g, float mag, float cell) {
 // the list with a min/max network on the distances alone, and the second pass offers only the <= K (+ ties)
 // candidates at or below that threshold.
 constexpr int kScanBatch = 4;
+// `pts` is the array the list lives in, `canon` the array canonical positions index (the same on level 0).
 template <int K>
-LR_HD void knn_scan_list(const float4* __restrict__ pts, KnnResult<K>& res, float qx, float qy, float qz, unsigned int beg,
-                         unsigned int cnt, bool two_pass) {
+LR_HD void knn_scan_list(const float4* __restrict__ pts, const float4* __restrict__ canon, KnnResult<K>& res, float qx, float qy,
+                         float qz, unsigned int beg, unsigned int cnt, bool two_pass) {
 #if defined(__CUDA_ARCH__)
     if (cnt == 0) return;
     const unsigned int last = beg + cnt - 1;
@@ -264,7 +265,7 @@ LR_HD void knn_scan_list(const float4* __restrict__ pts, KnnResult<K>& res, floa
 #pragma unroll
             for (int u = 0; u < kScanBatch; ++u) d2[u] = dis2_f32(qx, qy, qz, p[u].x, p[u].y, p[u].z);
 #pragma unroll
-            for (int u = 0; u < kScanBatch; ++u) knn_offer(pts, res, d2[u], static_cast<unsigned int>(float_as_int(p[u].w)));
+            for (int u = 0; u < kScanBatch; ++u) knn_offer(canon, res, d2[u], static_cast<unsigned int>(float_as_int(p[u].w)));
         }
         return;
     }
@@ -291,14 +292,14 @@ LR_HD void knn_scan_list(const float4* __restrict__ pts, KnnResult<K>& res, floa
             const int bit = ffs64(marks) - 1;
             marks &= marks - 1;
             const float4 p = pts[chunk + bit];
-            knn_offer(pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), static_cast<unsigned int>(float_as_int(p.w)));
+            knn_offer(canon, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), static_cast<unsigned int>(float_as_int(p.w)));
         }
     }
 #else
     (void)two_pass;
     for (unsigned int i = beg; i < beg + cnt; ++i) {
         const float4 p = pts[i];
-        knn_offer(pts, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), static_cast<unsigned int>(float_as_int(p.w)));
+        knn_offer(canon, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), static_cast<unsigned int>(float_as_int(p.w)));
     }
 #endif
 }
@@ -378,6 +379,20 @@ LR_HD void knn_seed(const VoxelMapView& m, float qx, float qy, float qz, const u
     // K == 1 needs no ordering
 }
 
+// After the list of the query's own cell on level `m` (the box [f-1, f+1]^3) has been scanned: is `res` final?
+template <int K>
+LR_HD bool knn_list_final(const VoxelMapView& m, const KnnCellFrame& c, const KnnResult<K>& res) {
+    if (res.pos[K - 1] != kNoPos) {
+        float mf = fminf(c.frx, 1.0f - c.frx);
+        mf = fminf(mf, fminf(c.fry, 1.0f - c.fry));
+        mf = fminf(mf, fminf(c.frz, 1.0f - c.frz));
+        const float g = safe_gap(1.0f + mf, c.mag + 1.0f, m.cell);
+        if (res.d2[K - 1] < g * g * 0.99999f) return true;
+    }
+    return c.fx - 1 <= m.cmin[0] && c.fx + 1 >= m.cmax[0] && c.fy - 1 <= m.cmin[1] && c.fy + 1 >= m.cmax[1] &&
+           c.fz - 1 <= m.cmin[2] && c.fz + 1 >= m.cmax[2];
+}
+
 // Stage 1 of the exact k-NN of a FINITE query against a NON-EMPTY map: seeds, then the one-list fast path.
 //   seeds    optional K canonical positions (kNoPos = none) that start the k-best set - the neighbours found in the
 //            previous Gauss-Newton iteration.  Any real, distinct points are valid seeds: they only tighten the
@@ -395,16 +410,8 @@ LR_HD bool knn_query_fast(const VoxelMapView& m, float qx, float qy, float qz, K
     unsigned int beg = 0, cnt = 0;
     knn_find_list(m, c.fx, c.fy, c.fz, beg, cnt);
     LR_STAT(0, 1); LR_STAT(1, cnt);  // fast-path queries, candidates
-    knn_scan_list<K>(m.pts, res, qx, qy, qz, beg, cnt, two_pass);
-    if (res.pos[K - 1] != kNoPos) {
-        float mf = fminf(c.frx, 1.0f - c.frx);
-        mf = fminf(mf, fminf(c.fry, 1.0f - c.fry));
-        mf = fminf(mf, fminf(c.frz, 1.0f - c.frz));
-        const float g = safe_gap(1.0f + mf, c.mag + 1.0f, m.cell);
-        if (res.d2[K - 1] < g * g * 0.99999f) return true;
-    }
-    return c.fx - 1 <= m.cmin[0] && c.fx + 1 >= m.cmax[0] && c.fy - 1 <= m.cmin[1] && c.fy + 1 >= m.cmax[1] &&
-           c.fz - 1 <= m.cmin[2] && c.fz + 1 >= m.cmax[2];
+    knn_scan_list<K>(m.pts, m.pts, res, qx, qy, qz, beg, cnt, two_pass);  // stage 1 runs on level 0: canon == pts
+    return knn_list_final<K>(m, c, res);
 }
 
 // Stage 2a: the 5x5x5 box through neighbourhood lists.  The list of the cell f + (sx, sy, sz), s = +-1, covers the
@@ -468,7 +475,7 @@ LR_HD bool knn_query_corners(const VoxelMapView& m, float qx, float qy, float qz
         unsigned int beg = 0, cnt = 0;
         knn_find_list(m, c.fx + ((o & 1) ? 1 : -1), c.fy + ((o & 2) ? 1 : -1), c.fz + ((o & 4) ? 1 : -1), beg, cnt);
         LR_STAT(3, 1); LR_STAT(4, cnt);  // corner lists scanned, candidates
-        knn_scan_list<K>(m.pts, res, qx, qy, qz, beg, cnt, false);
+        knn_scan_list<K>(m.pts, m.canon, res, qx, qy, qz, beg, cnt, false);
     }
     return knn_corners_final<K>(m, c, res);
 }
@@ -594,22 +601,48 @@ constexpr int kFineShells = 4;
 constexpr int kCoarseFactor = 4;   // cell edge ratio between consecutive levels
 constexpr int kCoarseLevels = 2;   // 4x and 16x the fine cell: shells reach 24 * 16 fine cells (192 m at 0.5 m)
 constexpr int kCoarseShells = 6;   // shells on a level that has a coarser one behind it
+constexpr int kMidFactor = 2;       // the mid level's cell edge / the fine level's
+constexpr int kMidShells = 2;       // shells on the mid level when a coarse level can take over
 struct CoarseLevels {
     VoxelMapView lv[kCoarseLevels];  // n_pts == 0: level absent
+    VoxelMapView mid;                // cells kMidFactor times the fine ones WITH neighbourhood lists; n_pts == 0: absent
 };
+// Stage 2 through the mid level: one list of the mid level covers a box three mid cells wide around the query - what
+// the corner lists and the first fine shells would have to collect from up to eight lists and dozens of hash-probed
+// blocks is one probe and one contiguous scan here.  Returns true when `res` is final; false: coarse levels next.
+template <int K>
+LR_HD bool knn_query_mid(const VoxelMapView& md, bool have_coarse, float qx, float qy, float qz, KnnResult<K>& res) {
+    const KnnCellFrame c = knn_frame(md, qx, qy, qz);
+    int boxes_done = 0;
+    if (knn_uses_list(md, c)) {
+        unsigned int beg = 0, cnt = 0;
+        knn_find_list(md, c.fx, c.fy, c.fz, beg, cnt);
+        LR_STAT(3, 1); LR_STAT(4, cnt);  // mid lists scanned, candidates
+        knn_scan_list<K>(md.pts, md.canon, res, qx, qy, qz, beg, cnt, res.pos[K - 1] == kNoPos);
+        if (knn_list_final<K>(md, c, res)) return true;
+        boxes_done = 1;
+    }
+    if (have_coarse && c.R0 > kMidShells) return false;
+    return knn_query_rings<K>(md, qx, qy, qz, res, boxes_done, have_coarse ? kMidShells : kBruteForceShell);
+}
 template <int K>
 LR_HD void knn_query_finish(const VoxelMapView& m, const CoarseLevels& coarse, float qx, float qy, float qz, KnnResult<K>& res) {
-    const KnnCellFrame c = knn_frame(m, qx, qy, qz);
-    int boxes_done = knn_uses_list(m, c) ? 1 : 0;
-    if (boxes_done == 1 && res.pos[K - 1] != kNoPos) {
-        if (knn_query_corners<K>(m, qx, qy, qz, res)) return;
-        boxes_done = 2;
-    }
     const bool have_coarse = coarse.lv[0].n_pts != 0;
-    // a query outside the occupied bounds by more than the fine reach goes straight to the coarse levels
-    if (!(have_coarse && c.R0 > kFineShells) &&
-        knn_query_rings<K>(m, qx, qy, qz, res, boxes_done, have_coarse ? kFineShells : kBruteForceShell))
-        return;
+    if (coarse.mid.n_pts != 0) {
+        LR_STAT(2, 1);  // queries entering stage 2a
+        if (knn_query_mid<K>(coarse.mid, have_coarse, qx, qy, qz, res)) return;
+    } else {
+        const KnnCellFrame c = knn_frame(m, qx, qy, qz);
+        int boxes_done = knn_uses_list(m, c) ? 1 : 0;
+        if (boxes_done == 1 && res.pos[K - 1] != kNoPos) {
+            if (knn_query_corners<K>(m, qx, qy, qz, res)) return;
+            boxes_done = 2;
+        }
+        // a query outside the occupied bounds by more than the fine reach goes straight to the coarse levels
+        if (!(have_coarse && c.R0 > kFineShells) &&
+            knn_query_rings<K>(m, qx, qy, qz, res, boxes_done, have_coarse ? kFineShells : kBruteForceShell))
+            return;
+    }
     for (int l = 0; l < kCoarseLevels; ++l) {
         const VoxelMapView& cl = coarse.lv[l];
         if (cl.n_pts == 0) break;

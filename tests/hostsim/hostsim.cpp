@@ -26,7 +26,8 @@ struct HsMap {
     VoxelMapView view;
     HsMap* coarse_map[kCoarseLevels] = {};   // coarser levels (no lists), or nullptr
     CoarseLevels coarse{};                   // lv[l].n_pts == 0: level absent
-    ~HsMap() { for (HsMap* c : coarse_map) delete c; }
+    HsMap* mid_map = nullptr;                // mid level (lists), or nullptr
+    ~HsMap() { for (HsMap* c : coarse_map) delete c; delete mid_map; }
 };
 
 static unsigned int next_pow2(unsigned int v) {
@@ -108,10 +109,22 @@ static HsMap* build_level(const float* xyz, size_t n, size_t stride, float cell,
     return m;
 }
 
-// capacity_hint: 0 = defaults; 0xFFFFFFFF = no neighbourhood lists; 0xFFFFFFFE = no lists and no coarse level
+// capacity_hint: 0 = defaults; 0xFFFFFFFF = no neighbourhood lists; 0xFFFFFFFE = no lists and no coarse level;
+// 0xFFFFFFFD = lists on the fine level only (no mid level)
 HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsigned int capacity_hint) {
     const bool want_coarse = capacity_hint != 0xFFFFFFFEu;
-    HsMap* m = build_level(xyz, n, stride, cell, capacity_hint == 0xFFFFFFFEu ? 0xFFFFFFFFu : capacity_hint);
+    HsMap* m = build_level(xyz, n, stride, cell, capacity_hint == 0xFFFFFFFEu ? 0xFFFFFFFFu : (capacity_hint == 0xFFFFFFFDu ? 0u : capacity_hint));
+    // the mid level (lists) exists whenever the fine level has lists; capacity_hint 0xFFFFFFFD: fine lists, no mid level
+    if (want_coarse && m->view.n_pts && m->view.nbr_slots != nullptr && capacity_hint != 0xFFFFFFFDu) {
+        HsMap* c = build_level(xyz, n, stride, cell * kMidFactor, 0);
+        const unsigned int np = c->view.n_pts;
+        for (unsigned int j = 0; j < np; ++j)  // what DeviceVoxelMap::attach_to does
+            c->pts[j].w = int_as_float(static_cast<int>(m->pos_of_index[float_as_int(c->pts[j].w)]));
+        for (size_t j = np; j < c->pts.size(); ++j) c->pts[j].w = c->pts[float_as_int(c->pts[j].w)].w;
+        c->view.canon = m->pts.data(); c->view.w_is_pos = 1;
+        m->mid_map = c;
+        m->coarse.mid = c->view;
+    }
     float cc = cell;
     for (int l = 0; want_coarse && m->view.n_pts && l < kCoarseLevels; ++l) {
         cc *= kCoarseFactor;

@@ -32,10 +32,12 @@ def _queries(scene):
     return (scene.scan[:, :3].astype(np.float64) @ R.T + scene.init[0][4:]).astype(np.float32)
 
 
-@pytest.mark.parametrize("lists", [True, False])
+@pytest.mark.parametrize("hint", [0, 0xFFFFFFFD, 0xFFFFFFFF], ids=["lists+mid", "lists", "blocks"])
 @pytest.mark.parametrize("cell", [0.5, 0.3, 1.3])
-def test_knn_bit_exact_near_and_far(scene, ref_icp, cell, lists):
-    m = HS.HsMap(scene.map, cell=cell, capacity_hint=0 if lists else 0xFFFFFFFF)
+def test_knn_bit_exact_near_and_far(scene, ref_icp, cell, hint):
+    """Every stage-2 route: the mid level's lists (default), the corner lists + fine shells (no mid level: what a
+    map too large for a second set of lists falls back to), block tables only."""
+    m = HS.HsMap(scene.map, cell=cell, capacity_hint=hint)
     rng = np.random.default_rng(7)
     far = rng.uniform(-60, 60, (1500, 3)).astype(np.float32)
     far[:, 2] = rng.uniform(-4, 25, 1500)
