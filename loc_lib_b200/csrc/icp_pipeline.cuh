@@ -202,25 +202,74 @@ __device__ __forceinline__ void tile_queue_append(bool mine, unsigned int row, u
         queue.entries[base + i] = make_uint2(reinterpret_cast<volatile unsigned int*>(staged)[i], scan);
 }
 
-template <int K>
+// mode bit 2 (kNnTrack):   with seeds, no pre-pass: a query that has moved less than its margin since its last full search
+//                          (KnnTrack, voxel_map.cuh) only re-sorts its K neighbours.  The queries that do need the list
+//                          are compacted over the tile first - by the eighth iteration they are 3 % of the points, and
+//                          left in place they would still keep a lane of nearly every warp busy for a whole scan.
+constexpr int kNnTrack = 4;
+template <int K, bool TRACKED>
 __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView map, BatchView bv,
                                                                     const AlignState* __restrict__ states, int ignore_stop,
                                                                     int mode, unsigned int* __restrict__ nn_pos,
-                                                                    unsigned char* __restrict__ plane_valid, RingQueue queue) {
+                                                                    unsigned char* __restrict__ plane_valid, KnnTrack* track,
+                                                                    RingQueue queue) {
     __shared__ Pose T;
     const TileCoord tc = locate_tile(bv, blockIdx.x);
     if (!tc.valid) return;
     const AlignState* st = states + tc.scan;
     if (st->stop && !ignore_stop) return;
     if (threadIdx.x == 0) pose_load(T, st->pose);
-    __syncthreads();
     // Unfinished queries are staged in shared memory; the LAST warp of the tile to finish appends them to the global
     // queue with one atomic.  No barrier after the search: a warp retires as soon as its own queries are done.
-    __shared__ unsigned int blk_pending, blk_done;
+    __shared__ unsigned int blk_pending, blk_done, blk_scan;
     __shared__ unsigned int staged[kTile];
-    if (threadIdx.x == 0) { blk_pending = 0u; blk_done = 0u; }
-    const bool in_tile = threadIdx.x < tc.count;
-    const unsigned int p = tc.first + (in_tile ? threadIdx.x : 0u);
+    __shared__ unsigned char scan_list[kTile];
+    if (threadIdx.x == 0) { blk_pending = 0u; blk_done = 0u; blk_scan = 0u; }
+    __syncthreads();
+    constexpr bool tracked = TRACKED;  // = (mode & kNnTrack) != 0
+    unsigned int slot = threadIdx.x;  // the point of the tile this thread searches
+    if (tracked) {
+        // phase A: every point tries the cheap way
+        bool need_scan = false;
+        if (threadIdx.x < tc.count) {
+            const unsigned int p = tc.first + threadIdx.x;
+            const size_t row = static_cast<size_t>(tc.out_base + p);
+            const float4 sp = bv.src[tc.src_base + p];
+            unsigned int* out = nn_pos + row * K;
+            unsigned int seeds[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) seeds[j] = out[j];
+            const KnnTrack t = track[row];
+            if (finite3(sp.x, sp.y, sp.z) && map.n_pts != 0) {
+                double wx, wy, wz;
+                pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
+                const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
+                KnnResult<K> nn;
+                if (knn_track_try<K>(map, qx, qy, qz, seeds, t, nn)) {
+                    bool same = true;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        same = same && seeds[j] == nn.pos[j];
+                        out[j] = nn.pos[j];
+                    }
+                    if (plane_valid && !same) plane_valid[row] = 0;
+                } else {
+                    need_scan = true;
+                }
+            }
+        }
+        const unsigned int lane = threadIdx.x & 31;
+        const unsigned int mask = __ballot_sync(0xffffffffu, need_scan);
+        unsigned int base = 0;
+        if (lane == 0 && mask != 0u) base = atomicAdd(&blk_scan, static_cast<unsigned int>(__popc(mask)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (need_scan) scan_list[base + __popc(mask & ((1u << lane) - 1u))] = static_cast<unsigned char>(threadIdx.x);
+        __syncthreads();
+        // phase B: the first blk_scan threads search the points that need it
+        slot = threadIdx.x < blk_scan ? scan_list[threadIdx.x] : kTile;
+    }
+    const bool in_tile = slot < tc.count;
+    const unsigned int p = tc.first + (in_tile ? slot : 0u);
     const float4 sp = bv.src[tc.src_base + p];
     const size_t row = static_cast<size_t>(tc.out_base + p);
     unsigned int* out = nn_pos + row * K;
@@ -230,7 +279,8 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
     bool done = true, same = false;
     KnnResult<K> nn;
     knn_init(nn);
-    __syncthreads();
+    KnnTrack tr;
+    tr.qx = tr.qy = tr.qz = 0.0f; tr.margin = -1.0f;
     // (loaded before sp is looked at: one round trip for the point and its seeds instead of two)
     unsigned int seeds[K];
 #pragma unroll
@@ -239,7 +289,8 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
         double wx, wy, wz;
         pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
         const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
-        done = knn_query_fast<K>(map, qx, qy, qz, nn, seeds, (mode & kNnTwoPass) != 0);
+        if (tracked) done = knn_query_fast_track<K>(map, qx, qy, qz, nn, seeds, tr);
+        else done = knn_query_fast<K>(map, qx, qy, qz, nn, seeds, (mode & kNnTwoPass) != 0);
         // same neighbours, in the same order, as in the previous iteration: what k_icp_fit derived from them still holds
         same = done && (mode & kNnSeeds) != 0;
 #pragma unroll
@@ -249,6 +300,7 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
 #pragma unroll
         for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
         if (plane_valid && !same) plane_valid[row] = 0;  // k_icp_fit sets it again
+        if (track) track[row] = tr;  // margin -1 unless this was a tracked search that ended here
     }
     tile_queue_append(!done, static_cast<unsigned int>(row), tc.scan, &blk_pending, &blk_done, staged, queue);
 }

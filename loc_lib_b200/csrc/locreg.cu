@@ -80,7 +80,7 @@ struct locreg_handle {
     DeviceIncNdtMap inc_ndt_map;  // LOCREG_NDT_INCREMENTAL
     bool has_target = false;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
-        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_global, d_local, d_same, d_plane, d_pstat;
+        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_global, d_local, d_same, d_plane, d_pstat, d_track;
     size_t n_global = 0, global_stride = 0;  // Loc's global map kept on the device (locreg_set_global_map)
     PinBuf h_in, h_out, h_small;
     double last_ms = 0;
@@ -292,6 +292,7 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     h->d_nnpos.reserve(job.n_scratch_points * K * sizeof(unsigned int));
     h->d_partials.reserve(static_cast<size_t>(job.n_tiles) * kPartialDoubles * sizeof(double));
     h->d_ringq.reserve(job.n_scratch_points * sizeof(uint2));
+    h->d_track.reserve(job.n_scratch_points * sizeof(KnnTrack));
     // P2Plane: per-point plane (k_icp_fit) and the flag that says it still belongs to the point's current neighbours
     const bool small = job.n_tiles <= 2u * static_cast<unsigned int>(h->num_sms);
     const bool cache = METHOD == kIcpP2Plane;
@@ -308,8 +309,12 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     // Queries stage 1 cannot finish: a small job (one scan) gives each of them a warp (lowest latency, the GPU is idle
     // anyway); a large job keeps one query per thread (most requests in flight).
     prof_mark(h, 0, true);
-    LR_LAUNCH(k_icp_nn<K>, job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, nn_mode, h->d_nnpos.as<unsigned int>(),
-              cache ? h->d_same.as<unsigned char>() : nullptr, queue);
+    if (nn_mode & kNnTrack)
+        LR_LAUNCH((k_icp_nn<K, true>), job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, nn_mode, h->d_nnpos.as<unsigned int>(),
+                  cache ? h->d_same.as<unsigned char>() : nullptr, h->d_track.as<KnnTrack>(), queue);
+    else
+        LR_LAUNCH((k_icp_nn<K, false>), job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, nn_mode, h->d_nnpos.as<unsigned int>(),
+                  cache ? h->d_same.as<unsigned char>() : nullptr, h->d_track.as<KnnTrack>(), queue);
     prof_mark(h, 0, false);
     prof_mark(h, 3, true);
     // The queue length is only known on the device, so both forms are launched and each one looks at the count:
@@ -352,7 +357,9 @@ template <int METHOD>
 void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
     for (int it = 0; it < h->opt.max_iteration; ++it) {
         static const int tp_iters = getenv("LOCREG_TWOPASS_ITERS") ? atoi(getenv("LOCREG_TWOPASS_ITERS")) : 2;  // iterations whose scan uses the threshold pre-pass (2 measured best)
-        icp_launch_eval<METHOD>(h, job, 0, it == 0 ? kNnTwoPass : (it < tp_iters ? (kNnSeeds | kNnTwoPass) : kNnSeeds), nullptr, nullptr);
+        static const int track = getenv("LOCREG_TRACK") ? atoi(getenv("LOCREG_TRACK")) : 1;  // 0: every query scans its list every time
+        const int seeded = track ? (kNnSeeds | kNnTrack) : kNnSeeds;
+        icp_launch_eval<METHOD>(h, job, 0, it == 0 ? kNnTwoPass : (it < tp_iters ? (kNnSeeds | kNnTwoPass) : seeded), nullptr, nullptr);
         icp_launch_solve<METHOD>(h, job, 1, nullptr);
     }
     if (final_eval) {

@@ -201,6 +201,20 @@ LR_HD void knn_offer(const float4* pts, KnnResult<K>& r, float d2, unsigned int 
     if (knn_accepts(pts, r, d2, pos)) knn_insert(pts, r, d2, pos);
 }
 
+// knn_offer that also keeps d6 = the smallest dis2 of any candidate that is NOT in the set afterwards (rejected, or
+// evicted by this insertion): the search's lower bound for "the best point outside the result" (knn_track_margin).
+template <int K>
+LR_HD void knn_offer_track(const float4* pts, KnnResult<K>& r, float d2, unsigned int pos, float& d6) {
+    if (!(d2 <= r.d2[K - 1])) { d6 = fminf(d6, d2); return; }  // fminf drops the NaN of a masked duplicate
+    bool member = false;
+#pragma unroll
+    for (int j = 0; j < K; ++j) member = member || (r.pos[j] == pos);
+    if (member) return;
+    if (d2 == r.d2[K - 1] && !(knn_index_of(pts, pos) < knn_index_of(pts, r.pos[K - 1]))) { d6 = fminf(d6, d2); return; }
+    d6 = fminf(d6, r.d2[K - 1]);  // the evicted k-th (INFINITY while the set is not full)
+    knn_insert(pts, r, d2, pos);
+}
+
 LR_HD float dis2_f32(float qx, float qy, float qz, float px, float py, float pz) {
     const float dx = LR_FSUB(qx, px), dy = LR_FSUB(qy, py), dz = LR_FSUB(qz, pz);
     return LR_FADD(LR_FMUL(dx, dx), LR_FADD(LR_FMUL(dy, dy), LR_FMUL(dz, dz)));
@@ -227,7 +241,32 @@ constexpr int kScanBatch = 4;
 // `pts` is the array the list lives in, `canon` the array canonical positions index (the same on level 0).
 template <int K>
 LR_HD void knn_scan_list(const float4* __restrict__ pts, const float4* __restrict__ canon, KnnResult<K>& res, float qx, float qy,
-                         float qz, unsigned int beg, unsigned int cnt, bool two_pass) {
+                         float qz, unsigned int beg, unsigned int cnt, bool two_pass, float* d6 = nullptr) {
+    if (d6 != nullptr) {  // seeded scan that also reports the best candidate left outside the set (never with two_pass)
+#if defined(__CUDA_ARCH__)
+        if (cnt == 0) return;
+        const unsigned int last = beg + cnt - 1;
+        float best_out = *d6;
+        for (unsigned int i = beg; i <= last; i += kScanBatch) {
+            float4 p[kScanBatch];
+#pragma unroll
+            for (int u = 0; u < kScanBatch; ++u) p[u] = pts[min(i + u, last)];
+            float d2[kScanBatch];
+#pragma unroll
+            for (int u = 0; u < kScanBatch; ++u) d2[u] = dis2_f32(qx, qy, qz, p[u].x, p[u].y, p[u].z);
+#pragma unroll
+            for (int u = 0; u < kScanBatch; ++u)  // a re-read final entry is a member by then, or was counted already
+                knn_offer_track(canon, res, d2[u], static_cast<unsigned int>(float_as_int(p[u].w)), best_out);
+        }
+        *d6 = best_out;
+#else
+        for (unsigned int i = beg; i < beg + cnt; ++i) {
+            const float4 p = pts[i];
+            knn_offer_track(canon, res, dis2_f32(qx, qy, qz, p.x, p.y, p.z), static_cast<unsigned int>(float_as_int(p.w)), *d6);
+        }
+#endif
+        return;
+    }
 #if defined(__CUDA_ARCH__)
     if (cnt == 0) return;
     const unsigned int last = beg + cnt - 1;
@@ -412,6 +451,67 @@ LR_HD bool knn_query_fast(const VoxelMapView& m, float qx, float qy, float qz, K
     LR_STAT(0, 1); LR_STAT(1, cnt);  // fast-path queries, candidates
     knn_scan_list<K>(m.pts, m.pts, res, qx, qy, qz, beg, cnt, two_pass);  // stage 1 runs on level 0: canon == pts
     return knn_list_final<K>(m, c, res);
+}
+
+// ---- skipping the list scan when the query has hardly moved --------------------------------------------------------
+// A full stage-1 search at q0 knows more than the K neighbours: every other point is at least r6 away, r6 = the best
+// candidate it rejected inside the box, or the distance to the faces of the box for the points outside.  When the query
+// of the next Gauss-Newton iteration has moved by delta, every member is at most r5 + delta away and every non-member
+// at least r6 - delta: while 2 delta < r6 - r5 (less the rounding of the float distances) the K nearest points are the
+// SAME SET, and recomputing and sorting their K distances (knn_seed) reproduces the exact search bit for bit - order
+// and ties included - without touching the list.  Late iterations move a query by a millimetre; r6 - r5 is
+// centimetres.
+struct __attribute__((aligned(16))) KnnTrack {
+    float qx, qy, qz;  // the query of the last full search
+    float margin;      // how far the query may move from there, metres; <= 0: always search
+};
+template <int K>
+LR_HD float knn_track_margin(const VoxelMapView& m, const KnnCellFrame& c, const KnnResult<K>& res, float d6, float qx, float qy,
+                             float qz) {
+    if (res.pos[K - 1] == kNoPos) return -1.0f;
+    float mf = fminf(c.frx, 1.0f - c.frx);
+    mf = fminf(mf, fminf(c.fry, 1.0f - c.fry));
+    mf = fminf(mf, fminf(c.frz, 1.0f - c.frz));
+    const float g = safe_gap(1.0f + mf, c.mag + 1.0f, m.cell);  // points outside the scanned box
+    const float r6 = fminf(sqrtf(d6) * 0.99999f, g);
+    const float r5 = sqrtf(res.d2[K - 1]) * 1.00001f;
+    // float coordinates this far from the origin carry half an ulp each, in the stored and in the moved query
+    const float mag = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+    return 0.5f * (r6 - r5) - (4e-7f * mag + 1e-6f);
+}
+LR_HD bool knn_track_holds(const KnnTrack& t, float qx, float qy, float qz) {
+    if (!(t.margin > 0.0f)) return false;
+    const float dx = qx - t.qx, dy = qy - t.qy, dz = qz - t.qz;
+    return sqrtf(dx * dx + dy * dy + dz * dz) * 1.00001f < t.margin;  // NaN anywhere: false
+}
+// Stage 1 with the bookkeeping above: `track` receives the query and its margin (-1 when the result is not final).
+template <int K>
+LR_HD bool knn_query_fast_track(const VoxelMapView& m, float qx, float qy, float qz, KnnResult<K>& res, const unsigned int* seeds,
+                                KnnTrack& track) {
+    knn_init(res);
+    track.qx = qx; track.qy = qy; track.qz = qz; track.margin = -1.0f;
+    const KnnCellFrame c = knn_frame(m, qx, qy, qz);
+    knn_seed<K>(m, qx, qy, qz, seeds, res);
+    if (!knn_uses_list(m, c)) return false;
+    unsigned int beg = 0, cnt = 0;
+    knn_find_list(m, c.fx, c.fy, c.fz, beg, cnt);
+    LR_STAT(0, 1); LR_STAT(1, cnt);  // fast-path queries, candidates
+    float d6 = INFINITY;
+    knn_scan_list<K>(m.pts, m.pts, res, qx, qy, qz, beg, cnt, false, &d6);
+    const bool done = knn_list_final<K>(m, c, res);
+    // (a query whose box covers the whole map is final too, with the box faces still the bound for "outside": fine)
+    if (done) track.margin = knn_track_margin<K>(m, c, res, d6, qx, qy, qz);
+    return done;
+}
+// The cheap attempt: K gathers and a sort.  True: `res` is the exact result for (qx, qy, qz).
+template <int K>
+LR_HD bool knn_track_try(const VoxelMapView& m, float qx, float qy, float qz, const unsigned int* seeds, const KnnTrack& track,
+                         KnnResult<K>& res) {
+    if (!knn_track_holds(track, qx, qy, qz)) return false;
+    knn_init(res);
+    knn_seed<K>(m, qx, qy, qz, seeds, res);
+    LR_STAT(9, 1);  // searches skipped
+    return res.pos[K - 1] != kNoPos;
 }
 
 // Stage 2a: the 5x5x5 box through neighbourhood lists.  The list of the cell f + (sx, sy, sz), s = +-1, covers the

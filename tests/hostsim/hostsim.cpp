@@ -175,6 +175,43 @@ void hs_knn_seeded(const HsMap* m, const float* q, const float* seed_q, size_t n
     }
 }
 
+// The tracked search of k_icp_nn<K, true> over a SEQUENCE of query sets (steps x nq points, the same points moving a
+// little from step to step): step 0 searches from scratch, later steps try the K-gathers shortcut first
+// (knn_track_try), else search with the bookkeeping (knn_query_fast_track), else finish through stage 2.
+// idx_out: steps x nq x K original indices; returns the number of searches the shortcut replaced.
+}  // extern "C"
+template <int K>
+static size_t knn_tracked_t(const HsMap* m, const float* q, size_t steps, size_t nq, int32_t* idx_out) {
+    std::vector<unsigned int> pos(nq * K, kNoPos);
+    std::vector<KnnTrack> track(nq, KnnTrack{0.0f, 0.0f, 0.0f, -1.0f});
+    size_t skipped = 0;
+    for (size_t s = 0; s < steps; ++s)
+        for (size_t i = 0; i < nq; ++i) {
+            const float* p = q + (s * nq + i) * 3;
+            KnnResult<K> r;
+            knn_init(r);
+            if (finite3(p[0], p[1], p[2]) && m->view.n_pts != 0) {
+                if (s == 0) {
+                    knn_query<K>(m->view, m->coarse, true, p[0], p[1], p[2], r);
+                    track[i].margin = -1.0f;
+                } else if (knn_track_try<K>(m->view, p[0], p[1], p[2], &pos[i * K], track[i], r)) {
+                    ++skipped;
+                } else if (!knn_query_fast_track<K>(m->view, p[0], p[1], p[2], r, &pos[i * K], track[i])) {
+                    knn_query_finish<K>(m->view, m->coarse, p[0], p[1], p[2], r);
+                }
+            }
+            for (int j = 0; j < K; ++j) {
+                pos[i * K + j] = r.pos[j];
+                idx_out[(s * nq + i) * K + j] = r.pos[j] != kNoPos ? knn_index_of(m->view.pts, r.pos[j]) : -1;
+            }
+        }
+    return skipped;
+}
+extern "C" {
+size_t hs_knn_tracked(const HsMap* m, const float* q, size_t steps, size_t nq, int k, int32_t* idx_out) {
+    return k == 1 ? knn_tracked_t<1>(m, q, steps, nq, idx_out) : knn_tracked_t<5>(m, q, steps, nq, idx_out);
+}
+
 }  // extern "C"
 
 // prm: max_nn_distance, max_plane_distance, plane_fit_eps, eps, max_iteration, min_effective_pts, max_line_distance

@@ -24,6 +24,8 @@ def lib():
         L.hs_knn.argtypes = [vp, vp, sz, sz, i32, vp]
         L.hs_knn_stats.argtypes = [vp]
         L.hs_knn_seeded.argtypes = [vp, vp, vp, sz, sz, vp]
+        L.hs_knn_tracked.argtypes = [vp, vp, sz, sz, i32, vp]
+        L.hs_knn_tracked.restype = sz
         L.hs_icp_hb.argtypes = [vp, i32, vp, vp, sz, sz, vp, vp, vp, vp, vp, vp, vp]
         L.hs_icp_align.restype = i32
         L.hs_icp_align.argtypes = [vp, i32, vp, vp, sz, sz, vp, vp, vp]
@@ -43,7 +45,7 @@ def _cloud(a):
 
 
 STAT_NAMES = ["fast_queries", "fast_candidates", "corner_queries", "corner_lists", "corner_candidates", "ring_queries",
-              "ring_block_probes", "ring_candidates", "linear_scans"]
+              "ring_block_probes", "ring_candidates", "linear_scans", "skipped_searches"]
 
 
 def knn_stats():
@@ -79,6 +81,15 @@ class HsMap:
         out = np.empty((n, k), np.int32)
         lib().hs_knn(self._h, a.ctypes.data, n, s, k, out.ctypes.data)
         return out
+
+    def knn_tracked(self, q_steps, k):
+        """k-NN of a sequence of query sets (steps, n, 3) with k_icp_nn's skip-the-scan bookkeeping carried from step to
+        step; returns (idx (steps, n, k), number of searches the shortcut replaced)."""
+        q = np.ascontiguousarray(q_steps, np.float32)
+        steps, n, _ = q.shape
+        out = np.empty((steps, n, k), np.int32)
+        skipped = lib().hs_knn_tracked(self._h, q.ctypes.data, steps, n, k, out.ctypes.data)
+        return out, int(skipped)
 
     def knn_seeded(self, q, seed_q):
         """5-NN of q, the search seeded with the 5-NN of seed_q (same shape)."""

@@ -67,6 +67,28 @@ def test_far_queries_use_the_coarse_level_not_a_linear_scan(scene, ref_icp):
     assert HS.knn_stats()["linear_scans"] == 2
 
 
+@pytest.mark.parametrize("k", [1, 5])
+def test_knn_tracked_shortcut_is_exact(scene, hs_map, ref_icp, k):
+    """Queries that moved less than their margin since their last full search only re-sort their k neighbours
+    (knn_track_try).  A converging sequence (steps of 30 cm down to 0.1 mm, as Gauss-Newton iterations produce) must
+    give the exact result at every step, and most late steps must take the shortcut."""
+    q0 = _queries(scene)[:3000]
+    rng = np.random.default_rng(11)
+    direction = rng.normal(0, 1, 3); direction /= np.linalg.norm(direction)
+    offsets = [0.3, 0.1, 0.03, 0.01, 0.003, 0.001, 0.0003, 0.0001, 0.0]
+    # a common translation plus a small per-point part (a rotation moves every point differently)
+    steps = np.stack([(q0 + direction * d + rng.normal(0, 0.2 * d, q0.shape)).astype(np.float32) for d in offsets])
+    got, skipped = hs_map.knn_tracked(steps, k)
+    for s in range(len(offsets)):
+        assert np.array_equal(got[s], ref_icp.knn(steps[s], k)), s
+    assert skipped > 2.0 * len(q0), skipped  # of 8 tracked steps per point, clearly more than two use the shortcut
+    # adversarial: jumps larger than any margin right after tiny ones must fall back to the search
+    jumpy = np.stack([steps[8], steps[7], steps[0], steps[8], steps[2], steps[8]])
+    got, _ = hs_map.knn_tracked(jumpy, k)
+    for s in range(len(jumpy)):
+        assert np.array_equal(got[s], ref_icp.knn(jumpy[s], k)), s
+
+
 def test_knn_seeded_search_is_still_exact(scene, hs_map, ref_icp):
     """Seeds (the previous Gauss-Newton iteration's neighbours) only tighten the threshold: near, far and useless
     seeds must all give the exact result, without duplicates."""
