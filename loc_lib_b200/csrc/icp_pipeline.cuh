@@ -573,8 +573,9 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
     constexpr int K = METHOD == kIcpP2P ? 1 : 5;
     constexpr int ROWS = METHOD == kIcpP2Plane ? 1 : 3;  // residual rows per inlier (P2P, P2Line: 3-vector residuals)
     __shared__ Pose T;
-    __shared__ double rows[kTile * ROWS * kRowStride];
-    __shared__ double wsum[kTile / 32][32];
+    __shared__ double rows[kTile * ROWS * kRowStride + 1];  // + 1: the pad column of the last row (see the Gram step)
+    __shared__ double gram[kTile / 32][64];
+    __shared__ int counts[kTile / 32][2];
     if (blockIdx.x == 0 && threadIdx.x == 0) { ring_count[0] = 0u; ring_count[1] = 0u; }  // both search stages of this evaluation are done
     const TileCoord tc = locate_tile(bv, blockIdx.x);
     if (!tc.valid) return;
@@ -620,36 +621,54 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
                 nn_idx[(tc.out_base + p) * K + j] = nn.pos[j] != kNoNeighbour ? __float_as_int(map.pts[nn.pos[j]].w) : -1;
         }
     }
-    // per-warp sums of products over the warp's own rows
+    // Per-warp Gram matrix G = R^T R of the warp's 32 * ROWS staged rows R = [J | r] on the fp64 tensor cores:
+    // mma.m8n8k4 takes A (8 x 4, A[m][k] = R[4 ks + k][m]) and B (4 x 8, B[k][n] = R[4 ks + k][n]); a lane's A and B
+    // fragments are the same element R[4 ks + (lane & 3)][lane >> 2], so one 8 B shared-memory load per lane feeds four
+    // rows - where one lane per matrix entry needed two loads and an FMA per row.  Column 7 does not exist (the load
+    // picks up the next row's first element): it only reaches row / column 7 of G, which nobody reads.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int eff_mask = __ballot_sync(0xffffffffu, sink.eff);
     __syncwarp();  // the warp's row stores are visible to its loads below
     const unsigned int inl_mask = __ballot_sync(0xffffffffu, sink.inl);
-    // lane -> (a, b): entries 0..20 = H(a, b) upper triangle, 21..26 = B[a] = -sum J[a] r (b = 6), 27 = sum r r
-    // (3 bits per lane, packed: rows 0 0 0 0 0 0 1 1 1 1 1 2 2 2 2 3 3 3 4 4 5, columns 0..5 1..5 2..5 3..5 4 5 5)
-    constexpr unsigned long long kTriRow = tri_table(false), kTriCol = tri_table(true);
-    int ea = 6, eb = 6;
-    if (lane < 21) {
-        ea = static_cast<int>(kTriRow >> (3 * lane)) & 7;
-        eb = static_cast<int>(kTriCol >> (3 * lane)) & 7;
-    } else if (lane < 27) {
-        ea = lane - 21;
+    const double* wrows = rows + warp * 32 * ROWS * kRowStride + (lane & 3) * kRowStride + (lane >> 2);
+    double g0 = 0.0, g1 = 0.0;  // G[lane >> 2][2 * (lane & 3) + {0, 1}]
+#pragma unroll
+    for (int ks = 0; ks < 8 * ROWS; ++ks) {
+        const double a = wrows[4 * ks * kRowStride];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                     : "+d"(g0), "+d"(g1)
+                     : "d"(a), "d"(a));
     }
-    double s = 0.0;
-    const double* wrows = rows + warp * 32 * ROWS * kRowStride;
-    const double* ra = wrows + ea;
-    const double* rb = wrows + eb;
-#pragma unroll
-    for (int i = 0; i < 32 * ROWS; ++i) s = fma(ra[i * kRowStride], rb[i * kRowStride], s);  // lanes 28..31: discarded
-    if (lane >= 21 && lane < 27) s = -s;
-    if (lane == 28) s = static_cast<double>(__popc(eff_mask));
-    if (lane == 29) s = static_cast<double>(__popc(inl_mask));
-    wsum[warp][lane] = s;
+    gram[warp][(lane >> 2) * 8 + 2 * (lane & 3)] = g0;
+    gram[warp][(lane >> 2) * 8 + 2 * (lane & 3) + 1] = g1;
+    if (lane == 0) {
+        counts[warp][0] = __popc(eff_mask);
+        counts[warp][1] = __popc(inl_mask);
+    }
     __syncthreads();
+    // thread -> entry: 0..20 = H(a, b) upper triangle, 21..26 = B[a] = -sum J[a] r, 27 = sum r r, 28 / 29 = counts
+    // (3 bits per entry, packed: rows 0 0 0 0 0 0 1 1 1 1 1 2 2 2 2 3 3 3 4 4 5, columns 0..5 1..5 2..5 3..5 4 5 5)
     if (threadIdx.x < 30) {
+        constexpr unsigned long long kTriRow = tri_table(false), kTriCol = tri_table(true);
+        const int e = threadIdx.x;
         double t = 0;
+        if (e < 28) {
+            int ea = 6, eb = 6;
+            if (e < 21) {
+                ea = static_cast<int>(kTriRow >> (3 * e)) & 7;
+                eb = static_cast<int>(kTriCol >> (3 * e)) & 7;
+            } else if (e < 27) {
+                ea = e - 21;
+            }
 #pragma unroll
-        for (int w = 0; w < kTile / 32; ++w) t += wsum[w][threadIdx.x];
+            for (int w = 0; w < kTile / 32; ++w) t += gram[w][ea * 8 + eb];
+            if (e >= 21 && e < 27) t = -t;
+        } else {
+            int c = 0;
+#pragma unroll
+            for (int w = 0; w < kTile / 32; ++w) c += counts[w][e - 28];
+            t = static_cast<double>(c);
+        }
         partials[static_cast<size_t>(blockIdx.x) * kPartialDoubles + threadIdx.x] = t;
     }
 }
