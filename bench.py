@@ -312,7 +312,8 @@ def run_ours(args):
                          "iteration_achieved": BYTES_PER_POINT_ITER * n_pts / (pipe_ms * 1e-3) / 1e9 if pipe_ms > 0 else None,
                          "iteration_frac": BYTES_PER_POINT_ITER * n_pts / (pipe_ms * 1e-3) / 1e9 / peak if pipe_ms > 0 else None,
                          "note": "96 B per point-iteration (SURVEY 8d) x points per launch; the map (16 MB of points + "
-                                 "neighbour lists) is mostly L2/L1 resident, so DRAM traffic is far below this"},
+                                 "neighbour lists) is mostly L2/L1 resident: the DRAM traffic (ncu, one steady-state launch) is "
+                                 "the scan points plus the per-point search state (seeds, margins), and stays below this"},
             "track": track,
             "map_build": {"wall_ms": map_build_ms, "kernel_ms": map_kernel_ms, "points": int(len(map_cloud))},
             "check": {"median_translation_error_m": float(err), "wall_s_timed_region": wall},
