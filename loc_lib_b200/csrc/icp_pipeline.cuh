@@ -207,8 +207,11 @@ __device__ __forceinline__ void tile_queue_append(bool mine, unsigned int row, u
 //                          are compacted over the tile first - by the eighth iteration they are 3 % of the points, and
 //                          left in place they would still keep a lane of nearly every warp busy for a whole scan.
 constexpr int kNnTrack = 4;
+#ifndef LR_NN_TRACK_MIN_BLOCKS
+#define LR_NN_TRACK_MIN_BLOCKS LR_NN_MIN_BLOCKS
+#endif
 template <int K, bool TRACKED>
-__global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView map, BatchView bv,
+__global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView map, BatchView bv,
                                                                     const AlignState* __restrict__ states, int ignore_stop,
                                                                     int mode, unsigned int* __restrict__ nn_pos,
                                                                     unsigned char* __restrict__ plane_valid, KnnTrack* track,
@@ -248,11 +251,12 @@ __global__ void __launch_bounds__(kTile, LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView
                 if (knn_track_try<K>(map, qx, qy, qz, seeds, t, nn)) {
                     bool same = true;
 #pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        same = same && seeds[j] == nn.pos[j];
-                        out[j] = nn.pos[j];
+                    for (int j = 0; j < K; ++j) same = same && seeds[j] == nn.pos[j];
+                    if (!same) {  // same points, new order
+#pragma unroll
+                        for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+                        if (plane_valid) plane_valid[row] = 0;
                     }
-                    if (plane_valid && !same) plane_valid[row] = 0;
                 } else {
                     need_scan = true;
                 }
@@ -591,9 +595,10 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
         const float4 sp = bv.src[tc.src_base + p];
         const unsigned int* in = nn_pos + (tc.out_base + p) * K;
         KnnResult<K> nn;
+        const bool want_nn = METHOD != kIcpP2Plane || nn_idx != nullptr;  // P2Plane works from k_icp_fit's plane
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            nn.pos[j] = in[j];
+            nn.pos[j] = want_nn ? in[j] : kNoPos;
             nn.d2[j] = 0.0f;  // not needed downstream
         }
         double4 pl = make_double4(0, 0, 0, 0);

@@ -358,7 +358,8 @@ void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
     for (int it = 0; it < h->opt.max_iteration; ++it) {
         static const int tp_iters = getenv("LOCREG_TWOPASS_ITERS") ? atoi(getenv("LOCREG_TWOPASS_ITERS")) : 2;  // iterations whose scan uses the threshold pre-pass (2 measured best)
         static const int track = getenv("LOCREG_TRACK") ? atoi(getenv("LOCREG_TRACK")) : 1;  // 0: every query scans its list every time
-        const int seeded = track ? (kNnSeeds | kNnTrack) : kNnSeeds;
+        static const int track_from = getenv("LOCREG_TRACK_FROM") ? atoi(getenv("LOCREG_TRACK_FROM")) : 2;
+        const int seeded = track && it >= track_from ? (kNnSeeds | kNnTrack) : kNnSeeds;
         icp_launch_eval<METHOD>(h, job, 0, it == 0 ? kNnTwoPass : (it < tp_iters ? (kNnSeeds | kNnTwoPass) : seeded), nullptr, nullptr);
         icp_launch_solve<METHOD>(h, job, 1, nullptr);
     }

@@ -701,7 +701,10 @@ constexpr int kFineShells = 4;
 constexpr int kCoarseFactor = 4;   // cell edge ratio between consecutive levels
 constexpr int kCoarseLevels = 2;   // 4x and 16x the fine cell: shells reach 24 * 16 fine cells (192 m at 0.5 m)
 constexpr int kCoarseShells = 6;   // shells on a level that has a coarser one behind it
-constexpr int kMidFactor = 2;       // the mid level's cell edge / the fine level's
+#ifndef LR_MID_FACTOR
+#define LR_MID_FACTOR 2.0f
+#endif
+constexpr float kMidFactor = LR_MID_FACTOR;  // the mid level's cell edge / the fine level's
 constexpr int kMidShells = 2;       // shells on the mid level when a coarse level can take over
 struct CoarseLevels {
     VoxelMapView lv[kCoarseLevels];  // n_pts == 0: level absent
