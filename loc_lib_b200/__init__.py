@@ -4,4 +4,4 @@ One hot path of maotian123/loc_lib rebuilt for sm_100a behind the reference's Ma
 see DESIGN.md for the scope and INTEGRATION.md for the drop-in binding.
 """
 from .registration import (IcpMethod, IcpOptions, IcpRegistration, NdtMethod, NdtNearbyType, NdtOptions,  # noqa: F401
-                           NdtRegistration, LocTracker, se3_inv, se3_mul)
+                           NdtRegistration, LocTracker, LioTracker, se3_inv, se3_mul)

@@ -18,6 +18,7 @@ SYMBOLS = [
     "locreg_transform_cloud", "locreg_ndt_num_voxels", "locreg_ndt_get_voxels", "locreg_last_timing",
     "locreg_profile", "locreg_last_error", "locreg_version", "locreg_filter_remove_nan", "locreg_filter_crop_box",
     "locreg_filter_voxel_grid", "locreg_set_global_map", "locreg_reset_local_map",
+    "locreg_local_map_add_keyframe", "locreg_local_map_get", "locreg_local_map_clear",
 ]
 
 
@@ -72,6 +73,9 @@ def lib():
         L.locreg_profile.argtypes = [vp, i32, vp, vp]
         L.locreg_set_global_map.argtypes = [vp, vp, sz, sz]
         L.locreg_reset_local_map.argtypes = [vp, vp, vp, C.POINTER(sz)]
+        L.locreg_local_map_add_keyframe.argtypes = [vp, vp, sz, sz, vp, i32, C.c_float, C.POINTER(sz)]
+        L.locreg_local_map_get.argtypes = [vp, vp, sz, C.POINTER(sz), C.POINTER(sz)]
+        L.locreg_local_map_clear.argtypes = [vp]
         L.locreg_filter_remove_nan.argtypes = [vp, vp, sz, sz, vp, C.POINTER(sz)]
         L.locreg_filter_crop_box.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(sz)]
         L.locreg_filter_voxel_grid.argtypes = [vp, vp, sz, sz, C.c_float, vp, C.POINTER(sz)]

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <deque>
 #include <vector>
 
 #include "align_kernels.cuh"
@@ -82,6 +83,16 @@ struct locreg_handle {
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
         d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_global, d_local, d_same, d_plane, d_pstat, d_track;
     size_t n_global = 0, global_stride = 0;  // Loc's global map kept on the device (locreg_set_global_map)
+    // Lio's sliding local map (locreg_local_map_add_keyframe): transformed key frames + the filtered local map
+    struct KeyFrame { void* p = nullptr; size_t n = 0; };
+    std::deque<KeyFrame> keyframes;
+    DevBuf d_lmap, d_lmap_tmp;
+    size_t n_lmap = 0, lmap_stride = 0;
+    void clear_keyframes() {
+        for (KeyFrame& k : keyframes) if (k.p) cudaFree(k.p);
+        keyframes.clear();
+        n_lmap = 0; lmap_stride = 0;
+    }
     PinBuf h_in, h_out, h_small;
     double last_ms = 0;
     long long last_launches = 0;
@@ -358,7 +369,7 @@ void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
     for (int it = 0; it < h->opt.max_iteration; ++it) {
         static const int tp_iters = getenv("LOCREG_TWOPASS_ITERS") ? atoi(getenv("LOCREG_TWOPASS_ITERS")) : 2;  // iterations whose scan uses the threshold pre-pass (2 measured best)
         static const int track = getenv("LOCREG_TRACK") ? atoi(getenv("LOCREG_TRACK")) : 1;  // 0: every query scans its list every time
-        static const int track_from = getenv("LOCREG_TRACK_FROM") ? atoi(getenv("LOCREG_TRACK_FROM")) : 2;
+        static const int track_from = getenv("LOCREG_TRACK_FROM") ? atoi(getenv("LOCREG_TRACK_FROM")) : 3;  // measured: 2 and 3 alike, 4 +1 % on batches; single scans converge sooner
         const int seeded = track && it >= track_from ? (kNnSeeds | kNnTrack) : kNnSeeds;
         icp_launch_eval<METHOD>(h, job, 0, it == 0 ? kNnTwoPass : (it < tp_iters ? (kNnSeeds | kNnTwoPass) : seeded), nullptr, nullptr);
         icp_launch_solve<METHOD>(h, job, 1, nullptr);
@@ -527,6 +538,7 @@ int locreg_destroy(locreg_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    h->clear_keyframes();
     cudaStream_t s = h->own_stream;
     delete h;
     if (s) cudaStreamDestroy(s);
@@ -983,6 +995,81 @@ int locreg_reset_local_map(locreg_handle* h, const float* origin3, const float* 
             kept = filter_crop_box(h->d_global.as<unsigned char>(), h->n_global, h->global_stride, lo, hi, h->d_local.as<unsigned char>(), h->stream);
         if (n_local) *n_local = kept;
         return set_target_impl(h, h->d_local.as<float>(), kept, h->global_stride, true);
+    });
+}
+
+// Lio::AddCloud's local-map bookkeeping (lio.cpp:238-307), on the device.
+int locreg_local_map_add_keyframe(locreg_handle* h, const float* scan_xyz, size_t n, size_t stride, const double* pose7,
+                                  int32_t max_keyframes, float leaf, size_t* n_local) {
+    const int rc = check_cloud_args(scan_xyz, n, stride);
+    if (rc) return rc;
+    if (!pose7 || max_keyframes < 1) { g_last_error = "null pose or max_keyframes < 1"; return LOCREG_E_ARG; }
+    if (h && h->lmap_stride && h->lmap_stride != stride) { g_last_error = "key frames of one local map must share a point stride"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        // key_frame_scan = transformPointCloud(scan, pose)
+        locreg_handle::KeyFrame kf;
+        kf.n = n;
+        if (n) {
+            stage_cloud(h, scan_xyz, n, stride, false);
+            LR_CUDA(cudaMalloc(&kf.p, n * stride));
+            h->d_acc.reserve(32 * sizeof(double));
+            LR_CUDA(cudaMemcpyAsync(h->d_acc.p, pose7, 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((n + 255) / 256, 4096));
+            LR_LAUNCH(k_transform, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>(), static_cast<unsigned char*>(kf.p), n, stride,
+                      h->d_acc.as<double>());
+        }
+        h->lmap_stride = stride;
+        h->keyframes.push_back(kf);
+        // the unfiltered local map: all scans of the window after a pop (:283-292), else the old map + the key frame (:296)
+        size_t total = 0;
+        if (h->keyframes.size() > static_cast<size_t>(max_keyframes)) {
+            LR_CUDA(cudaStreamSynchronize(h->stream));
+            if (h->keyframes.front().p) cudaFree(h->keyframes.front().p);
+            h->keyframes.pop_front();
+            for (const auto& k : h->keyframes) total += k.n;
+            h->d_lmap_tmp.reserve(std::max<size_t>(total * stride, 1));
+            size_t at = 0;
+            for (const auto& k : h->keyframes) {
+                if (k.n) LR_CUDA(cudaMemcpyAsync(h->d_lmap_tmp.as<unsigned char>() + at * stride, k.p, k.n * stride, cudaMemcpyDeviceToDevice, h->stream));
+                at += k.n;
+            }
+        } else {
+            total = h->n_lmap + n;
+            h->d_lmap_tmp.reserve(std::max<size_t>(total * stride, 1));
+            if (h->n_lmap) LR_CUDA(cudaMemcpyAsync(h->d_lmap_tmp.p, h->d_lmap.p, h->n_lmap * stride, cudaMemcpyDeviceToDevice, h->stream));
+            if (n) LR_CUDA(cudaMemcpyAsync(h->d_lmap_tmp.as<unsigned char>() + h->n_lmap * stride, kf.p, n * stride, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        // local_map_filter_ptr_->Filter(local_map_, local_map_)
+        h->d_lmap.reserve(std::max<size_t>(total * stride, 1));
+        if (leaf > 0.0f && total) {
+            h->n_lmap = filter_voxel_grid(h->d_lmap_tmp.as<unsigned char>(), total, stride, leaf, h->d_lmap.as<unsigned char>(), h->stream);
+        } else {
+            if (total) LR_CUDA(cudaMemcpyAsync(h->d_lmap.p, h->d_lmap_tmp.p, total * stride, cudaMemcpyDeviceToDevice, h->stream));
+            h->n_lmap = total;
+        }
+        if (n_local) *n_local = h->n_lmap;
+        if (h->opt.method == LOCREG_NDT_INCREMENTAL) return set_target_impl(h, static_cast<const float*>(kf.p), kf.n, stride, true);
+        return set_target_impl(h, h->d_lmap.as<float>(), h->n_lmap, stride, true);
+    });
+}
+int locreg_local_map_get(locreg_handle* h, float* out_xyz, size_t capacity_points, size_t* n_local, size_t* stride_bytes) {
+    if (!n_local) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        *n_local = h->n_lmap;
+        if (stride_bytes) *stride_bytes = h->lmap_stride;
+        if (out_xyz && h->n_lmap) {
+            if (capacity_points < h->n_lmap) { g_last_error = "output buffer too small for the local map"; return LOCREG_E_ARG; }
+            LR_CUDA(cudaStreamSynchronize(h->stream));
+            LR_CUDA(cudaMemcpy(out_xyz, h->d_lmap.p, h->n_lmap * h->lmap_stride, cudaMemcpyDeviceToHost));
+        }
+        return LOCREG_OK;
+    });
+}
+int locreg_local_map_clear(locreg_handle* h) {
+    return guarded(h, [&]() {
+        LR_CUDA(cudaStreamSynchronize(h->stream));
+        h->clear_keyframes();
+        return LOCREG_OK;
     });
 }
 

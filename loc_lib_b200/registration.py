@@ -224,6 +224,29 @@ class _Registration:
         _lib.check(_lib.lib().locreg_reset_local_map(self._h, o.ctypes.data, hs.ctypes.data, C.byref(n_local)))
         return n_local.value
 
+    def AddKeyFrame(self, scan, pose, max_keyframes=10, leaf=0.5):
+        """Lio::AddCloud's local-map update (lio.cpp:277-307) on the device: transform the key-frame scan by `pose`,
+        slide the window of `max_keyframes` scans, voxel-filter the local map with `leaf` (<= 0: no filter) and make it
+        the target (incremental NDT: add the key frame to the voxel cache).  Returns the size of the local map."""
+        a, n, s = _cloud(scan)
+        p = np.ascontiguousarray(pose, np.float64)
+        n_local = C.c_size_t(0)
+        _lib.check(_lib.lib().locreg_local_map_add_keyframe(self._h, a.ctypes.data, n, s, p.ctypes.data, int(max_keyframes),
+                                                            float(leaf), C.byref(n_local)))
+        return n_local.value
+
+    def GetLocalMap(self):
+        """The current sliding local map, copied to the host: (n, stride / 4) float32."""
+        n, stride = C.c_size_t(0), C.c_size_t(0)
+        _lib.check(_lib.lib().locreg_local_map_get(self._h, None, 0, C.byref(n), C.byref(stride)))
+        out = np.empty((n.value, max(stride.value // 4, 3)), np.float32)
+        if n.value:
+            _lib.check(_lib.lib().locreg_local_map_get(self._h, out.ctypes.data, n.value, C.byref(n), C.byref(stride)))
+        return out
+
+    def ClearLocalMap(self):
+        _lib.check(_lib.lib().locreg_local_map_clear(self._h))
+
     def profile(self, enable):
         """Returns ({'search','fit','solve','rings'} -> (ms, launches)) accumulated so far, then switches instrumentation."""
         ms = np.zeros(4)
@@ -326,6 +349,55 @@ def se3_mul(a, b):
 def se3_inv(a):
     qi = np.array([-a[0], -a[1], -a[2], a[3]])
     return np.concatenate([qi, -_q_rot(qi, a[4:])])
+
+
+def se3_log_angle(a):
+    """|log(R)| of a pose's rotation, radians."""
+    q = np.asarray(a[:4], np.float64)
+    return 2.0 * np.arctan2(np.linalg.norm(q[:3]), abs(q[3]))
+
+
+class LioTracker:
+    """Lio::AddCloud / AlignWithLocalMap without the ROS / ESKF / file parts (lio.cpp:238-307, 445-470, 616-623): the
+    first scan becomes the local map at the initial pose; every later scan is matched against the local map from the
+    constant-velocity prediction predict = result * last^-1 * result (starting from identity, like the function's
+    statics), and becomes a key frame - transformed, pushed into the sliding window of `num_kfs_in_local_map` scans,
+    local map re-filtered and re-indexed, all on the device - when it moved more than kf_distance metres or
+    kf_angle_deg degrees from the last key frame."""
+
+    def __init__(self, registration, init_pose=None, num_kfs_in_local_map=10, kf_distance=1.0, kf_angle_deg=10.0,
+                 local_map_leaf=0.5):
+        self.reg = registration
+        self.max_kfs, self.kf_distance, self.kf_angle = num_kfs_in_local_map, kf_distance, np.deg2rad(kf_angle_deg)
+        self.leaf = local_map_leaf
+        ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+        self.last_kf_pose = ident.copy() if init_pose is None else np.asarray(init_pose, np.float64).copy()
+        self.last_pose, self.predict = ident.copy(), ident.copy()
+        self.keyframes = 0
+        self.n_local = 0
+        self.reg.ClearLocalMap()
+
+    def IsKeyframe(self, pose):
+        delta = se3_mul(se3_inv(self.last_kf_pose), pose)
+        return np.linalg.norm(delta[4:]) > self.kf_distance or se3_log_angle(delta) > self.kf_angle
+
+    def AddCloud(self, scan, filtered_scan=None):
+        """scan: the raw scan (what a key frame stores, lio.cpp:279); filtered_scan: cur_scan_filter_ptr_'s output (what
+        is matched, and what the FIRST key frame stores, :236,:244); defaults to scan.  Returns (pose, is_keyframe)."""
+        src = scan if filtered_scan is None else filtered_scan
+        if self.keyframes == 0:
+            self.n_local = self.reg.AddKeyFrame(src, self.last_kf_pose, self.max_kfs, self.leaf)
+            self.keyframes = 1
+            return self.last_kf_pose.copy(), True
+        _, _, result = self.reg.ScanMatch(self.reg.RemoveNanPoint(src), self.predict, want_cloud=False)
+        self.predict = se3_mul(se3_mul(result, se3_inv(self.last_pose)), result)
+        self.last_pose = result
+        if not self.IsKeyframe(result):
+            return result, False
+        self.last_kf_pose = result.copy()
+        self.n_local = self.reg.AddKeyFrame(scan, result, self.max_kfs, self.leaf)
+        self.keyframes += 1
+        return result, True
 
 
 class LocTracker:

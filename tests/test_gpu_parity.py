@@ -350,6 +350,59 @@ def test_loc_tracker_device_local_map_equals_host_path(scene):
     assert trk.resets == resets
 
 
+@pytest.mark.parametrize("kind", ["icp", "inc_ndt"])
+def test_lio_tracker_device_local_map_equals_host_path(scene, kind):
+    """Lio's loop (lio.cpp:238-307): first scan = local map; later scans matched from the constant-velocity prediction;
+    key frames transformed, pushed into a sliding window (3 here, so the pop-and-rebuild branch runs), local map
+    voxel-filtered and re-indexed - all on the device.  Poses and the local map must equal the host path bit for bit:
+    oracle transform + oracle voxel grid + SetInputTarget + ScanMatch."""
+    import loc_lib_b200 as L
+    if kind == "icp":
+        make = lambda: L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=6, eps_=0.0))
+    else:
+        make = lambda: L.NdtRegistration(L.NdtOptions(method_=L.NdtMethod.INCREMENTAL_NDT, max_iteration_=6, eps_=0.0))
+    max_kfs, leaf, kf_dist = 3, 0.5, 0.3
+    dev, host = make(), make()
+    trk = L.LioTracker(dev, num_kfs_in_local_map=max_kfs, kf_distance=kf_dist, kf_angle_deg=10.0, local_map_leaf=leaf)
+    base = scene.scans[0]
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+    kfs, local = [], None
+    predict, last, last_kf = ident.copy(), ident.copy(), ident.copy()
+    n_kf = 0
+    for step in range(9):
+        scan = base.copy()
+        scan[:, 0] -= np.float32(0.2 * step)  # the sensor moves 0.2 m along x per scan
+        if step % 3 == 2:
+            scan = scan[::2].copy()
+        pose, is_kf = trk.AddCloud(scan)
+        if step == 0:
+            ref, ref_kf = ident.copy(), True
+        else:
+            _, _, ref = host.ScanMatch(O.filter_remove_nan(scan), predict, want_cloud=False)
+            predict = L.se3_mul(L.se3_mul(ref, L.se3_inv(last)), ref)
+            last = ref
+            delta = L.se3_mul(L.se3_inv(last_kf), ref)
+            ref_kf = np.linalg.norm(delta[4:]) > kf_dist
+        assert np.array_equal(pose, ref), step
+        assert is_kf == ref_kf, step
+        if ref_kf:
+            last_kf = ref.copy()
+            kf = O.transform_cloud(scan, ref)
+            kfs.append(kf)
+            if len(kfs) > max_kfs:
+                kfs.pop(0)
+                local = np.concatenate(kfs)
+            else:
+                local = kf if local is None else np.concatenate([local, kf])
+            local = O.filter_voxel_grid(local, leaf)
+            host.SetInputTarget(kf if kind == "inc_ndt" else local)
+            n_kf += 1
+            assert trk.n_local == len(local), step
+            got = dev.GetLocalMap()
+            assert np.array_equal(got[:, :3], local[:, :3]), step
+    assert n_kf > max_kfs + 1 and trk.keyframes == n_kf  # the window slid at least twice
+
+
 def test_ndt_degenerate_early_return(scene, ndt_pair):
     """det(H)==0 on the first iteration: result_pose keeps the caller's value (quirk Q11)."""
     gpu, ref = ndt_pair
