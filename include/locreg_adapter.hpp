@@ -87,6 +87,30 @@ class CudaRegistrationBase : public MatchingInterface {
 
     float GetFitnessScore() override { return 0.0f; }  // icp_registration.cpp:246-250, ndt_registration.cpp:466-471
 
+    // ---- the callers' map state, kept on the device (no counterpart in MatchingInterface) ----
+    // Loc::InitGlobalMap (loc.cpp:268-283): the global map is uploaded once.
+    void SetGlobalMap(const CloudPtr& global_map) {
+        locreg_detail::check(locreg_set_global_map(handle_, locreg_detail::cloud_xyz(*global_map), global_map->points.size(),
+                                                   sizeof(PointType)),
+                             "locreg_set_global_map");
+    }
+    // Loc::ResetLocalMap (loc.cpp:187-206): BoxFilter::SetOrigin + Filter + SetInputTarget; returns the local map's size.
+    size_t ResetLocalMap(float x, float y, float z, const float (&half_size)[3]) {
+        const float origin[3] = {x, y, z};
+        size_t n_local = 0;
+        locreg_detail::check(locreg_reset_local_map(handle_, origin, half_size, &n_local), "locreg_reset_local_map");
+        return n_local;
+    }
+    // The key-frame block of Lio::AddCloud (lio.cpp:277-307): transformPointCloud(scan, pose), slide the window of
+    // num_kfs_in_local_map scans, voxel-filter the local map (leaf <= 0: NoFilter), SetInputTarget.
+    size_t AddKeyFrame(const CloudPtr& scan, const SE3& pose, int num_kfs_in_local_map, float leaf) {
+        size_t n_local = 0;
+        locreg_detail::check(locreg_local_map_add_keyframe(handle_, locreg_detail::cloud_xyz(*scan), scan->points.size(), sizeof(PointType),
+                                                           pose.data(), num_kfs_in_local_map, leaf, &n_local),
+                             "locreg_local_map_add_keyframe");
+        return n_local;
+    }
+
     // what the reference logs or drops: iterations, effective points, convergence, degeneracy
     const locreg_result& LastResult() const { return last_result_; }
     locreg_handle* Handle() const { return handle_; }

@@ -124,5 +124,21 @@ int main() {
     SE3 nres;
     ndt->ScanMatch(scan, predict, aligned, nres);
     std::printf("adapter: NDT t = (%.4f %.4f %.4f)\n", nres.data()[4], nres.data()[5], nres.data()[6]);
+    // the callers' map state on the device: Loc's crop (whole room inside the box) and Lio's key-frame window give the
+    // same registration as the plain SetInputTarget above
+    auto icp = std::dynamic_pointer_cast<CudaIcpRegistration>(match);
+    icp->SetGlobalMap(map);
+    const float half[3] = {50.0f, 50.0f, 50.0f};
+    if (icp->ResetLocalMap(3.0f, 3.0f, 3.0f, half) != map->points.size()) return 1;
+    SE3 again;
+    icp->ScanMatch(scan, predict, aligned, again);
+    for (int i = 0; i < 7; ++i)
+        if (again.data()[i] != result.data()[i]) return 1;
+    SE3 identity;
+    if (icp->AddKeyFrame(map, identity, 10, 0.0f) != map->points.size()) return 1;  // leaf 0: NoFilter
+    icp->ScanMatch(scan, predict, aligned, again);
+    for (int i = 0; i < 7; ++i)
+        if (again.data()[i] != result.data()[i]) return 1;
+    std::printf("adapter: Loc / Lio map state on the device reproduces the pose\n");
     return 0;
 }
