@@ -121,7 +121,7 @@ def run_reference(args):
         return
     world, map_cloud = make_world(args)
     threads = os.cpu_count() or 1
-    S = max(threads, 8)
+    S = max(4 * threads, 8)  # bounded sample of the workload: ~1-2 s of CPU work per step on all host threads
     clouds, offsets, init, _ = make_scans(world, 0, S, max(S, 4096))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_py as O
@@ -138,7 +138,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, S, note="bounded sample: %d scans per step on %d host threads" % (S, used)),
+            "config": workload_config(args, args.scans_per_gpu,
+                                      note="reference arm: each step is a bounded sample of this workload, %d scans on %d host threads" % (S, used)),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": int(used), "kind": "port",
                              "sample": f"{S} scans x {args.steps} steps, oracle ANN kd-tree (reference semantics)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
