@@ -338,7 +338,7 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
                   small ? 0xFFFFFFFFu : kWarpFinishMax);
     }
     if (!small) {
-        const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * 8));
+        const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * LR_FINISH_MIN_BLOCKS));
         LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue,
                   kWarpFinishMax);
     }
