@@ -510,20 +510,23 @@ k_icp_fit(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __res
     if (threadIdx.x == 0) list_n = 0u;
     __syncthreads();
     const unsigned int lane = threadIdx.x & 31;
-    for (unsigned int g = 0; g < group; ++g) {
-        const TileCoord& c = tcs[g];
-        unsigned int row = 0;
-        bool need = false;
-        if (c.valid && threadIdx.x < c.count) {
-            row = static_cast<unsigned int>(c.out_base + c.first + threadIdx.x);
-            need = plane_valid[row] == 0;
+    // all of the thread's flags first (independent loads: one round trip instead of `group` of them), then the appends
+    unsigned int need_bits = 0u;
+#pragma unroll
+    for (unsigned int g = 0; g < static_cast<unsigned int>(kFitGroup); ++g) {
+        if (g < group && tcs[g].valid && threadIdx.x < tcs[g].count) {
+            const size_t row = static_cast<size_t>(tcs[g].out_base + tcs[g].first + threadIdx.x);
+            need_bits |= (plane_valid[row] == 0 ? 1u : 0u) << g;
         }
+    }
+    for (unsigned int g = 0; g < group; ++g) {
+        const bool need = (need_bits >> g) & 1u;
         const unsigned int mask = __ballot_sync(0xffffffffu, need);
         if (mask == 0u) continue;
         unsigned int base = 0;
         if (lane == 0) base = atomicAdd(&list_n, static_cast<unsigned int>(__popc(mask)));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (need) list[base + __popc(mask & ((1u << lane) - 1u))] = row;
+        if (need) list[base + __popc(mask & ((1u << lane) - 1u))] = static_cast<unsigned int>(tcs[g].out_base + tcs[g].first + threadIdx.x);
     }
     __syncthreads();
     const unsigned int n = list_n;
