@@ -228,21 +228,27 @@ __global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_N
     __shared__ unsigned int staged[kTile];
     __shared__ unsigned char scan_list[kTile];
     if (threadIdx.x == 0) { blk_pending = 0u; blk_done = 0u; blk_scan = 0u; }
-    __syncthreads();
     constexpr bool tracked = TRACKED;  // = (mode & kNnTrack) != 0
     unsigned int slot = threadIdx.x;  // the point of the tile this thread searches
     if (tracked) {
-        // phase A: every point tries the cheap way
+        // phase A: every point tries the cheap way (its data is requested before the barrier thread 0's pose needs)
         bool need_scan = false;
-        if (threadIdx.x < tc.count) {
-            const unsigned int p = tc.first + threadIdx.x;
-            const size_t row = static_cast<size_t>(tc.out_base + p);
-            const float4 sp = bv.src[tc.src_base + p];
-            unsigned int* out = nn_pos + row * K;
-            unsigned int seeds[K];
+        const bool mine = threadIdx.x < tc.count;
+        const unsigned int p = tc.first + (mine ? threadIdx.x : 0u);
+        const size_t row = static_cast<size_t>(tc.out_base + p);
+        unsigned int* out = nn_pos + row * K;
+        float4 sp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        unsigned int seeds[K];
+        KnnTrack t;
+        t.qx = t.qy = t.qz = 0.0f; t.margin = -1.0f;
+        if (mine) {
+            sp = bv.src[tc.src_base + p];
 #pragma unroll
             for (int j = 0; j < K; ++j) seeds[j] = out[j];
-            const KnnTrack t = track[row];
+            t = track[row];
+        }
+        __syncthreads();
+        if (mine) {
             if (finite3(sp.x, sp.y, sp.z) && map.n_pts != 0) {
                 double wx, wy, wz;
                 pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
@@ -277,6 +283,11 @@ __global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_N
     const float4 sp = bv.src[tc.src_base + p];
     const size_t row = static_cast<size_t>(tc.out_base + p);
     unsigned int* out = nn_pos + row * K;
+    // (loaded before sp is looked at, and - in the untracked kernel - before the barrier the pose needs)
+    unsigned int seeds[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) seeds[j] = (mode & kNnSeeds) && in_tile ? out[j] : kNoPos;
+    if (!tracked) __syncthreads();
     // non-finite source points are skipped: P2P as the reference (pcl::isFinite, icp_registration.cpp:64),
     // P2Plane as deviation D1 (the reference would poison H with NaN)
     const bool valid = in_tile && finite3(sp.x, sp.y, sp.z) && map.n_pts != 0;
@@ -285,10 +296,6 @@ __global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_N
     knn_init(nn);
     KnnTrack tr;
     tr.qx = tr.qy = tr.qz = 0.0f; tr.margin = -1.0f;
-    // (loaded before sp is looked at: one round trip for the point and its seeds instead of two)
-    unsigned int seeds[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) seeds[j] = (mode & kNnSeeds) && in_tile ? out[j] : kNoPos;
     if (valid) {
         double wx, wy, wz;
         pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
@@ -589,27 +596,32 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
     const AlignState* st = states + tc.scan;
     if (st->stop && !ignore_stop) return;
     if (threadIdx.x == 0) pose_load(T, st->pose);
-    __syncthreads();
-    RowSink<ROWS> sink{rows + threadIdx.x * ROWS * kRowStride, 0, false, false};
-#pragma unroll
-    for (int i = 0; i < ROWS * kRowStride; ++i) sink.rows[i] = 0.0;  // points without a residual contribute zero rows
-    if (threadIdx.x < tc.count) {
-        const unsigned int p = tc.first + threadIdx.x;
-        const float4 sp = bv.src[tc.src_base + p];
+    // the point's own data is requested before the barrier: its round trip overlaps thread 0's pose load
+    const bool in_tile = threadIdx.x < tc.count;
+    const unsigned int p = tc.first + (in_tile ? threadIdx.x : 0u);
+    float4 sp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    KnnResult<K> nn;
+    double4 pl = make_double4(0, 0, 0, 0);
+    unsigned char pst = kPlaneNone;
+    if (in_tile) {
+        sp = bv.src[tc.src_base + p];
         const unsigned int* in = nn_pos + (tc.out_base + p) * K;
-        KnnResult<K> nn;
         const bool want_nn = METHOD != kIcpP2Plane || nn_idx != nullptr;  // P2Plane works from k_icp_fit's plane
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             nn.pos[j] = want_nn ? in[j] : kNoPos;
             nn.d2[j] = 0.0f;  // not needed downstream
         }
-        double4 pl = make_double4(0, 0, 0, 0);
-        unsigned char pst = kPlaneNone;
         if (METHOD == kIcpP2Plane) {  // the plane comes from k_icp_fit; fetched together with the point
             pl = reinterpret_cast<const double4*>(plane_cache)[tc.out_base + p];
             pst = plane_stat[tc.out_base + p];
         }
+    }
+    RowSink<ROWS> sink{rows + threadIdx.x * ROWS * kRowStride, 0, false, false};
+#pragma unroll
+    for (int i = 0; i < ROWS * kRowStride; ++i) sink.rows[i] = 0.0;  // points without a residual contribute zero rows
+    __syncthreads();
+    if (in_tile) {
         unsigned char g = kGateSkipped;
         if (finite3(sp.x, sp.y, sp.z)) {
             const double qx = sp.x, qy = sp.y, qz = sp.z;
