@@ -908,7 +908,8 @@ int locreg_relocalise(locreg_handle* h, const float* src, size_t n, size_t strid
         LR_CUDA(cudaStreamSynchronize(h->stream));
         h->begin_timing();
         if (is_ndt(h)) { g_last_error = "relocalisation is built for the ICP methods"; return LOCREG_E_UNSUPPORTED; }
-        // hypotheses run in waves so that the per-point neighbour scratch stays below ~1 GiB
+        // hypotheses run in waves so that the per-point neighbour scratch stays below ~1 GiB (the rest of the per-point
+        // scratch - planes, margins, queues - scales with it: ~4.5 GiB in all for P2Plane)
         const int K = h->opt.method == LOCREG_ICP_P2P ? 1 : 5;
         const size_t per_hyp = std::max<size_t>(n, 1) * K * sizeof(unsigned int);
         const size_t wave = std::max<size_t>(1, std::min<size_t>(n_hyp, (size_t(1) << 30) / per_hyp));
