@@ -172,3 +172,28 @@ def test_se3_helpers_of_the_loc_slice():
         assert np.allclose(mat(L.se3_inv(a)), np.linalg.inv(mat(a)), atol=1e-13)
         pred = L.se3_mul(L.se3_mul(a, L.se3_inv(b)), a)
         assert np.allclose(mat(pred), mat(a) @ np.linalg.inv(mat(b)) @ mat(a), atol=1e-12)
+
+
+def test_lio_keyframe_criterion():
+    """Lio::IsKeyframe (lio.cpp:616-623): |t| of last_kf^-1 * pose above kf_distance, or |log R| above kf_angle_deg."""
+    import loc_lib_b200 as L
+    from loc_lib_b200.registration import LioTracker, se3_log_angle
+
+    class NoDevice:  # IsKeyframe touches no registration call
+        def ClearLocalMap(self):
+            pass
+
+    def rot_z(deg, t=(0.0, 0.0, 0.0)):
+        h = np.deg2rad(deg) / 2
+        return np.array([0, 0, np.sin(h), np.cos(h), *t], np.float64)
+
+    for deg in (0.0, 3.0, 9.9, 45.0, 179.0, -30.0):
+        assert abs(se3_log_angle(rot_z(deg)) - abs(np.deg2rad(deg))) < 1e-12
+    q = rot_z(30.0)
+    assert abs(se3_log_angle(-q) - np.deg2rad(30.0)) < 1e-12  # q and -q are the same rotation
+    base = rot_z(40.0, (10.0, -3.0, 1.0))
+    trk = LioTracker(NoDevice(), init_pose=base, kf_distance=1.0, kf_angle_deg=10.0)
+    assert not trk.IsKeyframe(base)
+    assert not trk.IsKeyframe(L.se3_mul(base, rot_z(9.0, (0.9, 0.0, 0.0))))
+    assert trk.IsKeyframe(L.se3_mul(base, rot_z(0.0, (0.8, 0.7, 0.0))))   # 1.06 m
+    assert trk.IsKeyframe(L.se3_mul(base, rot_z(11.0)))                   # 11 degrees on the spot
