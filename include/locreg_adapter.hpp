@@ -20,8 +20,10 @@
 //   (pcl::PointXYZI: 32 B stride, point_types.h:18); cloud->width/height/is_dense; cloud.reset(new PointCloudType);
 //   SE3::data() -> 7 doubles [qx qy qz qw tx ty tz] (Sophus::SE3d; eigen_types.h:66); Mat6d/Vec6d::data() column-major.
 #pragma once
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 #include "locreg.h"
 
@@ -32,6 +34,44 @@ inline void check(int rc, const char* what) {
     // The reference's methods cannot report errors (bool, always true).  A CUDA failure is not an algorithmic outcome,
     // so it is raised instead of being swallowed: there is no CPU path to fall back to.
     if (rc != LOCREG_OK) throw std::runtime_error(std::string(what) + ": " + locreg_last_error());
+}
+// Pose algebra on Sophus::SE3d's memory layout [qx qy qz qw tx ty tz] (the trackers below stay independent of the
+// host's SE3 type; inside LocUtils `a * b` and `a.inverse()` do the same).
+inline void quat_rotate(const double* q, const double* v, double* out) {
+    const double tx = 2.0 * (q[1] * v[2] - q[2] * v[1]), ty = 2.0 * (q[2] * v[0] - q[0] * v[2]), tz = 2.0 * (q[0] * v[1] - q[1] * v[0]);
+    out[0] = v[0] + q[3] * tx + (q[1] * tz - q[2] * ty);
+    out[1] = v[1] + q[3] * ty + (q[2] * tx - q[0] * tz);
+    out[2] = v[2] + q[3] * tz + (q[0] * ty - q[1] * tx);
+}
+inline void se3_mul(const double* a, const double* b, double* out) {  // out = a * b (out may not alias a or b)
+    const double qx = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1], qy = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0],
+                 qz = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3], qw = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    double n = qx * qx + qy * qy + qz * qz + qw * qw;
+    n = n > 0.0 ? 1.0 / __builtin_sqrt(n) : 1.0;
+    out[0] = qx * n; out[1] = qy * n; out[2] = qz * n; out[3] = qw * n;
+    double r[3];
+    quat_rotate(a, b + 4, r);
+    out[4] = a[4] + r[0]; out[5] = a[5] + r[1]; out[6] = a[6] + r[2];
+}
+inline void se3_inv(const double* a, double* out) {
+    const double qi[4] = {-a[0], -a[1], -a[2], a[3]};
+    double r[3];
+    quat_rotate(qi, a + 4, r);
+    out[0] = qi[0]; out[1] = qi[1]; out[2] = qi[2]; out[3] = qi[3];
+    out[4] = -r[0]; out[5] = -r[1]; out[6] = -r[2];
+}
+inline double se3_rotation_angle(const double* a) {  // |log(R)|
+    return 2.0 * __builtin_atan2(__builtin_sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]), __builtin_fabs(a[3]));
+}
+// predict = result * last^-1 * result: the constant-velocity model of Loc::Update (loc.cpp:232) and
+// Lio::AlignWithLocalMap (lio.cpp:464)
+template <class SE3T>
+inline void predict_next(const SE3T& result, const SE3T& last, SE3T& predict) {
+    double inv[7], tmp[7], out[7];
+    se3_inv(last.data(), inv);
+    se3_mul(result.data(), inv, tmp);
+    se3_mul(tmp, result.data(), out);
+    for (int i = 0; i < 7; ++i) predict.data()[i] = out[i];
 }
 template <class Cloud>
 inline const float* cloud_xyz(const Cloud& c) {
@@ -170,6 +210,100 @@ class CudaNdtRegistration : public CudaRegistrationBase {
         return c;
     }
     NdtOptions options_;
+};
+
+// ---- the two callers' loops around ScanMatch, with the map state on the device ------------------------------------
+// Loc::Update without the ROS / ESKF parts (loc.cpp:208-246): ScanMatch from the constant-velocity prediction, and a new
+// local map (crop of the device-resident global map) whenever the pose comes within `margin` of the box edge.
+class CudaLocTracker {
+   public:
+    CudaLocTracker(std::shared_ptr<CudaRegistrationBase> reg, const CloudPtr& global_map, const SE3& init_pose, float half_size = 150.0f,
+                   double margin = 50.0)
+        : reg_(std::move(reg)), half_{half_size, half_size, half_size}, margin_(margin), last_(init_pose), predict_(init_pose) {
+        reg_->SetGlobalMap(global_map);
+        Reset(init_pose);
+    }
+    // returns the registered pose; result_cloud as in ScanMatch
+    SE3 Update(const CloudPtr& scan, CloudPtr& result_cloud) {
+        SE3 result = predict_;
+        reg_->ScanMatch(scan, predict_, result_cloud, result);
+        locreg_detail::predict_next(result, last_, predict_);
+        last_ = result;
+        const double* t = result.data() + 4;
+        for (int i = 0; i < 3; ++i) {  // loc.cpp:235-246
+            const double lo = -half_[i] + origin_[i], hi = half_[i] + origin_[i];
+            if (__builtin_fabs(t[i] - lo) > margin_ && __builtin_fabs(t[i] - hi) > margin_) continue;
+            Reset(result);
+            break;
+        }
+        return result;
+    }
+    size_t LocalMapSize() const { return n_local_; }
+    int Resets() const { return resets_; }
+    const SE3& Predict() const { return predict_; }
+
+   private:
+    void Reset(const SE3& pose) {
+        for (int i = 0; i < 3; ++i) origin_[i] = static_cast<float>(pose.data()[4 + i]);
+        n_local_ = reg_->ResetLocalMap(origin_[0], origin_[1], origin_[2], half_);
+        ++resets_;
+    }
+    std::shared_ptr<CudaRegistrationBase> reg_;
+    float half_[3], origin_[3] = {0, 0, 0};
+    double margin_;
+    SE3 last_, predict_;
+    size_t n_local_ = 0;
+    int resets_ = 0;
+};
+
+// Lio::AddCloud / AlignWithLocalMap without the ROS / ESKF / file parts (lio.cpp:238-307, 445-470, 616-623).
+class CudaLioTracker {
+   public:
+    explicit CudaLioTracker(std::shared_ptr<CudaRegistrationBase> reg, int num_kfs_in_local_map = 10, double kf_distance = 1.0,
+                            double kf_angle_deg = 10.0, float local_map_leaf = 0.5f)
+        : reg_(std::move(reg)), max_kfs_(num_kfs_in_local_map), kf_distance_(kf_distance),
+          kf_angle_(kf_angle_deg * 3.14159265358979323846 / 180.0), leaf_(local_map_leaf) {
+        locreg_detail::check(locreg_local_map_clear(reg_->Handle()), "locreg_local_map_clear");
+    }
+    // scan: the raw scan (what a key frame stores, :279); filtered: cur_scan_filter_ptr_'s output (what is matched, and
+    // what the FIRST key frame stores, :236,:244), free of NaN points (Lio runs RemoveNanPoint first, :452).  Returns the
+    // pose; *is_keyframe tells whether the local map moved on.
+    SE3 AddCloud(const CloudPtr& scan, const CloudPtr& filtered, bool* is_keyframe = nullptr) {
+        if (keyframes_ == 0) {
+            n_local_ = reg_->AddKeyFrame(filtered, last_kf_pose_, max_kfs_, leaf_);
+            keyframes_ = 1;
+            if (is_keyframe) *is_keyframe = true;
+            return last_kf_pose_;
+        }
+        SE3 result = predict_;
+        CloudPtr aligned;
+        reg_->ScanMatch(filtered, predict_, aligned, result);
+        locreg_detail::predict_next(result, last_pose_, predict_);
+        last_pose_ = result;
+        double inv[7], delta[7];
+        locreg_detail::se3_inv(last_kf_pose_.data(), inv);
+        locreg_detail::se3_mul(inv, result.data(), delta);
+        const double dist = __builtin_sqrt(delta[4] * delta[4] + delta[5] * delta[5] + delta[6] * delta[6]);
+        const bool kf = dist > kf_distance_ || locreg_detail::se3_rotation_angle(delta) > kf_angle_;
+        if (kf) {
+            last_kf_pose_ = result;
+            n_local_ = reg_->AddKeyFrame(scan, result, max_kfs_, leaf_);
+            ++keyframes_;
+        }
+        if (is_keyframe) *is_keyframe = kf;
+        return result;
+    }
+    size_t LocalMapSize() const { return n_local_; }
+    int KeyFrames() const { return keyframes_; }
+
+   private:
+    std::shared_ptr<CudaRegistrationBase> reg_;
+    int max_kfs_;
+    double kf_distance_, kf_angle_;
+    float leaf_;
+    SE3 last_kf_pose_, last_pose_, predict_;  // identity: the function statics of AlignWithLocalMap start there too
+    size_t n_local_ = 0;
+    int keyframes_ = 0;
 };
 
 }  // namespace LocUtils

@@ -140,5 +140,40 @@ int main() {
     for (int i = 0; i < 7; ++i)
         if (again.data()[i] != result.data()[i]) return 1;
     std::printf("adapter: Loc / Lio map state on the device reproduces the pose\n");
+    // the two callers' loops (CudaLocTracker / CudaLioTracker): first step from the identity prediction = the pose above,
+    // second step from the constant-velocity prediction lands on it again
+    {
+        IcpOptions o2;
+        o2.method_ = IcpMethod::P2PLANE;
+        auto reg = std::make_shared<CudaIcpRegistration>(o2);
+        CudaLocTracker loc(reg, map, SE3(), 50.0f, 10.0);
+        if (loc.LocalMapSize() != map->points.size() || loc.Resets() != 1) return 1;
+        CloudPtr out;
+        SE3 p1 = loc.Update(scan, out);
+        for (int i = 0; i < 7; ++i)
+            if (p1.data()[i] != result.data()[i]) return 1;
+        SE3 p2 = loc.Update(scan, out);
+        for (int i = 4; i < 7; ++i)
+            if (std::fabs(p2.data()[i] - result.data()[i]) > 1e-3) return 1;
+        if (std::fabs(loc.Predict().data()[4] - (2 * p2.data()[4] - p1.data()[4])) > 1e-4) return 1;  // (almost) pure translation: 2 b - a
+    }
+    {
+        IcpOptions o2;
+        o2.method_ = IcpMethod::P2PLANE;
+        auto reg = std::make_shared<CudaIcpRegistration>(o2);
+        CudaLioTracker lio(reg, 3, 0.02, 10.0, 0.0f);  // key frame every 2 cm, NoFilter
+        bool kf = false;
+        lio.AddCloud(map, map, &kf);
+        if (!kf || lio.LocalMapSize() != map->points.size()) return 1;
+        SE3 p1 = lio.AddCloud(scan, scan, &kf);
+        for (int i = 0; i < 7; ++i)
+            if (p1.data()[i] != result.data()[i]) return 1;
+        if (!kf || lio.KeyFrames() != 2 || lio.LocalMapSize() != map->points.size() + scan->points.size()) return 1;
+        SE3 p2 = lio.AddCloud(scan, scan, &kf);  // not a key frame: it has not moved since the last one
+        if (kf || lio.KeyFrames() != 2) return 1;
+        for (int i = 4; i < 7; ++i)
+            if (std::fabs(p2.data()[i] - result.data()[i]) > 1e-3) return 1;
+    }
+    std::printf("adapter: CudaLocTracker / CudaLioTracker loops ok\n");
     return 0;
 }
