@@ -1,4 +1,4 @@
-"""loc_lib_b200 — B200-native scan-to-map registration (ICP P2P / P2Plane, direct NDT).
+"""loc_lib_b200 — B200-native scan-to-map registration (ICP P2P / P2Line / P2Plane, direct and incremental NDT).
 
 One hot path of maotian123/loc_lib rebuilt for sm_100a behind the reference's MatchingInterface:
 see DESIGN.md for the scope and INTEGRATION.md for the drop-in binding.
