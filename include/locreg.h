@@ -33,7 +33,7 @@ extern "C" {
 #define LOCREG_E_ARG (-1)         /* invalid argument */
 #define LOCREG_E_CUDA (-2)        /* CUDA runtime error (no device, out of memory, launch failure) */
 #define LOCREG_E_STATE (-3)       /* call order (e.g. align before set_target) */
-#define LOCREG_E_UNSUPPORTED (-4) /* not built (PCLICP; relocalisation with NDT) */
+#define LOCREG_E_UNSUPPORTED (-4) /* not built (PCLICP), or NCCL is not available for the multi-GPU entry points */
 
 /* IcpMethod (icp_registration.hpp:15-20) and NdtMethod (ndt_registration.hpp:21-26) in one enum */
 enum locreg_method {
@@ -46,8 +46,10 @@ enum locreg_method {
 /* NdtNearbyType (ndt_registration.hpp:16-20) */
 enum locreg_nearby { LOCREG_NEARBY_CENTER = 0, LOCREG_NEARBY6 = 1 };
 /* how the Gauss-Newton loop is kept on the device */
-enum locreg_loop { LOCREG_LOOP_PERSISTENT = 0, /* one cooperative kernel, grid barrier per iteration */
-                   LOCREG_LOOP_GRAPH = 1 /* one captured CUDA graph of per-iteration kernels */ };
+enum locreg_loop { LOCREG_LOOP_PERSISTENT = 0, /* the whole Gauss-Newton loop of one ScanMatch in ONE cooperative kernel
+                                                  (grid barrier per iteration): k_align_persist (NDT), k_icp_persist (ICP) */
+                   LOCREG_LOOP_GRAPH = 1 /* per-iteration kernels, the loop captured once into a CUDA graph and replayed
+                                            with one cudaGraphLaunch per ScanMatch (re-captured when the scan size changes) */ };
 
 /* POD mirror of IcpOptions (icp_registration.hpp:22-39) + NdtOptions (ndt_registration.hpp:27-42). */
 typedef struct locreg_options {
@@ -65,10 +67,16 @@ typedef struct locreg_options {
     int32_t nearby_type;          /* enum locreg_nearby, default NEARBY6 */
     /* GPU-side knobs (no reference counterpart) */
     double knn_cell_size;         /* voxel-hash cell edge in metres for ICP k-NN; <= 0: 0.5 */
-    int32_t loop_mode;            /* enum locreg_loop (NDT; ICP always runs the three-kernel pipeline) */
+    int32_t loop_mode;            /* enum locreg_loop: how ONE ScanMatch keeps its loop on the device (batches always run
+                                     the per-iteration pipeline: there is enough work per launch) */
     int32_t knn_lists;            /* 1 (default): build per-cell 3x3x3 neighbourhood lists (27x point storage) for the fast k-NN path */
     int32_t ndt_capacity;         /* NdtOptions::capacity_ = 100000: voxels the incremental NDT cache holds (LRU) */
-    int32_t pad_;
+    int32_t zero_initial_translation; /* 1 = IcpOptions::use_initial_translation_ == false or NdtOptions::remove_centroid_
+                                         == true: Align* replaces the translation of the initial pose by target_center_ -
+                                         source_center_ (icp_registration.cpp:272-276,311-314,352-355; ndt_registration.cpp:
+                                         380-384), and both centres are never computed (the code that would is commented
+                                         out, icp_registration.cpp:22-26,261-264), so the translation starts from ZERO.
+                                         AlignIncNdt and CaculateMatrixHAndB do not look at the flag. */
 } locreg_options;
 
 /* Outcome of one registration (what the reference logs or silently drops). */
@@ -143,6 +151,44 @@ int locreg_relocalise(locreg_handle* h, const float* src, size_t n, size_t strid
                       double* poses_out);
 /* (float32 score bits << 32) | index: unsigned order = (score, index) order for score >= 0. */
 uint64_t locreg_pack_score(double score, uint32_t index);
+
+/* ---- multi-GPU: one process (or thread) per GPU, one handle each, NCCL inside this library -----------
+ * The two workloads that shard keep a replica of the map per GPU and need ONE exchange step each; it runs on the
+ * handle's stream right behind the kernels, so nothing returns to the host in between.  NCCL is bound at run time
+ * (dlopen of libnccl.so.2: the copy already in the process - e.g. torch's - or the system's), so single-GPU users
+ * need no NCCL at all; without it these entry points fail with LOCREG_E_UNSUPPORTED.
+ *   locreg_comm_unique_id   ncclGetUniqueId: call on ONE rank, hand the 128 bytes to every rank (MPI, a file, a socket,
+ *                           torch.distributed ...)
+ *   locreg_comm_init        ncclCommInitRank for this handle's device; collective over all `world` ranks
+ *   locreg_comm_destroy     ncclCommDestroy (also done by locreg_destroy)
+ *   locreg_shard_range      the block partition [lo, hi) of n items rank `rank` owns (remainder to the first ranks) */
+#define LOCREG_UNIQUE_ID_BYTES 128
+int locreg_comm_unique_id(unsigned char* id128);
+int locreg_comm_init(locreg_handle* h, const unsigned char* id128, int32_t rank, int32_t world);
+int locreg_comm_destroy(locreg_handle* h);
+int locreg_comm_info(locreg_handle* h, int32_t* rank, int32_t* world, int32_t* nccl_version);
+int locreg_shard_range(size_t n, int32_t rank, int32_t world, size_t* lo, size_t* hi);
+
+/* Global relocalisation over all ranks of the handle's communicator (BASELINE config 5).  EVERY rank passes the same
+ * scan and the same n_hyp hypotheses; rank r registers hypotheses r, r + world, ... (neighbouring hypotheses cost
+ * alike, far-off ones several times more: a strided deal balances the ranks), reduces its scores to one packed key
+ * (locreg_pack_score) on the device, and then, on the handle's stream:
+ *     ncclAllReduce(key, ncclUint64, ncclMin, count 1)       the argmin, lowest global index winning ties
+ *     ncclBroadcast(8 doubles: pose + score, root = winner's owner)
+ * best_pose / best_idx (GLOBAL hypothesis index) / best_score are identical on every rank.  A handle without a
+ * communicator behaves as world = 1 (no NCCL call). */
+int locreg_relocalise_sharded(locreg_handle* h, const float* src, size_t n, size_t stride_bytes, const double* poses_in,
+                              size_t n_hyp, double* best_pose, int64_t* best_idx, double* best_score);
+
+/* Batch offline mapping over all ranks (BASELINE config 4).  The batch has S_global scans; this rank owns the block
+ * [lo, hi) = locreg_shard_range(S_global, rank, world) and passes ONLY that block: srcs / offsets (S_local + 1
+ * entries, relative to srcs) / poses_in (S_local * 7) with S_local = hi - lo.  No collective on the data path; at the
+ * end the poses (and results) of all blocks are exchanged on the handle's stream with one grouped
+ * ncclBroadcast per rank (an all-gather with ragged counts), so poses_out (S_global * 7, IN/OUT as in locreg_align)
+ * and results (S_global entries or NULL) are complete on every rank. */
+int locreg_align_batch_sharded(locreg_handle* h, const float* srcs, const int64_t* offsets, size_t stride_bytes,
+                               const double* poses_in, size_t S_local, size_t S_global, double* poses_out,
+                               locreg_result* results);
 
 /* pcl::transformPointCloud (icp_registration.cpp:241) on its own. */
 int locreg_transform_cloud(locreg_handle* h, const float* src, size_t n, size_t stride_bytes, const double* pose,

@@ -185,6 +185,9 @@ class CudaIcpRegistration : public CudaRegistrationBase {
         c.min_effective_pts = o.min_effective_pts_;
         c.eps = o.eps_;
         c.use_ann = o.use_ann ? 1 : 0;  // accepted, ignored: the search is exact (deviation Q1)
+        // !use_initial_translation_: Align* start from target_center_ - source_center_, which is zero - neither centre is
+        // ever computed (icp_registration.cpp:22-26,261-264,272-276)
+        c.zero_initial_translation = o.use_initial_translation_ ? 0 : 1;
         return c;
     }
     IcpOptions options_;
@@ -207,6 +210,7 @@ class CudaNdtRegistration : public CudaRegistrationBase {
         c.eps = o.eps_;
         c.res_outlier_th = o.res_outlier_th_;
         c.nearby_type = o.nearby_type_ == NdtNearbyType::NEARBY6 ? LOCREG_NEARBY6 : LOCREG_NEARBY_CENTER;
+        c.zero_initial_translation = o.remove_centroid_ ? 1 : 0;  // AlignNdt only (ndt_registration.cpp:380-384)
         return c;
     }
     NdtOptions options_;

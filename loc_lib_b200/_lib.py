@@ -19,6 +19,8 @@ SYMBOLS = [
     "locreg_profile", "locreg_last_error", "locreg_version", "locreg_filter_remove_nan", "locreg_filter_crop_box",
     "locreg_filter_voxel_grid", "locreg_set_global_map", "locreg_reset_local_map",
     "locreg_local_map_add_keyframe", "locreg_local_map_get", "locreg_local_map_clear",
+    "locreg_comm_unique_id", "locreg_comm_init", "locreg_comm_destroy", "locreg_comm_info", "locreg_shard_range",
+    "locreg_relocalise_sharded", "locreg_align_batch_sharded",
 ]
 
 
@@ -28,7 +30,7 @@ class Options(C.Structure):
                 ("max_plane_distance", C.c_double), ("max_line_distance", C.c_double), ("voxel_size", C.c_double),
                 ("res_outlier_th", C.c_double), ("min_pts_in_voxel", C.c_int32), ("nearby_type", C.c_int32),
                 ("knn_cell_size", C.c_double), ("loop_mode", C.c_int32), ("knn_lists", C.c_int32),
-                ("ndt_capacity", C.c_int32), ("pad_", C.c_int32)]
+                ("ndt_capacity", C.c_int32), ("zero_initial_translation", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -79,6 +81,13 @@ def lib():
         L.locreg_filter_remove_nan.argtypes = [vp, vp, sz, sz, vp, C.POINTER(sz)]
         L.locreg_filter_crop_box.argtypes = [vp, vp, sz, sz, vp, vp, vp, C.POINTER(sz)]
         L.locreg_filter_voxel_grid.argtypes = [vp, vp, sz, sz, C.c_float, vp, C.POINTER(sz)]
+        L.locreg_comm_unique_id.argtypes = [vp]
+        L.locreg_comm_init.argtypes = [vp, vp, i32, i32]
+        L.locreg_comm_destroy.argtypes = [vp]
+        L.locreg_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.locreg_shard_range.argtypes = [sz, i32, i32, C.POINTER(sz), C.POINTER(sz)]
+        L.locreg_relocalise_sharded.argtypes = [vp, vp, sz, sz, vp, sz, vp, vp, vp]
+        L.locreg_align_batch_sharded.argtypes = [vp, vp, vp, sz, vp, sz, sz, vp, vp]
         L.locreg_last_error.restype = C.c_char_p
         L.locreg_version.restype = C.c_char_p
         _LIB = L

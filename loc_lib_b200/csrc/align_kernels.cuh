@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256, LR_MIN_BLOCKS) k_align_batch(Problem pb, 
                                                      const long long* __restrict__ offsets, unsigned int n_single,
                                                      const double* __restrict__ poses_in, double* poses_out,
                                                      DevResult* results, unsigned int S, unsigned int* work_counter,
-                                                     int final_eval) {
+                                                     int final_eval, int zero_t) {
     extern __shared__ double dyn_acc[];
     __shared__ Pose T;
     __shared__ double red[8 * kPartialDoubles];
@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(256, LR_MIN_BLOCKS) k_align_batch(Problem pb, 
         const unsigned int n = offsets ? static_cast<unsigned int>(offsets[s + 1] - beg) : n_single;
         const float4* pts = src + beg;
         if (threadIdx.x == 0) {
-            pose_load(T, poses_in + static_cast<size_t>(s) * 7);
+            double p7[7];
+            for (int i = 0; i < 7; ++i) p7[i] = (zero_t && i >= 4) ? 0.0 : poses_in[static_cast<size_t>(s) * 7 + i];
+            pose_load(T, p7);
             res = DevResult{0, 0, 0, 0, 0, 0, 0.0, 1, 0};
             stop = 0;
         }
@@ -249,7 +251,8 @@ __global__ void __launch_bounds__(256, LR_MIN_BLOCKS) k_align_batch(Problem pb, 
 
 // ---- relocalisation score + argmin --------------------------------------------------------------
 // key = (float32 score bits << 32) | index; score = sum_sq / n_inlier, +inf if degenerate / no inlier.
-__global__ void k_score_argmin(const DevResult* __restrict__ results, unsigned int S, unsigned int index_base,
+// The index in the key is index_base + s * index_stride (a rank's share of a strided deal of the hypotheses).
+__global__ void k_score_argmin(const DevResult* __restrict__ results, unsigned int S, unsigned int index_base, unsigned int index_stride,
                                double* scores, unsigned long long* best_key) {
     const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long key = ~0ull;
@@ -259,7 +262,7 @@ __global__ void k_score_argmin(const DevResult* __restrict__ results, unsigned i
         if (!r.degenerate && r.n_inlier > 0 && r.pose_written) sc = r.sum_sq_res / static_cast<double>(r.n_inlier);
         if (scores) scores[s] = sc;
         const float f = static_cast<float>(sc);
-        key = (static_cast<unsigned long long>(__float_as_uint(f)) << 32) | static_cast<unsigned long long>(index_base + s);
+        key = (static_cast<unsigned long long>(__float_as_uint(f)) << 32) | static_cast<unsigned long long>(index_base + s * index_stride);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {

@@ -759,11 +759,12 @@ __global__ void __launch_bounds__(128) k_icp_solve(IcpParams prm, BatchView bv, 
 }
 
 // poses_in -> fresh states (stop is raised at once when max_iteration <= 0: the reference's loop body never runs)
-__global__ void k_states_init(const double* __restrict__ poses_in, unsigned int S, int max_iteration, AlignState* states) {
+// zero_t: the Align* loops start from a zero translation (locreg_options::zero_initial_translation)
+__global__ void k_states_init(const double* __restrict__ poses_in, unsigned int S, int max_iteration, int zero_t, AlignState* states) {
     const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     AlignState st;
-    for (int i = 0; i < 7; ++i) st.pose[i] = poses_in[static_cast<size_t>(s) * 7 + i];
+    for (int i = 0; i < 7; ++i) st.pose[i] = (zero_t && i >= 4) ? 0.0 : poses_in[static_cast<size_t>(s) * 7 + i];
     st.res = DevResult{0, 0, 0, 0, 0, 0, 0.0, 1, 0};
     st.stop = max_iteration <= 0 ? 1 : 0;
     st.pad = 0;

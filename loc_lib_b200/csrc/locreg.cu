@@ -15,6 +15,9 @@
 #include "device_inc_ndt.cuh"
 #include "device_ndt.cuh"
 #include "filters.cuh"
+#include "nccl_dyn.h"
+
+#include <nvtx3/nvToolsExt.h>
 
 using namespace locreg;
 
@@ -51,6 +54,14 @@ struct PinBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+// NVTX range per phase of an entry point: visible in Nsight Systems / `ncu --nvtx`, free otherwise.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 bool is_pinned_or_device(const void* p) {
     cudaPointerAttributes a{};
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -80,6 +91,10 @@ struct locreg_handle {
     DeviceNdtMap ndt_map;
     DeviceIncNdtMap inc_ndt_map;  // LOCREG_NDT_INCREMENTAL
     bool has_target = false;
+    // multi-GPU: the communicator of this handle's rank (locreg_comm_init); nullptr = world of one
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    DevBuf d_gather_pose, d_gather_res, d_bcast;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
         d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_global, d_local, d_same, d_plane, d_pstat, d_track;
     size_t n_global = 0, global_stride = 0;  // Loc's global map kept on the device (locreg_set_global_map)
@@ -164,12 +179,14 @@ const float4* stage_cloud(locreg_handle* h, const float* src, size_t n, size_t s
     return h->d_src4.as<float4>();
 }
 
-void init_state(locreg_handle* h, const double* pose7) {
+// align = true: the pose starts an Align* loop, which honours zero_initial_translation (see locreg.h)
+void init_state(locreg_handle* h, const double* pose7, bool align = false) {
     h->d_state.reserve(sizeof(AlignState));
     h->h_small.reserve(4096);
     AlignState* s = h->h_small.as<AlignState>();
     std::memset(s, 0, sizeof(AlignState));
     std::memcpy(s->pose, pose7, 7 * sizeof(double));
+    if (align && h->opt.zero_initial_translation && h->opt.method != LOCREG_NDT_INCREMENTAL) s->pose[4] = s->pose[5] = s->pose[6] = 0.0;
     s->res.pose_written = 1;
     s->stop = 0;
     LR_CUDA(cudaMemcpyAsync(h->d_state.p, s, sizeof(AlignState), cudaMemcpyHostToDevice, h->stream));
@@ -237,9 +254,10 @@ void ndt_run_eval(locreg_handle* h, PB pb, const float4* src, unsigned int n, un
     LR_LAUNCH(k_eval<PB>, grid, 256, kAccSmemBytes, h->stream, pb, src, n, ppw, st, h->d_partials.as<double>(), gate, nullptr);
     LR_LAUNCH(k_finalize<PB>, 1, 256, 0, h->stream, pb, h->d_partials.as<double>(), grid, st, 0, h->d_acc.as<double>());
 }
+// offsets == nullptr: every item registers the same scan src[0, n_single) (relocalisation)
 template <class PB>
 void ndt_run_batch(locreg_handle* h, PB pb, const float4* src, const long long* offsets, const double* poses_in, double* poses_out,
-                   DevResult* results, unsigned int S) {
+                   DevResult* results, unsigned int S, unsigned int n_single = 0u, int final_eval = 0) {
     int per_sm = 0;
     LR_CUDA(cudaFuncSetAttribute(k_align_batch<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAccSmemBytes)));
     LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align_batch<PB>, 256, kAccSmemBytes));
@@ -247,8 +265,9 @@ void ndt_run_batch(locreg_handle* h, PB pb, const float4* src, const long long* 
     const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(S, static_cast<long long>(per_sm) * h->num_sms)));
     h->d_misc.reserve(64);
     LR_CUDA(cudaMemsetAsync(h->d_misc.p, 0, 64, h->stream));
-    LR_LAUNCH(k_align_batch<PB>, grid, 256, kAccSmemBytes, h->stream, pb, src, offsets, 0u, poses_in, poses_out, results, S,
-              h->d_misc.as<unsigned int>(), 0);
+    const int zero_t = h->opt.zero_initial_translation && h->opt.method != LOCREG_NDT_INCREMENTAL;
+    LR_LAUNCH(k_align_batch<PB>, grid, 256, kAccSmemBytes, h->stream, pb, src, offsets, n_single, poses_in, poses_out, results, S,
+              h->d_misc.as<unsigned int>(), final_eval, zero_t);
 }
 // direct or incremental NDT problem of this handle -> f(problem)
 #define NDT_DISPATCH(h, CALL)                                                                   \
@@ -444,6 +463,9 @@ int guarded(locreg_handle* h, F&& f) {
         g_last_error = e.what();
         cudaGetLastError();
         return LOCREG_E_CUDA;
+    } catch (const NcclError& e) {
+        g_last_error = e.what();
+        return LOCREG_E_CUDA;
     } catch (const std::invalid_argument& e) {
         g_last_error = e.what();
         return LOCREG_E_ARG;
@@ -538,6 +560,7 @@ int locreg_destroy(locreg_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->comm && nccl_api().ok()) nccl_api().CommDestroy(h->comm);
     h->clear_keyframes();
     cudaStream_t s = h->own_stream;
     delete h;
@@ -602,7 +625,7 @@ int locreg_align(locreg_handle* h, const float* src, size_t n, size_t stride, co
     return guarded(h, [&]() {
         if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
         const float4* src4 = stage_cloud(h, src, n, stride, false);
-        init_state(h, pose_in);
+        init_state(h, pose_in, true);
         h->begin_timing();
         if (is_ndt(h)) {
             NDT_DISPATCH(h, ndt_run_align(h, PB, src4, static_cast<unsigned int>(n)));
@@ -771,7 +794,7 @@ int locreg_align_batch_device(locreg_handle* h, const float* d_srcs, const int64
             NDT_DISPATCH(h, ndt_run_batch(h, PB, src4, offs, d_poses_in, d_poses_out, results, Su));
         } else {
             const IcpJob job = icp_batch_job(h, src4, offs, Su, total_points);
-            LR_LAUNCH(k_states_init, (Su + 255) / 256, 256, 0, h->stream, d_poses_in, Su, h->opt.max_iteration, job.states);
+            LR_LAUNCH(k_states_init, (Su + 255) / 256, 256, 0, h->stream, d_poses_in, Su, h->opt.max_iteration, h->opt.zero_initial_translation, job.states);
             ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
             LR_LAUNCH(k_states_export, (Su + 255) / 256, 256, 0, h->stream, job.states, Su, d_poses_out, results);
         }
@@ -780,104 +803,162 @@ int locreg_align_batch_device(locreg_handle* h, const float* d_srcs, const int64
     });
 }
 
-int locreg_align_batch(locreg_handle* h, const float* srcs, const int64_t* offsets, size_t stride, const double* poses_in,
-                       size_t S, double* poses_out, locreg_result* results) {
+// S ScanMatch calls of a host batch; the poses and results stay in h->d_poses_out / h->d_results (S entries, device).
+// offsets[0..S] are relative to srcs; poses_out_init = the IN values of the IN/OUT poses_out.
+static void align_batch_resident(locreg_handle* h, const float* srcs, const int64_t* offsets, size_t stride, const double* poses_in,
+                                 size_t S, const double* poses_out_init) {
+    NvtxRange nvtx_r("locreg:align_batch");
+    const size_t total = static_cast<size_t>(offsets[S]);
+    const float* first = reinterpret_cast<const float*>(reinterpret_cast<const char*>(srcs) + static_cast<size_t>(offsets[0]) * stride);
+    const double* poses_out = poses_out_init;
+    const size_t base = static_cast<size_t>(offsets[0]);
+    const size_t n_pts = total - base;
+    // Large ICP batches from pinned (or device-visible) memory are cut into chunks of whole scans: the copy of
+    // chunk c + 1 runs on a second stream while chunk c is being registered (scans are independent).
+    const bool pipelined = !is_ndt(h) && S >= 16 && n_pts >= (1u << 20) && is_pinned_or_device(first);
+    const float4* src4 = pipelined ? nullptr : stage_cloud(h, first, n_pts, stride, false);
+    h->d_offsets.reserve((S + 1) * sizeof(long long));
+    h->d_poses_in.reserve(S * 7 * sizeof(double));
+    h->d_poses_out.reserve(S * 7 * sizeof(double));
+    h->d_results.reserve(S * sizeof(DevResult));
+    std::vector<long long> rel(S + 1);
+    for (size_t s = 0; s <= S; ++s) rel[s] = offsets[s] - static_cast<long long>(base);
+    LR_CUDA(cudaMemcpyAsync(h->d_offsets.p, rel.data(), (S + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    LR_CUDA(cudaMemcpyAsync(h->d_poses_in.p, poses_in, S * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    LR_CUDA(cudaMemcpyAsync(h->d_poses_out.p, poses_out, S * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    LR_CUDA(cudaStreamSynchronize(h->stream));  // rel[] is pageable
+    const unsigned int Su = static_cast<unsigned int>(S);
+    if (pipelined) {
+        static const size_t kChunks = getenv("LOCREG_CHUNKS") ? std::max(1, atoi(getenv("LOCREG_CHUNKS"))) : 2;  // 2 measured best on B200 (LOCREG_CHUNKS overrides)
+        if (!h->copy_stream) LR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        while (h->chunk_events.size() < kChunks) {
+            cudaEvent_t e;
+            LR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->chunk_events.push_back(e);
+        }
+        h->d_raw.reserve(n_pts * stride);
+        if (stride != 16) h->d_src4.reserve(n_pts * sizeof(float4));
+        h->d_states.reserve(S * sizeof(AlignState));
+        // chunk boundaries: whole scans, about equal point counts
+        std::vector<size_t> cut{0};
+        for (size_t c = 1; c < kChunks; ++c) {
+            const long long want = static_cast<long long>(n_pts * c / kChunks);
+            size_t s = std::lower_bound(rel.begin(), rel.end(), want) - rel.begin();
+            s = std::min(std::max(s, cut.back()), S);
+            cut.push_back(s);
+        }
+        cut.push_back(S);
+        for (size_t c = 0; c < kChunks; ++c) {
+            const size_t p0 = static_cast<size_t>(rel[cut[c]]), p1 = static_cast<size_t>(rel[cut[c + 1]]);
+            if (p1 > p0)
+                LR_CUDA(cudaMemcpyAsync(h->d_raw.as<unsigned char>() + p0 * stride, reinterpret_cast<const char*>(first) + p0 * stride,
+                                        (p1 - p0) * stride, cudaMemcpyHostToDevice, h->copy_stream));
+            LR_CUDA(cudaEventRecord(h->chunk_events[c], h->copy_stream));
+        }
+        h->begin_timing();
+        long long launches = 0;
+        for (size_t c = 0; c < kChunks; ++c) {
+            const size_t s0 = cut[c], s1 = cut[c + 1];
+            LR_CUDA(cudaStreamWaitEvent(h->stream, h->chunk_events[c], 0));
+            if (s1 == s0) continue;
+            const size_t p0 = static_cast<size_t>(rel[s0]), p1 = static_cast<size_t>(rel[s1]);
+            const unsigned int Sc = static_cast<unsigned int>(s1 - s0);
+            if (stride != 16 && p1 > p0) {
+                const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((p1 - p0 + 255) / 256, 4096));
+                LR_LAUNCH(k_pack_float4, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>() + p0 * stride, p1 - p0, stride,
+                          h->d_src4.as<float4>() + p0);
+            }
+            const float4* all4 = stride == 16 ? h->d_raw.as<float4>() : h->d_src4.as<float4>();
+            // offsets stay absolute (into the whole batch); only the scan range of the job moves
+            IcpJob job = icp_batch_job(h, all4, h->d_offsets.as<long long>() + s0, Sc, p1 - p0);
+            job.states = h->d_states.as<AlignState>() + s0;
+            job.n_scratch_points = n_pts;  // scratch rows are indexed by absolute point number
+            LR_LAUNCH(k_states_init, (Sc + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>() + s0 * 7, Sc, h->opt.max_iteration, h->opt.zero_initial_translation, job.states);
+            ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
+            LR_LAUNCH(k_states_export, (Sc + 255) / 256, 256, 0, h->stream, job.states, Sc, h->d_poses_out.as<double>() + s0 * 7,
+                      h->d_results.as<DevResult>() + s0);
+            launches = g_launch_count;
+        }
+        (void)launches;
+        h->end_timing();
+    } else {
+        h->begin_timing();
+        if (is_ndt(h)) {
+            NDT_DISPATCH(h, ndt_run_batch(h, PB, src4, h->d_offsets.as<long long>(), h->d_poses_in.as<double>(),
+                                          h->d_poses_out.as<double>(), h->d_results.as<DevResult>(), Su));
+        } else {
+            const IcpJob job = icp_batch_job(h, src4, h->d_offsets.as<long long>(), Su, n_pts);
+            LR_LAUNCH(k_states_init, (Su + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>(), Su, h->opt.max_iteration, h->opt.zero_initial_translation, job.states);
+            ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
+            LR_LAUNCH(k_states_export, (Su + 255) / 256, 256, 0, h->stream, job.states, Su, h->d_poses_out.as<double>(), h->d_results.as<DevResult>());
+        }
+        h->end_timing();
+    }
+}
+
+static int align_batch_check(const float* srcs, const int64_t* offsets, size_t stride, const double* poses_in, size_t S, double* poses_out) {
     if (!offsets || !poses_in || !poses_out) { g_last_error = "null argument"; return LOCREG_E_ARG; }
     if (S >= (1ull << 31)) { g_last_error = "too many scans"; return LOCREG_E_ARG; }
-    if (S == 0) return LOCREG_OK;
     for (size_t s = 0; s < S; ++s)
         if (offsets[s + 1] < offsets[s] || offsets[s] < 0) { g_last_error = "offsets must be non-decreasing"; return LOCREG_E_ARG; }
     const size_t total = static_cast<size_t>(offsets[S]);
     const float* first = reinterpret_cast<const float*>(reinterpret_cast<const char*>(srcs) + static_cast<size_t>(offsets[0]) * stride);
-    const int rc = check_cloud_args(first, total - static_cast<size_t>(offsets[0]), stride);
+    return check_cloud_args(first, total - static_cast<size_t>(offsets[0]), stride);
+}
+
+int locreg_align_batch(locreg_handle* h, const float* srcs, const int64_t* offsets, size_t stride, const double* poses_in,
+                       size_t S, double* poses_out, locreg_result* results) {
+    if (S == 0) return LOCREG_OK;
+    const int rc = align_batch_check(srcs, offsets, stride, poses_in, S, poses_out);
     if (rc) return rc;
     return guarded(h, [&]() {
         if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
-        const size_t base = static_cast<size_t>(offsets[0]);
-        const size_t n_pts = total - base;
-        // Large ICP batches from pinned (or device-visible) memory are cut into chunks of whole scans: the copy of
-        // chunk c + 1 runs on a second stream while chunk c is being registered (scans are independent).
-        const bool pipelined = !is_ndt(h) && S >= 16 && n_pts >= (1u << 20) && is_pinned_or_device(first);
-        const float4* src4 = pipelined ? nullptr : stage_cloud(h, first, n_pts, stride, false);
-        h->d_offsets.reserve((S + 1) * sizeof(long long));
-        h->d_poses_in.reserve(S * 7 * sizeof(double));
-        h->d_poses_out.reserve(S * 7 * sizeof(double));
-        h->d_results.reserve(S * sizeof(DevResult));
-        std::vector<long long> rel(S + 1);
-        for (size_t s = 0; s <= S; ++s) rel[s] = offsets[s] - static_cast<long long>(base);
-        LR_CUDA(cudaMemcpyAsync(h->d_offsets.p, rel.data(), (S + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-        LR_CUDA(cudaMemcpyAsync(h->d_poses_in.p, poses_in, S * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        LR_CUDA(cudaMemcpyAsync(h->d_poses_out.p, poses_out, S * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        LR_CUDA(cudaStreamSynchronize(h->stream));  // rel[] is pageable
-        const unsigned int Su = static_cast<unsigned int>(S);
-        if (pipelined) {
-            static const size_t kChunks = getenv("LOCREG_CHUNKS") ? std::max(1, atoi(getenv("LOCREG_CHUNKS"))) : 2;  // 2 measured best on B200 (LOCREG_CHUNKS overrides)
-            if (!h->copy_stream) LR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-            while (h->chunk_events.size() < kChunks) {
-                cudaEvent_t e;
-                LR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                h->chunk_events.push_back(e);
-            }
-            h->d_raw.reserve(n_pts * stride);
-            if (stride != 16) h->d_src4.reserve(n_pts * sizeof(float4));
-            h->d_states.reserve(S * sizeof(AlignState));
-            // chunk boundaries: whole scans, about equal point counts
-            std::vector<size_t> cut{0};
-            for (size_t c = 1; c < kChunks; ++c) {
-                const long long want = static_cast<long long>(n_pts * c / kChunks);
-                size_t s = std::lower_bound(rel.begin(), rel.end(), want) - rel.begin();
-                s = std::min(std::max(s, cut.back()), S);
-                cut.push_back(s);
-            }
-            cut.push_back(S);
-            for (size_t c = 0; c < kChunks; ++c) {
-                const size_t p0 = static_cast<size_t>(rel[cut[c]]), p1 = static_cast<size_t>(rel[cut[c + 1]]);
-                if (p1 > p0)
-                    LR_CUDA(cudaMemcpyAsync(h->d_raw.as<unsigned char>() + p0 * stride, reinterpret_cast<const char*>(first) + p0 * stride,
-                                            (p1 - p0) * stride, cudaMemcpyHostToDevice, h->copy_stream));
-                LR_CUDA(cudaEventRecord(h->chunk_events[c], h->copy_stream));
-            }
-            h->begin_timing();
-            long long launches = 0;
-            for (size_t c = 0; c < kChunks; ++c) {
-                const size_t s0 = cut[c], s1 = cut[c + 1];
-                LR_CUDA(cudaStreamWaitEvent(h->stream, h->chunk_events[c], 0));
-                if (s1 == s0) continue;
-                const size_t p0 = static_cast<size_t>(rel[s0]), p1 = static_cast<size_t>(rel[s1]);
-                const unsigned int Sc = static_cast<unsigned int>(s1 - s0);
-                if (stride != 16 && p1 > p0) {
-                    const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((p1 - p0 + 255) / 256, 4096));
-                    LR_LAUNCH(k_pack_float4, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>() + p0 * stride, p1 - p0, stride,
-                              h->d_src4.as<float4>() + p0);
-                }
-                const float4* all4 = stride == 16 ? h->d_raw.as<float4>() : h->d_src4.as<float4>();
-                // offsets stay absolute (into the whole batch); only the scan range of the job moves
-                IcpJob job = icp_batch_job(h, all4, h->d_offsets.as<long long>() + s0, Sc, p1 - p0);
-                job.states = h->d_states.as<AlignState>() + s0;
-                job.n_scratch_points = n_pts;  // scratch rows are indexed by absolute point number
-                LR_LAUNCH(k_states_init, (Sc + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>() + s0 * 7, Sc, h->opt.max_iteration, job.states);
-                ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
-                LR_LAUNCH(k_states_export, (Sc + 255) / 256, 256, 0, h->stream, job.states, Sc, h->d_poses_out.as<double>() + s0 * 7,
-                          h->d_results.as<DevResult>() + s0);
-                launches = g_launch_count;
-            }
-            (void)launches;
-            h->end_timing();
-        } else {
-            h->begin_timing();
-            if (is_ndt(h)) {
-                NDT_DISPATCH(h, ndt_run_batch(h, PB, src4, h->d_offsets.as<long long>(), h->d_poses_in.as<double>(),
-                                              h->d_poses_out.as<double>(), h->d_results.as<DevResult>(), Su));
-            } else {
-                const IcpJob job = icp_batch_job(h, src4, h->d_offsets.as<long long>(), Su, n_pts);
-                LR_LAUNCH(k_states_init, (Su + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>(), Su, h->opt.max_iteration, job.states);
-                ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
-                LR_LAUNCH(k_states_export, (Su + 255) / 256, 256, 0, h->stream, job.states, Su, h->d_poses_out.as<double>(), h->d_results.as<DevResult>());
-            }
-            h->end_timing();
-        }
+        align_batch_resident(h, srcs, offsets, stride, poses_in, S, poses_out);
         LR_CUDA(cudaMemcpy(poses_out, h->d_poses_out.p, S * 7 * sizeof(double), cudaMemcpyDeviceToHost));
         if (results) LR_CUDA(cudaMemcpy(results, h->d_results.p, S * sizeof(DevResult), cudaMemcpyDeviceToHost));
+        return LOCREG_OK;
+    });
+}
+
+int locreg_align_batch_sharded(locreg_handle* h, const float* srcs, const int64_t* offsets, size_t stride, const double* poses_in,
+                               size_t S_local, size_t S_global, double* poses_out, locreg_result* results) {
+    if (!h) { g_last_error = "null handle"; return LOCREG_E_ARG; }
+    if (!poses_out || S_global >= (1ull << 31)) { g_last_error = "invalid arguments"; return LOCREG_E_ARG; }
+    size_t lo = 0, hi = 0;
+    locreg_shard_range(S_global, h->comm_rank, h->comm_world, &lo, &hi);
+    if (S_local != hi - lo) { g_last_error = "S_local must be this rank's block of locreg_shard_range(S_global, rank, world)"; return LOCREG_E_ARG; }
+    if (S_local) {
+        const int rc = align_batch_check(srcs, offsets, stride, poses_in, S_local, poses_out);
+        if (rc) return rc;
+    }
+    return guarded(h, [&]() {
+        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
+        if (S_global == 0) return LOCREG_OK;
+        if (S_local) align_batch_resident(h, srcs, offsets, stride, poses_in, S_local, poses_out + lo * 7);
+        // exchange: every rank's block into the global arrays, on the handle's stream (ragged all-gather = one grouped
+        // broadcast per rank)
+        h->d_gather_pose.reserve(S_global * 7 * sizeof(double));
+        h->d_gather_res.reserve(S_global * sizeof(DevResult));
+        const NcclApi& nc = nccl_api();
+        if (h->comm) {
+            NvtxRange r("locreg:align_batch:allgather");
+            LR_NCCL(nc.GroupStart());
+            for (int r = 0; r < h->comm_world; ++r) {
+                size_t rlo = 0, rhi = 0;
+                locreg_shard_range(S_global, r, h->comm_world, &rlo, &rhi);
+                if (rhi == rlo) continue;
+                const bool me = r == h->comm_rank;
+                LR_NCCL(nc.Broadcast(me ? h->d_poses_out.p : nullptr, h->d_gather_pose.as<double>() + rlo * 7, (rhi - rlo) * 7, ncclDouble, r, h->comm, h->stream));
+                LR_NCCL(nc.Broadcast(me ? h->d_results.p : nullptr, h->d_gather_res.as<DevResult>() + rlo, (rhi - rlo) * sizeof(DevResult), ncclUint8, r, h->comm, h->stream));
+            }
+            LR_NCCL(nc.GroupEnd());
+        } else if (S_local) {
+            LR_CUDA(cudaMemcpyAsync(h->d_gather_pose.p, h->d_poses_out.p, S_local * 7 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            LR_CUDA(cudaMemcpyAsync(h->d_gather_res.p, h->d_results.p, S_local * sizeof(DevResult), cudaMemcpyDeviceToDevice, h->stream));
+        }
+        LR_CUDA(cudaMemcpyAsync(poses_out, h->d_gather_pose.p, S_global * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (results) LR_CUDA(cudaMemcpyAsync(results, h->d_gather_res.p, S_global * sizeof(DevResult), cudaMemcpyDeviceToHost, h->stream));
+        LR_CUDA(cudaStreamSynchronize(h->stream));
         return LOCREG_OK;
     });
 }
@@ -890,32 +971,36 @@ uint64_t locreg_pack_score(double score, uint32_t index) {
     return (static_cast<uint64_t>(bits) << 32) | index;
 }
 
-int locreg_relocalise(locreg_handle* h, const float* src, size_t n, size_t stride, const double* poses_in, size_t n_hyp,
-                      double* best_pose, int64_t* best_idx, double* best_score, double* scores, double* poses_out) {
-    const int rc = check_cloud_args(src, n, stride);
-    if (rc) return rc;
-    if (!poses_in || n_hyp == 0 || n_hyp >= (1ull << 31)) { g_last_error = "invalid hypotheses"; return LOCREG_E_ARG; }
-    return guarded(h, [&]() {
-        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
-        const float4* src4 = stage_cloud(h, src, n, stride, false);
-        h->d_poses_in.reserve(n_hyp * 7 * sizeof(double));
-        h->d_poses_out.reserve(n_hyp * 7 * sizeof(double));
-        h->d_results.reserve(n_hyp * sizeof(DevResult));
-        h->d_scores.reserve(n_hyp * sizeof(double));
-        h->d_misc.reserve(64);
-        LR_CUDA(cudaMemcpyAsync(h->d_poses_in.p, poses_in, n_hyp * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        LR_CUDA(cudaMemcpyAsync(h->d_poses_out.p, poses_in, n_hyp * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        LR_CUDA(cudaStreamSynchronize(h->stream));
-        h->begin_timing();
-        if (is_ndt(h)) { g_last_error = "relocalisation is built for the ICP methods"; return LOCREG_E_UNSUPPORTED; }
+// n_local hypotheses (host, 7 doubles each) of ONE scan -> h->d_poses_out / d_results / d_scores and the packed best key
+// in device memory (returned pointer); the index in the key is index_base + i * index_stride.  Everything is queued on
+// the handle's stream; nothing is synchronised.
+static unsigned long long* relocalise_core(locreg_handle* h, const float4* src4, size_t n, const double* poses_in, size_t n_local,
+                                           unsigned int index_base, unsigned int index_stride) {
+    NvtxRange r("locreg:relocalise");
+    h->d_poses_in.reserve(std::max<size_t>(n_local, 1) * 7 * sizeof(double));
+    h->d_poses_out.reserve(std::max<size_t>(n_local, 1) * 7 * sizeof(double));
+    h->d_results.reserve(std::max<size_t>(n_local, 1) * sizeof(DevResult));
+    h->d_scores.reserve(std::max<size_t>(n_local, 1) * sizeof(double));
+    h->d_misc.reserve(64);
+    unsigned long long* d_key = reinterpret_cast<unsigned long long*>(h->d_misc.as<unsigned char>() + 32);
+    if (n_local) {
+        LR_CUDA(cudaMemcpyAsync(h->d_poses_in.p, poses_in, n_local * 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        LR_CUDA(cudaMemcpyAsync(h->d_poses_out.p, h->d_poses_in.p, n_local * 7 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->begin_timing();
+    if (n_local && is_ndt(h)) {
+        // one CTA per hypothesis: Gauss-Newton loop + one evaluation at the final pose (the score), all inside the CTA
+        NDT_DISPATCH(h, ndt_run_batch(h, PB, src4, nullptr, h->d_poses_in.as<double>(), h->d_poses_out.as<double>(),
+                                      h->d_results.as<DevResult>(), static_cast<unsigned int>(n_local), static_cast<unsigned int>(n), 1));
+    } else if (n_local) {
         // hypotheses run in waves so that the per-point neighbour scratch stays below ~1 GiB (the rest of the per-point
         // scratch - planes, margins, queues - scales with it: ~4.5 GiB in all for P2Plane)
         const int K = h->opt.method == LOCREG_ICP_P2P ? 1 : 5;
         const size_t per_hyp = std::max<size_t>(n, 1) * K * sizeof(unsigned int);
-        const size_t wave = std::max<size_t>(1, std::min<size_t>(n_hyp, (size_t(1) << 30) / per_hyp));
+        const size_t wave = std::max<size_t>(1, std::min<size_t>(n_local, (size_t(1) << 30) / per_hyp));
         h->d_states.reserve(wave * sizeof(AlignState));
-        for (size_t w0 = 0; w0 < n_hyp; w0 += wave) {
-            const unsigned int W = static_cast<unsigned int>(std::min(wave, n_hyp - w0));
+        for (size_t w0 = 0; w0 < n_local; w0 += wave) {
+            const unsigned int W = static_cast<unsigned int>(std::min(wave, n_local - w0));
             IcpJob job;
             job.bv.src = src4; job.bv.offsets = nullptr; job.bv.tile_begin = nullptr; job.bv.tiles = nullptr;
             job.bv.n_single = static_cast<unsigned int>(n);
@@ -924,15 +1009,28 @@ int locreg_relocalise(locreg_handle* h, const float* src, size_t n, size_t strid
             job.states = h->d_states.as<AlignState>();
             job.n_tiles = static_cast<unsigned int>(n ? static_cast<size_t>(job.bv.tiles_per_item) * W : 0);
             job.n_scratch_points = static_cast<size_t>(n) * W;
-            LR_LAUNCH(k_states_init, (W + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>() + w0 * 7, W, h->opt.max_iteration, job.states);
+            LR_LAUNCH(k_states_init, (W + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>() + w0 * 7, W, h->opt.max_iteration, h->opt.zero_initial_translation, job.states);
             ICP_DISPATCH(h, icp_run_loop<M>(h, job, 1));
             LR_LAUNCH(k_states_export, (W + 255) / 256, 256, 0, h->stream, job.states, W, h->d_poses_out.as<double>() + w0 * 7,
                       h->d_results.as<DevResult>() + w0);
         }
-        unsigned long long* d_key = reinterpret_cast<unsigned long long*>(h->d_misc.as<unsigned char>() + 32);
-        LR_CUDA(cudaMemsetAsync(d_key, 0xFF, sizeof(unsigned long long), h->stream));
-        LR_LAUNCH(k_score_argmin, static_cast<unsigned int>((n_hyp + 255) / 256), 256, 0, h->stream, h->d_results.as<DevResult>(),
-                  static_cast<unsigned int>(n_hyp), 0u, h->d_scores.as<double>(), d_key);
+    }
+    LR_CUDA(cudaMemsetAsync(d_key, 0xFF, sizeof(unsigned long long), h->stream));
+    if (n_local)
+        LR_LAUNCH(k_score_argmin, static_cast<unsigned int>((n_local + 255) / 256), 256, 0, h->stream, h->d_results.as<DevResult>(),
+                  static_cast<unsigned int>(n_local), index_base, index_stride, h->d_scores.as<double>(), d_key);
+    return d_key;
+}
+
+int locreg_relocalise(locreg_handle* h, const float* src, size_t n, size_t stride, const double* poses_in, size_t n_hyp,
+                      double* best_pose, int64_t* best_idx, double* best_score, double* scores, double* poses_out) {
+    const int rc = check_cloud_args(src, n, stride);
+    if (rc) return rc;
+    if (!poses_in || n_hyp == 0 || n_hyp >= (1ull << 31)) { g_last_error = "invalid hypotheses"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
+        const float4* src4 = stage_cloud(h, src, n, stride, false);
+        unsigned long long* d_key = relocalise_core(h, src4, n, poses_in, n_hyp, 0u, 1u);
         h->end_timing();
         unsigned long long key = 0;
         LR_CUDA(cudaMemcpy(&key, d_key, sizeof(key), cudaMemcpyDeviceToHost));
@@ -942,6 +1040,120 @@ int locreg_relocalise(locreg_handle* h, const float* src, size_t n, size_t strid
         if (best_pose) LR_CUDA(cudaMemcpy(best_pose, h->d_poses_out.as<double>() + static_cast<size_t>(bi) * 7, 7 * sizeof(double), cudaMemcpyDeviceToHost));
         if (scores) LR_CUDA(cudaMemcpy(scores, h->d_scores.p, n_hyp * sizeof(double), cudaMemcpyDeviceToHost));
         if (poses_out) LR_CUDA(cudaMemcpy(poses_out, h->d_poses_out.p, n_hyp * 7 * sizeof(double), cudaMemcpyDeviceToHost));
+        return LOCREG_OK;
+    });
+}
+
+// ---- multi-GPU: NCCL inside the library ---------------------------------------------------------------
+int locreg_shard_range(size_t n, int32_t rank, int32_t world, size_t* lo, size_t* hi) {
+    if (world < 1 || rank < 0 || rank >= world || !lo || !hi) { g_last_error = "invalid rank / world"; return LOCREG_E_ARG; }
+    const size_t base = n / static_cast<size_t>(world), rem = n % static_cast<size_t>(world), r = static_cast<size_t>(rank);
+    *lo = r * base + std::min(r, rem);
+    *hi = *lo + base + (r < rem ? 1 : 0);
+    return LOCREG_OK;
+}
+
+int locreg_comm_unique_id(unsigned char* id128) {
+    if (!id128) { g_last_error = "null argument"; return LOCREG_E_ARG; }
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok()) { g_last_error = nc.why; return LOCREG_E_UNSUPPORTED; }
+    static_assert(sizeof(ncclUniqueId) == LOCREG_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    const ncclResult_t r = nc.GetUniqueId(&id);
+    if (r != ncclSuccess) { g_last_error = std::string("ncclGetUniqueId: ") + nc.GetErrorString(r); return LOCREG_E_CUDA; }
+    std::memcpy(id128, &id, sizeof(id));
+    return LOCREG_OK;
+}
+
+int locreg_comm_init(locreg_handle* h, const unsigned char* id128, int32_t rank, int32_t world) {
+    if (!id128 || world < 1 || rank < 0 || rank >= world) { g_last_error = "invalid rank / world / id"; return LOCREG_E_ARG; }
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok()) { g_last_error = nc.why; return LOCREG_E_UNSUPPORTED; }
+    return guarded(h, [&]() {
+        if (h->comm) { g_last_error = "the handle already has a communicator"; return LOCREG_E_STATE; }
+        ncclUniqueId id;
+        std::memcpy(&id, id128, sizeof(id));
+        LR_NCCL(nc.CommInitRank(&h->comm, world, id, rank));
+        h->comm_rank = rank;
+        h->comm_world = world;
+        return LOCREG_OK;
+    });
+}
+
+int locreg_comm_destroy(locreg_handle* h) {
+    return guarded(h, [&]() {
+        if (h->comm) {
+            LR_CUDA(cudaStreamSynchronize(h->stream));
+            nccl_api().CommDestroy(h->comm);
+            h->comm = nullptr;
+        }
+        h->comm_rank = 0;
+        h->comm_world = 1;
+        return LOCREG_OK;
+    });
+}
+
+int locreg_comm_info(locreg_handle* h, int32_t* rank, int32_t* world, int32_t* nccl_version) {
+    if (!h) { g_last_error = "null handle"; return LOCREG_E_ARG; }
+    if (rank) *rank = h->comm_rank;
+    if (world) *world = h->comm_world;
+    if (nccl_version) {
+        int v = 0;
+        if (nccl_api().ok()) nccl_api().GetVersion(&v);
+        *nccl_version = v;
+    }
+    return LOCREG_OK;
+}
+
+int locreg_relocalise_sharded(locreg_handle* h, const float* src, size_t n, size_t stride, const double* poses_in, size_t n_hyp,
+                              double* best_pose, int64_t* best_idx, double* best_score) {
+    const int rc = check_cloud_args(src, n, stride);
+    if (rc) return rc;
+    if (!poses_in || n_hyp == 0 || n_hyp >= (1ull << 31)) { g_last_error = "invalid hypotheses"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        if (!h->has_target) { g_last_error = "SetInputTarget has not been called"; return LOCREG_E_STATE; }
+        const unsigned int rank = static_cast<unsigned int>(h->comm_rank), world = static_cast<unsigned int>(h->comm_world);
+        const float4* src4 = stage_cloud(h, src, n, stride, false);
+        // this rank's share of the strided deal: hypotheses rank, rank + world, ...
+        const size_t n_local = n_hyp > rank ? (n_hyp - rank + world - 1) / world : 0;
+        LR_CUDA(cudaStreamSynchronize(h->stream));  // stage_cloud's copy out of h_in has finished: the buffer can be reused
+        h->h_in.reserve(std::max<size_t>(n_local, 1) * 7 * sizeof(double));
+        double* mine = h->h_in.as<double>();
+        for (size_t i = 0; i < n_local; ++i) std::memcpy(mine + i * 7, poses_in + (rank + i * world) * 7, 7 * sizeof(double));
+        unsigned long long* d_key = relocalise_core(h, src4, n, mine, n_local, rank, world);
+        // the one exchange step, on the same stream: MIN over the packed (score, global index) keys, then the winner's
+        // owner broadcasts pose + score
+        h->d_bcast.reserve(16 * sizeof(double));
+        double* d_b = h->d_bcast.as<double>();
+        unsigned long long* d_gkey = reinterpret_cast<unsigned long long*>(d_b + 8);
+        const NcclApi& nc = nccl_api();
+        {
+            NvtxRange r("locreg:relocalise:allreduce_min");
+            if (h->comm) LR_NCCL(nc.AllReduce(d_key, d_gkey, 1, ncclUint64, ncclMin, h->comm, h->stream));
+            else LR_CUDA(cudaMemcpyAsync(d_gkey, d_key, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+        }
+        h->h_small.reserve(4096);
+        unsigned long long* h_key = reinterpret_cast<unsigned long long*>(h->h_small.as<unsigned char>() + 2048);
+        LR_CUDA(cudaMemcpyAsync(h_key, d_gkey, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        LR_CUDA(cudaStreamSynchronize(h->stream));  // the owner of the winner is a host decision (the root of the broadcast)
+        const uint32_t gi = static_cast<uint32_t>(*h_key & 0xFFFFFFFFull);
+        const bool none = gi == 0xFFFFFFFFu;  // no rank had a hypothesis
+        const unsigned int owner = none ? 0u : gi % world;
+        if (owner == rank && !none) {
+            const size_t li = (gi - rank) / world;
+            LR_CUDA(cudaMemcpyAsync(d_b, h->d_poses_out.as<double>() + li * 7, 7 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            LR_CUDA(cudaMemcpyAsync(d_b + 7, h->d_scores.as<double>() + li, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        }
+        if (h->comm) {
+            NvtxRange r("locreg:relocalise:broadcast_pose");
+            LR_NCCL(nc.Broadcast(d_b, d_b, 8, ncclDouble, static_cast<int>(owner), h->comm, h->stream));
+        }
+        double* h_b = h->h_small.as<double>() + 128;
+        LR_CUDA(cudaMemcpyAsync(h_b, d_b, 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        h->end_timing();  // synchronises the stream: kernels + both collectives
+        if (best_idx) *best_idx = none ? -1 : static_cast<int64_t>(gi);
+        if (best_pose && !none) std::memcpy(best_pose, h_b, 7 * sizeof(double));
+        if (best_score) *best_score = none ? INFINITY : h_b[7];
         return LOCREG_OK;
     });
 }

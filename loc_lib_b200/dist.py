@@ -6,6 +6,12 @@
   min-all-reduce of a packed (float32 score bits << 32 | global hypothesis index) key picks the winner
   (lowest index wins ties), followed by a broadcast of the winning pose from its owner.
 torch is used for process-group plumbing only; all registration work goes through liblocreg.so.
+
+The product path keeps the exchange step INSIDE liblocreg.so (locreg_comm_init / locreg_relocalise_sharded /
+locreg_align_batch_sharded: NCCL on the handle's stream, usable from a C++ host without Python): `comm_init` below only
+carries the 128-byte NCCL id from rank 0 to the others through the process group torchrun set up, and
+`relocalise_sharded` / `align_batch_sharded` call the C ABI when the handle has a communicator.  The torch-collective
+forms remain for backends NCCL cannot serve (gloo on CPU: the host-logic tests of tests/test_dist.py).
 """
 import struct
 
@@ -56,6 +62,28 @@ def broadcast_pose(pose7, owner_rank, device=None):
     return t.cpu().numpy()
 
 
+def comm_init(reg, device=None):
+    """Gives `reg` (an IcpRegistration / NdtRegistration of this rank) an NCCL communicator over all ranks of the
+    initialised torch process group: rank 0 draws the id (locreg_comm_unique_id), the process group carries it."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return False
+    rank, world = dist.get_rank(), dist.get_world_size()
+    t = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(reg.CommUniqueId()), dtype=torch.uint8).to(device) if device is not None else \
+            torch.frombuffer(bytearray(reg.CommUniqueId()), dtype=torch.uint8).clone()
+    dist.broadcast(t, src=0)
+    reg.CommInit(bytes(t.cpu().numpy().tobytes()), rank, world)
+    return True
+
+
+def align_batch_sharded(reg, clouds, offsets, predict_poses, S_global):
+    """Batch mapping over the ranks of reg's communicator: this rank's block in, ALL poses out (C ABI, NCCL inside)."""
+    return reg.ScanMatchBatchSharded(clouds, offsets, predict_poses, S_global)
+
+
 def relocalise_sharded(reg, scan, hypotheses, rank=0, world=1, device=None):
     """Global relocalisation over `world` ranks; `reg` is this rank's IcpRegistration with the map set.
 
@@ -64,6 +92,8 @@ def relocalise_sharded(reg, scan, hypotheses, rank=0, world=1, device=None):
     strided split balances the ranks where a block split would not.  Returns (best_pose, best_global_index,
     best_score), identical on every rank."""
     hyp = np.ascontiguousarray(hypotheses, np.float64).reshape(-1, 7)
+    if hasattr(reg, "CommInfo") and reg.CommInfo()[1] == world:
+        return reg.RelocaliseSharded(scan, hyp)  # the product path: key, all-reduce and broadcast on the handle's stream
     mine = hyp[rank::world]
     if len(mine):
         pose, idx, score, _, _ = reg.Relocalise(scan, mine)
@@ -77,12 +107,21 @@ def relocalise_sharded(reg, scan, hypotheses, rank=0, world=1, device=None):
 
 
 def gather_poses(local_poses, device=None):
-    """All-gather of per-rank pose blocks (equal block sizes) -> (world * S_local, 7)."""
+    """All-gather of per-rank pose blocks -> (sum of block sizes, 7), in rank order.  Blocks may differ in size
+    (shard_range gives the first S % world ranks one scan more): the sizes are exchanged first, the blocks are padded
+    to the largest and trimmed after the gather."""
     import torch
     import torch.distributed as dist
-    t = torch.as_tensor(np.ascontiguousarray(local_poses, np.float64), device=device)
+    t = torch.as_tensor(np.ascontiguousarray(local_poses, np.float64).reshape(-1, 7), device=device)
     if not (dist.is_initialized() and dist.get_world_size() > 1):
         return t.cpu().numpy()
-    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
-    dist.all_gather(out, t)
-    return torch.cat(out).cpu().numpy()
+    world = dist.get_world_size()
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    pad = torch.zeros((max(sizes), 7), dtype=torch.float64, device=device)
+    pad[:t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[:k] for o, k in zip(out, sizes)]).cpu().numpy()

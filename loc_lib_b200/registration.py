@@ -167,6 +167,56 @@ class _Registration:
                                                 poses.ctypes.data if want_all else None))
         return best_pose, int(best_idx.value), float(best_score.value), scores, poses
 
+    # ---- multi-GPU: NCCL inside liblocreg.so (one process per GPU; see loc_lib_b200/dist.py for the torchrun plumbing) ----
+    @staticmethod
+    def CommUniqueId():
+        """ncclGetUniqueId: 128 bytes to be created on ONE rank and handed to all of them."""
+        buf = (C.c_ubyte * 128)()
+        _lib.check(_lib.lib().locreg_comm_unique_id(buf))
+        return bytes(buf)
+
+    def CommInit(self, unique_id, rank, world):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        _lib.check(_lib.lib().locreg_comm_init(self._h, buf, int(rank), int(world)))
+
+    def CommDestroy(self):
+        _lib.check(_lib.lib().locreg_comm_destroy(self._h))
+
+    def CommInfo(self):
+        r, w, v = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(_lib.lib().locreg_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return r.value, w.value, v.value
+
+    def RelocaliseSharded(self, cloud, hypotheses):
+        """All ranks pass the same scan and hypotheses; the argmin is one ncclAllReduce(MIN) on the handle's stream.
+        Returns (best_pose, best GLOBAL index, best_score), identical on every rank."""
+        a, n, s = _cloud(cloud)
+        hyp = np.ascontiguousarray(hypotheses, np.float64).reshape(-1, 7)
+        best_pose = np.zeros(7)
+        best_idx = C.c_int64(-1)
+        best_score = C.c_double(np.inf)
+        _lib.check(_lib.lib().locreg_relocalise_sharded(self._h, a.ctypes.data, n, s, hyp.ctypes.data, hyp.shape[0],
+                                                        best_pose.ctypes.data, C.byref(best_idx), C.byref(best_score)))
+        return best_pose, int(best_idx.value), float(best_score.value)
+
+    def ScanMatchBatchSharded(self, clouds, offsets, predict_poses, S_global):
+        """This rank's block of a batch of S_global scans (block partition: shard_range); returns the poses and results
+        of ALL scans, exchanged over NCCL on the handle's stream."""
+        a, n, s = _cloud(clouds)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        S = offsets.shape[0] - 1
+        pin = np.ascontiguousarray(predict_poses, np.float64).reshape(S, 7)
+        rank, world, _ = self.CommInfo()
+        lo = C.c_size_t()
+        hi = C.c_size_t()
+        _lib.check(_lib.lib().locreg_shard_range(S_global, rank, world, C.byref(lo), C.byref(hi)))
+        pout = np.zeros((S_global, 7))
+        pout[lo.value:hi.value] = pin
+        res = (_lib.Result * S_global)()
+        _lib.check(_lib.lib().locreg_align_batch_sharded(self._h, a.ctypes.data, offsets.ctypes.data, s, pin.ctypes.data, S,
+                                                         S_global, pout.ctypes.data, res))
+        return pout, [r.as_dict() for r in res]
+
     # ---- parity probes ----
     def Knn(self, queries, k):
         a, n, s = _cloud(queries)
@@ -286,6 +336,8 @@ class IcpRegistration(_Registration):
         o.knn_cell_size = options.knn_cell_size
         o.knn_lists = int(options.knn_lists)
         o.loop_mode = options.loop_mode
+        # Align* start from target_center_ - source_center_ = 0 when the flag is cleared (icp_registration.cpp:272-276)
+        o.zero_initial_translation = 0 if options.use_initial_translation_ else 1
         self.options_ = options
         super().__init__(o, device)
 
@@ -309,6 +361,7 @@ class NdtRegistration(_Registration):
         o.res_outlier_th = options.res_outlier_th_
         o.nearby_type = options.nearby_type_
         o.loop_mode = options.loop_mode
+        o.zero_initial_translation = 1 if options.remove_centroid_ else 0  # ndt_registration.cpp:380-384 (AlignNdt only)
         self.options_ = options
         super().__init__(o, device)
 

@@ -47,7 +47,7 @@ def _worker(rank, world, port, out_dir):
     target = hyp[13, 4:].copy()
     pose, idx, score = D.relocalise_sharded(FakeReg(target), None, hyp, rank, world)
     # batch mapping: every rank registers its block, poses are gathered in rank order
-    S = 4 * world
+    S = 4 * world + 1  # not divisible: the first rank's block is one scan longer (ragged gather)
     lo, hi = D.shard_range(S, rank, world)
     local = np.arange(lo, hi, dtype=np.float64)[:, None] * np.ones((1, 7))
     allp = D.gather_poses(local)
@@ -67,7 +67,7 @@ def test_relocalise_and_gather_over_gloo(tmp_path, world):
         exp = o["hyp13"].copy()
         exp[4:] += 0.125
         assert np.array_equal(o["pose"], exp)  # identical winner pose on every rank
-        assert np.array_equal(o["allp"][:, 0], np.arange(4 * world))
+        assert np.array_equal(o["allp"][:, 0], np.arange(4 * world + 1))
 
 
 def test_shard_range_partitions_exactly():
@@ -80,6 +80,21 @@ def test_shard_range_partitions_exactly():
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
     assert [D.shard_range(4096, r, 8) for r in (0, 7)] == [(0, 512), (3584, 4096)]
+
+
+def test_c_abi_shard_range_equals_python():
+    """locreg_shard_range (pure host code of liblocreg.so: no device needed) is the partition dist.shard_range states."""
+    import ctypes as C
+    from loc_lib_b200 import _lib, dist as D
+    L = _lib.lib()
+    for n in (0, 1, 7, 4097, 65536):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                lo, hi = C.c_size_t(), C.c_size_t()
+                assert L.locreg_shard_range(n, r, world, C.byref(lo), C.byref(hi)) == 0
+                assert (lo.value, hi.value) == D.shard_range(n, r, world)
+    lo, hi = C.c_size_t(), C.c_size_t()
+    assert L.locreg_shard_range(10, 3, 3, C.byref(lo), C.byref(hi)) == -1
 
 
 def test_single_process_paths_need_no_process_group():
