@@ -232,19 +232,18 @@ __global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_N
     unsigned int slot = threadIdx.x;  // the point of the tile this thread searches
     if (tracked) {
         // phase A: every point tries the cheap way (its data is requested before the barrier thread 0's pose needs)
+        // A query inside its margin keeps its K neighbours as a SET (KnnTrack, voxel_map.cuh): nothing is gathered, sorted
+        // or stored for it - nn_pos keeps the order of the last full search, and what k_icp_fit derived from the set
+        // (a plane / a line does not depend on the order of its five points beyond rounding) stays valid.
         bool need_scan = false;
         const bool mine = threadIdx.x < tc.count;
         const unsigned int p = tc.first + (mine ? threadIdx.x : 0u);
         const size_t row = static_cast<size_t>(tc.out_base + p);
-        unsigned int* out = nn_pos + row * K;
         float4 sp = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        unsigned int seeds[K];
         KnnTrack t;
         t.qx = t.qy = t.qz = 0.0f; t.margin = -1.0f;
         if (mine) {
             sp = bv.src[tc.src_base + p];
-#pragma unroll
-            for (int j = 0; j < K; ++j) seeds[j] = out[j];
             t = track[row];
         }
         __syncthreads();
@@ -252,20 +251,7 @@ __global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_N
             if (finite3(sp.x, sp.y, sp.z) && map.n_pts != 0) {
                 double wx, wy, wz;
                 pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
-                const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
-                KnnResult<K> nn;
-                if (knn_track_try<K>(map, qx, qy, qz, seeds, t, nn)) {
-                    bool same = true;
-#pragma unroll
-                    for (int j = 0; j < K; ++j) same = same && seeds[j] == nn.pos[j];
-                    if (!same) {  // same points, new order
-#pragma unroll
-                        for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
-                        if (plane_valid) plane_valid[row] = 0;
-                    }
-                } else {
-                    need_scan = true;
-                }
+                need_scan = !knn_track_holds(t, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz));
             }
         }
         const unsigned int lane = threadIdx.x & 31;
@@ -712,9 +698,11 @@ __device__ __forceinline__ bool apply_outcome(int outcome, DevResult& r) {
 // One warp per scan.  mode 1: Gauss-Newton iteration (update the pose; stop on convergence or after
 // max_iteration trips); mode 0: evaluation only (compute_hb, relocalisation's final score pass): record the sums,
 // leave the pose.  acc_out (optional, 32 doubles per scan) receives the raw sums.
+// partials_b (optional): a second partial row per tile (k_icp_pending, icp_fused.cuh), added after the first ones.
 template <int METHOD>
 __global__ void __launch_bounds__(128) k_icp_solve(IcpParams prm, BatchView bv, AlignState* states,
-                                                   const double* __restrict__ partials, int mode, double* acc_out) {
+                                                   const double* __restrict__ partials, const double* __restrict__ partials_b,
+                                                   int mode, double* acc_out) {
     __shared__ double sums[4][32];
     const unsigned int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned int s = blockIdx.x * 4 + warp;
@@ -739,6 +727,19 @@ __global__ void __launch_bounds__(128) k_icp_solve(IcpParams prm, BatchView bv, 
             v3 += col[static_cast<size_t>(t + 3) * kPartialDoubles];
         }
         for (; t < t1; ++t) v0 += col[static_cast<size_t>(t) * kPartialDoubles];
+        if (partials_b) {
+            double w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            const double* colb = partials_b + lane;
+            for (t = t0; t + 4 <= t1; t += 4) {
+                w0 += colb[static_cast<size_t>(t) * kPartialDoubles];
+                w1 += colb[static_cast<size_t>(t + 1) * kPartialDoubles];
+                w2 += colb[static_cast<size_t>(t + 2) * kPartialDoubles];
+                w3 += colb[static_cast<size_t>(t + 3) * kPartialDoubles];
+            }
+            for (; t < t1; ++t) w0 += colb[static_cast<size_t>(t) * kPartialDoubles];
+            v0 = ((v0 + v1) + (v2 + v3)) + ((w0 + w1) + (w2 + w3));
+            v1 = v2 = v3 = 0;
+        }
     }
     sums[warp][lane] = (v0 + v1) + (v2 + v3);
     __syncwarp();

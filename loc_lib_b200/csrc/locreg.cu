@@ -166,7 +166,7 @@ const float4* stage_cloud(locreg_handle* h, const float* src, size_t n, size_t s
     if (src_on_device) {
         LR_CUDA(cudaMemcpyAsync(h->d_raw.p, src, bytes, cudaMemcpyDeviceToDevice, h->stream));
     } else if (is_pinned_or_device(src)) {
-        LR_CUDA(cudaMemcpyAsync(h->d_raw.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        LR_CUDA(cudaMemcpyAsync(h->d_raw.p, src, bytes, cudaMemcpyDefault, h->stream));
     } else {
         h->h_in.reserve(bytes);
         std::memcpy(h->h_in.p, src, bytes);

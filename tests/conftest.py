@@ -14,19 +14,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def _has_gpu():
+def _gpu_count():
     try:
         import ctypes
         lib = ctypes.CDLL("libcuda.so.1")
         if lib.cuInit(0) != 0:
-            return False
+            return 0
         n = ctypes.c_int(0)
-        return lib.cuDeviceGetCount(ctypes.byref(n)) == 0 and n.value > 0
+        return n.value if lib.cuDeviceGetCount(ctypes.byref(n)) == 0 else 0
     except OSError:
-        return False
+        return 0
 
 
-HAS_GPU = _has_gpu()
+GPU_COUNT = _gpu_count()
+HAS_GPU = GPU_COUNT > 0
 
 
 def pytest_collection_modifyitems(config, items):
