@@ -5,15 +5,19 @@
 // through five points does not depend on their order (beyond rounding, 1e-16 relative), so for such a point the plane
 // cached by the last fit is still THE plane: the iteration needs the point (16 B), its margin record (16 B) and the
 // plane (32 B + 1 B status) - no neighbour gather, no sort, no store.  The three-kernel pipeline of icp_pipeline.cuh
-// read the point twice and its five neighbours once for the same result; here one kernel does
+// read the point twice and its five neighbours once for the same result.  Here:
 //
-//   k_icp_track_p2plane   per tile of 256 points: margin check -> residual row from the cached plane -> per-warp Gram
-//                         matrix -> partial row A of the tile.  Points outside their margin are compacted over the
-//                         tile and searched by its first warps (exact tracked search, as k_icp_nn phase B); when the
-//                         search returns the same ordered neighbours the cached plane is reused at once, otherwise
-//                         the point is PENDING (plane_valid = 0; unfinished searches also go to the stage-2 queue).
-//   k_icp_pending         per group of tiles: the pending points (1 % by the tenth iteration) compacted in point
-//                         order, plane fit, residual row, and a fixed-order sum per tile -> partial row B.
+//   k_icp_track_p2plane   per tile of 256 points, a pure streaming pass: margin check -> residual row from the cached
+//                         plane -> per-warp Gram matrix -> partial row A of the tile.  Points outside their margin
+//                         (3 % by the tenth iteration) are appended to a global queue, one atomic per tile - left in
+//                         the block they would keep it on its SM waiting for one warp with a few busy lanes.
+//   k_icp_rescan          one queued point per thread, every lane busy: exact tracked search.  The same ordered
+//                         neighbours as before: the cached plane stays (flag 2 = residual outstanding); otherwise the
+//                         point needs a new fit (flag 0); unfinished searches also go to the stage-2 queue.
+//   k_icp_fit_queue       after stage 2: the queued points whose neighbours changed (1 %), compacted per block so that
+//                         every lane runs a fit -> plane cache, flag 2.
+//   k_icp_pending         per group of tiles: the flag-2 points in point order, residual row from the cached plane,
+//                         fixed-order sum per tile -> partial row B.
 //
 // k_icp_solve adds the A rows and then the B rows of a scan in tile order: the sums are reproducible and do not
 // depend on how many scans share the launch (a batch equals single ScanMatch calls bit for bit).
@@ -88,20 +92,52 @@ __device__ __forceinline__ void tile_gram_store(const double* rows, const unsign
     }
 }
 
+// plane_valid[] states of a point in the tracked iterations
+constexpr unsigned char kPlaneStale = 0;     // neighbours changed: fit + residual outstanding (k_icp_pending)
+constexpr unsigned char kPlaneCurrent = 1;   // plane valid, residual accumulated (or nothing to do)
+constexpr unsigned char kPlaneResidual = 2;  // plane valid, residual outstanding (k_icp_pending)
+
+// One tracked search of scratch row `srow` (point sp, pose T): neighbours, margin record and flag are updated in place.
+// Returns false when stage 2 has to finish the search.
+__device__ __forceinline__ bool track_rescan_point(const VoxelMapView& map, const Pose& T, const float4 sp, size_t srow,
+                                                   unsigned int* __restrict__ nn_pos, unsigned char* __restrict__ plane_valid, KnnTrack* track) {
+    constexpr int K = 5;
+    unsigned int* out = nn_pos + srow * K;
+    unsigned int seeds[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) seeds[j] = out[j];
+    double wx, wy, wz;
+    pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
+    KnnResult<K> nn;
+    KnnTrack tr;
+    const bool done = knn_query_fast_track<K>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, seeds, tr);
+    bool same = done;
+#pragma unroll
+    for (int j = 0; j < K; ++j) same = same && seeds[j] == nn.pos[j] && seeds[j] != kNoPos;
+    track[srow] = tr;
+    if (same) {
+        // the same ordered neighbours as the last fit saw: its plane is what a new fit would return bit for bit
+        plane_valid[srow] = kPlaneResidual;
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+        plane_valid[srow] = kPlaneStale;
+    }
+    return done;
+}
+
 #ifndef LR_TRACK_MIN_BLOCKS
-#define LR_TRACK_MIN_BLOCKS 5
+#define LR_TRACK_MIN_BLOCKS 6
 #endif
 __global__ void __launch_bounds__(kTile, LR_TRACK_MIN_BLOCKS)
 k_icp_track_p2plane(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
-                    unsigned int* __restrict__ nn_pos, unsigned char* __restrict__ plane_valid, KnnTrack* track, RingQueue queue,
-                    const double* __restrict__ plane_cache, const unsigned char* __restrict__ plane_stat, double* __restrict__ partials) {
-    constexpr int K = 5;
+                    const KnnTrack* __restrict__ track, RingQueue rescan, const double* __restrict__ plane_cache,
+                    const unsigned char* __restrict__ plane_stat, double* __restrict__ partials) {
     __shared__ Pose T;
     __shared__ double rows[kTile * kRowStride + 1];
     __shared__ double gram[kTile / 32][64];
     __shared__ int counts[kTile / 32][2];
-    __shared__ unsigned int blk_pending, blk_done, blk_scan;
-    __shared__ unsigned int staged[kTile];
+    __shared__ unsigned int blk_scan, blk_base;
     __shared__ unsigned char scan_list[kTile];
     __shared__ unsigned char flags[kTile];
     const TileCoord tc = locate_tile(bv, blockIdx.x);
@@ -110,9 +146,9 @@ k_icp_track_p2plane(VoxelMapView map, IcpParams prm, BatchView bv, const AlignSt
     if (st->stop && !ignore_stop) return;
     if (threadIdx.x == 0) {
         pose_load(T, st->pose);
-        blk_pending = 0u; blk_done = 0u; blk_scan = 0u;
+        blk_scan = 0u;
     }
-    // ---- phase A: one thread per point.  Everything a point inside its margin needs is requested before the barrier.
+    // everything a point inside its margin needs is requested at once, before the barrier the pose needs
     const bool mine = threadIdx.x < tc.count;
     const unsigned int p = tc.first + (mine ? threadIdx.x : 0u);
     const size_t row = static_cast<size_t>(tc.out_base + p);
@@ -124,20 +160,18 @@ k_icp_track_p2plane(VoxelMapView map, IcpParams prm, BatchView bv, const AlignSt
     if (mine) {
         sp = bv.src[tc.src_base + p];
         t = track[row];
-        if (t.margin > 0.0f) {  // (the plane is only needed when the margin can hold at all)
-            pl = reinterpret_cast<const double4*>(plane_cache)[row];
-            pst = plane_stat[row];
-        }
+        pl = reinterpret_cast<const double4*>(plane_cache)[row];
+        pst = plane_stat[row];
     }
     {
         double* r = rows + threadIdx.x * kRowStride;
 #pragma unroll
         for (int i = 0; i < kRowStride; ++i) r[i] = 0.0;  // points without a residual contribute zero rows
         if (threadIdx.x == 0) rows[kTile * kRowStride] = 0.0;
-        flags[threadIdx.x] = 0;
     }
     __syncthreads();
     bool need_scan = false;
+    unsigned char fl = 0;
     if (mine && finite3(sp.x, sp.y, sp.z) && map.n_pts != 0) {
         const double qx = sp.x, qy = sp.y, qz = sp.z;
         double wx, wy, wz;
@@ -146,11 +180,12 @@ k_icp_track_p2plane(VoxelMapView map, IcpParams prm, BatchView bv, const AlignSt
             const double n[4] = {pl.x, pl.y, pl.z, pl.w};
             FlagSink sink{rows + threadIdx.x * kRowStride, 0};
             icp_p2plane_residual(prm, T, qx, qy, qz, wx, wy, wz, pst, n, sink);
-            flags[threadIdx.x] = sink.flags;
+            fl = sink.flags;
         } else {
             need_scan = true;
         }
     }
+    flags[threadIdx.x] = fl;
     {
         const unsigned int lane = threadIdx.x & 31;
         const unsigned int mask = __ballot_sync(0xffffffffu, need_scan);
@@ -160,60 +195,103 @@ k_icp_track_p2plane(VoxelMapView map, IcpParams prm, BatchView bv, const AlignSt
         if (need_scan) scan_list[base + __popc(mask & ((1u << lane) - 1u))] = static_cast<unsigned char>(threadIdx.x);
     }
     __syncthreads();
-    // ---- phase B: the first blk_scan threads search the points that left their margin (exact tracked search)
-    {
-        const unsigned int slot = threadIdx.x < blk_scan ? scan_list[threadIdx.x] : kTile;
-        const bool in_tile = slot < tc.count;  // (listed slots are finite points of a non-empty map)
-        bool done = true;
-        size_t srow = 0;
-        if (in_tile) {
-            const unsigned int ps = tc.first + slot;
-            const float4 s2 = bv.src[tc.src_base + ps];
-            srow = static_cast<size_t>(tc.out_base + ps);
-            unsigned int* out = nn_pos + srow * K;
-            unsigned int seeds[K];
-#pragma unroll
-            for (int j = 0; j < K; ++j) seeds[j] = out[j];
-            const double qx = s2.x, qy = s2.y, qz = s2.z;
-            double wx, wy, wz;
-            pose_apply(T, qx, qy, qz, wx, wy, wz);
-            KnnResult<K> nn;
-            KnnTrack tr;
-            done = knn_query_fast_track<K>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, seeds, tr);
-            bool same = done;
-#pragma unroll
-            for (int j = 0; j < K; ++j) same = same && seeds[j] == nn.pos[j] && seeds[j] != kNoPos;
-            track[srow] = tr;
-            if (same) {
-                // the same ordered neighbours as the last fit saw: its plane is what a new fit would return bit for bit
-                const double4 pc = reinterpret_cast<const double4*>(plane_cache)[srow];
-                const double n[4] = {pc.x, pc.y, pc.z, pc.w};
-                FlagSink sink{rows + slot * kRowStride, 0};
-                icp_p2plane_residual(prm, T, qx, qy, qz, wx, wy, wz, plane_stat[srow], n, sink);
-                flags[slot] = sink.flags;
-            } else {
-#pragma unroll
-                for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
-                plane_valid[srow] = 0;  // pending: k_icp_pending fits and accumulates it (after stage 2, if queued)
-            }
-        }
-        tile_queue_append(!done, static_cast<unsigned int>(srow), tc.scan, &blk_pending, &blk_done, staged, queue);
+    const unsigned int n_scan = blk_scan;
+    if (n_scan != 0u) {  // one atomic per tile; the entries of a tile stay together (neighbouring rays, the same lists)
+        if (threadIdx.x == 0) blk_base = atomicAdd(rescan.count, n_scan);
+        __syncthreads();
+        if (threadIdx.x < n_scan)
+            rescan.entries[blk_base + threadIdx.x] = make_uint2(static_cast<unsigned int>(tc.out_base + tc.first + scan_list[threadIdx.x]), tc.scan);
     }
-    __syncthreads();
     tile_gram_store(rows, flags, gram, counts, partials + static_cast<size_t>(blockIdx.x) * kPartialDoubles);
 }
 
-// The pending points of `group` consecutive tiles: compacted in (tile, point) order, fitted, and summed per tile in
-// that order into the tile's partial row B (partials_b + tile * kPartialDoubles; zeros for a tile without any).
-// Launched after both search stages: also re-arms the stage-2 queue counters for the next evaluation.
+// The queued points of k_icp_track_p2plane, one per thread (grid-stride: the queue length is only known on the device).
+// Unfinished searches are appended to the stage-2 queue warp by warp.
+__global__ void __launch_bounds__(128, 8)
+k_icp_rescan(VoxelMapView map, BatchView bv, const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
+             unsigned char* __restrict__ plane_valid, KnnTrack* track, RingQueue queue, RingQueue rescan) {
+    const unsigned int n = *rescan.count;
+    const unsigned int lane = threadIdx.x & 31;
+    for (unsigned int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const unsigned int e = base + threadIdx.x;
+        bool done = true;
+        uint2 q = make_uint2(0u, 0u);
+        if (e < n) {
+            q = rescan.entries[e];
+            const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
+            Pose T;
+            pose_load(T, states[q.y].pose);
+            done = track_rescan_point(map, T, bv.src[src_idx], q.x, nn_pos, plane_valid, track);
+        }
+        const unsigned int mask = __ballot_sync(0xffffffffu, !done);
+        if (mask != 0u) {
+            unsigned int qb = 0;
+            if (lane == 0) qb = atomicAdd(queue.count, static_cast<unsigned int>(__popc(mask)));
+            qb = __shfl_sync(0xffffffffu, qb, 0);
+            if (!done) queue.entries[qb + __popc(mask & ((1u << lane) - 1u))] = q;
+        }
+    }
+}
+
+// After both search stages: the queued points whose neighbours changed get a new plane.  A block takes kFitChunk queue
+// entries at a time, compacts the stale ones in shared memory and fits them with every lane busy (a fit is ~500
+// dependent fp64 instructions).  Flag 0 -> 2.
+constexpr int kFitChunk = 1024;
+__global__ void __launch_bounds__(128, 4)
+k_icp_fit_queue(VoxelMapView map, IcpParams prm, const unsigned int* __restrict__ nn_pos, unsigned char* plane_valid, double* plane_cache,
+                unsigned char* plane_stat, RingQueue rescan) {
+    __shared__ unsigned int list[kFitChunk];
+    __shared__ unsigned int list_n;
+    const unsigned int n = *rescan.count;
+    const unsigned int lane = threadIdx.x & 31;
+    for (unsigned int base = blockIdx.x * kFitChunk; base < n; base += gridDim.x * kFitChunk) {
+        if (threadIdx.x == 0) list_n = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kFitChunk / 128; ++k) {
+            const unsigned int e = base + k * 128 + threadIdx.x;
+            unsigned int row = 0;
+            bool stale = false;
+            if (e < n) {
+                row = rescan.entries[e].x;
+                stale = plane_valid[row] == kPlaneStale;
+            }
+            const unsigned int mask = __ballot_sync(0xffffffffu, stale);
+            unsigned int lb = 0;
+            if (lane == 0 && mask != 0u) lb = atomicAdd(&list_n, static_cast<unsigned int>(__popc(mask)));
+            lb = __shfl_sync(0xffffffffu, lb, 0);
+            if (stale) list[lb + __popc(mask & ((1u << lane) - 1u))] = row;
+        }
+        __syncthreads();
+        const unsigned int m = list_n;
+        for (unsigned int i = threadIdx.x; i < m; i += 128) {
+            const size_t row = list[i];
+            KnnResult<5> nn;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                nn.pos[j] = nn_pos[row * 5 + j];
+                nn.d2[j] = 0.0f;  // not needed by the fit
+            }
+            double pl[4] = {0, 0, 0, 0};
+            plane_stat[row] = icp_fit_plane(map, prm, nn, pl);
+            reinterpret_cast<double4*>(plane_cache)[row] = make_double4(pl[0], pl[1], pl[2], pl[3]);
+            plane_valid[row] = kPlaneResidual;
+        }
+        __syncthreads();
+    }
+}
+
+// The flag-2 points of `group` consecutive tiles: residual rows from the cached planes, summed per tile in point order
+// into the tile's partial row B (partials_b + tile * kPartialDoubles; zeros for a tile without any).  Flag 2 -> 1.
+// Launched after both search stages and the fits: also re-arms the stage-2 queue counters for the next evaluation.
 constexpr int kPendGroup = 16;
 #ifndef LR_PEND_MIN_BLOCKS
-#define LR_PEND_MIN_BLOCKS 3
+#define LR_PEND_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(kTile, LR_PEND_MIN_BLOCKS)
-k_icp_pending(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
-              const unsigned int* __restrict__ nn_pos, unsigned char* plane_valid, double* plane_cache, unsigned char* plane_stat,
-              unsigned int group, double* __restrict__ partials_b, unsigned int* ring_count) {
+k_icp_pending(IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop, unsigned char* plane_valid,
+              const double* __restrict__ plane_cache, const unsigned char* __restrict__ plane_stat, unsigned int group,
+              double* __restrict__ partials_b, unsigned int* ring_count) {
     __shared__ TileCoord tcs[kPendGroup];
     __shared__ Pose Ts[kPendGroup];
     __shared__ unsigned short warp_cnt[kPendGroup][kTile / 32];
@@ -237,7 +315,7 @@ k_icp_pending(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* _
     for (unsigned int g = 0; g < static_cast<unsigned int>(kPendGroup); ++g) {
         if (g < group && tcs[g].valid && threadIdx.x < tcs[g].count) {
             const size_t row = static_cast<size_t>(tcs[g].out_base + tcs[g].first + threadIdx.x);
-            need_bits |= (plane_valid[row] == 0 ? 1u : 0u) << g;
+            need_bits |= (plane_valid[row] != kPlaneCurrent ? 1u : 0u) << g;
         }
     }
     for (unsigned int g = 0; g < group; ++g) {
@@ -255,74 +333,64 @@ k_icp_pending(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* _
     }
     __syncthreads();
     const unsigned int n = seg_begin[group];
-    if (n != 0u) {
-        // chunk by chunk of kTile list entries: entry i belongs to the thread that holds its flag - found again by
-        // position, so the list itself is never materialised beyond the chunk in flight
-        for (unsigned int c0 = 0; c0 < n; c0 += kTile) {
-            // which of my flagged points fall into [c0, c0 + kTile)?  (a thread has at most one per tile)
-            for (unsigned int g = 0; g < group; ++g) {
-                const bool need = (need_bits >> g) & 1u;
-                const unsigned int mask = __ballot_sync(0xffffffffu, need);
-                if (!need) continue;
-                unsigned int pos = seg_begin[g] + __popc(mask & ((1u << lane) - 1u));
-                for (unsigned int w = 0; w < warp; ++w) pos += warp_cnt[g][w];
-                if (pos < c0 || pos >= c0 + kTile) continue;
-                const unsigned int i = pos - c0;
-                const TileCoord& tc = tcs[g];
-                const unsigned int ps = tc.first + threadIdx.x;
-                const size_t row = static_cast<size_t>(tc.out_base + ps);
-                KnnResult<5> nn;
+    // chunk by chunk of kTile flagged points: a point belongs to the thread that holds its flag and finds its place in
+    // the chunk by position, so no list is materialised
+    for (unsigned int c0 = 0; c0 < n; c0 += kTile) {
+        for (unsigned int g = 0; g < group; ++g) {
+            const bool need = (need_bits >> g) & 1u;
+            const unsigned int mask = __ballot_sync(0xffffffffu, need);
+            if (!need) continue;
+            unsigned int pos = seg_begin[g] + __popc(mask & ((1u << lane) - 1u));
+            for (unsigned int w = 0; w < warp; ++w) pos += warp_cnt[g][w];
+            if (pos < c0 || pos >= c0 + kTile) continue;
+            const unsigned int i = pos - c0;
+            const TileCoord& tc = tcs[g];
+            const unsigned int ps = tc.first + threadIdx.x;
+            const size_t row = static_cast<size_t>(tc.out_base + ps);
+            const double4 pc = reinterpret_cast<const double4*>(plane_cache)[row];
+            const unsigned char pst = plane_stat[row];
+            const float4 sp = bv.src[tc.src_base + ps];
+            plane_valid[row] = kPlaneCurrent;
+            double* r = rows + i * kRowStride;
 #pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    nn.pos[j] = nn_pos[row * 5 + j];
-                    nn.d2[j] = 0.0f;  // not needed by the fit
-                }
-                double plv[4] = {0, 0, 0, 0};
-                const unsigned char pst = icp_fit_plane(map, prm, nn, plv);
-                plane_stat[row] = pst;
-                reinterpret_cast<double4*>(plane_cache)[row] = make_double4(plv[0], plv[1], plv[2], plv[3]);
-                plane_valid[row] = 1;
-                double* r = rows + i * kRowStride;
-#pragma unroll
-                for (int k = 0; k < kRowStride; ++k) r[k] = 0.0;
-                FlagSink sink{r, 0};
-                const float4 sp = bv.src[tc.src_base + ps];
-                if (finite3(sp.x, sp.y, sp.z)) {
-                    const double qx = sp.x, qy = sp.y, qz = sp.z;
-                    double wx, wy, wz;
-                    pose_apply(Ts[g], qx, qy, qz, wx, wy, wz);
-                    icp_p2plane_residual(prm, Ts[g], qx, qy, qz, wx, wy, wz, pst, plv, sink);
-                }
-                rflags[i] = sink.flags;
+            for (int k = 0; k < kRowStride; ++k) r[k] = 0.0;
+            FlagSink sink{r, 0};
+            if (finite3(sp.x, sp.y, sp.z)) {
+                const double plv[4] = {pc.x, pc.y, pc.z, pc.w};
+                const double qx = sp.x, qy = sp.y, qz = sp.z;
+                double wx, wy, wz;
+                pose_apply(Ts[g], qx, qy, qz, wx, wy, wz);
+                icp_p2plane_residual(prm, Ts[g], qx, qy, qz, wx, wy, wz, pst, plv, sink);
             }
-            __syncthreads();
-            // fixed-order sums: warp w owns the tiles g = w, w + 8, ...; lane e < 28 owns one entry, lanes 28 / 29 the counts
-            const unsigned int c1 = min(c0 + kTile, n);
-            for (unsigned int g = warp; g < group; g += kTile / 32) {
-                const unsigned int b = max(seg_begin[g], c0), e = min(seg_begin[g + 1], c1);
-                if (b >= e) continue;
-                constexpr unsigned long long kTriRow = tri_table(false), kTriCol = tri_table(true);
-                int ea = 6, eb = 6;
-                if (lane < 21) {
-                    ea = static_cast<int>(kTriRow >> (3 * lane)) & 7;
-                    eb = static_cast<int>(kTriCol >> (3 * lane)) & 7;
-                } else if (lane < 27) {
-                    ea = static_cast<int>(lane) - 21;
-                }
-                double s = acc[g][lane];
-                if (lane < 28) {
-                    for (unsigned int i = b; i < e; ++i) {
-                        const double* r = rows + (i - c0) * kRowStride;
-                        s += r[ea] * r[eb];
-                    }
-                } else if (lane < 30) {
-                    const unsigned char bit = lane == 28 ? kRowEff : kRowInl;
-                    for (unsigned int i = b; i < e; ++i) s += (rflags[i - c0] & bit) ? 1.0 : 0.0;
-                }
-                acc[g][lane] = s;
-            }
-            __syncthreads();
+            rflags[i] = sink.flags;
         }
+        __syncthreads();
+        // fixed-order sums: warp w owns the tiles g = w, w + 8, ...; lane e < 28 owns one entry, lanes 28 / 29 the counts
+        const unsigned int c1 = min(c0 + kTile, n);
+        for (unsigned int g = warp; g < group; g += kTile / 32) {
+            const unsigned int b = max(seg_begin[g], c0), e = min(seg_begin[g + 1], c1);
+            if (b >= e) continue;
+            constexpr unsigned long long kTriRow = tri_table(false), kTriCol = tri_table(true);
+            int ea = 6, eb = 6;
+            if (lane < 21) {
+                ea = static_cast<int>(kTriRow >> (3 * lane)) & 7;
+                eb = static_cast<int>(kTriCol >> (3 * lane)) & 7;
+            } else if (lane < 27) {
+                ea = static_cast<int>(lane) - 21;
+            }
+            double s = acc[g][lane];
+            if (lane < 28) {
+                for (unsigned int i = b; i < e; ++i) {
+                    const double* r = rows + (i - c0) * kRowStride;
+                    s += r[ea] * r[eb];
+                }
+            } else if (lane < 30) {
+                const unsigned char bit = lane == 28 ? kRowEff : kRowInl;
+                for (unsigned int i = b; i < e; ++i) s += (rflags[i - c0] & bit) ? 1.0 : 0.0;
+            }
+            acc[g][lane] = s;
+        }
+        __syncthreads();
     }
     // partial rows B (B[a] = -sum J[a] r)
     for (unsigned int i = threadIdx.x; i < group * 32u; i += kTile) {

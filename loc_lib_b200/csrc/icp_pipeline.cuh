@@ -207,6 +207,8 @@ __device__ __forceinline__ void tile_queue_append(bool mine, unsigned int row, u
 //                          are compacted over the tile first - by the eighth iteration they are 3 % of the points, and
 //                          left in place they would still keep a lane of nearly every warp busy for a whole scan.
 constexpr int kNnTrack = 4;
+constexpr int kNnFirstTrack = 16;  // host-side only: nothing can take the margin shortcut yet (every point is searched)
+constexpr int kNnFused = 8;  // host-side only: run the evaluation through icp_fused.cuh (tracked P2Plane iterations after the first)
 #ifndef LR_NN_TRACK_MIN_BLOCKS
 #define LR_NN_TRACK_MIN_BLOCKS LR_NN_MIN_BLOCKS
 #endif

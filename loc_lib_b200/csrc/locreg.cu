@@ -15,6 +15,8 @@
 #include "device_inc_ndt.cuh"
 #include "device_ndt.cuh"
 #include "filters.cuh"
+#include "icp_fused.cuh"
+#include "icp_staged.cuh"
 #include "nccl_dyn.h"
 
 #include <nvtx3/nvToolsExt.h>
@@ -96,7 +98,7 @@ struct locreg_handle {
     int comm_rank = 0, comm_world = 1;
     DevBuf d_gather_pose, d_gather_res, d_bcast;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
-        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_global, d_local, d_same, d_plane, d_pstat, d_track;
+        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_rescanq, d_rescanc, d_global, d_local, d_same, d_plane, d_pstat, d_track;
     size_t n_global = 0, global_stride = 0;  // Loc's global map kept on the device (locreg_set_global_map)
     // Lio's sliding local map (locreg_local_map_add_keyframe): transformed key frames + the filtered local map
     struct KeyFrame { void* p = nullptr; size_t n = 0; };
@@ -315,12 +317,14 @@ struct IcpJob {
 
 // nn_mode: kNnSeeds when the per-point neighbour scratch still holds THIS job's previous iteration, kNnTwoPass for the
 // first iterations (see k_icp_nn)
+// Returns the second partial-row array when the evaluation produced one (the fused tracked path of icp_fused.cuh), else
+// nullptr; icp_launch_solve takes it.
 template <int METHOD>
-void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int nn_mode, unsigned char* gate, int* nn_idx) {
+const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int nn_mode, unsigned char* gate, int* nn_idx) {
     constexpr int K = METHOD == kIcpP2P ? 1 : 5;
     const VoxelMapView map = h->icp_map.view();
     h->d_nnpos.reserve(job.n_scratch_points * K * sizeof(unsigned int));
-    h->d_partials.reserve(static_cast<size_t>(job.n_tiles) * kPartialDoubles * sizeof(double));
+    h->d_partials.reserve(2 * static_cast<size_t>(job.n_tiles) * kPartialDoubles * sizeof(double));
     h->d_ringq.reserve(job.n_scratch_points * sizeof(uint2));
     h->d_track.reserve(job.n_scratch_points * sizeof(KnnTrack));
     // P2Plane: per-point plane (k_icp_fit) and the flag that says it still belongs to the point's current neighbours
@@ -334,12 +338,48 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     h->d_ringc.reserve(2 * sizeof(unsigned int));
     // k_icp_post re-zeroes the counters after every use; the first evaluation of a job starts from a known state
     if (!(nn_mode & kNnSeeds)) LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, 2 * sizeof(unsigned int), h->stream));
-    if (job.n_tiles == 0) return;
+    if (job.n_tiles == 0) return nullptr;
     const RingQueue queue{h->d_ringc.as<unsigned int>(), h->d_ringq.as<uint2>()};
+    // P2Plane, tracked iterations: search + residual + normal equations in one pass (icp_fused.cuh)
+    static const int fused_on = getenv("LOCREG_FUSED") ? atoi(getenv("LOCREG_FUSED")) : 0;
+    const bool fused = METHOD == kIcpP2Plane && (nn_mode & kNnFused) && !gate && !nn_idx && fused_on;
+    double* partials_b = h->d_partials.as<double>() + static_cast<size_t>(job.n_tiles) * kPartialDoubles;
+    // searches that look at every point of the tile: candidate lists staged in shared memory (icp_staged.cuh)
+    // LOCREG_STAGED: bit 0 = the unseeded first iteration (measured 1.51 ms against 1.75 ms per 14.1 M points), bit 1 =
+    // seeded searches, bit 2 = the first tracked one (both measured slower than k_icp_nn, 1.8 against 1.5-1.7 ms: with
+    // good seeds the thread-per-query scan rejects nearly every candidate with one comparison, the branch-free selection
+    // pays its compare-exchange chain for all of them)
+    static const int staged_on = getenv("LOCREG_STAGED") ? atoi(getenv("LOCREG_STAGED")) : 1;
+    int staged_mode = -1;
+    if (map.nbr_slots != nullptr) {
+        if (nn_mode == kNnTwoPass && (staged_on & 1)) staged_mode = 0;
+        else if (nn_mode == kNnSeeds && (staged_on & 2)) staged_mode = 1;
+        else if ((nn_mode & kNnTrack) && (nn_mode & kNnFirstTrack) && (staged_on & 4)) staged_mode = 2;
+    }
     // Queries stage 1 cannot finish: a small job (one scan) gives each of them a warp (lowest latency, the GPU is idle
     // anyway); a large job keeps one query per thread (most requests in flight).
     prof_mark(h, 0, true);
-    if (nn_mode & kNnTrack)
+    if (fused)
+    {
+        h->d_rescanq.reserve(job.n_scratch_points * sizeof(uint2));
+        h->d_rescanc.reserve(2 * sizeof(unsigned int));
+        const RingQueue rescan{h->d_rescanc.as<unsigned int>(), h->d_rescanq.as<uint2>()};
+        LR_CUDA(cudaMemsetAsync(h->d_rescanc.p, 0, 2 * sizeof(unsigned int), h->stream));
+        LR_LAUNCH(k_icp_track_p2plane, job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
+                  h->d_track.as<KnnTrack>(), rescan, h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(), h->d_partials.as<double>());
+        const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * 8));
+        LR_LAUNCH(k_icp_rescan, g, 128, 0, h->stream, map, job.bv, job.states, h->d_nnpos.as<unsigned int>(), h->d_same.as<unsigned char>(),
+                  h->d_track.as<KnnTrack>(), queue, rescan);
+    }
+    else if (staged_mode >= 0) {
+        unsigned char* pv = cache ? h->d_same.as<unsigned char>() : nullptr;
+        if (staged_mode == 0)
+            LR_LAUNCH((k_icp_nn_staged<K, 0>), job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, h->d_nnpos.as<unsigned int>(), pv, h->d_track.as<KnnTrack>(), queue);
+        else if (staged_mode == 1)
+            LR_LAUNCH((k_icp_nn_staged<K, 1>), job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, h->d_nnpos.as<unsigned int>(), pv, h->d_track.as<KnnTrack>(), queue);
+        else
+            LR_LAUNCH((k_icp_nn_staged<K, 2>), job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, h->d_nnpos.as<unsigned int>(), pv, h->d_track.as<KnnTrack>(), queue);
+    } else if (nn_mode & kNnTrack)
         LR_LAUNCH((k_icp_nn<K, true>), job.n_tiles, kTile, 0, h->stream, map, job.bv, job.states, ignore_stop, nn_mode, h->d_nnpos.as<unsigned int>(),
                   cache ? h->d_same.as<unsigned char>() : nullptr, h->d_track.as<KnnTrack>(), queue);
     else
@@ -363,6 +403,18 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
     }
     prof_mark(h, 3, false);
     prof_mark(h, 1, true);
+    if (fused) {
+        const unsigned int group = small ? 1u : static_cast<unsigned int>(kPendGroup);
+        const RingQueue rescan{h->d_rescanc.as<unsigned int>(), h->d_rescanq.as<uint2>()};
+        const unsigned int gf = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + kFitChunk - 1) / kFitChunk, static_cast<size_t>(h->num_sms) * 4));
+        LR_LAUNCH(k_icp_fit_queue, gf, 128, 0, h->stream, map, h->icp_params(), h->d_nnpos.as<unsigned int>(), h->d_same.as<unsigned char>(),
+                  h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(), rescan);
+        LR_LAUNCH(k_icp_pending, (job.n_tiles + group - 1) / group, kTile, 0, h->stream, h->icp_params(), job.bv, job.states, ignore_stop,
+                  h->d_same.as<unsigned char>(), h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(), group, partials_b,
+                  h->d_ringc.as<unsigned int>());
+        prof_mark(h, 1, false);
+        return partials_b;
+    }
     if (cache) {
         // a single scan spreads its tiles over the SMs (latency); a batch compacts over 16 tiles per block (throughput).
         // The same kernel either way: batch results equal those of single ScanMatch calls bit for bit.
@@ -374,12 +426,13 @@ void icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_stop, int n
               h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx, h->d_ringc.as<unsigned int>(),
               cache ? h->d_plane.as<double>() : nullptr, cache ? h->d_pstat.as<unsigned char>() : nullptr);
     prof_mark(h, 1, false);
+    return nullptr;
 }
 template <int METHOD>
-void icp_launch_solve(locreg_handle* h, const IcpJob& job, int mode, double* acc_out) {
+void icp_launch_solve(locreg_handle* h, const IcpJob& job, int mode, double* acc_out, const double* partials_b = nullptr) {
     prof_mark(h, 2, true);
     LR_LAUNCH(k_icp_solve<METHOD>, (job.bv.S + 3) / 4, 128, 0, h->stream, h->icp_params(), job.bv, job.states,
-              h->d_partials.as<double>(), mode, acc_out);
+              h->d_partials.as<double>(), partials_b, mode, acc_out);
     prof_mark(h, 2, false);
 }
 // The whole Gauss-Newton loop, queued on the stream without a host round-trip; stopped scans make their tiles exit.
@@ -389,13 +442,15 @@ void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
         static const int tp_iters = getenv("LOCREG_TWOPASS_ITERS") ? atoi(getenv("LOCREG_TWOPASS_ITERS")) : 1;  // iterations whose scan uses the threshold pre-pass (the unseeded one; 1 measured best: 11.2 ms vs 11.5 at 2, 12.0 at 3)
         static const int track = getenv("LOCREG_TRACK") ? atoi(getenv("LOCREG_TRACK")) : 1;  // 0: every query scans its list every time
         static const int track_from = getenv("LOCREG_TRACK_FROM") ? atoi(getenv("LOCREG_TRACK_FROM")) : 3;  // measured: 2 and 3 alike, 4 +1 % on batches; single scans converge sooner
-        const int seeded = track && it >= track_from ? (kNnSeeds | kNnTrack) : kNnSeeds;
-        icp_launch_eval<METHOD>(h, job, 0, it == 0 ? kNnTwoPass : (it < tp_iters ? (kNnSeeds | kNnTwoPass) : seeded), nullptr, nullptr);
-        icp_launch_solve<METHOD>(h, job, 1, nullptr);
+        // the first tracked iteration searches every point (no margins yet): the three-kernel pipeline; from then on the
+        // streaming pass of icp_fused.cuh (P2Plane)
+        const int seeded = track && it >= track_from ? (kNnSeeds | kNnTrack | (it > track_from ? kNnFused : kNnFirstTrack)) : kNnSeeds;
+        const double* pb = icp_launch_eval<METHOD>(h, job, 0, it == 0 ? kNnTwoPass : (it < tp_iters ? (kNnSeeds | kNnTwoPass) : seeded), nullptr, nullptr);
+        icp_launch_solve<METHOD>(h, job, 1, nullptr, pb);
     }
     if (final_eval) {
-        icp_launch_eval<METHOD>(h, job, 1, h->opt.max_iteration > 0 ? kNnSeeds : kNnTwoPass, nullptr, nullptr);
-        icp_launch_solve<METHOD>(h, job, 0, nullptr);
+        const double* pb = icp_launch_eval<METHOD>(h, job, 1, h->opt.max_iteration > 0 ? kNnSeeds : kNnTwoPass, nullptr, nullptr);
+        icp_launch_solve<METHOD>(h, job, 0, nullptr, pb);
     }
 }
 #define ICP_DISPATCH(h, CALL)                                              \
