@@ -5,3 +5,4 @@ see DESIGN.md for the scope and INTEGRATION.md for the drop-in binding.
 """
 from .registration import (IcpMethod, IcpOptions, IcpRegistration, NdtMethod, NdtNearbyType, NdtOptions,  # noqa: F401
                            NdtRegistration, LocTracker, LioTracker, se3_inv, se3_mul)
+from ._lib import LOOP_GRAPH, LOOP_PERSISTENT  # noqa: F401

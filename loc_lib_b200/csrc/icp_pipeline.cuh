@@ -212,14 +212,15 @@ constexpr int kNnFused = 8;  // host-side only: run the evaluation through icp_f
 #ifndef LR_NN_TRACK_MIN_BLOCKS
 #define LR_NN_TRACK_MIN_BLOCKS LR_NN_MIN_BLOCKS
 #endif
+// The work of one block on one tile: the body of k_icp_nn, also called tile after tile by the persistent single-scan
+// kernel (icp_persist.cuh), which separates the calls by block barriers.
 template <int K, bool TRACKED>
-__global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView map, BatchView bv,
-                                                                    const AlignState* __restrict__ states, int ignore_stop,
-                                                                    int mode, unsigned int* __restrict__ nn_pos,
-                                                                    unsigned char* __restrict__ plane_valid, KnnTrack* track,
-                                                                    RingQueue queue) {
+__device__ __forceinline__ void icp_nn_tile(unsigned int tile, const VoxelMapView& map, const BatchView& bv,
+                                            const AlignState* __restrict__ states, int ignore_stop, int mode,
+                                            unsigned int* __restrict__ nn_pos, unsigned char* __restrict__ plane_valid, KnnTrack* track,
+                                            const RingQueue& queue) {
     __shared__ Pose T;
-    const TileCoord tc = locate_tile(bv, blockIdx.x);
+    const TileCoord tc = locate_tile(bv, tile);
     if (!tc.valid) return;
     const AlignState* st = states + tc.scan;
     if (st->stop && !ignore_stop) return;
@@ -303,6 +304,14 @@ __global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_N
     }
     tile_queue_append(!done, static_cast<unsigned int>(row), tc.scan, &blk_pending, &blk_done, staged, queue);
 }
+template <int K, bool TRACKED>
+__global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView map, BatchView bv,
+                                                                    const AlignState* __restrict__ states, int ignore_stop,
+                                                                    int mode, unsigned int* __restrict__ nn_pos,
+                                                                    unsigned char* __restrict__ plane_valid, KnnTrack* track,
+                                                                    RingQueue queue) {
+    icp_nn_tile<K, TRACKED>(blockIdx.x, map, bv, states, ignore_stop, mode, nn_pos, plane_valid, track, queue);
+}
 
 // Stage 2 of LARGE jobs (batches, relocalisation), one queued query per thread (knn_query_finish: corner lists, fine
 // shells, coarse levels).  With tens of thousands of queued queries the 32-queries-per-warp form keeps far more
@@ -314,7 +323,7 @@ __global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_N
 template <int K>
 __global__ void __launch_bounds__(128, LR_FINISH_MIN_BLOCKS) k_icp_nn_finish(VoxelMapView map, CoarseLevels coarse, BatchView bv,
                                                        const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
-                                                       RingQueue queue, unsigned int min_count) {
+                                                       KnnTrack* track, RingQueue queue, unsigned int min_count) {
     const unsigned int n = *queue.count;
     if (n < min_count) return;  // short queues are k_icp_nn_rings'
     // Queries differ several-fold in cost, so warps do not own a fixed share of the queue: each one takes the next
@@ -346,9 +355,17 @@ __global__ void __launch_bounds__(128, LR_FINISH_MIN_BLOCKS) k_icp_nn_finish(Vox
                 knn_offer(map.pts, nn, dis2_f32(qx, qy, qz, c.x, c.y, c.z), sp_j);
             }
         }
-        knn_query_finish<K>(map, coarse, qx, qy, qz, nn);
+        // a search that ends with the mid level's list leaves a margin behind, like a tracked stage-1 search: the far
+        // points of a scan (sparse parts of the map) take the shortcut in the next iterations instead of queueing again
+        float margin = -1.0f;
+        knn_query_finish<K>(map, coarse, qx, qy, qz, nn, track ? &margin : nullptr);
 #pragma unroll
         for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+        if (track) {
+            KnnTrack tr;
+            tr.qx = qx; tr.qy = qy; tr.qz = qz; tr.margin = margin;
+            track[q.x] = tr;
+        }
     }
 }
 
@@ -356,13 +373,10 @@ __global__ void __launch_bounds__(128, LR_FINISH_MIN_BLOCKS) k_icp_nn_finish(Vox
 // mostly idle, so what counts is the latency of the slowest query, and 32 lanes cut that ~10x.
 // Persistent warp-stride launch: the queue length is only known on the device.
 template <int K>
-__global__ void __launch_bounds__(128) k_icp_nn_rings(VoxelMapView map, CoarseLevels coarse, BatchView bv,
-                                                      const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
-                                                      RingQueue queue, unsigned int max_count) {
-    const unsigned int n = *queue.count;
-    if (n >= max_count) return;  // long queues are k_icp_nn_finish's
+__device__ __forceinline__ void icp_rings_warps(unsigned int n, unsigned int warp, unsigned int n_warps, const VoxelMapView& map,
+                                                const CoarseLevels& coarse, const BatchView& bv, const AlignState* __restrict__ states,
+                                                unsigned int* __restrict__ nn_pos, KnnTrack* track, const RingQueue& queue) {
     const unsigned int lane = threadIdx.x & 31;
-    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int e = warp; e < n; e += n_warps) {
         const uint2 q = queue.entries[e];
         // scratch rows and source points coincide for a batch; hypotheses of one scan share its points
@@ -384,13 +398,27 @@ __global__ void __launch_bounds__(128) k_icp_nn_rings(VoxelMapView map, CoarseLe
                 knn_offer(map.pts, nn, dis2_f32(qx, qy, qz, c.x, c.y, c.z), sp_j);
             }
         }
-        warp_query_finish<K>(map, coarse, qx, qy, qz, nn);
+        float margin = -1.0f;
+        warp_query_finish<K>(map, coarse, qx, qy, qz, nn, track ? &margin : nullptr);
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
             for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+            if (track) {  // (see k_icp_nn_finish)
+                KnnTrack tr;
+                tr.qx = qx; tr.qy = qy; tr.qz = qz; tr.margin = margin;
+                track[q.x] = tr;
+            }
         }
     }
+}
+template <int K>
+__global__ void __launch_bounds__(128) k_icp_nn_rings(VoxelMapView map, CoarseLevels coarse, BatchView bv,
+                                                      const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
+                                                      KnnTrack* track, RingQueue queue, unsigned int max_count) {
+    const unsigned int n = *queue.count;
+    if (n >= max_count) return;  // long queues are k_icp_nn_finish's
+    icp_rings_warps<K>(n, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, (gridDim.x * blockDim.x) >> 5, map, coarse, bv, states, nn_pos, track, queue);
 }
 
 // ---- the search on its own (locreg_knn parity probe): the same two stages on raw queries ---------------------------
@@ -490,15 +518,16 @@ constexpr int kFitGroup = 16;
 #ifndef LR_FIT_MIN_BLOCKS
 #define LR_FIT_MIN_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(kTile, LR_FIT_MIN_BLOCKS)
-k_icp_fit(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
-          const unsigned int* __restrict__ nn_pos, unsigned char* plane_valid, double* plane_cache, unsigned char* plane_stat,
-          unsigned int group) {
-    __shared__ TileCoord tcs[kFitGroup];
-    __shared__ unsigned int list[kFitGroup * kTile];
+// MAXG: the largest `group` the caller passes (sizes the shared-memory list)
+template <int MAXG>
+__device__ __forceinline__ void icp_fit_group(unsigned int block_index, const VoxelMapView& map, const IcpParams& prm, const BatchView& bv,
+                                              const AlignState* __restrict__ states, int ignore_stop, const unsigned int* __restrict__ nn_pos,
+                                              unsigned char* plane_valid, double* plane_cache, unsigned char* plane_stat, unsigned int group) {
+    __shared__ TileCoord tcs[MAXG];
+    __shared__ unsigned int list[MAXG * kTile];
     __shared__ unsigned int list_n;
     if (threadIdx.x < group) {
-        TileCoord c = locate_tile_thread(bv, blockIdx.x * group + threadIdx.x);
+        TileCoord c = locate_tile_thread(bv, block_index * group + threadIdx.x);
         if (c.valid && states[c.scan].stop && !ignore_stop) c.valid = false;
         tcs[threadIdx.x] = c;
     }
@@ -508,7 +537,7 @@ k_icp_fit(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __res
     // all of the thread's flags first (independent loads: one round trip instead of `group` of them), then the appends
     unsigned int need_bits = 0u;
 #pragma unroll
-    for (unsigned int g = 0; g < static_cast<unsigned int>(kFitGroup); ++g) {
+    for (unsigned int g = 0; g < static_cast<unsigned int>(MAXG); ++g) {
         if (g < group && tcs[g].valid && threadIdx.x < tcs[g].count) {
             const size_t row = static_cast<size_t>(tcs[g].out_base + tcs[g].first + threadIdx.x);
             need_bits |= (plane_valid[row] == 0 ? 1u : 0u) << g;
@@ -539,6 +568,12 @@ k_icp_fit(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __res
         plane_valid[row] = 1;
     }
 }
+__global__ void __launch_bounds__(kTile, LR_FIT_MIN_BLOCKS)
+k_icp_fit(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
+          const unsigned int* __restrict__ nn_pos, unsigned char* plane_valid, double* plane_cache, unsigned char* plane_stat,
+          unsigned int group) {
+    icp_fit_group<kFitGroup>(blockIdx.x, map, prm, bv, states, ignore_stop, nn_pos, plane_valid, plane_cache, plane_stat, group);
+}
 
 // Upper-triangle entry e = 0..20 of a 6x6 matrix -> its row (col = false) or column (col = true), 3 bits per entry.
 constexpr unsigned long long tri_table(bool col) {
@@ -568,18 +603,17 @@ struct RowSink {
 #define LR_POST_MIN_BLOCKS 6  // 40 registers; the fit lives in k_icp_fit, what is left is latency-bound
 #endif
 template <int METHOD>
-__global__ void __launch_bounds__(kTile, METHOD == kIcpP2Plane ? LR_POST_MIN_BLOCKS : 2)
-k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
-           const unsigned int* __restrict__ nn_pos, double* __restrict__ partials, unsigned char* gate, int* nn_idx,
-           unsigned int* ring_count, const double* __restrict__ plane_cache, const unsigned char* __restrict__ plane_stat) {
+__device__ __forceinline__ void icp_post_tile(unsigned int tile, const VoxelMapView& map, const IcpParams& prm, const BatchView& bv,
+                                              const AlignState* __restrict__ states, int ignore_stop, const unsigned int* __restrict__ nn_pos,
+                                              double* __restrict__ partials, unsigned char* gate, int* nn_idx,
+                                              const double* __restrict__ plane_cache, const unsigned char* __restrict__ plane_stat) {
     constexpr int K = METHOD == kIcpP2P ? 1 : 5;
     constexpr int ROWS = METHOD == kIcpP2Plane ? 1 : 3;  // residual rows per inlier (P2P, P2Line: 3-vector residuals)
     __shared__ Pose T;
     __shared__ double rows[kTile * ROWS * kRowStride + 1];  // + 1: the pad column of the last row (see the Gram step)
     __shared__ double gram[kTile / 32][64];
     __shared__ int counts[kTile / 32][2];
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ring_count[0] = 0u; ring_count[1] = 0u; }  // both search stages of this evaluation are done
-    const TileCoord tc = locate_tile(bv, blockIdx.x);
+    const TileCoord tc = locate_tile(bv, tile);
     if (!tc.valid) return;
     const AlignState* st = states + tc.scan;
     if (st->stop && !ignore_stop) return;
@@ -677,8 +711,16 @@ k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __re
             for (int w = 0; w < kTile / 32; ++w) c += counts[w][e - 28];
             t = static_cast<double>(c);
         }
-        partials[static_cast<size_t>(blockIdx.x) * kPartialDoubles + threadIdx.x] = t;
+        partials[static_cast<size_t>(tile) * kPartialDoubles + threadIdx.x] = t;
     }
+}
+template <int METHOD>
+__global__ void __launch_bounds__(kTile, METHOD == kIcpP2Plane ? LR_POST_MIN_BLOCKS : 2)
+k_icp_post(VoxelMapView map, IcpParams prm, BatchView bv, const AlignState* __restrict__ states, int ignore_stop,
+           const unsigned int* __restrict__ nn_pos, double* __restrict__ partials, unsigned char* gate, int* nn_idx,
+           unsigned int* ring_count, const double* __restrict__ plane_cache, const unsigned char* __restrict__ plane_stat) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ring_count[0] = 0u; ring_count[1] = 0u; }  // both search stages of this evaluation are done
+    icp_post_tile<METHOD>(blockIdx.x, map, prm, bv, states, ignore_stop, nn_pos, partials, gate, nn_idx, plane_cache, plane_stat);
 }
 
 // ---- K_C: per-scan reduction + Gauss-Newton update ------------------------------------------------------------

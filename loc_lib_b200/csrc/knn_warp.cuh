@@ -49,6 +49,61 @@ __device__ __forceinline__ void warp_merge(const float4* __restrict__ canon, Knn
     }
 }
 
+// warp_merge that also reports d6 = the smallest dis2 of any candidate left OUTSIDE the global set: what the merge
+// evicts from it, and the heads that stay behind in the private sets (sorted: a lane's head is its smallest).
+template <int K>
+__device__ __forceinline__ float warp_merge_track(const float4* __restrict__ canon, KnnResult<K>& res, KnnResult<K>& priv) {
+    const unsigned int lane = threadIdx.x & 31;
+    float evicted = INFINITY;
+    while (true) {
+        const unsigned int bits = priv.pos[0] != kNoPos ? __float_as_uint(priv.d2[0]) : 0x7f800001u;  // > +inf: no head
+        const unsigned int best = __reduce_min_sync(kFullMask, bits);
+        if (best > __float_as_uint(res.d2[K - 1])) break;
+        const bool tied = bits == best;
+        const unsigned int idx = tied ? static_cast<unsigned int>(knn_index_of(canon, priv.pos[0])) : 0x7fffffffu;
+        const unsigned int best_idx = __reduce_min_sync(kFullMask, idx);
+        const int src = __ffs(__ballot_sync(kFullMask, tied && idx == best_idx)) - 1;
+        const unsigned int wpos = __shfl_sync(kFullMask, priv.pos[0], src);
+        const float wd2 = __uint_as_float(best);
+        bool member = false;
+#pragma unroll
+        for (int j = 0; j < K; ++j) member = member || (res.pos[j] == wpos);
+        if (!member) {
+            if (!knn_accepts(canon, res, wd2, wpos)) break;
+            evicted = fminf(evicted, res.d2[K - 1]);  // INFINITY while the set is not full
+            knn_insert(canon, res, wd2, wpos);
+        }
+        if (lane == static_cast<unsigned int>(src)) {
+#pragma unroll
+            for (int j = 0; j + 1 < K; ++j) { priv.d2[j] = priv.d2[j + 1]; priv.pos[j] = priv.pos[j + 1]; }
+            priv.d2[K - 1] = INFINITY;
+            priv.pos[K - 1] = kNoPos;
+        }
+    }
+    // (a member met again that is still a head counts as left outside: d6 can only come out too small, never too large)
+    const float left = priv.pos[0] != kNoPos ? priv.d2[0] : INFINITY;
+    const unsigned int m = __reduce_min_sync(kFullMask, __float_as_uint(fminf(left, evicted)));
+    return __uint_as_float(m);
+}
+// warp_scan_list with the bookkeeping of knn_scan_list's tracked form: returns d6 over the whole list.
+template <int K>
+__device__ __forceinline__ float warp_scan_list_track(const float4* __restrict__ pts, const float4* __restrict__ canon, KnnResult<K>& res,
+                                                      float qx, float qy, float qz, unsigned int beg, unsigned int cnt) {
+    const unsigned int lane = threadIdx.x & 31;
+    KnnResult<K> priv;
+    knn_init(priv);
+    const float bound = res.d2[K - 1];
+    float rej = INFINITY;
+    for (unsigned int i = lane; i < cnt; i += 32) {
+        const float4 p = pts[beg + i];
+        const float d2 = dis2_f32(qx, qy, qz, p.x, p.y, p.z);
+        if (d2 <= bound) knn_offer_track(canon, priv, d2, static_cast<unsigned int>(float_as_int(p.w)), rej);
+        else rej = fminf(rej, d2);  // fminf drops the NaN of a masked duplicate
+    }
+    const float d6 = warp_merge_track<K>(canon, res, priv);
+    return fminf(d6, __uint_as_float(__reduce_min_sync(kFullMask, __float_as_uint(rej))));
+}
+
 // One contiguous neighbourhood list (entries carry the canonical position in w), lanes striding over it.
 template <int K>
 __device__ __forceinline__ void warp_scan_list(const float4* __restrict__ pts, const float4* __restrict__ canon, KnnResult<K>& res,
@@ -146,11 +201,14 @@ __device__ __forceinline__ bool warp_query_rings(const VoxelMapView& m, float qx
 }
 
 // Everything after stage 1 for one query, by one warp (see knn_query_finish for the escalation logic).
+// margin (optional): receives the KnnTrack margin when the search ends with the mid level's list (the stage-2 form of
+// knn_query_fast_track: the list holds every point of the mid box, so the scan knows d6), else -1.
 template <int K>
 __device__ __forceinline__ void warp_query_finish(const VoxelMapView& m, const CoarseLevels& coarse, float qx, float qy, float qz,
-                                                  KnnResult<K>& res) {
+                                                  KnnResult<K>& res, float* margin = nullptr) {
     const unsigned int lane = threadIdx.x & 31;
     const bool have_mid = coarse.mid.n_pts != 0;
+    if (margin) *margin = -1.0f;
     if (have_mid) {  // knn_query_mid, lists and shells scanned cooperatively
         const VoxelMapView& md = coarse.mid;
         const bool have_coarse = coarse.lv[0].n_pts != 0;
@@ -159,8 +217,16 @@ __device__ __forceinline__ void warp_query_finish(const VoxelMapView& m, const C
         if (knn_uses_list(md, c)) {
             unsigned int beg = 0, cnt = 0;
             knn_find_list(md, c.fx, c.fy, c.fz, beg, cnt);
-            warp_scan_list<K>(md.pts, md.canon, res, qx, qy, qz, beg, cnt);
-            if (knn_list_final<K>(md, c, res)) return;
+            if (margin && res.pos[K - 1] != kNoPos) {
+                const float d6 = warp_scan_list_track<K>(md.pts, md.canon, res, qx, qy, qz, beg, cnt);
+                if (knn_list_final<K>(md, c, res)) {
+                    *margin = knn_track_margin<K>(md, c, res, d6, qx, qy, qz);
+                    return;
+                }
+            } else {
+                warp_scan_list<K>(md.pts, md.canon, res, qx, qy, qz, beg, cnt);
+                if (knn_list_final<K>(md, c, res)) return;
+            }
             boxes_done = 1;
         }
         if (!(have_coarse && c.R0 > kMidShells) &&

@@ -17,6 +17,7 @@
 #include "filters.cuh"
 #include "icp_fused.cuh"
 #include "icp_staged.cuh"
+#include "icp_persist.cuh"
 #include "nccl_dyn.h"
 
 #include <nvtx3/nvToolsExt.h>
@@ -391,14 +392,17 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
     // below kWarpFinishMax entries the warp-per-query kernel takes the queue (what matters is the latency of the
     // slowest query), from there on the thread-per-query kernel (throughput).  A small job never gets there.
     constexpr unsigned int kWarpFinishMax = 16384;
+    // stage 2 leaves margins behind only while the loop tracks (LOCREG_TRACK=0: every query searches every time)
+    static const int track_env = getenv("LOCREG_TRACK") ? atoi(getenv("LOCREG_TRACK")) : 1;
+    KnnTrack* stage2_track = track_env ? h->d_track.as<KnnTrack>() : nullptr;
     {
         const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 3) / 4, static_cast<size_t>(h->num_sms) * 8));
-        LR_LAUNCH(k_icp_nn_rings<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue,
+        LR_LAUNCH(k_icp_nn_rings<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), stage2_track, queue,
                   small ? 0xFFFFFFFFu : kWarpFinishMax);
     }
     if (!small) {
         const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * LR_FINISH_MIN_BLOCKS));
-        LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), queue,
+        LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), stage2_track, queue,
                   kWarpFinishMax);
     }
     prof_mark(h, 3, false);
@@ -452,6 +456,73 @@ void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
         const double* pb = icp_launch_eval<METHOD>(h, job, 1, h->opt.max_iteration > 0 ? kNnSeeds : kNnTwoPass, nullptr, nullptr);
         icp_launch_solve<METHOD>(h, job, 0, nullptr, pb);
     }
+}
+// One scan, whole loop in ONE cooperative launch (icp_persist.cuh).  Returns false when the job does not suit it (then
+// the per-iteration pipeline runs): the persistent grid holds two blocks per SM, a scan of more tiles than 8x that would
+// serialise what the pipeline spreads over the whole GPU.
+template <int METHOD>
+bool icp_run_persistent(locreg_handle* h, const IcpJob& job) {
+    constexpr int K = METHOD == kIcpP2P ? 1 : 5;
+    static const int persist_on = getenv("LOCREG_ICP_PERSIST") ? atoi(getenv("LOCREG_ICP_PERSIST")) : 1;
+    if (!persist_on || h->profile || job.bv.S != 1 || job.n_tiles == 0 || h->opt.max_iteration <= 0) return false;
+    int per_sm = 0;
+    LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persist<METHOD>, kTile, 0));
+    if (per_sm < 1) return false;
+    const unsigned int capacity = static_cast<unsigned int>(per_sm) * static_cast<unsigned int>(h->num_sms);
+    if (job.n_tiles > 8u * capacity) return false;
+    const VoxelMapView map = h->icp_map.view();
+    const bool cache = METHOD == kIcpP2Plane;
+    h->d_nnpos.reserve(job.n_scratch_points * K * sizeof(unsigned int));
+    h->d_partials.reserve(2 * static_cast<size_t>(job.n_tiles) * kPartialDoubles * sizeof(double));
+    h->d_ringq.reserve(job.n_scratch_points * sizeof(uint2));
+    h->d_track.reserve(job.n_scratch_points * sizeof(KnnTrack));
+    h->d_same.reserve(job.n_scratch_points);
+    h->d_plane.reserve(job.n_scratch_points * 4 * sizeof(double));
+    h->d_pstat.reserve(job.n_scratch_points);
+    h->d_ringc.reserve(2 * sizeof(unsigned int));
+    LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, 2 * sizeof(unsigned int), h->stream));
+    (void)cache;
+    // every block of the grid lends its warps to the stage-2 queue, so the grid is the full co-resident capacity even
+    // when the scan has fewer tiles
+    unsigned int grid = capacity;
+    CoarseLevels coarse = h->coarse_views();
+    IcpParams prm = h->icp_params();
+    BatchView bv = job.bv;
+    AlignState* st = job.states;
+    unsigned int n_tiles = job.n_tiles;
+    unsigned int* nn_pos = h->d_nnpos.as<unsigned int>();
+    unsigned char* pv = h->d_same.as<unsigned char>();
+    KnnTrack* track = h->d_track.as<KnnTrack>();
+    RingQueue queue{h->d_ringc.as<unsigned int>(), h->d_ringq.as<uint2>()};
+    double* plane = h->d_plane.as<double>();
+    unsigned char* pstat = h->d_pstat.as<unsigned char>();
+    double* partials = h->d_partials.as<double>();
+    static const int track_on = getenv("LOCREG_TRACK") ? atoi(getenv("LOCREG_TRACK")) : 1;
+    static const int track_from_env = getenv("LOCREG_TRACK_FROM") ? atoi(getenv("LOCREG_TRACK_FROM")) : 3;
+    int track_from = track_on ? track_from_env : 0x7fffffff;
+    VoxelMapView mapv = map;
+    // LOCREG_PERSIST_STAMPS=1 (tools): phase time stamps of block 0, printed after the launch
+    static const bool stamps = getenv("LOCREG_PERSIST_STAMPS") != nullptr;
+    unsigned long long* dbg = nullptr;
+    if (stamps) {
+        h->d_misc.reserve(64 + 6 * 64 * sizeof(unsigned long long));
+        dbg = reinterpret_cast<unsigned long long*>(h->d_misc.as<unsigned char>() + 64);
+        LR_CUDA(cudaMemsetAsync(dbg, 0, 6 * 64 * sizeof(unsigned long long), h->stream));
+    }
+    void* args[] = {&mapv, &coarse, &prm, &bv, &st, &n_tiles, &nn_pos, &pv, &track, &queue, &plane, &pstat, &partials, &track_from, &dbg};
+    LR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_icp_persist<METHOD>), dim3(grid), dim3(kTile), args, 0, h->stream));
+    ++g_launch_count;
+    if (stamps) {
+        unsigned long long t[6 * 64];
+        LR_CUDA(cudaMemcpyAsync(t, dbg, sizeof(t), cudaMemcpyDeviceToHost, h->stream));
+        LR_CUDA(cudaStreamSynchronize(h->stream));
+        for (int it = 0; it < std::min(h->opt.max_iteration, 64) && t[it * 6]; ++it)
+            fprintf(stderr, "persist it %2d: search %6.1f us  barrier %5.1f  stage2 %6.1f  fit+post %6.1f  barrier %5.1f  | iteration %6.1f us\n", it,
+                    (t[it * 6 + 1] - t[it * 6]) * 1e-3, (t[it * 6 + 2] - t[it * 6 + 1]) * 1e-3, (t[it * 6 + 3] - t[it * 6 + 2]) * 1e-3,
+                    (t[it * 6 + 4] - t[it * 6 + 3]) * 1e-3, (t[it * 6 + 5] - t[it * 6 + 4]) * 1e-3,
+                    ((it + 1 < h->opt.max_iteration && t[(it + 1) * 6] ? t[(it + 1) * 6] : t[it * 6 + 5]) - t[it * 6]) * 1e-3);
+    }
+    return true;
 }
 #define ICP_DISPATCH(h, CALL)                                              \
     switch ((h)->opt.method) {                                             \
@@ -686,7 +757,11 @@ int locreg_align(locreg_handle* h, const float* src, size_t n, size_t stride, co
             NDT_DISPATCH(h, ndt_run_align(h, PB, src4, static_cast<unsigned int>(n)));
         } else {
             const IcpJob job = icp_single_job(h, src4, static_cast<unsigned int>(n));
-            ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
+            bool ran = false;
+            // (P2P / P2Line stage three residual rows per point: their tile bodies together exceed the static shared memory
+            // of one kernel, so they keep the per-iteration pipeline)
+            if (h->opt.loop_mode == LOCREG_LOOP_PERSISTENT && h->opt.method == LOCREG_ICP_P2PLANE) ran = icp_run_persistent<kIcpP2Plane>(h, job);
+            if (!ran) ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
         }
         AlignState* st = h->d_state.as<AlignState>();
         const size_t bytes = n * stride;

@@ -719,27 +719,43 @@ struct CoarseLevels {
 // Stage 2 through the mid level: one list of the mid level covers a box three mid cells wide around the query - what
 // the corner lists and the first fine shells would have to collect from up to eight lists and dozens of hash-probed
 // blocks is one probe and one contiguous scan here.  Returns true when `res` is final; false: coarse levels next.
+// margin (optional): the KnnTrack margin when the search ends with the list (which holds every point of the mid box, so
+// a seeded scan knows d6 as in knn_query_fast_track), else -1.
 template <int K>
-LR_HD bool knn_query_mid(const VoxelMapView& md, bool have_coarse, float qx, float qy, float qz, KnnResult<K>& res) {
+LR_HD bool knn_query_mid(const VoxelMapView& md, bool have_coarse, float qx, float qy, float qz, KnnResult<K>& res,
+                         float* margin = nullptr) {
     const KnnCellFrame c = knn_frame(md, qx, qy, qz);
     int boxes_done = 0;
+    if (margin) *margin = -1.0f;
     if (knn_uses_list(md, c)) {
         unsigned int beg = 0, cnt = 0;
         knn_find_list(md, c.fx, c.fy, c.fz, beg, cnt);
         LR_STAT(3, 1); LR_STAT(4, cnt);  // mid lists scanned, candidates
-        knn_scan_list<K>(md.pts, md.canon, res, qx, qy, qz, beg, cnt, res.pos[K - 1] == kNoPos);
-        if (knn_list_final<K>(md, c, res)) return true;
+        if (margin && res.pos[K - 1] != kNoPos) {
+            float d6 = INFINITY;
+            knn_scan_list<K>(md.pts, md.canon, res, qx, qy, qz, beg, cnt, false, &d6);
+            if (knn_list_final<K>(md, c, res)) {
+                *margin = knn_track_margin<K>(md, c, res, d6, qx, qy, qz);
+                return true;
+            }
+        } else {
+            knn_scan_list<K>(md.pts, md.canon, res, qx, qy, qz, beg, cnt, res.pos[K - 1] == kNoPos);
+            if (knn_list_final<K>(md, c, res)) return true;
+        }
         boxes_done = 1;
     }
     if (have_coarse && c.R0 > kMidShells) return false;
     return knn_query_rings<K>(md, qx, qy, qz, res, boxes_done, have_coarse ? kMidShells : kBruteForceShell);
 }
 template <int K>
-LR_HD void knn_query_finish(const VoxelMapView& m, const CoarseLevels& coarse, float qx, float qy, float qz, KnnResult<K>& res) {
+LR_HD void knn_query_finish(const VoxelMapView& m, const CoarseLevels& coarse, float qx, float qy, float qz, KnnResult<K>& res,
+                            float* margin = nullptr) {
     const bool have_coarse = coarse.lv[0].n_pts != 0;
+    if (margin) *margin = -1.0f;
     if (coarse.mid.n_pts != 0) {
         LR_STAT(2, 1);  // queries entering stage 2a
-        if (knn_query_mid<K>(coarse.mid, have_coarse, qx, qy, qz, res)) return;
+        if (knn_query_mid<K>(coarse.mid, have_coarse, qx, qy, qz, res, margin)) return;
+        if (margin) *margin = -1.0f;
     } else {
         const KnnCellFrame c = knn_frame(m, qx, qy, qz);
         int boxes_done = knn_uses_list(m, c) ? 1 : 0;

@@ -2,8 +2,9 @@
 too slow to run on everything: size-independent properties plus oracle spot checks on samples.
 
   * k-NN: a sample of the transformed scan points against brute force over the whole 1 M-point map (bit-exact);
-  * batch == single: every scan of a batch gets the same pose as its own ScanMatch call (bit-identical: the
-    pipeline sums per-tile partials in tile order either way);
+  * batch == single: every scan of a batch gets the same pose as its own ScanMatch call - bit-identical through the
+    per-iteration pipeline (loop_mode 1: per-tile partials summed in tile order either way), and to 1e-9 through the
+    one-launch persistent kernel (loop_mode 0, the default: the same partial rows summed in another fixed order);
   * registration recovers the ground truth the scans were generated from (the synthetic world is the fixture);
   * idempotence: restarting from the converged pose moves it by less than the convergence threshold;
   * relocalisation: argmin == numpy argmin of the returned scores, ties to the lowest index; the sharded form
@@ -55,11 +56,21 @@ def test_fullsize_knn_sample_vs_brute_force(full):
 def test_fullsize_batch_equals_single_and_recovers_ground_truth(full):
     clouds = np.concatenate(full.scans)
     offsets = np.concatenate([[0], np.cumsum([len(s) for s in full.scans])]).astype(np.int64)
+    import loc_lib_b200 as L
     poses, results = full.reg.ScanMatchBatch(clouds, offsets, full.init)
+    piped = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=10, eps_=0.0, loop_mode=L.LOOP_GRAPH))
+    piped.SetInputTarget(full.map)
     for i in range(full.S):
-        _, _, single = full.reg.ScanMatch(full.scans[i], full.init[i], want_cloud=False)
+        _, _, single = piped.ScanMatch(full.scans[i], full.init[i], want_cloud=False)
         assert np.array_equal(single, poses[i])
-        assert full.reg.last_result == results[i]
+        assert piped.last_result == results[i]
+        _, _, one_launch = full.reg.ScanMatch(full.scans[i], full.init[i], want_cloud=False)
+        dr, dt = pose_delta(one_launch, poses[i])
+        assert dr < 1e-9 and dt < 1e-9
+        assert full.reg.last_timing()[1] <= 2  # the loop is ONE launch (+ nothing else: no cloud requested)
+        r1 = full.reg.last_result
+        assert (r1["iters"], r1["updates"], r1["n_effective"], r1["n_inlier"]) == \
+            (results[i]["iters"], results[i]["updates"], results[i]["n_effective"], results[i]["n_inlier"])
         assert results[i]["iters"] == 10 and results[i]["degenerate"] == 0
         dr, dt = pose_delta(poses[i], full.gt[i])
         assert dr < 2e-3 and dt < 0.03  # 2 cm range noise, 1 cm map jitter
