@@ -138,3 +138,116 @@ def test_fullsize_relocalise_argmin_and_sharding(full):
         key = D.pack_score(sc, rank + gi * 3)
         best = key if best is None else min(best, key)
     assert D.unpack_score(best)[1] == idx
+
+
+# ---------------------------------------------------------------------------------------------- config 5 at scale
+def test_fullsize_relocalise_4096_hypotheses_with_oracle_spot_checks(full):
+    """A 16 x 16 xy grid (0.5 m pitch) x 16 yaws around the truth = 4096 hypotheses of one scan through the wave logic of
+    locreg_relocalise: argmin == numpy's over the returned scores, the winner sits at the truth, and a sample of
+    hypotheses - near, far, rotated by 180 degrees - agrees with the oracle run on the same start pose."""
+    gt = full.gt[7]
+    g = (np.arange(16) - 7.5) * 0.5
+    hyp = []
+    ax, ay, az, aw = gt[:4]
+    for k in range(16):
+        a = k * np.pi / 8
+        bz, bw = np.sin(a / 2), np.cos(a / 2)
+        q = np.array([ax * bw + ay * bz, ay * bw - ax * bz, az * bw + aw * bz, aw * bw - az * bz])
+        for y in g:
+            for x in g:
+                hyp.append(np.concatenate([q, [gt[4] + x, gt[5] + y, gt[6]]]))
+    hyp = np.array(hyp)
+    assert len(hyp) == 4096
+    pose, idx, score, scores, poses = full.reg.Relocalise(full.scans[7], hyp, want_all=True)
+    f32 = np.float32(scores)
+    assert idx == int(np.lexsort((np.arange(len(f32)), f32))[0])
+    assert np.array_equal(pose, poses[idx]) and score == scores[idx]
+    assert idx < 256 and pose_delta(pose, gt)[1] < 0.03  # yaw 0, and at the truth
+    ref = O.OracleIcp(method=O.P2PLANE, max_iteration=10, eps=0.0, nn_mode=O.NN_EXACT_TIEBREAK, skip_nonfinite=1)
+    ref.set_target(full.map)
+    for i in (idx, 0, 8 * 256 + 100, 4095):
+        rpose, _, _, _ = ref.align(full.scans[7], hyp[i], want_cloud=False)
+        _, _, _, rres, _, _ = ref.compute_hb(full.scans[7], rpose, False, False)
+        dr, dt = pose_delta(poses[i], rpose)
+        # the north-star gate for the winner; hypotheses that end in a wrong basin are ill-conditioned (near-singular H)
+        tol = (1e-5, 1e-4) if i == idx else (1e-3, 1e-2)
+        assert dr < tol[0] and dt < tol[1], (i, dr, dt)
+        if i == idx:
+            assert abs(scores[i] - rres["sum_sq_res"] / rres["n_inlier"]) <= 1e-5 * scores[i]
+
+
+# ---------------------------------------------------------------------------------------------- config 3 at scale
+@pytest.fixture(scope="module")
+def ndt_full():
+    import loc_lib_b200 as L
+    from loc_lib_b200 import synth
+
+    class F:
+        pass
+    f = F()
+    f.world = synth.World(900.0)
+    f.map = f.world.sample_map(20_000_000)
+    f.gt = f.world.poses(3)
+    f.scans = [f.world.scan(g, beams=128, azimuth=1953, seed=synth.SEED_SCAN + i) for i, g in enumerate(f.gt)]
+    f.init = synth.perturb_poses(f.gt)
+    f.reg = L.NdtRegistration(L.NdtOptions(max_iteration_=10, eps_=0.0))
+    f.reg.SetInputTarget(f.map)
+    f.ref = O.OracleNdt(max_iteration=10, eps=0.0, skip_nonfinite=1)
+    f.ref.set_target(f.map)
+    return f
+
+
+def test_fullsize_ndt_grid_of_the_20m_point_map(ndt_full):
+    """SetDirectNdtTargetCloud on BASELINE config 3's map: every voxel of the oracle's grid, bit-exact keys / counts /
+    means (same summation order, no FMA), information matrices to 1e-9."""
+    k, mu, info, npts = ndt_full.reg.Voxels()
+    rk, rmu, rinfo, rn = ndt_full.ref.voxels()
+    assert len(k) == len(rk) > 1_000_000
+
+    def order(keys):
+        return np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
+    a, b = order(k), order(rk)
+    assert np.array_equal(k[a], rk[b]) and np.array_equal(npts[a], rn[b])
+    assert np.array_equal(mu[a], rmu[b])
+    scale = np.abs(rinfo[b]).reshape(len(rk), -1).max(axis=1)
+    err = np.abs(info[a] - rinfo[b]).reshape(len(rk), -1).max(axis=1)
+    assert np.all(err <= 1e-9 * scale)
+
+
+def test_fullsize_ndt_128_beam_scan_hb_and_pose(ndt_full):
+    """AlignNdt of a 128 x 1953-ray scan (~225 k points) against the 20 M-point map: per-point hit masks equal, H / B to
+    1e-6, final pose to the north-star tolerances - CENTER and NEARBY6 - and the batch kernel (one CTA per scan) against
+    single ScanMatch calls."""
+    import loc_lib_b200 as L
+    f = ndt_full
+    assert 200_000 < len(f.scans[0]) < 250_000
+    ok, H, B = f.reg.CaculateMatrixHAndB(f.scans[0], f.init[0])
+    rH, rB, rres, rhits = f.ref.compute_hb(f.scans[0], f.init[0])
+    hits, _ = f.reg.DebugPoints(f.scans[0], f.init[0], 0)
+    assert np.array_equal(hits, rhits) and f.reg.last_result["n_inlier"] == rres["n_inlier"]
+    assert np.linalg.norm(H - rH) < 1e-6 * np.linalg.norm(rH) and np.linalg.norm(B - rB) < 1e-6 * np.linalg.norm(rB)
+    singles = []
+    for i in range(3):
+        _, _, pose = f.reg.ScanMatch(f.scans[i], f.init[i], want_cloud=False)
+        singles.append(pose)
+        if i == 0:
+            rpose, _, rr, _ = f.ref.align(f.scans[0], f.init[0], want_cloud=False)
+            dr, dt = pose_delta(pose, rpose)
+            assert dr < 1e-5 and dt < 1e-4 and f.reg.last_result["iters"] == rr["iters"] == 10
+    # k_align_batch<NdtProblem>: the same three registrations as one batch
+    clouds = np.concatenate(f.scans)
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in f.scans])]).astype(np.int64)
+    poses, results = f.reg.ScanMatchBatch(clouds, offsets, f.init)
+    for i in range(3):
+        dr, dt = pose_delta(poses[i], singles[i])
+        assert dr < 1e-9 and dt < 1e-9  # another summation order (one CTA per scan), the same algorithm
+        assert results[i]["iters"] == 10 and results[i]["pose_written"] == 1
+    # CENTER mode on the same map
+    c = L.NdtRegistration(L.NdtOptions(max_iteration_=10, eps_=0.0, nearby_type_=L.NdtNearbyType.CENTER))
+    c.SetInputTarget(f.map)
+    cref = O.OracleNdt(max_iteration=10, eps=0.0, nearby6=0, skip_nonfinite=1)
+    cref.set_target(f.map)
+    _, _, pose = c.ScanMatch(f.scans[1], f.init[1], want_cloud=False)
+    rpose, _, _, _ = cref.align(f.scans[1], f.init[1], want_cloud=False)
+    dr, dt = pose_delta(pose, rpose)
+    assert dr < 1e-5 and dt < 1e-4
