@@ -55,7 +55,7 @@ __device__ __forceinline__ void tile_gram_store(const double* rows, const unsign
     double g0 = 0.0, g1 = 0.0;  // G[lane >> 2][2 * (lane & 3) + {0, 1}]
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-        const double a = wrows[4 * ks * kRowStride];
+        const double a = lane < 28 ? wrows[4 * ks * kRowStride] : 0.0;  // (column 7 does not exist, see k_icp_post)
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                      : "+d"(g0), "+d"(g1)
                      : "d"(a), "d"(a));

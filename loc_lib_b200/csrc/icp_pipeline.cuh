@@ -184,6 +184,23 @@ struct RingQueue {
 __device__ __forceinline__ void tile_queue_append(bool mine, unsigned int row, unsigned int scan, unsigned int* pending,
                                                   unsigned int* done, unsigned int* staged, const RingQueue& queue) {
     const unsigned int lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+#if defined(LR_APPEND_BARRIER)
+    // Checking build (compute-sanitizer racecheck does not model the fence + arrival-counter hand-over below and reports
+    // it as a hazard): the same append behind a block barrier.  profiles/ holds the racecheck logs of both builds.
+    if (mine) staged[atomicAdd(pending, 1u)] = row;
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    (void)done; (void)n_warps;
+    {
+        const unsigned int n = *pending;
+        if (n == 0u) return;
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(queue.count, n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (unsigned int i = lane; i < n; i += 32) queue.entries[base + i] = make_uint2(staged[i], scan);
+        return;
+    }
+#endif
     if (mine) staged[atomicAdd(pending, 1u)] = row;
     __syncwarp();
     unsigned int last = 0;
@@ -193,6 +210,7 @@ __device__ __forceinline__ void tile_queue_append(bool mine, unsigned int row, u
         __threadfence_block();  // the other warps' staged rows after having seen their arrivals
     }
     if (!__shfl_sync(0xffffffffu, last, 0)) return;
+    __syncwarp();  // lane 0's acquire fence orders the other lanes' reads below as well
     const unsigned int n = *reinterpret_cast<volatile unsigned int*>(pending);
     if (n == 0u) return;
     unsigned int base = 0;
@@ -666,8 +684,8 @@ __device__ __forceinline__ void icp_post_tile(unsigned int tile, const VoxelMapV
     // Per-warp Gram matrix G = R^T R of the warp's 32 * ROWS staged rows R = [J | r] on the fp64 tensor cores:
     // mma.m8n8k4 takes A (8 x 4, A[m][k] = R[4 ks + k][m]) and B (4 x 8, B[k][n] = R[4 ks + k][n]); a lane's A and B
     // fragments are the same element R[4 ks + (lane & 3)][lane >> 2], so one 8 B shared-memory load per lane feeds four
-    // rows - where one lane per matrix entry needed two loads and an FMA per row.  Column 7 does not exist (the load
-    // picks up the next row's first element): it only reaches row / column 7 of G, which nobody reads.
+    // rows - where one lane per matrix entry needed two loads and an FMA per row.  Column 7 does not exist: the lanes that
+    // would load it pass zeros, which only reach row / column 7 of G (nobody reads them).
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int eff_mask = __ballot_sync(0xffffffffu, sink.eff);
     __syncwarp();  // the warp's row stores are visible to its loads below
@@ -676,7 +694,9 @@ __device__ __forceinline__ void icp_post_tile(unsigned int tile, const VoxelMapV
     double g0 = 0.0, g1 = 0.0;  // G[lane >> 2][2 * (lane & 3) + {0, 1}]
 #pragma unroll
     for (int ks = 0; ks < 8 * ROWS; ++ks) {
-        const double a = wrows[4 * ks * kRowStride];
+        // (lanes 28..31 would read column 7 = the next row's first element, for the warp's last row another warp's
+        // data: they feed row / column 7 of G, which nobody reads, with zeros instead)
+        const double a = lane < 28 ? wrows[4 * ks * kRowStride] : 0.0;
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                      : "+d"(g0), "+d"(g1)
                      : "d"(a), "d"(a));

@@ -1,0 +1,52 @@
+"""compute-sanitizer target: every kernel family on a small scene (all methods, both loop modes, batch, relocalisation,
+stage-2 queues, incremental NDT, filters, the k-NN probe).  Run as
+    compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitize_small.py
+Sizes are tiny on purpose (the tools slow kernels down 10-100x); far-off queries are included so that the stage-2 search
+and its queue append - the barrier-free code - run."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import loc_lib_b200 as L
+from loc_lib_b200 import synth
+
+w = synth.World(60.0)
+m = w.sample_map(40_000)
+gt = w.poses(3)
+scans = [w.scan(g, beams=8, azimuth=180, seed=synth.SEED_SCAN + i) for i, g in enumerate(gt)]
+init = synth.perturb_poses(gt)
+far = init[0].copy(); far[4:] += [6.0, -5.0, 1.0]  # queries outside the lists: stage 2
+clouds = np.concatenate(scans)
+offsets = np.concatenate([[0], np.cumsum([len(s) for s in scans])]).astype(np.int64)
+done = []
+for method in (L.IcpMethod.P2PLANE, L.IcpMethod.P2P, L.IcpMethod.P2LINE):
+    for loop_mode in (L.LOOP_PERSISTENT, L.LOOP_GRAPH):
+        r = L.IcpRegistration(L.IcpOptions(method_=method, max_iteration_=5, eps_=0.0, loop_mode=loop_mode))
+        r.SetInputTarget(m)
+        r.ScanMatch(scans[0], init[0])
+        r.ScanMatch(scans[0], far, want_cloud=False)
+        done.append(f"icp{method}/loop{loop_mode}")
+    r.CaculateMatrixHAndB(scans[1], init[1])
+    r.ScanMatchBatch(clouds, offsets, init)
+    r.Relocalise(scans[0], np.stack([init[0], far, init[1]]), want_all=True)
+    r.Knn(m[:500, :3] + 0.01, 5 if method != L.IcpMethod.P2P else 1)
+    r.DebugPoints(scans[0], init[0], 5 if method != L.IcpMethod.P2P else 1)
+for nearby in (L.NdtNearbyType.CENTER, L.NdtNearbyType.NEARBY6):
+    for loop_mode in (L.LOOP_PERSISTENT, L.LOOP_GRAPH):
+        r = L.NdtRegistration(L.NdtOptions(max_iteration_=5, eps_=0.0, nearby_type_=nearby, loop_mode=loop_mode))
+        r.SetInputTarget(m)
+        r.ScanMatch(scans[0], init[0])
+        done.append(f"ndt{nearby}/loop{loop_mode}")
+    r.ScanMatchBatch(clouds, offsets, init)
+    r.Relocalise(scans[0], np.stack([init[0], far]), want_all=True)
+    r.CaculateMatrixHAndB(scans[1], init[1])
+r = L.NdtRegistration(L.NdtOptions(max_iteration_=5, eps_=0.0, method_=L.NdtMethod.INCREMENTAL_NDT, capacity_=3000))
+for part in (m[:15_000], m[10_000:30_000], m[25_000:]):
+    r.SetInputTarget(part)
+r.ScanMatch(scans[0], init[0])
+done.append("inc_ndt")
+pts = np.concatenate([clouds, np.full((3, 4), np.nan, np.float32)])
+r2 = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE))
+r2.RemoveNanPoint(pts); r2.BoxFilter(clouds, clouds[:, :3].min(0) / 2, clouds[:, :3].max(0) / 2); r2.VoxelFilter(clouds, 1.0)
+done.append("filters")
+print("sanitize_small ok:", ", ".join(done))
