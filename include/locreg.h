@@ -215,13 +215,16 @@ int locreg_set_global_map(locreg_handle* h, const float* xyz, size_t n, size_t s
 int locreg_reset_local_map(locreg_handle* h, const float* origin3, const float* half_size3, size_t* n_local);
 
 /* Lio's sliding local map of key frames (Lio::AddCloud, LocUtils/src/slam/3d/lio.cpp:238-307), kept on the device.
- * locreg_local_map_add_keyframe: key_frame = pcl::transformPointCloud(scan, pose) (float32 matrix, :244,:279) joins the
- * window (:281).  If the window then holds more than max_keyframes scans the oldest is dropped and the local map is
+ * locreg_local_map_add_keyframe: key_frame = pcl::transformPointCloud(scan, pose.matrix()) - the Matrix4d is passed
+ * without a cast (:243,:278), so PCL evaluates in double and casts once to float; ScanMatch's result cloud is the one
+ * that uses the float32 matrix - joins the window (:281).  If the window then holds more than max_keyframes scans the oldest is dropped and the local map is
  * rebuilt as the concatenation of the scans left (:283-292); otherwise the key frame is appended to the local map as it
  * stands, i.e. to the OUTPUT of the previous filter pass (:294-297).  The local map is voxel-grid filtered in place with
  * leaf size `leaf` (local_map_filter_ptr_->Filter, :299; leaf <= 0: NoFilter) and becomes the registration target
  * (:307) - for LOCREG_NDT_INCREMENTAL the key frame alone is added to the voxel cache (:301-303).  Nothing but the scan
- * crosses PCIe.  *n_local (may be NULL) receives the size of the local map.
+ * crosses PCIe.  *n_local (may be NULL) receives the size of the local map.  The call is transactional: when a step
+ * fails (out of memory, a voxel grid whose extent / leaf exceeds the 2^28-cell index space) the window and the local
+ * map are left as they were.
  * locreg_local_map_get copies the local map to the host (parity probe / PCD dump); locreg_local_map_clear forgets it. */
 int locreg_local_map_add_keyframe(locreg_handle* h, const float* scan_xyz, size_t n, size_t stride_bytes, const double* pose7,
                                   int32_t max_keyframes, float leaf, size_t* n_local);

@@ -304,6 +304,38 @@ __global__ void k_transform(const unsigned char* __restrict__ raw_in, unsigned c
     }
 }
 
+// pcl::transformPointCloud<PointT, double> (Lio's key frames, lio.cpp:243,278: pose.matrix() is a Matrix4d and is not cast):
+// m00*x + m01*y + m02*z + m03 in DOUBLE, left to right, no FMA, one cast to float.
+__global__ void k_transform_d(const unsigned char* __restrict__ raw_in, unsigned char* raw_out, size_t n, size_t stride,
+                              const double* __restrict__ pose7) {
+    __shared__ double m[12];
+    if (threadIdx.x == 0) {
+        Pose T;
+        pose_load(T, pose7);
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) m[r * 4 + c] = T.R[r * 3 + c];
+        }
+        m[3] = T.tx; m[7] = T.ty; m[11] = T.tz;
+    }
+    __syncthreads();
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float* p = reinterpret_cast<const float*>(raw_in + i * stride);
+        float* o = reinterpret_cast<float*>(raw_out + i * stride);
+        const float x = p[0], y = p[1], z = p[2];
+        const size_t words = stride / 4;
+        for (size_t w = 3; w < words; ++w) o[w] = p[w];
+        if (finite3(x, y, z)) {
+            const double xd = x, yd = y, zd = z;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                o[r] = static_cast<float>(LR_DADD(LR_DADD(LR_DADD(LR_DMUL(m[r * 4], xd), LR_DMUL(m[r * 4 + 1], yd)), LR_DMUL(m[r * 4 + 2], zd)), m[r * 4 + 3]));
+        } else {
+            o[0] = x; o[1] = y; o[2] = z;
+        }
+    }
+}
+
 // raw strided cloud -> float4 (x, y, z, 0)
 __global__ void k_pack_float4(const unsigned char* __restrict__ raw, size_t n, size_t stride, float4* out) {
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;

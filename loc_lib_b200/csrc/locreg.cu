@@ -99,7 +99,7 @@ struct locreg_handle {
     int comm_rank = 0, comm_world = 1;
     DevBuf d_gather_pose, d_gather_res, d_bcast;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
-        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_rescanq, d_rescanc, d_global, d_local, d_same, d_plane, d_pstat, d_track;
+        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_rescanq, d_rescanc, d_lmap_new, d_global, d_local, d_same, d_plane, d_pstat, d_track;
     size_t n_global = 0, global_stride = 0;  // Loc's global map kept on the device (locreg_set_global_map)
     // Lio's sliding local map (locreg_local_map_add_keyframe): transformed key frames + the filtered local map
     struct KeyFrame { void* p = nullptr; size_t n = 0; };
@@ -1349,47 +1349,67 @@ int locreg_local_map_add_keyframe(locreg_handle* h, const float* scan_xyz, size_
     if (!pose7 || max_keyframes < 1) { g_last_error = "null pose or max_keyframes < 1"; return LOCREG_E_ARG; }
     if (h && h->lmap_stride && h->lmap_stride != stride) { g_last_error = "key frames of one local map must share a point stride"; return LOCREG_E_ARG; }
     return guarded(h, [&]() {
-        // key_frame_scan = transformPointCloud(scan, pose)
+        // key_frame_scan = transformPointCloud(scan, pose) - the Scalar = double instantiation (pose.matrix() is a Matrix4d)
+        // The call is transactional: the window, the local map and its size change only after every step that can fail
+        // (allocations, the voxel grid's extent check) has succeeded.
         locreg_handle::KeyFrame kf;
         kf.n = n;
+        struct KfGuard {  // frees the new key frame's buffer unless the window has taken it over
+            void* p = nullptr;
+            ~KfGuard() { if (p) cudaFree(p); }
+        } guard;
         if (n) {
             stage_cloud(h, scan_xyz, n, stride, false);
             LR_CUDA(cudaMalloc(&kf.p, n * stride));
+            guard.p = kf.p;
             h->d_acc.reserve(32 * sizeof(double));
             LR_CUDA(cudaMemcpyAsync(h->d_acc.p, pose7, 7 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((n + 255) / 256, 4096));
-            LR_LAUNCH(k_transform, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>(), static_cast<unsigned char*>(kf.p), n, stride,
+            LR_LAUNCH(k_transform_d, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>(), static_cast<unsigned char*>(kf.p), n, stride,
                       h->d_acc.as<double>());
         }
-        h->lmap_stride = stride;
-        h->keyframes.push_back(kf);
         // the unfiltered local map: all scans of the window after a pop (:283-292), else the old map + the key frame (:296)
+        const bool pop = h->keyframes.size() + 1 > static_cast<size_t>(max_keyframes);
         size_t total = 0;
-        if (h->keyframes.size() > static_cast<size_t>(max_keyframes)) {
-            LR_CUDA(cudaStreamSynchronize(h->stream));
-            if (h->keyframes.front().p) cudaFree(h->keyframes.front().p);
-            h->keyframes.pop_front();
-            for (const auto& k : h->keyframes) total += k.n;
+        if (pop) {
+            bool first = true;
+            for (const auto& k : h->keyframes) { if (!first) total += k.n; first = false; }
+            total += n;
             h->d_lmap_tmp.reserve(std::max<size_t>(total * stride, 1));
             size_t at = 0;
+            first = true;
             for (const auto& k : h->keyframes) {
-                if (k.n) LR_CUDA(cudaMemcpyAsync(h->d_lmap_tmp.as<unsigned char>() + at * stride, k.p, k.n * stride, cudaMemcpyDeviceToDevice, h->stream));
-                at += k.n;
+                if (!first && k.n) LR_CUDA(cudaMemcpyAsync(h->d_lmap_tmp.as<unsigned char>() + at * stride, k.p, k.n * stride, cudaMemcpyDeviceToDevice, h->stream));
+                if (!first) at += k.n;
+                first = false;
             }
+            if (n) LR_CUDA(cudaMemcpyAsync(h->d_lmap_tmp.as<unsigned char>() + at * stride, kf.p, n * stride, cudaMemcpyDeviceToDevice, h->stream));
         } else {
             total = h->n_lmap + n;
             h->d_lmap_tmp.reserve(std::max<size_t>(total * stride, 1));
             if (h->n_lmap) LR_CUDA(cudaMemcpyAsync(h->d_lmap_tmp.p, h->d_lmap.p, h->n_lmap * stride, cudaMemcpyDeviceToDevice, h->stream));
             if (n) LR_CUDA(cudaMemcpyAsync(h->d_lmap_tmp.as<unsigned char>() + h->n_lmap * stride, kf.p, n * stride, cudaMemcpyDeviceToDevice, h->stream));
         }
-        // local_map_filter_ptr_->Filter(local_map_, local_map_)
-        h->d_lmap.reserve(std::max<size_t>(total * stride, 1));
+        // local_map_filter_ptr_->Filter(local_map_, local_map_): into a second buffer that replaces d_lmap only on success
+        h->d_lmap_new.reserve(std::max<size_t>(total * stride, 1));
+        size_t n_new = total;
         if (leaf > 0.0f && total) {
-            h->n_lmap = filter_voxel_grid(h->d_lmap_tmp.as<unsigned char>(), total, stride, leaf, h->d_lmap.as<unsigned char>(), h->stream);
-        } else {
-            if (total) LR_CUDA(cudaMemcpyAsync(h->d_lmap.p, h->d_lmap_tmp.p, total * stride, cudaMemcpyDeviceToDevice, h->stream));
-            h->n_lmap = total;
+            n_new = filter_voxel_grid(h->d_lmap_tmp.as<unsigned char>(), total, stride, leaf, h->d_lmap_new.as<unsigned char>(), h->stream);
+        } else if (total) {
+            LR_CUDA(cudaMemcpyAsync(h->d_lmap_new.p, h->d_lmap_tmp.p, total * stride, cudaMemcpyDeviceToDevice, h->stream));
         }
+        // ---- commit
+        if (pop) {
+            LR_CUDA(cudaStreamSynchronize(h->stream));
+            if (h->keyframes.front().p) cudaFree(h->keyframes.front().p);
+            h->keyframes.pop_front();
+        }
+        h->keyframes.push_back(kf);
+        guard.p = nullptr;
+        h->lmap_stride = stride;
+        std::swap(h->d_lmap.p, h->d_lmap_new.p);
+        std::swap(h->d_lmap.cap, h->d_lmap_new.cap);
+        h->n_lmap = n_new;
         if (n_local) *n_local = h->n_lmap;
         if (h->opt.method == LOCREG_NDT_INCREMENTAL) return set_target_impl(h, static_cast<const float*>(kf.p), kf.n, stride, true);
         return set_target_impl(h, h->d_lmap.as<float>(), h->n_lmap, stride, true);

@@ -246,28 +246,49 @@ LR_HD unsigned char ndt_point(const NdtMapView& map, const NdtParams& prm, const
 // (:181), so only its first branch (:186-198) is ever taken.  The statistics of a voxel are those of the points the
 // CURRENT cloud put into it (pts_ is cleared after every update): mean and covariance (/(n-1), math_utils.h:55-72) in
 // arrival order and info = (sigma + 1e-3 I)^-1 for two or more points, mu = the point and info = 100 I for one.
-LR_HD void inc_ndt_voxel_stats(const unsigned int* idx, unsigned int cnt, const void* xyz, size_t stride, NdtVoxel& out) {
+// The member points of a voxel come either as an index list (tests/hostsim) or as RUNS of consecutive point indices
+// (the device path: a scan line enters and leaves a voxel a few times, so a voxel's points are a handful of runs).
+struct IncMembersList {
+    const unsigned int* idx;
+    unsigned int cnt;
+    template <class F> LR_HD void for_each(F f) const {
+        for (unsigned int j = 0; j < cnt; ++j) f(idx[j]);
+    }
+    LR_HD unsigned int first() const { return idx[0]; }
+};
+struct IncRun { unsigned int first, len; };
+struct IncMembersRuns {
+    const IncRun* runs;
+    unsigned int n_runs;
+    template <class F> LR_HD void for_each(F f) const {
+        for (unsigned int r = 0; r < n_runs; ++r)
+            for (unsigned int j = 0; j < runs[r].len; ++j) f(runs[r].first + j);
+    }
+    LR_HD unsigned int first() const { return runs[0].first; }
+};
+template <class Members>
+LR_HD void inc_ndt_voxel_stats_of(const Members& mem, unsigned int cnt, const void* xyz, size_t stride, NdtVoxel& out) {
     if (cnt == 1) {
-        const float* p = reinterpret_cast<const float*>(static_cast<const char*>(xyz) + static_cast<size_t>(idx[0]) * stride);
+        const float* p = reinterpret_cast<const float*>(static_cast<const char*>(xyz) + static_cast<size_t>(mem.first()) * stride);
         out.mu[0] = p[0]; out.mu[1] = p[1]; out.mu[2] = p[2];
         for (int k = 0; k < 9; ++k) out.info[k] = (k % 4 == 0) ? 1e2 : 0.0;
         return;
     }
     double sx = 0, sy = 0, sz = 0;
-    for (unsigned int j = 0; j < cnt; ++j) {
-        const float* p = reinterpret_cast<const float*>(static_cast<const char*>(xyz) + static_cast<size_t>(idx[j]) * stride);
+    mem.for_each([&](unsigned int i) {
+        const float* p = reinterpret_cast<const float*>(static_cast<const char*>(xyz) + static_cast<size_t>(i) * stride);
         sx = LR_DADD(sx, static_cast<double>(p[0])); sy = LR_DADD(sy, static_cast<double>(p[1])); sz = LR_DADD(sz, static_cast<double>(p[2]));
-    }
+    });
     const double len = static_cast<double>(cnt);
     const double mx = sx / len, my = sy / len, mz = sz / len;
     double c[6] = {0, 0, 0, 0, 0, 0};  // xx xy xz yy yz zz
-    for (unsigned int j = 0; j < cnt; ++j) {
-        const float* p = reinterpret_cast<const float*>(static_cast<const char*>(xyz) + static_cast<size_t>(idx[j]) * stride);
+    mem.for_each([&](unsigned int i) {
+        const float* p = reinterpret_cast<const float*>(static_cast<const char*>(xyz) + static_cast<size_t>(i) * stride);
         const double dx = LR_DSUB(static_cast<double>(p[0]), mx), dy = LR_DSUB(static_cast<double>(p[1]), my),
                      dz = LR_DSUB(static_cast<double>(p[2]), mz);
         c[0] = LR_DADD(c[0], LR_DMUL(dx, dx)); c[1] = LR_DADD(c[1], LR_DMUL(dx, dy)); c[2] = LR_DADD(c[2], LR_DMUL(dx, dz));
         c[3] = LR_DADD(c[3], LR_DMUL(dy, dy)); c[4] = LR_DADD(c[4], LR_DMUL(dy, dz)); c[5] = LR_DADD(c[5], LR_DMUL(dz, dz));
-    }
+    });
     const double len1 = static_cast<double>(cnt - 1);
     // A = sigma + 1e-3 I (symmetric), info = adj(A) / det(A): Eigen's fixed-size 3x3 inverse is the cofactor formula
     const double a = c[0] / len1 + 1e-3, b = c[1] / len1, cc = c[2] / len1, d = c[3] / len1 + 1e-3, e = c[4] / len1,
@@ -280,6 +301,10 @@ LR_HD void inc_ndt_voxel_stats(const unsigned int* idx, unsigned int cnt, const 
     out.info[0] = A00 * inv; out.info[1] = A01 * inv; out.info[2] = A02 * inv;
     out.info[3] = A01 * inv; out.info[4] = A11 * inv; out.info[5] = A12 * inv;
     out.info[6] = A02 * inv; out.info[7] = A12 * inv; out.info[8] = A22 * inv;
+}
+
+LR_HD void inc_ndt_voxel_stats(const unsigned int* idx, unsigned int cnt, const void* xyz, size_t stride, NdtVoxel& out) {
+    inc_ndt_voxel_stats_of(IncMembersList{idx, cnt}, cnt, xyz, stride, out);
 }
 
 // Per-point body of AlignIncNdt (ndt_registration.cpp:289-324, 334-347): every gated-in voxel is one residual,

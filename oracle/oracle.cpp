@@ -332,6 +332,21 @@ static void transform_cloud(const float* src, size_t n, size_t stride, const SE3
     }
 }
 
+// pcl::transformPointCloud<PointT, double> with a Matrix4d (lio.cpp:243,278: pose.matrix() is passed WITHOUT the
+// .cast<float>() of ScanMatch): PCL 1.8 transforms.hpp evaluates m00*x + m01*y + m02*z + m03 in double, left to right,
+// and casts once to float.
+static void transform_cloud_d(const float* src, size_t n, size_t stride, const SE3& T, float* out) {
+    const Mat3 R = T.matrix();
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = pt_at(src, i, stride);
+        float* o = pt_at(out, i, stride);
+        if (o != p) std::memcpy(o, p, stride < 16 ? 12 : stride);
+        if (!finite3(p)) continue;
+        const double x = p[0], y = p[1], z = p[2];
+        for (int r = 0; r < 3; ++r) o[r] = static_cast<float>(R.m[r][0] * x + R.m[r][1] * y + R.m[r][2] * z + T.t[r]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // IcpRegistration
 // ---------------------------------------------------------------------------------------------
@@ -1188,6 +1203,9 @@ size_t oracle_filter_voxel_grid(const float* src, size_t n, size_t stride, float
 
 void oracle_transform_cloud(const float* src, size_t n, size_t stride, const double* pose7, float* out_xyz) {
     transform_cloud(src, n, stride, SE3::from7(pose7), out_xyz);
+}
+void oracle_transform_cloud_d(const float* src, size_t n, size_t stride, const double* pose7, float* out_xyz) {
+    transform_cloud_d(src, n, stride, SE3::from7(pose7), out_xyz);
 }
 void oracle_pose_update(double* pose7, const double* dx6) {
     SE3 T = SE3::from7(pose7);

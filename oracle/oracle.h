@@ -127,6 +127,8 @@ size_t oracle_filter_voxel_grid(const float* src, size_t n, size_t stride_bytes,
 
 /* pcl::transformPointCloud (icp_registration.cpp:241, ndt_registration.cpp:258) */
 void oracle_transform_cloud(const float* src, size_t n, size_t stride_bytes, const double* pose7, float* out_xyz);
+/* the Scalar = double instantiation Lio::AddCloud uses for key frames (lio.cpp:243,278): double arithmetic, one cast */
+void oracle_transform_cloud_d(const float* src, size_t n, size_t stride_bytes, const double* pose7, float* out_xyz);
 /* pose helpers for tests: pose7 <- pose7 * (exp(w), +dt) in the reference's split update form */
 void oracle_pose_update(double* pose7, const double* dx6);
 void oracle_pose_matrix(const double* pose7, double* R9_rowmajor);

@@ -85,6 +85,7 @@ def lib():
         L.oracle_filter_voxel_grid.restype = sz
         L.oracle_filter_voxel_grid.argtypes = [vp, sz, sz, C.c_float, vp]
         L.oracle_transform_cloud.argtypes = [vp, sz, sz, vp, vp]
+        L.oracle_transform_cloud_d.argtypes = [vp, sz, sz, vp, vp]
         L.oracle_pose_update.argtypes = [vp, vp]
         L.oracle_pose_matrix.argtypes = [vp, vp]
         _LIB = L
@@ -312,6 +313,15 @@ def transform_cloud(src, pose7):
     pose7 = np.ascontiguousarray(pose7, np.float64)
     out = np.zeros_like(a)
     lib().oracle_transform_cloud(a.ctypes.data, n, s, pose7.ctypes.data, out.ctypes.data)
+    return out
+
+
+def transform_cloud_d(src, pose7):
+    """pcl::transformPointCloud with a double matrix (Lio's key frames): double arithmetic, one cast to float."""
+    a, n, s = _cloud(src)
+    pose7 = np.ascontiguousarray(pose7, np.float64)
+    out = np.zeros_like(a)
+    lib().oracle_transform_cloud_d(a.ctypes.data, n, s, pose7.ctypes.data, out.ctypes.data)
     return out
 
 

@@ -387,7 +387,7 @@ def test_lio_tracker_device_local_map_equals_host_path(scene, kind):
         assert is_kf == ref_kf, step
         if ref_kf:
             last_kf = ref.copy()
-            kf = O.transform_cloud(scan, ref)
+            kf = O.transform_cloud_d(scan, ref)  # Lio transforms key frames with the DOUBLE matrix (lio.cpp:278)
             kfs.append(kf)
             if len(kfs) > max_kfs:
                 kfs.pop(0)
