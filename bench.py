@@ -54,8 +54,8 @@ def parse():
     ap.add_argument("--map-points", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-scans", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--configs", default="C4S,C3,C5",
-                    help="comma list of the extra configs measured after the headline (C4S, C3, C5); 'none' = headline only")
+    ap.add_argument("--configs", default="C4S,C3,C5,LIO",
+                    help="comma list of the extra measurements after the headline (C4S, C3, C5, LIO); 'none' = headline only")
     ap.add_argument("--hyp", type=int, default=65536, help="C5: number of pose hypotheses (64x64 xy grid x 16 yaws)")
     ap.add_argument("--ndt-map-points", type=int, default=20_000_000)
     ap.add_argument("--c4-scans", type=int, default=C4_SCANS)
@@ -635,6 +635,35 @@ def bench_reloc(ctx, reg, world, map_cloud):
     return out
 
 
+# ---- Lio key-frame step: incremental NDT voxel cache updated on the device ---------------------------------
+def bench_lio_keyframe(ctx, world):
+    """Lio::AddCloud's key-frame block for incremental NDT (lio.cpp:277-307, ndt_registration.cpp:150-236): transform the
+    scan, add it to the LRU voxel cache (order, evictions, statistics: all kernels, nothing copied back), publish the
+    table.  Timed per key frame through locreg_local_map_add_keyframe with a pinned host scan; the small-capacity run
+    evicts on every key frame."""
+    import loc_lib_b200 as L
+    torch = ctx.torch
+    gt = world.poses(40)
+    scans = [torch.from_numpy(world.scan(g)).pin_memory().numpy() for g in gt]
+    out = {}
+    for name, capacity in (("capacity_100000", 100000), ("capacity_20000", 20000)):
+        reg = L.NdtRegistration(L.NdtOptions(method_=L.NdtMethod.INCREMENTAL_NDT, capacity_=capacity), device=ctx.local)
+        wall, kern = [], []
+        for sc, g in zip(scans, gt):
+            ctx.torch.cuda.synchronize(ctx.dev)
+            t0 = time.perf_counter()
+            reg.AddKeyFrame(sc, g, max_keyframes=10, leaf=0.5)
+            ctx.torch.cuda.synchronize(ctx.dev)
+            wall.append((time.perf_counter() - t0) * 1e3)
+            kern.append(reg.last_timing()[0])
+        out[name] = {"keyframe_wall_ms": float(np.median(wall[8:])), "cache_update_kernel_ms": float(np.median(kern[8:])),
+                     "voxels_cached": int(len(reg.Voxels()[0])), "scan_points": int(len(scans[0])), "keyframes": len(scans)}
+        del reg
+    out["note"] = ("locreg_local_map_add_keyframe, method = incremental NDT: H2D of the scan, double-precision transform, LRU cache "
+                   "update + statistics + table publish on the device (no D2H, no host LRU); median over key frames 9-40")
+    return out
+
+
 def run_ours(args):
     import loc_lib_b200 as L
     from loc_lib_b200 import dist as D
@@ -668,6 +697,8 @@ def run_ours(args):
     ctx.torch.cuda.empty_cache()
     if "C3" in want:
         extra["C3"] = bench_ndt(ctx)
+    if "LIO" in want and ctx.rank == 0:
+        extra["lio_keyframe"] = bench_lio_keyframe(ctx, world)
     if ctx.rank == 0:
         if extra:
             line["configs"] = extra

@@ -112,8 +112,7 @@ __device__ __forceinline__ bool track_rescan_point(const VoxelMapView& map, cons
     KnnTrack tr;
     const bool done = knn_query_fast_track<K>(map, static_cast<float>(wx), static_cast<float>(wy), static_cast<float>(wz), nn, seeds, tr);
     bool same = done;
-#pragma unroll
-    for (int j = 0; j < K; ++j) same = same && seeds[j] == nn.pos[j] && seeds[j] != kNoPos;
+    same = same && knn_same_set<K>(seeds, nn.pos);
     track[srow] = tr;
     if (same) {
         // the same ordered neighbours as the last fit saw: its plane is what a new fit would return bit for bit

@@ -309,10 +309,9 @@ __device__ __forceinline__ void icp_nn_tile(unsigned int tile, const VoxelMapVie
         const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
         if (tracked) done = knn_query_fast_track<K>(map, qx, qy, qz, nn, seeds, tr);
         else done = knn_query_fast<K>(map, qx, qy, qz, nn, seeds, (mode & kNnTwoPass) != 0);
-        // same neighbours, in the same order, as in the previous iteration: what k_icp_fit derived from them still holds
+        // the same neighbours (as a set) as in the previous iteration: what k_icp_fit derived from them still holds
         same = done && (mode & kNnSeeds) != 0;
-#pragma unroll
-        for (int j = 0; j < K; ++j) same = same && seeds[j] == nn.pos[j] && seeds[j] != kNoPos;
+        same = same && knn_same_set<K>(seeds, nn.pos);
     }
     if (in_tile) {
 #pragma unroll

@@ -268,8 +268,7 @@ k_icp_nn_staged(VoxelMapView map, BatchView bv, const AlignState* __restrict__ s
             if (MODE == 2 && done) tr.margin = knn_track_margin<K>(map, c, res, sel.d6, qx, qy, qz);
         }
         same = done && MODE != 0;
-#pragma unroll
-        for (int j = 0; j < K; ++j) same = same && seeds[j] == res.pos[j] && seeds[j] != kNoPos;
+        same = same && knn_same_set<K>(seeds, res.pos);
     }
     if (in_tile) {
 #pragma unroll

@@ -720,16 +720,8 @@ static int set_target_impl(locreg_handle* h, const float* xyz, size_t n, size_t 
         if (h->opt.method == LOCREG_NDT_DIRECT) {
             h->ndt_map.build(d_xyz, n, stride, h->opt.voxel_size, h->opt.min_pts_in_voxel, h->stream);
         } else if (h->opt.method == LOCREG_NDT_INCREMENTAL) {
-            // SetIncNdtTargetCloud ADDS the cloud to the voxel cache; the LRU bookkeeping needs the cloud on the host
-            std::vector<unsigned char> tmp;
-            const void* h_xyz = xyz;
-            if (on_device && n) {
-                tmp.resize(n * stride);
-                LR_CUDA(cudaMemcpyAsync(tmp.data(), xyz, n * stride, cudaMemcpyDeviceToHost, h->stream));
-                LR_CUDA(cudaStreamSynchronize(h->stream));
-                h_xyz = tmp.data();
-            }
-            h->inc_ndt_map.add_cloud(h_xyz, d_xyz, n, stride, h->stream);
+            // SetIncNdtTargetCloud ADDS the cloud to the voxel cache: LRU order, evictions and statistics all on the device
+            h->inc_ndt_map.add_cloud(d_xyz, n, stride, h->stream);
         } else {
             static const bool use_mid = !(getenv("LOCREG_MID") && atoi(getenv("LOCREG_MID")) == 0);
             if (!use_mid) h->icp_mid.clear();
@@ -1475,7 +1467,7 @@ int locreg_filter_voxel_grid(locreg_handle* h, const float* xyz, size_t n, size_
 
 int locreg_ndt_num_voxels(locreg_handle* h, size_t* nv) {
     if (!h || !nv) return LOCREG_E_ARG;
-    *nv = h->opt.method == LOCREG_NDT_INCREMENTAL ? h->inc_ndt_map.size() : h->ndt_map.view().n_voxels;
+    *nv = h->opt.method == LOCREG_NDT_INCREMENTAL ? h->inc_ndt_map.size(h->stream) : h->ndt_map.view().n_voxels;
     return LOCREG_OK;
 }
 int locreg_ndt_get_voxels(locreg_handle* h, int32_t* keys, double* mu, double* info, int32_t* npts) {

@@ -418,6 +418,22 @@ LR_HD void knn_seed(const VoxelMapView& m, float qx, float qy, float qz, const u
     // K == 1 needs no ordering
 }
 
+// Do the K (distinct, real) positions of `a` and the K positions of `b` form the same SET?  What k_icp_fit derives from
+// a point's neighbours - a plane through five points - does not depend on their order beyond rounding, and early
+// Gauss-Newton iterations often only swap neighbours of nearly equal distance.
+template <int K>
+LR_HD bool knn_same_set(const unsigned int* a, const unsigned int* b) {
+    bool same = true;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        bool found = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) found = found || a[j] == b[k];
+        same = same && found && a[j] != kNoPos;
+    }
+    return same;
+}
+
 // After the list of the query's own cell on level `m` (the box [f-1, f+1]^3) has been scanned: is `res` final?
 template <int K>
 LR_HD bool knn_list_final(const VoxelMapView& m, const KnnCellFrame& c, const KnnResult<K>& res) {

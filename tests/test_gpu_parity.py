@@ -295,6 +295,37 @@ def test_inc_ndt_cache_hb_and_pose(scene):
     assert np.array_equal(pose, scene.init[0])
 
 
+@pytest.mark.parametrize("capacity,n_keys,n_pts,seed", [(4, 6, 60, 0), (9, 12, 400, 1), (33, 40, 3000, 2), (33, 200, 3000, 3),
+                                                         (120, 150, 5000, 4), (2, 5, 50, 5), (50, 30, 2000, 6), (700, 900, 40000, 7)])
+def test_inc_ndt_device_lru_adversarial(capacity, n_keys, n_pts, seed):
+    """The device-side LRU of the incremental NDT cache against the oracle's literal std::list (ndt_registration.cpp:150-183):
+    tiny capacities, voxels evicted and re-inserted within one cloud, runs of equal keys, non-finite points in between."""
+    import loc_lib_b200 as L
+    rng = np.random.default_rng(seed)
+    gpu = L.NdtRegistration(L.NdtOptions(method_=L.NdtMethod.INCREMENTAL_NDT, capacity_=capacity))
+    ref = O.OracleIncNdt(capacity=capacity, skip_nonfinite=1)
+    for cloud in range(6):
+        base = cloud * (n_keys // 3)
+        ks = []
+        while len(ks) < n_pts:
+            ks += [int(base + rng.integers(0, n_keys))] * int(rng.integers(1, 4))
+        ks = np.array(ks[:n_pts])
+        pts = np.zeros((n_pts, 4), np.float32)
+        pts[:, 0] = (ks % 37) + rng.random(n_pts) * 0.98 + 0.01   # voxel (k % 37, k // 37, 0), 1 m voxels
+        pts[:, 1] = (ks // 37) + rng.random(n_pts) * 0.98 + 0.01
+        pts[:, 2] = rng.random(n_pts) * 0.98 + 0.01
+        pts[rng.integers(0, n_pts, n_pts // 50), rng.integers(0, 3, n_pts // 50)] = np.nan
+        gpu.SetInputTarget(pts)
+        ref.set_target(pts)
+        k, mu, info, npts = gpu.Voxels()
+        rk, rmu, rinfo, rn = ref.voxels()
+        assert len(rk) <= capacity - 1
+        assert np.array_equal(k, rk), cloud
+        assert np.array_equal(npts, rn), cloud
+        assert np.array_equal(mu, rmu), cloud
+        assert np.abs(info - rinfo).max() <= 1e-9 * np.abs(rinfo).max()
+
+
 def test_prefilters_match_oracle(scene, icp_pair):
     gpu, _ = icp_pair
     for width in (8, 4):  # pcl::PointXYZI (32 B) and float4
