@@ -238,6 +238,9 @@ int locreg_ndt_get_voxels(locreg_handle* h, int32_t* keys, double* mu, double* i
 /* Device time in milliseconds of the last align / align_batch / relocalise / set_target call's kernels
  * (CUDA events on the handle's stream), and how many kernels that call launched. */
 int locreg_last_timing(locreg_handle* h, double* kernel_ms, int64_t* launches);
+/* Size of the search index the last locreg_set_target* built (diagnostics / bench): bytes of device memory over all
+ * levels, points indexed, neighbourhood lists (ICP; 0 for NDT) or voxels (NDT).  Any pointer may be NULL. */
+int locreg_index_info(locreg_handle* h, size_t* bytes, size_t* points, size_t* lists_or_voxels);
 
 /* Per-kernel-class device timing for the ICP pipeline (0 neighbour search stage 1, 1 fit + reduce, 2 solve,
  * 3 neighbour search stage 2): returns and clears the milliseconds / launch counts (4 entries each) accumulated

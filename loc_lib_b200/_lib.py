@@ -20,7 +20,7 @@ SYMBOLS = [
     "locreg_filter_voxel_grid", "locreg_set_global_map", "locreg_reset_local_map",
     "locreg_local_map_add_keyframe", "locreg_local_map_get", "locreg_local_map_clear",
     "locreg_comm_unique_id", "locreg_comm_init", "locreg_comm_destroy", "locreg_comm_info", "locreg_shard_range",
-    "locreg_relocalise_sharded", "locreg_align_batch_sharded",
+    "locreg_relocalise_sharded", "locreg_align_batch_sharded", "locreg_index_info",
 ]
 
 
@@ -72,6 +72,7 @@ def lib():
         L.locreg_ndt_num_voxels.argtypes = [vp, C.POINTER(sz)]
         L.locreg_ndt_get_voxels.argtypes = [vp, vp, vp, vp, vp]
         L.locreg_last_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+        L.locreg_index_info.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
         L.locreg_profile.argtypes = [vp, i32, vp, vp]
         L.locreg_set_global_map.argtypes = [vp, vp, sz, sz]
         L.locreg_reset_local_map.argtypes = [vp, vp, vp, C.POINTER(sz)]

@@ -1495,6 +1495,26 @@ int locreg_profile(locreg_handle* h, int32_t enable, double* ms4, int64_t* launc
     });
 }
 
+int locreg_index_info(locreg_handle* h, size_t* bytes, size_t* points, size_t* lists_or_voxels) {
+    if (!h) { g_last_error = "null handle"; return LOCREG_E_ARG; }
+    return guarded(h, [&]() {
+        size_t b = 0, p = 0, l = 0;
+        if (h->opt.method == LOCREG_NDT_DIRECT) {
+            b = h->ndt_map.bytes(); l = h->ndt_map.view().n_voxels;
+        } else if (h->opt.method == LOCREG_NDT_INCREMENTAL) {
+            l = h->inc_ndt_map.size(h->stream);
+        } else {
+            b = h->icp_map.bytes() + h->icp_mid.bytes();
+            for (int i = 0; i < kCoarseLevels; ++i) b += h->icp_coarse[i].bytes();
+            p = h->icp_map.view().n_pts;
+            l = h->icp_map.n_lists();
+        }
+        if (bytes) *bytes = b;
+        if (points) *points = p;
+        if (lists_or_voxels) *lists_or_voxels = l;
+        return LOCREG_OK;
+    });
+}
 int locreg_last_timing(locreg_handle* h, double* kernel_ms, int64_t* launches) {
     if (!h) return LOCREG_E_ARG;
     if (kernel_ms) *kernel_ms = h->last_ms;

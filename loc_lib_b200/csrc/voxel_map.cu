@@ -171,20 +171,84 @@ __global__ void k_nbr_clear(NbrSlot* nbr, unsigned int cap) {
     const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < cap) nbr[s] = NbrSlot{kEmptyKey, 0u, 0u};
 }
-__global__ void k_nbr_pass(size_t n, int pass, const void* __restrict__ xyz, size_t stride, float inv_cell,
-                           const unsigned int* __restrict__ pt_cell, const unsigned int* __restrict__ pt_pos,
-                           const unsigned char* __restrict__ dup, NbrSlot* nbr, unsigned int nbr_mask, unsigned int* cursor,
-                           float4* pts, unsigned int* counters) {
-    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) build_nbr_body<DeviceAtomics>(i, pass, xyz, stride, inv_cell, pt_cell, pt_pos, dup, nbr, nbr_mask, cursor, pts, counters);
+// ---- neighbourhood lists by GATHER ----------------------------------------------------------------------------------------
+// The lists used to be built from the points' side: every point probed the table of list cells 27 times to count itself
+// and 27 times more to write itself - 54 atomics and 27 scattered 16 B stores per map point.  From the lists' side the
+// same arrays cost a fraction: (1) every OCCUPIED CELL marks the 27 cells whose neighbourhood it belongs to (cells are
+// 2-3x fewer than points); (2) one warp per list cell, lane o < 27 looking up neighbour cell o in the block table (a
+// read-only 32 B record, L2 resident), a shuffle scan of the 27 counts, ONE atomic to reserve the list's range, and the
+// lanes copy their cells' points into consecutive places: coalesced stores, a deterministic order inside every list
+// (cell by cell, canonical position ascending), no second pass.  Masked duplicates (quirk Q3) are left out.
+__device__ __forceinline__ void unpack_coord(unsigned long long key, int& x, int& y, int& z) {
+    x = static_cast<int>((key >> 42) & 0x1FFFFFull) - kCoordBias;
+    y = static_cast<int>((key >> 21) & 0x1FFFFFull) - kCoordBias;
+    z = static_cast<int>(key & 0x1FFFFFull) - kCoordBias;
 }
-__global__ void k_nbr_counts(const NbrSlot* __restrict__ nbr, unsigned int cap, unsigned int* out) {
-    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < cap) out[s] = nbr[s].count;
+// counters: [0] lists created, [1] overflow flag
+__global__ void k_nbr_mark(const VoxelSlot* __restrict__ slots, unsigned int cap, NbrSlot* nbr, unsigned int nbr_mask, unsigned int* counters) {
+    const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t s = t >> 6;
+    const int bit = static_cast<int>(t & 63);
+    if (s >= cap) return;
+    const VoxelSlot sl = slots[s];
+    if (sl.key == kEmptyKey || !((sl.mask >> bit) & 1ull)) return;
+    int bx, by, bz;
+    unpack_coord(sl.key, bx, by, bz);
+    const int cx = (bx << 2) + (bit & 3), cy = (by << 2) + ((bit >> 2) & 3), cz = (bz << 2) + (bit >> 4);
+    for (int o = 0; o < 27; ++o) {
+        const unsigned long long key = pack_cell(cx + (o % 3) - 1, cy + ((o / 3) % 3) - 1, cz + (o / 9) - 1);
+        unsigned int h = hash_block(key) & nbr_mask;
+        unsigned int probes = 0;
+        while (true) {
+            const unsigned long long k = atomicCAS(&nbr[h].key, kEmptyKey, key);
+            if (k == kEmptyKey) { atomicAdd(&counters[0], 1u); break; }
+            if (k == key) break;
+            h = (h + 1) & nbr_mask;
+            if (++probes > nbr_mask) { counters[1] = 1u; return; }
+        }
+    }
 }
-__global__ void k_nbr_set_start(NbrSlot* nbr, unsigned int cap, const unsigned int* __restrict__ start, unsigned int base) {
-    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < cap) nbr[s].start = base + start[s];
+// one warp per slot of the list table; list_cursor counts the list entries handed out so far
+__global__ void k_nbr_gather(VoxelMapView map, NbrSlot* nbr, unsigned int nbr_cap, float4* pts, unsigned int n_kept, unsigned int* list_cursor) {
+    const unsigned int w = static_cast<unsigned int>((static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+    const unsigned int lane = threadIdx.x & 31;
+    if (w >= nbr_cap) return;
+    const unsigned long long key = nbr[w].key;
+    if (key == kEmptyKey) return;
+    int lx, ly, lz;
+    unpack_coord(key, lx, ly, lz);
+    unsigned int beg = 0, end = 0;
+    if (lane < 27) {
+        const int cx = lx + static_cast<int>(lane % 3) - 1, cy = ly + static_cast<int>((lane / 3) % 3) - 1, cz = lz + static_cast<int>(lane / 9) - 1;
+        const VoxelSlot* s = find_block(map, cx >> 2, cy >> 2, cz >> 2);
+        if (s != nullptr) {
+            const int bit = (cx & 3) | ((cy & 3) << 2) | ((cz & 3) << 4);
+            const unsigned long long occ = s->mask;
+            if ((occ >> bit) & 1ull) {
+                const unsigned int cid = s->cell_base + static_cast<unsigned int>(__popcll(occ & ((1ull << bit) - 1ull)));
+                beg = map.cell_start[cid];
+                end = map.cell_start[cid + 1];
+            }
+        }
+    }
+    unsigned int live = 0;
+    for (unsigned int i = beg; i < end; ++i) live += pts[i].x == pts[i].x ? 1u : 0u;  // a masked duplicate is NaN
+    unsigned int inc = live;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= static_cast<unsigned int>(off)) inc += v;
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, inc, 31);
+    unsigned int start = 0;
+    if (lane == 0) start = n_kept + atomicAdd(list_cursor, total);
+    start = __shfl_sync(0xffffffffu, start, 0);
+    unsigned int at = start + inc - live;
+    for (unsigned int i = beg; i < end; ++i) {
+        const float4 p = pts[i];
+        if (p.x == p.x) pts[at++] = make_float4(p.x, p.y, p.z, __int_as_float(static_cast<int>(i)));  // w = canonical position
+    }
+    if (lane == 0) { nbr[w].start = start; nbr[w].count = total; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -284,17 +348,17 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     unsigned int n_dup = 0;
     LR_CUDA(cudaMemcpyAsync(&n_dup, counters + 5, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     LR_CUDA(cudaStreamSynchronize(stream));
-    // 7 neighbourhood lists
+    // 7 neighbourhood lists (gathered per list cell, see k_nbr_gather)
     unsigned int nbr_cap = 0;
     if (lists) {
         nbr_cap = next_pow2(static_cast<size_t>(n_cells_) * 8);
-        unsigned int* ncursor = nullptr;
+        view_.slots = slots_; view_.cell_start = cell_start_; view_.pts = pts_; view_.slot_mask = cap - 1;  // what find_block needs
         while (true) {
             nbr_ = nbr_buf_.ensure(nbr_cap);
             LR_LAUNCH(k_nbr_clear, (nbr_cap + T - 1) / T, T, 0, stream, nbr_, nbr_cap);
-            LR_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream));
-            LR_LAUNCH(k_nbr_pass, gridN, T, 0, stream, n, 0, d_xyz, stride, inv_cell, pt_slot, pt_pos, dup, nbr_, nbr_cap - 1,
-                      static_cast<unsigned int*>(nullptr), pts_, counters);
+            LR_CUDA(cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned int), stream));
+            LR_LAUNCH(k_nbr_mark, static_cast<unsigned int>((static_cast<size_t>(cap) * 64 + T - 1) / T), T, 0, stream, slots_, cap, nbr_,
+                      nbr_cap - 1, counters);
             LR_CUDA(cudaMemcpyAsync(h_counters, counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
             LR_CUDA(cudaStreamSynchronize(stream));
             if (h_counters[1] || static_cast<size_t>(h_counters[0]) * 2 > nbr_cap) {
@@ -307,17 +371,8 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
         }
         n_lists_ = h_counters[0];
         n_list_entries_ = static_cast<size_t>(n_kept - n_dup) * 27;  // every surviving point, once per cell of its 3x3x3 box
-        LR_CUDA(cudaMallocAsync(&tmp, static_cast<size_t>(nbr_cap) * sizeof(unsigned int), stream));
-        LR_CUDA(cudaMallocAsync(&ncursor, static_cast<size_t>(nbr_cap) * sizeof(unsigned int), stream));
-        LR_LAUNCH(k_nbr_counts, (nbr_cap + T - 1) / T, T, 0, stream, nbr_, nbr_cap, tmp);
-        exclusive_scan_u32(tmp, tmp, nbr_cap, nullptr, stream);
-        LR_LAUNCH(k_nbr_set_start, (nbr_cap + T - 1) / T, T, 0, stream, nbr_, nbr_cap, tmp, n_kept);
-        LR_CUDA(cudaMemsetAsync(ncursor, 0, static_cast<size_t>(nbr_cap) * sizeof(unsigned int), stream));
-        LR_LAUNCH(k_nbr_pass, gridN, T, 0, stream, n, 1, d_xyz, stride, inv_cell, pt_slot, pt_pos, dup, nbr_, nbr_cap - 1, ncursor, pts_,
-                  counters);
-        LR_CUDA(cudaStreamSynchronize(stream));
-        LR_CUDA(cudaFreeAsync(tmp, stream));
-        LR_CUDA(cudaFreeAsync(ncursor, stream));
+        LR_LAUNCH(k_nbr_gather, static_cast<unsigned int>((static_cast<size_t>(nbr_cap) * 32 + T - 1) / T), T, 0, stream, view_, nbr_, nbr_cap,
+                  pts_, n_kept, counters + 2);
     }
     LR_CUDA(cudaFreeAsync(cursor, stream));
     LR_CUDA(cudaFreeAsync(pt_slot, stream));

@@ -310,6 +310,12 @@ class _Registration:
                                                         C.c_void_p(d_poses_in), S, total_points,
                                                         C.c_void_p(d_poses_out), C.c_void_p(d_results)))
 
+    def index_info(self):
+        """(bytes of device memory, points indexed, neighbourhood lists or voxels) of the current target's search index."""
+        b, p, l = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        _lib.check(_lib.lib().locreg_index_info(self._h, C.byref(b), C.byref(p), C.byref(l)))
+        return b.value, p.value, l.value
+
     def last_timing(self):
         ms = C.c_double()
         launches = C.c_int64()
