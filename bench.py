@@ -212,16 +212,22 @@ def _peak():
         return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
-def _traffic(kernel_prefix):
-    """Mean dram__bytes_read + dram__bytes_write per launch of a kernel over ALL its launches in one timed step of this
-    command, from the committed ncu pass (tools/profile_remote.sh -> profiles/roofline_traffic.json)."""
+def _traffic(kernel_names, grid=None):
+    """Mean dram__bytes_read + dram__bytes_write per launch over ALL launches of the named kernels (base names, at the
+    batch's grid size) in one ncu pass of this command: profiles/roofline_traffic.json, written by
+    tools/traffic_from_ncu.py from the launch list tools/profile_remote.sh captures."""
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
     except (OSError, ValueError):
         return None
-    v = tj.get("mean_bytes_per_launch", tj)
-    cands = [b for k, b in v.items() if k.startswith(kernel_prefix)]
-    return float(np.mean(cands)) if cands else None
+    recs = [r for r in tj.get("launch_groups", []) if r["kernel"] in kernel_names]
+    if not recs:
+        return None
+    if grid is None:
+        grid = max(r["grid"] for r in recs)  # the whole batch (halves of it = the e2e chunks, small grids = single scans)
+    tot = sum(r["mean_bytes"] * r["launches"] for r in recs if r["grid"] == grid)
+    cnt = sum(r["launches"] for r in recs if r["grid"] == grid)
+    return tot / cnt if cnt else None
 
 
 class Ctx:
@@ -362,8 +368,8 @@ def bench_icp(ctx, reg, map_cloud, clouds, offsets, init, gt, map_build):
         "roofline": {"bound": "hbm", "kernel": "k_icp_nn<5> (neighbour search stage 1, %.0f%% of pipeline kernel time)" %
                      (100 * nn_ms / max(nn_ms + fit_ms + ring_ms + solve_ms, 1e-9)),
                      "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak if achieved else None,
-                     "traffic": _traffic("k_icp_nn<"), "peak_source": ctx.peak_src,
-                     "traffic_note": "mean dram read+write bytes per k_icp_nn launch over ALL launches of a step of this command (ncu pass, profiles/)",
+                     "traffic": _traffic(("k_icp_nn", "k_icp_nn_staged")) if B == 512 else None, "peak_source": ctx.peak_src,
+                     "traffic_note": "mean dram read+write bytes per stage-1 search launch (k_icp_nn, k_icp_nn_staged) over ALL such launches of the batch in an ncu pass of this command (profiles/roofline_traffic.json; null when the pass was taken on another batch size)",
                      "algorithmic_bytes_per_launch": BYTES_PER_POINT_ITER * n_pts, "launch_ms": per_launch_ms,
                      "fit_kernel_launch_ms": fit_ms / max(fit_launches, 1),
                      "rings_kernel_launch_ms": ring_ms / max(nn_launches, 1),
@@ -550,6 +556,21 @@ def bench_ndt(ctx):
                                    "pose_vs_gpu": {"rad": drad, "m": dm}}
     del reg
     torch.cuda.empty_cache()
+    if ctx.rank == 0:
+        # the ICP search index over the same 20 M-point map (SURVEY 8a-1 at config 3's map size): build time and size
+        icp = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=MAX_ITER, eps_=0.0), device=ctx.local)
+        t0 = time.perf_counter()
+        icp.SetInputTarget(m)
+        w0 = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        icp.SetInputTarget(m)
+        w1 = (time.perf_counter() - t0) * 1e3
+        ib, ip, il = icp.index_info()
+        out["icp_index_20M"] = {"first_build_wall_ms": w0, "rebuild_wall_ms": w1, "rebuild_device_ms": icp.last_timing()[0],
+                                "index_bytes": int(ib), "index_bytes_per_point": ib / max(ip, 1), "neighbourhood_lists": int(il),
+                                "note": "wall includes the H2D copy of the 320 MB cloud (pageable)"}
+        del icp
+        torch.cuda.empty_cache()
     return out
 
 
@@ -646,7 +667,7 @@ def bench_lio_keyframe(ctx, world):
     gt = world.poses(40)
     scans = [torch.from_numpy(world.scan(g)).pin_memory().numpy() for g in gt]
     out = {}
-    for name, capacity in (("capacity_100000", 100000), ("capacity_20000", 20000)):
+    for name, capacity in (("capacity_100000", 100000), ("capacity_5000", 5000)):
         reg = L.NdtRegistration(L.NdtOptions(method_=L.NdtMethod.INCREMENTAL_NDT, capacity_=capacity), device=ctx.local)
         wall, kern = [], []
         for sc, g in zip(scans, gt):
@@ -677,6 +698,32 @@ def run_ours(args):
     t0 = time.perf_counter()
     reg.SetInputTarget(map_cloud)
     map_build = {"wall_ms": (time.perf_counter() - t0) * 1e3, "kernel_ms": reg.last_timing()[0], "points": int(len(map_cloud))}
+    # the same index again on warm buffers (what Loc's re-crop and Lio's key frames pay), and its size
+    walls, spans = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        reg.SetInputTarget(map_cloud)
+        walls.append((time.perf_counter() - t0) * 1e3)
+        spans.append(reg.last_timing()[0])
+    ib, ip, il = reg.index_info()
+    map_build.update({"rebuild_wall_ms": float(np.median(walls)), "rebuild_device_ms": float(np.median(spans)), "index_bytes": int(ib),
+                      "index_bytes_per_point": ib / max(ip, 1), "neighbourhood_lists": int(il),
+                      "note": "wall_ms / kernel_ms: first build (allocates the index); rebuild_*: warm buffers, H2D of the 16 MB cloud included in wall"})
+    if ctx.rank == 0:
+        nl = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=MAX_ITER, eps_=0.0, knn_lists=0), device=ctx.local)
+        nl.SetInputTarget(map_cloud)
+        t0 = time.perf_counter()
+        nl.SetInputTarget(map_cloud)
+        w_nl = (time.perf_counter() - t0) * 1e3
+        nb, np_, _ = nl.index_info()
+        map_build["knn_lists_0"] = {"rebuild_wall_ms": w_nl, "index_bytes_per_point": nb / max(np_, 1)}
+        sc, so, si, _ = make_scans(world, 0, 64, 4096)
+        nl.ScanMatchBatch(sc, so, si)
+        t0 = time.perf_counter()
+        nl.ScanMatchBatch(sc, so, si)
+        map_build["knn_lists_0"]["points_per_s_64_scans"] = int(so[-1]) / max(nl.last_timing()[0] * 1e-3, 1e-9)
+        map_build["knn_lists_0"]["note"] = "block tables only (no neighbourhood lists): every query takes the shell search; 64-scan batch, device time"
+        del nl
     if W > 1:
         D.comm_init(reg, ctx.dev)  # NCCL communicator INSIDE liblocreg.so (the id travels over the torchrun process group)
 

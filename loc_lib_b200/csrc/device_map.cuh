@@ -17,8 +17,11 @@ class DeviceVoxelMap {
     // table is sized from the number of occupied blocks, read back once).
     // keep_pos (optional): receives a device array (cudaMallocAsync on `stream`, caller frees) mapping every input
     // index to its canonical position in pts (undefined for dropped points).
+    // dups (optional): with flags == nullptr on entry it receives this build's duplicate flags (one byte per input point,
+    // cudaMallocAsync on `stream`, caller frees) and their number; with flags set, the build takes them as given.
+    struct DupFlags { unsigned char* flags = nullptr; unsigned int count = 0; };
     void build(const void* d_xyz, size_t n, size_t stride, float cell, bool want_lists, cudaStream_t stream,
-               unsigned int** keep_pos = nullptr);
+               unsigned int** keep_pos = nullptr, DupFlags* dups = nullptr);
     // Turns this map into a coarse level of `fine`: every entry's w (original index) is replaced by the point's
     // canonical position in fine's pts, which is what the search reports on every level.
     void attach_to(const VoxelMapView& fine, const unsigned int* fine_pos_of_index, cudaStream_t stream);
@@ -62,6 +65,8 @@ class DeviceVoxelMap {
     size_t bytes_ = 0;
     unsigned int n_cells_ = 0, n_blocks_ = 0, n_lists_ = 0;
     size_t n_list_entries_ = 0;
+    size_t last_n_ = 0;                      // size of the last cloud built and the table capacities that held it
+    unsigned int last_cap_ = 0, last_nbr_cap_ = 0;
 };
 
 // Level 0 (cell, lists) + the mid level (cells kMidFactor times larger, lists; nullptr: none) + kCoarseLevels coarser

@@ -268,9 +268,10 @@ static unsigned int next_pow2(size_t v) {
 }
 
 void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cell, bool want_lists, cudaStream_t stream,
-                           unsigned int** keep_pos) {
+                           unsigned int** keep_pos, DupFlags* dups) {
     release();
     if (keep_pos) *keep_pos = nullptr;
+    const bool dup_given = dups != nullptr && dups->flags != nullptr;
     if (n == 0) return;
     if (n >= (1ull << 31)) throw std::invalid_argument("target cloud too large (>= 2^31 points)");
     const float inv_cell = 1.0f / cell;
@@ -282,10 +283,15 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     LR_CUDA(cudaMallocAsync(&pt_slot, n * sizeof(unsigned int), stream));
     LR_CUDA(cudaMallocAsync(&pt_pos, n * sizeof(unsigned int), stream));
     LR_CUDA(cudaMallocAsync(&pt_bit, n, stream));
-    LR_CUDA(cudaMallocAsync(&dup, n, stream));
+    if (dup_given) dup = dups->flags;
+    else LR_CUDA(cudaMallocAsync(&dup, n, stream));
     LR_CUDA(cudaMallocAsync(&counters, 8 * sizeof(unsigned int), stream));
     LR_CUDA(cudaMallocAsync(&bounds, 6 * sizeof(int), stream));
+    // table sizes start from the last build's when the cloud is of similar size (Loc's re-crops, Lio's key frames): a
+    // guess that proves too small costs a whole insert pass and a synchronisation
+    const bool similar = last_n_ != 0 && n <= 2 * last_n_ && 2 * n >= last_n_;
     unsigned int cap = next_pow2(n / 4 + 1024);
+    if (similar && last_cap_ > cap) cap = last_cap_;
     unsigned int h_counters[8];
     int h_bounds[6];
     while (true) {
@@ -312,7 +318,8 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     if (n_kept == 0) {  // every point was non-finite
         slots_ = nullptr;
         cudaFreeAsync(pt_slot, stream); cudaFreeAsync(pt_pos, stream); cudaFreeAsync(pt_bit, stream);
-        cudaFreeAsync(dup, stream); cudaFreeAsync(counters, stream); cudaFreeAsync(bounds, stream);
+        if (!dup_given) cudaFreeAsync(dup, stream);
+        cudaFreeAsync(counters, stream); cudaFreeAsync(bounds, stream);
         return;
     }
     // 2 rank: slot.cell_base = exclusive scan of popcount(mask)
@@ -341,17 +348,25 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
                        (list_entries + n_kept) * sizeof(float4) < free_b / 2;
     pts_ = pts_buf_.ensure(static_cast<size_t>(n_kept) + (lists ? list_entries : 0));
     LR_LAUNCH(k_build_scatter, gridN, T, 0, stream, d_xyz, n, stride, pt_slot, cursor, pts_, pt_pos);
-    // 6 dedupe (quirk Q3)
-    LR_CUDA(cudaMemsetAsync(counters + 5, 0, sizeof(unsigned int), stream));
-    LR_LAUNCH(k_build_dup_flag, gridN, T, 0, stream, n, pt_slot, pt_pos, cell_start_, pts_, dup, counters + 5);
-    LR_LAUNCH(k_build_dup_apply, gridN, T, 0, stream, n, dup, pt_pos, pts_);
+    // 6 dedupe (quirk Q3).  Which input points are duplicates does not depend on the cell size: a coarser level takes the
+    // flags of the fine one instead of comparing every point with the thousands that share its (large) cell.
     unsigned int n_dup = 0;
-    LR_CUDA(cudaMemcpyAsync(&n_dup, counters + 5, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-    LR_CUDA(cudaStreamSynchronize(stream));
+    if (dup_given) {
+        n_dup = dups->count;
+    } else {
+        LR_CUDA(cudaMemsetAsync(counters + 5, 0, sizeof(unsigned int), stream));
+        LR_LAUNCH(k_build_dup_flag, gridN, T, 0, stream, n, pt_slot, pt_pos, cell_start_, pts_, dup, counters + 5);
+    }
+    LR_LAUNCH(k_build_dup_apply, gridN, T, 0, stream, n, dup, pt_pos, pts_);
+    if (!dup_given) {
+        LR_CUDA(cudaMemcpyAsync(&n_dup, counters + 5, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        LR_CUDA(cudaStreamSynchronize(stream));
+    }
     // 7 neighbourhood lists (gathered per list cell, see k_nbr_gather)
     unsigned int nbr_cap = 0;
     if (lists) {
         nbr_cap = next_pow2(static_cast<size_t>(n_cells_) * 8);
+        if (similar && last_nbr_cap_ > nbr_cap) nbr_cap = last_nbr_cap_;
         view_.slots = slots_; view_.cell_start = cell_start_; view_.pts = pts_; view_.slot_mask = cap - 1;  // what find_block needs
         while (true) {
             nbr_ = nbr_buf_.ensure(nbr_cap);
@@ -378,9 +393,11 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
     LR_CUDA(cudaFreeAsync(pt_slot, stream));
     if (keep_pos) *keep_pos = pt_pos; else LR_CUDA(cudaFreeAsync(pt_pos, stream));
     LR_CUDA(cudaFreeAsync(pt_bit, stream));
-    LR_CUDA(cudaFreeAsync(dup, stream));
+    if (dups != nullptr && !dup_given) { dups->flags = dup; dups->count = n_dup; }  // handed to the caller (who frees it)
+    else if (!dup_given) LR_CUDA(cudaFreeAsync(dup, stream));
     LR_CUDA(cudaFreeAsync(counters, stream));
     LR_CUDA(cudaFreeAsync(bounds, stream));
+    last_n_ = n; last_cap_ = cap; last_nbr_cap_ = nbr_cap;
     view_.slots = slots_; view_.cell_start = cell_start_; view_.pts = pts_;
     view_.canon = pts_; view_.w_is_pos = 0;
     view_.nbr_slots = nbr_; view_.nbr_mask = nbr_cap ? nbr_cap - 1 : 0;
@@ -413,19 +430,22 @@ void DeviceVoxelMap::attach_to(const VoxelMapView& fine, const unsigned int* fin
 void build_icp_maps(DeviceVoxelMap& fine, DeviceVoxelMap* coarse, DeviceVoxelMap* mid, const void* d_xyz, size_t n, size_t stride,
                     float cell, bool want_lists, cudaStream_t stream) {
     unsigned int* pos = nullptr;
-    fine.build(d_xyz, n, stride, cell, want_lists, stream, &pos);
+    DeviceVoxelMap::DupFlags dups;
+    fine.build(d_xyz, n, stride, cell, want_lists, stream, &pos, &dups);
+    DeviceVoxelMap::DupFlags* dp = dups.flags ? &dups : nullptr;
     if (mid) {
-        mid->build(d_xyz, n, stride, cell * kMidFactor, want_lists, stream);
+        mid->build(d_xyz, n, stride, cell * kMidFactor, want_lists, stream, nullptr, dp);
         if (pos && mid->view().nbr_slots != nullptr) mid->attach_to(fine.view(), pos, stream);
         else mid->clear();  // no lists (memory): stage 2 takes the corner-list path
     }
     float c = cell;
     for (int l = 0; l < kCoarseLevels; ++l) {
         c *= kCoarseFactor;
-        coarse[l].build(d_xyz, n, stride, c, false, stream);
+        coarse[l].build(d_xyz, n, stride, c, false, stream, nullptr, dp);
         if (pos) coarse[l].attach_to(fine.view(), pos, stream);
     }
     if (pos) LR_CUDA(cudaFreeAsync(pos, stream));
+    if (dups.flags) LR_CUDA(cudaFreeAsync(dups.flags, stream));
 }
 
 }  // namespace locreg
