@@ -45,6 +45,24 @@ for part in (m[:15_000], m[10_000:30_000], m[25_000:]):
     r.SetInputTarget(part)
 r.ScanMatch(scans[0], init[0])
 done.append("inc_ndt")
+# the device-side LRU at a tiny capacity: voxels evicted and re-inserted within one cloud (the reuse-distance count runs)
+r = L.NdtRegistration(L.NdtOptions(method_=L.NdtMethod.INCREMENTAL_NDT, capacity_=40))
+rng = np.random.default_rng(0)
+for c in range(3):
+    k = np.repeat(rng.integers(0, 90, 700) + 20 * c, rng.integers(1, 4, 700))
+    p = np.zeros((len(k), 4), np.float32)
+    p[:, 0] = (k % 10) + rng.random(len(k)) * 0.9; p[:, 1] = (k // 10) + rng.random(len(k)) * 0.9; p[:, 2] = rng.random(len(k)) * 0.9
+    p[::97, 1] = np.nan
+    r.SetInputTarget(p)
+r.Voxels()
+done.append("inc_ndt_lru")
+# Lio's key-frame block on the device (double-precision transform, window, voxel grid, target)
+for kind in (L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE, max_iteration_=3)),
+             L.NdtRegistration(L.NdtOptions(method_=L.NdtMethod.INCREMENTAL_NDT, capacity_=2000, max_iteration_=3))):
+    for i in range(4):
+        kind.AddKeyFrame(scans[i % 3], gt[i % 3], max_keyframes=2, leaf=0.5)
+    kind.ScanMatch(scans[0], init[0], want_cloud=False)
+done.append("lio_keyframes")
 pts = np.concatenate([clouds, np.full((3, 4), np.nan, np.float32)])
 r2 = L.IcpRegistration(L.IcpOptions(method_=L.IcpMethod.P2PLANE))
 r2.RemoveNanPoint(pts); r2.BoxFilter(clouds, clouds[:, :3].min(0) / 2, clouds[:, :3].max(0) / 2); r2.VoxelFilter(clouds, 1.0)
