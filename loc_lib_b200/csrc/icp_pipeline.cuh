@@ -531,9 +531,12 @@ constexpr int kRowStride = 7;  // J[6] + r
 // coefficients are then the ones a new fit would reproduce bit for bit.  A fit is ~500 dependent fp64 instructions, so
 // the rows that need one are compacted first: a block gathers them over `group` consecutive tiles and only then fits,
 // every lane busy, instead of one divergent lane holding a warp (and a barrier its whole tile) for the length of a fit.
-constexpr int kFitGroup = 16;
+#ifndef LR_FIT_GROUP
+#define LR_FIT_GROUP 16
+#endif
+constexpr int kFitGroup = LR_FIT_GROUP;
 #ifndef LR_FIT_MIN_BLOCKS
-#define LR_FIT_MIN_BLOCKS 3
+#define LR_FIT_MIN_BLOCKS 4  // 64 registers: measured 2..6 on B200 (3: +2 % step time, 2: +4 %, 5-6: +0.5 %)
 #endif
 // MAXG: the largest `group` the caller passes (sizes the shared-memory list)
 template <int MAXG>
@@ -657,8 +660,6 @@ __device__ __forceinline__ void icp_post_tile(unsigned int tile, const VoxelMapV
         }
     }
     RowSink<ROWS> sink{rows + threadIdx.x * ROWS * kRowStride, 0, false, false};
-#pragma unroll
-    for (int i = 0; i < ROWS * kRowStride; ++i) sink.rows[i] = 0.0;  // points without a residual contribute zero rows
     __syncthreads();
     if (in_tile) {
         unsigned char g = kGateSkipped;
@@ -680,6 +681,8 @@ __device__ __forceinline__ void icp_post_tile(unsigned int tile, const VoxelMapV
                 nn_idx[(tc.out_base + p) * K + j] = nn.pos[j] != kNoNeighbour ? __float_as_int(map.pts[nn.pos[j]].w) : -1;
         }
     }
+    // points without a residual contribute zero rows (written here, once, rather than zeroing every row up front)
+    for (int i = sink.n_rows * kRowStride; i < ROWS * kRowStride; ++i) sink.rows[i] = 0.0;
     // Per-warp Gram matrix G = R^T R of the warp's 32 * ROWS staged rows R = [J | r] on the fp64 tensor cores:
     // mma.m8n8k4 takes A (8 x 4, A[m][k] = R[4 ks + k][m]) and B (4 x 8, B[k][n] = R[4 ks + k][n]); a lane's A and B
     // fragments are the same element R[4 ks + (lane & 3)][lane >> 2], so one 8 B shared-memory load per lane feeds four
