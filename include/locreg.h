@@ -200,7 +200,8 @@ int locreg_transform_cloud(locreg_handle* h, const float* src, size_t n, size_t 
  *   remove_nan : pcl::removeNaNFromPointCloud - points with finite x, y, z, order kept
  *   crop_box   : pcl::CropBox(min, max), identity transform - finite points with min <= p <= max per axis, order kept
  *   voxel_grid : pcl::VoxelGrid(leaf, leaf, leaf), all fields - per occupied voxel the float32 mean of every float
- *                word of its points (summed in point order), voxels in ascending PCL voxel index */
+ *                word of its points (summed in point order), voxels in ascending PCL voxel index; when extent / leaf
+ *                would overflow PCL's int voxel index (> 2^31 - 1 voxels) the cloud is returned unfiltered, as PCL does */
 int locreg_filter_remove_nan(locreg_handle* h, const float* xyz, size_t n, size_t stride_bytes, float* out_xyz, size_t* n_out);
 int locreg_filter_crop_box(locreg_handle* h, const float* xyz, size_t n, size_t stride_bytes, const float* min3,
                            const float* max3, float* out_xyz, size_t* n_out);
@@ -223,7 +224,7 @@ int locreg_reset_local_map(locreg_handle* h, const float* origin3, const float* 
  * leaf size `leaf` (local_map_filter_ptr_->Filter, :299; leaf <= 0: NoFilter) and becomes the registration target
  * (:307) - for LOCREG_NDT_INCREMENTAL the key frame alone is added to the voxel cache (:301-303).  Nothing but the scan
  * crosses PCIe.  *n_local (may be NULL) receives the size of the local map.  The call is transactional: when a step
- * fails (out of memory, a voxel grid whose extent / leaf exceeds the 2^28-cell index space) the window and the local
+ * fails (out of memory) the window and the local
  * map are left as they were.
  * locreg_local_map_get copies the local map to the host (parity probe / PCD dump); locreg_local_map_clear forgets it. */
 int locreg_local_map_add_keyframe(locreg_handle* h, const float* scan_xyz, size_t n, size_t stride_bytes, const double* pose7,

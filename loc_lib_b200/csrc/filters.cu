@@ -77,32 +77,47 @@ __device__ __forceinline__ unsigned int voxel_index(const GridSpec& g, const flo
     const int i2 = static_cast<int>(floorf(__fmul_rn(p[2], g.inv_leaf)) - static_cast<float>(g.min_b[2]));
     return static_cast<unsigned int>(i0 * g.div_mul[0] + i1 * g.div_mul[1] + i2 * g.div_mul[2]);
 }
-__global__ void k_vg_count(const unsigned char* __restrict__ raw, size_t n, size_t stride, GridSpec g, unsigned int* pt_idx,
-                           unsigned int* hist) {
+// Voxel grid through a BITMAP of the index space (1 bit per voxel: 256 MB at PCL's own limit of 2^31 voxels, where dense
+// per-voxel arrays would take tens of GB): occupied voxels are marked, a voxel's place in the output - PCL emits the
+// voxels in ascending index - is the number of set bits below it (prefix sum over the bitmap's words + popcount), and
+// everything else is sized by the number of points.
+__global__ void k_vg_mark(const unsigned char* __restrict__ raw, size_t n, size_t stride, GridSpec g, unsigned int* pt_idx,
+                          unsigned int* bitmap) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* p = reinterpret_cast<const float*>(raw + i * stride);
     if (!finite3(p[0], p[1], p[2])) { pt_idx[i] = 0xFFFFFFFFu; return; }
     const unsigned int idx = voxel_index(g, p);
     pt_idx[i] = idx;
-    atomicAdd(&hist[idx], 1u);
+    atomicOr(&bitmap[idx >> 5], 1u << (idx & 31u));
 }
-__global__ void k_vg_occupied(const unsigned int* __restrict__ hist, size_t cells, unsigned int* occ) {
-    const size_t c = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (c < cells) occ[c] = hist[c] ? 1u : 0u;
+__global__ void k_vg_popc(const unsigned int* __restrict__ bitmap, size_t words, unsigned int* wcount) {
+    const size_t w = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w < words) wcount[w] = static_cast<unsigned int>(__popc(bitmap[w]));
 }
-__global__ void k_vg_scatter(size_t n, const unsigned int* __restrict__ pt_idx, const unsigned int* __restrict__ start,
+// pt_idx[i] becomes the rank of the point's voxel among the occupied ones; vcount[rank]++
+__global__ void k_vg_rank(size_t n, unsigned int* pt_idx, const unsigned int* __restrict__ bitmap, const unsigned int* __restrict__ wprefix,
+                          unsigned int* vcount) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int idx = pt_idx[i];
+    if (idx == 0xFFFFFFFFu) return;
+    const unsigned int r = wprefix[idx >> 5] + static_cast<unsigned int>(__popc(bitmap[idx >> 5] & ((1u << (idx & 31u)) - 1u)));
+    pt_idx[i] = r;
+    atomicAdd(&vcount[r], 1u);
+}
+__global__ void k_vg_scatter(size_t n, const unsigned int* __restrict__ pt_rank, const unsigned int* __restrict__ start,
                              unsigned int* cursor, unsigned int* members) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n || pt_idx[i] == 0xFFFFFFFFu) return;
-    members[start[pt_idx[i]] + atomicAdd(&cursor[pt_idx[i]], 1u)] = static_cast<unsigned int>(i);
+    if (i >= n || pt_rank[i] == 0xFFFFFFFFu) return;
+    members[start[pt_rank[i]] + atomicAdd(&cursor[pt_rank[i]], 1u)] = static_cast<unsigned int>(i);
 }
-__global__ void k_vg_centroid(const unsigned char* __restrict__ raw, size_t stride, size_t cells, const unsigned int* __restrict__ start,
-                              const unsigned int* __restrict__ rank, unsigned int* members, unsigned char* out) {
-    const size_t c = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (c >= cells) return;
-    const unsigned int beg = start[c], cnt = start[c + 1] - beg;
-    if (cnt == 0) return;
+// one thread per occupied voxel (rank r < *n_out): float32 mean of every float word over its points in point order
+__global__ void k_vg_centroid(const unsigned char* __restrict__ raw, size_t stride, const unsigned int* __restrict__ n_out,
+                              const unsigned int* __restrict__ start, unsigned int* members, unsigned char* out) {
+    const size_t r = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= *n_out) return;
+    const unsigned int beg = start[r], cnt = start[r + 1] - beg;
     unsigned int* idx = members + beg;
     for (unsigned int a = 1; a < cnt; ++a) {  // point-index order: the atomics above arrive in any order
         const unsigned int v = idx[a];
@@ -116,7 +131,7 @@ __global__ void k_vg_centroid(const unsigned char* __restrict__ raw, size_t stri
         const float* p = reinterpret_cast<const float*>(raw + static_cast<size_t>(idx[j]) * stride);
         for (size_t w = 0; w < words; ++w) sum[w] = __fadd_rn(sum[w], p[w]);
     }
-    float* o = reinterpret_cast<float*>(out + static_cast<size_t>(rank[c]) * stride);
+    float* o = reinterpret_cast<float*>(out + r * stride);
     const float fn = static_cast<float>(cnt);
     for (size_t w = 0; w < words; ++w) o[w] = __fdiv_rn(sum[w], fn);
     for (size_t w = words; w < stride / 4; ++w) o[w] = 0.0f;
@@ -185,28 +200,34 @@ size_t filter_voxel_grid(const unsigned char* d_raw, size_t n, size_t stride, fl
         g.min_b[a] = static_cast<int>(floorf(lo * g.inv_leaf));
         div[a] = static_cast<long long>(static_cast<int>(floorf(hi * g.inv_leaf))) - g.min_b[a] + 1;
     }
-    // PCL refuses when the index would overflow an int ("Leaf size is too small for the input dataset"); a dense
-    // histogram additionally has to fit in memory: 2^28 cells = 3 GB of scratch on a 180 GB part
-    if (div[0] * div[1] * div[2] > (1ll << 28)) throw std::invalid_argument("voxel grid: leaf size too small for the extent of the cloud");
+    // PCL gives up when the voxel index would overflow an int ("Leaf size is too small for the input dataset. Integer
+    // indices would overflow.") and returns the cloud UNFILTERED (voxel_grid.hpp: output = *input): one far outlier in a
+    // key frame must not stop Lio
+    if (div[0] * div[1] * div[2] > 0x7fffffffll) {
+        LR_CUDA(cudaMemcpyAsync(d_out, d_raw, n * stride, cudaMemcpyDeviceToDevice, stream));
+        LR_CUDA(cudaStreamSynchronize(stream));
+        return n;
+    }
     g.div_mul[0] = 1; g.div_mul[1] = static_cast<int>(div[0]); g.div_mul[2] = static_cast<int>(div[0] * div[1]);
     const size_t cells = static_cast<size_t>(div[0] * div[1] * div[2]);
+    const size_t words = (cells + 31) / 32;
     unsigned int* pt_idx = tmp.get<unsigned int>(n);
-    unsigned int* hist = tmp.get<unsigned int>(cells + 1);
-    unsigned int* start = tmp.get<unsigned int>(cells + 1);
-    unsigned int* occ = tmp.get<unsigned int>(cells);
-    unsigned int* rank = tmp.get<unsigned int>(cells);
-    unsigned int* cursor = tmp.get<unsigned int>(cells);
+    unsigned int* bitmap = tmp.get<unsigned int>(words);
+    unsigned int* wprefix = tmp.get<unsigned int>(words);
+    unsigned int* vstart = tmp.get<unsigned int>(n + 1);  // occupied voxels <= points
+    unsigned int* cursor = tmp.get<unsigned int>(n);
     unsigned int* members = tmp.get<unsigned int>(n);
     unsigned int* total = tmp.get<unsigned int>(1);
-    LR_CUDA(cudaMemsetAsync(hist, 0, (cells + 1) * sizeof(unsigned int), stream));
-    LR_CUDA(cudaMemsetAsync(cursor, 0, cells * sizeof(unsigned int), stream));
-    LR_LAUNCH(k_vg_count, gridN, 256, 0, stream, d_raw, n, stride, g, pt_idx, hist);
-    exclusive_scan_u32(hist, start, cells + 1, nullptr, stream);
-    const unsigned int gridC = static_cast<unsigned int>((cells + 255) / 256);
-    LR_LAUNCH(k_vg_occupied, gridC, 256, 0, stream, hist, cells, occ);
-    exclusive_scan_u32(occ, rank, cells, total, stream);
-    LR_LAUNCH(k_vg_scatter, gridN, 256, 0, stream, n, pt_idx, start, cursor, members);
-    LR_LAUNCH(k_vg_centroid, gridC, 256, 0, stream, d_raw, stride, cells, start, rank, members, d_out);
+    LR_CUDA(cudaMemsetAsync(bitmap, 0, words * sizeof(unsigned int), stream));
+    LR_CUDA(cudaMemsetAsync(vstart, 0, (n + 1) * sizeof(unsigned int), stream));
+    LR_CUDA(cudaMemsetAsync(cursor, 0, n * sizeof(unsigned int), stream));
+    LR_LAUNCH(k_vg_mark, gridN, 256, 0, stream, d_raw, n, stride, g, pt_idx, bitmap);
+    LR_LAUNCH(k_vg_popc, static_cast<unsigned int>((words + 255) / 256), 256, 0, stream, bitmap, words, wprefix);
+    exclusive_scan_u32(wprefix, wprefix, words, total, stream);
+    LR_LAUNCH(k_vg_rank, gridN, 256, 0, stream, n, pt_idx, bitmap, wprefix, vstart);
+    exclusive_scan_u32(vstart, vstart, n + 1, nullptr, stream);
+    LR_LAUNCH(k_vg_scatter, gridN, 256, 0, stream, n, pt_idx, vstart, cursor, members);
+    LR_LAUNCH(k_vg_centroid, gridN, 256, 0, stream, d_raw, stride, total, vstart, members, d_out);
     unsigned int n_out = 0;
     LR_CUDA(cudaMemcpyAsync(&n_out, total, sizeof(n_out), cudaMemcpyDeviceToHost, stream));
     LR_CUDA(cudaStreamSynchronize(stream));

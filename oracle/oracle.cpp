@@ -1152,8 +1152,8 @@ size_t oracle_filter_crop_box(const float* src, size_t n, size_t stride, const f
 }
 /* pcl::VoxelGrid::applyFilter (voxel_grid.hpp), cubic leaf, downsample_all_data: voxel index from float floor(p *
  * inverse_leaf) - min_b, points sorted by voxel index (stable here: PCL's std::sort leaves the order inside a voxel
- * unspecified), float32 mean of every float word, voxels in ascending index.  Returns (size_t)-1 if the index space
- * exceeds 2^28 cells (PCL itself gives up at 2^31). */
+ * unspecified), float32 mean of every float word, voxels in ascending index.  When the index space exceeds an int
+ * ("Leaf size is too small for the input dataset. Integer indices would overflow.") PCL returns the cloud unfiltered. */
 size_t oracle_filter_voxel_grid(const float* src, size_t n, size_t stride, float leaf, float* out) {
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     bool any = false;
@@ -1171,7 +1171,10 @@ size_t oracle_filter_voxel_grid(const float* src, size_t n, size_t stride, float
         min_b[a] = static_cast<int>(std::floor(mn[a] * inv));
         div[a] = static_cast<long long>(static_cast<int>(std::floor(mx[a] * inv))) - min_b[a] + 1;
     }
-    if (div[0] * div[1] * div[2] > (1ll << 28)) return static_cast<size_t>(-1);
+    if (div[0] * div[1] * div[2] > 0x7fffffffll) {  // output = *input
+        for (size_t i = 0; i < n; ++i) std::memcpy(pt_at(out, i, stride), pt_at(src, i, stride), stride);
+        return n;
+    }
     const int mul[3] = {1, static_cast<int>(div[0]), static_cast<int>(div[0] * div[1])};
     std::vector<std::pair<unsigned int, unsigned int>> iv;  // (voxel index, point index)
     for (size_t i = 0; i < n; ++i) {

@@ -295,6 +295,23 @@ def test_inc_ndt_cache_hb_and_pose(scene):
     assert np.array_equal(pose, scene.init[0])
 
 
+def test_voxel_grid_large_extent_and_overflow(icp_pair):
+    """pcl::VoxelGrid over an index space far larger than the cloud (a far outlier in a key frame): filtered exactly like
+    the oracle up to PCL's limit of 2^31 - 1 voxels, returned unfiltered beyond it (voxel_grid.hpp)."""
+    gpu, _ = icp_pair
+    rng = np.random.default_rng(5)
+    pts = np.zeros((20000, 4), np.float32)
+    pts[:, :3] = rng.normal(0, 8, (20000, 3))
+    pts[:, 3] = rng.random(20000)
+    far = pts.copy()
+    far[0, :3] = [600.0, -550.0, 40.0]      # 0.5 m leaf: ~1300 x 1200 x 200 = 3e8 voxels (> 2^28, < 2^31)
+    got, exp = gpu.VoxelFilter(far, 0.5), O.filter_voxel_grid(far, 0.5)
+    assert len(got) == len(exp) and np.array_equal(got, exp)
+    far[0, :3] = [9000.0, -9000.0, 900.0]   # 18000 x 18000 x 1900 voxels: the int index would overflow
+    got, exp = gpu.VoxelFilter(far, 0.5), O.filter_voxel_grid(far, 0.5)
+    assert len(exp) == len(far) and np.array_equal(got, exp) and np.array_equal(got, far)
+
+
 @pytest.mark.parametrize("capacity,n_keys,n_pts,seed", [(4, 6, 60, 0), (9, 12, 400, 1), (33, 40, 3000, 2), (33, 200, 3000, 3),
                                                          (120, 150, 5000, 4), (2, 5, 50, 5), (50, 30, 2000, 6), (700, 900, 40000, 7)])
 def test_inc_ndt_device_lru_adversarial(capacity, n_keys, n_pts, seed):

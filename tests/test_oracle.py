@@ -473,3 +473,15 @@ def test_oracle_reproduces_golden():
         assert np.array_equal(cur[k], g[k]), k
     for k in G.CLOSE_KEYS:
         assert np.allclose(cur[k], g[k], rtol=1e-9, atol=1e-12), k
+
+
+def test_voxel_grid_overflow_returns_cloud_unfiltered():
+    """pcl::VoxelGrid gives up when dx * dy * dz overflows its int voxel index and returns the input cloud (voxel_grid.hpp:
+    "Leaf size is too small for the input dataset. Integer indices would overflow.")."""
+    rng = np.random.default_rng(2)
+    pts = np.zeros((500, 4), np.float32)
+    pts[:, :3] = rng.normal(0, 3, (500, 3))
+    assert len(O.filter_voxel_grid(pts, 0.5)) < 500
+    pts[0, :3] = [9000.0, -9000.0, 900.0]
+    out = O.filter_voxel_grid(pts, 0.5)
+    assert np.array_equal(out, pts)
