@@ -48,8 +48,11 @@ enum locreg_nearby { LOCREG_NEARBY_CENTER = 0, LOCREG_NEARBY6 = 1 };
 /* how the Gauss-Newton loop is kept on the device */
 enum locreg_loop { LOCREG_LOOP_PERSISTENT = 0, /* the whole Gauss-Newton loop of one ScanMatch in ONE cooperative kernel
                                                   (grid barrier per iteration): k_align_persist (NDT), k_icp_persist (ICP) */
-                   LOCREG_LOOP_GRAPH = 1 /* per-iteration kernels, the loop captured once into a CUDA graph and replayed
-                                            with one cudaGraphLaunch per ScanMatch (re-captured when the scan size changes) */ };
+                   LOCREG_LOOP_GRAPH = 1 /* per-iteration kernels (search, stage 2, fit, normal equations, solve) queued back
+                                            to back on the stream for all iterations with no host round trip; stop flags in
+                                            device memory make the kernels of a finished scan exit at once.  (The name is
+                                            historical: the launches are plain stream launches, not a captured CUDA graph;
+                                            batches and relocalisation always run this way.) */ };
 
 /* POD mirror of IcpOptions (icp_registration.hpp:22-39) + NdtOptions (ndt_registration.hpp:27-42). */
 typedef struct locreg_options {
