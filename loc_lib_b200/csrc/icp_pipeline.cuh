@@ -394,7 +394,15 @@ __device__ __forceinline__ void icp_rings_warps(unsigned int n, unsigned int war
                                                 const CoarseLevels& coarse, const BatchView& bv, const AlignState* __restrict__ states,
                                                 unsigned int* __restrict__ nn_pos, KnnTrack* track, const RingQueue& queue) {
     const unsigned int lane = threadIdx.x & 31;
-    for (unsigned int e = warp; e < n; e += n_warps) {
+    // Queries differ many-fold in cost (a list scan, or shells up the coarse levels for a point far from everything), and
+    // the phase ends with the slowest warp: warps take the next query from a shared cursor (queue.count[1], zero at the
+    // start of every evaluation) instead of owning a fixed stride of the queue.
+    (void)warp; (void)n_warps;
+    while (true) {
+        unsigned int e = 0;
+        if (lane == 0) e = atomicAdd(queue.count + 1, 1u);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= n) break;
         const uint2 q = queue.entries[e];
         // scratch rows and source points coincide for a batch; hypotheses of one scan share its points
         const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
