@@ -44,7 +44,7 @@ __device__ __forceinline__ void persist_sum_rows(const double* __restrict__ part
 // partials: 2 * n_tiles rows, double-buffered by iteration parity (a fast block starts the next evaluation while a slow
 // one still sums the rows of this one).  track_from: first iteration that runs the tracked search.
 #ifndef LR_PERSIST_MIN_BLOCKS
-#define LR_PERSIST_MIN_BLOCKS 2
+#define LR_PERSIST_MIN_BLOCKS 1  // 174 registers, no spills: 0.436 ms per ScanMatch against 0.468 at 2 blocks per SM (128 registers), 0.49 at 3, 0.52 at 4
 #endif
 template <int METHOD>
 __global__ void __launch_bounds__(kTile, LR_PERSIST_MIN_BLOCKS)

@@ -458,7 +458,7 @@ void icp_run_loop(locreg_handle* h, const IcpJob& job, int final_eval) {
     }
 }
 // One scan, whole loop in ONE cooperative launch (icp_persist.cuh).  Returns false when the job does not suit it (then
-// the per-iteration pipeline runs): the persistent grid holds two blocks per SM, a scan of more tiles than 8x that would
+// the per-iteration pipeline runs): the persistent grid holds one block per SM, a scan of more tiles than 8x that would
 // serialise what the pipeline spreads over the whole GPU.
 template <int METHOD>
 bool icp_run_persistent(locreg_handle* h, const IcpJob& job) {
