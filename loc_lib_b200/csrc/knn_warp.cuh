@@ -200,6 +200,15 @@ __device__ __forceinline__ bool warp_query_rings(const VoxelMapView& m, float qx
     }
 }
 
+// Escalation limits of the warp-cooperative search (the thread-per-query form has its own, voxel_map.cuh): a warp walks
+// the cells of a mid-level shell one after the other, so it leaves that level sooner.
+#ifndef LR_WARP_MID_SHELLS
+#define LR_WARP_MID_SHELLS 1  // measured 0..3 (stage 2 of a single scan, first iteration: 57 / 55 / 65 / 71 us; the thread form's 4: 85 us)
+#endif
+#ifndef LR_WARP_COARSE_SHELLS
+#define LR_WARP_COARSE_SHELLS 16  // measured 8..24: flat from 12 on
+#endif
+constexpr int kWarpMidShells = LR_WARP_MID_SHELLS, kWarpCoarseShells = LR_WARP_COARSE_SHELLS;
 // Everything after stage 1 for one query, by one warp (see knn_query_finish for the escalation logic).
 // margin (optional): receives the KnnTrack margin when the search ends with the mid level's list (the stage-2 form of
 // knn_query_fast_track: the list holds every point of the mid box, so the scan knows d6), else -1.
@@ -229,8 +238,8 @@ __device__ __forceinline__ void warp_query_finish(const VoxelMapView& m, const C
             }
             boxes_done = 1;
         }
-        if (!(have_coarse && c.R0 > kMidShells) &&
-            warp_query_rings<K>(md, qx, qy, qz, res, boxes_done, have_coarse ? kMidShells : kBruteForceShell))
+        if (!(have_coarse && c.R0 > kWarpMidShells) &&
+            warp_query_rings<K>(md, qx, qy, qz, res, boxes_done, have_coarse ? kWarpMidShells : kBruteForceShell))
             return;
     }
     if (!have_mid) {
@@ -249,8 +258,8 @@ __device__ __forceinline__ void warp_query_finish(const VoxelMapView& m, const C
         const VoxelMapView& cl = coarse.lv[l];
         if (cl.n_pts == 0) break;
         const bool last = l + 1 == kCoarseLevels || coarse.lv[l + 1].n_pts == 0;
-        if (!last && knn_frame(cl, qx, qy, qz).R0 > kCoarseShells) continue;
-        if (warp_query_rings<K>(cl, qx, qy, qz, res, 0, last ? kBruteForceShell : kCoarseShells)) return;
+        if (!last && knn_frame(cl, qx, qy, qz).R0 > kWarpCoarseShells) continue;
+        if (warp_query_rings<K>(cl, qx, qy, qz, res, 0, last ? kBruteForceShell : kWarpCoarseShells)) return;
     }
     // linear scan, lanes striding over the whole map
     knn_init(res);
