@@ -12,7 +12,8 @@
 //                   grid barrier; every block sums the rows in a fixed order and solves the 6x6 system itself: the
 //                   new pose is in every block's shared memory without another exchange.
 //
-// Two barriers in an iteration whose searches all finish in stage 1 (from the third iteration on, typically).
+// Three barriers in an iteration with many queued queries (the first one or two); with few, the block that searched a
+// tile finishes its queued queries itself and there is ONE barrier per iteration.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -43,6 +44,9 @@ __device__ __forceinline__ void persist_sum_rows(const double* __restrict__ part
 
 // partials: 2 * n_tiles rows, double-buffered by iteration parity (a fast block starts the next evaluation while a slow
 // one still sums the rows of this one).  track_from: first iteration that runs the tracked search.
+#ifndef LR_PERSIST_LOCAL_PER_TILE
+#define LR_PERSIST_LOCAL_PER_TILE 16  // queued queries per tile (previous iteration, average) up to which a block serves its own
+#endif
 #ifndef LR_PERSIST_MIN_BLOCKS
 #define LR_PERSIST_MIN_BLOCKS 1  // 174 registers, no spills: 0.436 ms per ScanMatch against 0.468 at 2 blocks per SM (128 registers), 0.49 at 3, 0.52 at 4
 #endif
@@ -67,38 +71,74 @@ k_icp_persist(VoxelMapView map, CoarseLevels coarse, IcpParams prm, BatchView bv
         dbg[it * 6 + (k)] = t_;                                                            \
     }
     unsigned char* pv = METHOD == kIcpP2Plane ? plane_valid : nullptr;
+    // Three (count, cursor) pairs of the stage-2 queue, used in rotation: iteration `it` appends to pair it % 3 and reads
+    // its count after a grid barrier; pair (it + 1) % 3 - last read two barriers ago - is zeroed meanwhile.
+    unsigned int* const counters = queue.count;
+    __shared__ unsigned int s_pend[kTile];
+    __shared__ unsigned int s_npend;
+    unsigned int last_n = 0xFFFFFFFFu;  // queries the previous iteration queued (none yet: take the grid-wide form)
     for (int it = 0; it < prm.max_iteration && !s_state.stop; ++it) {
         const int mode = it == 0 ? kNnTwoPass : (it >= track_from ? (kNnSeeds | kNnTrack) : kNnSeeds);
+        const RingQueue q_it{counters + 2 * (it % 3), queue.entries};
+        if (blockIdx.x == 0 && threadIdx.x == 0) { counters[2 * ((it + 1) % 3)] = 0u; counters[2 * ((it + 1) % 3) + 1] = 0u; }
+        double* rows = partials + static_cast<size_t>(it & 1) * n_tiles * kPartialDoubles;
+        // Few queued queries (a handful per tile from the second or third iteration on): the block that searched the tile
+        // finishes them itself, a warp each, and goes straight on to the tile's planes and normal equations - ONE grid
+        // barrier per iteration instead of three, and no block waits for the slowest tile more than once.
+        const bool local = last_n <= static_cast<unsigned int>(LR_PERSIST_LOCAL_PER_TILE) * n_tiles;
         LR_STAMP(0)
-        for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            if (mode & kNnTrack) icp_nn_tile<K, true>(tile, map, bv, &s_state, 0, mode, nn_pos, pv, track, queue);
-            else icp_nn_tile<K, false>(tile, map, bv, &s_state, 0, mode, nn_pos, pv, track, queue);
-            __syncthreads();
-        }
-        LR_STAMP(1)
-        __threadfence();
-        grid.sync();
-        LR_STAMP(2)
-        const unsigned int n_queued = __ldcg(queue.count);
-        if (n_queued != 0u) {  // the same value in every block: nobody appends between the two barriers
-            icp_rings_warps<K>(n_queued, warp, n_warps, map, coarse, bv, &s_state, nn_pos, track, queue);
+        if (local) {
+            for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                if (threadIdx.x == 0) s_npend = 0u;
+                __syncthreads();
+                if (mode & kNnTrack) icp_nn_tile<K, true>(tile, map, bv, &s_state, 0, mode, nn_pos, pv, track, q_it, s_pend, &s_npend);
+                else icp_nn_tile<K, false>(tile, map, bv, &s_state, 0, mode, nn_pos, pv, track, q_it, s_pend, &s_npend);
+                __syncthreads();
+                const unsigned int n_p = s_npend;
+                for (unsigned int e = threadIdx.x >> 5; e < n_p; e += kTile / 32)
+                    icp_rings_query<K>(make_uint2(s_pend[e], 0u), map, coarse, bv, &s_state, nn_pos, track);
+                __syncthreads();
+                if (METHOD == kIcpP2Plane) {
+                    icp_fit_group<1>(tile, map, prm, bv, &s_state, 0, nn_pos, plane_valid, plane_cache, plane_stat, 1u);
+                    __syncthreads();
+                }
+                icp_post_tile<METHOD>(tile, map, prm, bv, &s_state, 0, nn_pos, rows, nullptr, nullptr, plane_cache, plane_stat);
+                __syncthreads();
+            }
+            LR_STAMP(1) LR_STAMP(2) LR_STAMP(3) LR_STAMP(4)
+            __threadfence();
+            grid.sync();
+            last_n = __ldcg(q_it.count);
+        } else {
+            for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                if (mode & kNnTrack) icp_nn_tile<K, true>(tile, map, bv, &s_state, 0, mode, nn_pos, pv, track, q_it);
+                else icp_nn_tile<K, false>(tile, map, bv, &s_state, 0, mode, nn_pos, pv, track, q_it);
+                __syncthreads();
+            }
+            LR_STAMP(1)
+            __threadfence();
+            grid.sync();
+            LR_STAMP(2)
+            const unsigned int n_queued = __ldcg(q_it.count);
+            last_n = n_queued;
+            if (n_queued != 0u) {  // the same value in every block: nobody appends between the two barriers
+                icp_rings_warps<K>(n_queued, warp, n_warps, map, coarse, bv, &s_state, nn_pos, track, q_it);
+                __threadfence();
+                grid.sync();
+            }
+            LR_STAMP(3)
+            for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                if (METHOD == kIcpP2Plane) {
+                    icp_fit_group<1>(tile, map, prm, bv, &s_state, 0, nn_pos, plane_valid, plane_cache, plane_stat, 1u);
+                    __syncthreads();
+                }
+                icp_post_tile<METHOD>(tile, map, prm, bv, &s_state, 0, nn_pos, rows, nullptr, nullptr, plane_cache, plane_stat);
+                __syncthreads();
+            }
+            LR_STAMP(4)
             __threadfence();
             grid.sync();
         }
-        LR_STAMP(3)
-        double* rows = partials + static_cast<size_t>(it & 1) * n_tiles * kPartialDoubles;
-        for (unsigned int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            if (METHOD == kIcpP2Plane) {
-                icp_fit_group<1>(tile, map, prm, bv, &s_state, 0, nn_pos, plane_valid, plane_cache, plane_stat, 1u);
-                __syncthreads();
-            }
-            icp_post_tile<METHOD>(tile, map, prm, bv, &s_state, 0, nn_pos, rows, nullptr, nullptr, plane_cache, plane_stat);
-            __syncthreads();
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) { queue.count[0] = 0u; queue.count[1] = 0u; }  // re-armed for the next search
-        LR_STAMP(4)
-        __threadfence();
-        grid.sync();
         LR_STAMP(5)
         persist_sum_rows(rows, n_tiles, stage, acc32);
         if (threadIdx.x == 0) {

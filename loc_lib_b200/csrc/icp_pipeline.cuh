@@ -181,8 +181,12 @@ struct RingQueue {
 
 // Block-aggregated queue append without a block barrier (see k_icp_nn).  pending/done/staged live in shared memory
 // and must have been zeroed before a __syncthreads() that every thread of the block has passed.
+// local_rows / local_n (optional, shared memory of the caller, *local_n zero on entry): the rows stay in the block - the
+// caller serves them itself after a barrier (the single-scan kernel from its second iteration on) - and the global queue
+// only counts them.
 __device__ __forceinline__ void tile_queue_append(bool mine, unsigned int row, unsigned int scan, unsigned int* pending,
-                                                  unsigned int* done, unsigned int* staged, const RingQueue& queue) {
+                                                  unsigned int* done, unsigned int* staged, const RingQueue& queue,
+                                                  unsigned int* local_rows = nullptr, unsigned int* local_n = nullptr) {
     const unsigned int lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
 #if defined(LR_APPEND_BARRIER)
     // Checking build (compute-sanitizer racecheck does not model the fence + arrival-counter hand-over below and reports
@@ -194,6 +198,11 @@ __device__ __forceinline__ void tile_queue_append(bool mine, unsigned int row, u
     {
         const unsigned int n = *pending;
         if (n == 0u) return;
+        if (local_rows != nullptr) {
+            for (unsigned int i = lane; i < n; i += 32) local_rows[i] = staged[i];
+            if (lane == 0) { *local_n = n; atomicAdd(queue.count, n); }
+            return;
+        }
         unsigned int base = 0;
         if (lane == 0) base = atomicAdd(queue.count, n);
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -213,6 +222,11 @@ __device__ __forceinline__ void tile_queue_append(bool mine, unsigned int row, u
     __syncwarp();  // lane 0's acquire fence orders the other lanes' reads below as well
     const unsigned int n = *reinterpret_cast<volatile unsigned int*>(pending);
     if (n == 0u) return;
+    if (local_rows != nullptr) {
+        for (unsigned int i = lane; i < n; i += 32) local_rows[i] = reinterpret_cast<volatile unsigned int*>(staged)[i];
+        if (lane == 0) { *local_n = n; atomicAdd(queue.count, n); }
+        return;
+    }
     unsigned int base = 0;
     if (lane == 0) base = atomicAdd(queue.count, n);
     base = __shfl_sync(0xffffffffu, base, 0);
@@ -236,7 +250,7 @@ template <int K, bool TRACKED>
 __device__ __forceinline__ void icp_nn_tile(unsigned int tile, const VoxelMapView& map, const BatchView& bv,
                                             const AlignState* __restrict__ states, int ignore_stop, int mode,
                                             unsigned int* __restrict__ nn_pos, unsigned char* __restrict__ plane_valid, KnnTrack* track,
-                                            const RingQueue& queue) {
+                                            const RingQueue& queue, unsigned int* local_rows = nullptr, unsigned int* local_n = nullptr) {
     __shared__ Pose T;
     const TileCoord tc = locate_tile(bv, tile);
     if (!tc.valid) return;
@@ -319,7 +333,7 @@ __device__ __forceinline__ void icp_nn_tile(unsigned int tile, const VoxelMapVie
         if (plane_valid && !same) plane_valid[row] = 0;  // k_icp_fit sets it again
         if (track) track[row] = tr;  // margin -1 unless this was a tracked search that ended here
     }
-    tile_queue_append(!done, static_cast<unsigned int>(row), tc.scan, &blk_pending, &blk_done, staged, queue);
+    tile_queue_append(!done, static_cast<unsigned int>(row), tc.scan, &blk_pending, &blk_done, staged, queue, local_rows, local_n);
 }
 template <int K, bool TRACKED>
 __global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_NN_MIN_BLOCKS) k_icp_nn(VoxelMapView map, BatchView bv,
@@ -386,6 +400,43 @@ __global__ void __launch_bounds__(128, LR_FINISH_MIN_BLOCKS) k_icp_nn_finish(Vox
     }
 }
 
+// One queued query, by one warp: everything after stage 1 (warp_query_finish), seeded with what stage 1 found.
+template <int K>
+__device__ __forceinline__ void icp_rings_query(const uint2 q, const VoxelMapView& map, const CoarseLevels& coarse, const BatchView& bv,
+                                                const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos, KnnTrack* track) {
+    const unsigned int lane = threadIdx.x & 31;
+    // scratch rows and source points coincide for a batch; hypotheses of one scan share its points
+    const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
+    const float4 sp = bv.src[src_idx];
+    Pose T;
+    pose_load(T, states[q.y].pose);
+    double wx, wy, wz;
+    pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
+    const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
+    unsigned int* out = nn_pos + static_cast<size_t>(q.x) * K;
+    KnnResult<K> nn;  // replicated: every lane holds the same set
+    knn_init(nn);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const unsigned int sp_j = out[j];
+        if (sp_j < map.n_pts) {
+            const float4 c = map.pts[sp_j];
+            knn_offer(map.pts, nn, dis2_f32(qx, qy, qz, c.x, c.y, c.z), sp_j);
+        }
+    }
+    float margin = -1.0f;
+    warp_query_finish<K>(map, coarse, qx, qy, qz, nn, track ? &margin : nullptr);
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
+        if (track) {  // (see k_icp_nn_finish)
+            KnnTrack tr;
+            tr.qx = qx; tr.qy = qy; tr.qz = qz; tr.margin = margin;
+            track[q.x] = tr;
+        }
+    }
+}
 // Stage 2 of SMALL jobs (one scan): ONE QUERY PER WARP (knn_warp.cuh), seeded with what stage 1 found.  The GPU is
 // mostly idle, so what counts is the latency of the slowest query, and 32 lanes cut that ~10x.
 // Persistent warp-stride launch: the queue length is only known on the device.
@@ -403,38 +454,7 @@ __device__ __forceinline__ void icp_rings_warps(unsigned int n, unsigned int war
         if (lane == 0) e = atomicAdd(queue.count + 1, 1u);
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e >= n) break;
-        const uint2 q = queue.entries[e];
-        // scratch rows and source points coincide for a batch; hypotheses of one scan share its points
-        const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
-        const float4 sp = bv.src[src_idx];
-        Pose T;
-        pose_load(T, states[q.y].pose);
-        double wx, wy, wz;
-        pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
-        const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
-        unsigned int* out = nn_pos + static_cast<size_t>(q.x) * K;
-        KnnResult<K> nn;  // replicated: every lane holds the same set
-        knn_init(nn);
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const unsigned int sp_j = out[j];
-            if (sp_j < map.n_pts) {
-                const float4 c = map.pts[sp_j];
-                knn_offer(map.pts, nn, dis2_f32(qx, qy, qz, c.x, c.y, c.z), sp_j);
-            }
-        }
-        float margin = -1.0f;
-        warp_query_finish<K>(map, coarse, qx, qy, qz, nn, track ? &margin : nullptr);
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < K; ++j) out[j] = nn.pos[j];
-            if (track) {  // (see k_icp_nn_finish)
-                KnnTrack tr;
-                tr.qx = qx; tr.qy = qy; tr.qz = qz; tr.margin = margin;
-                track[q.x] = tr;
-            }
-        }
+        icp_rings_query<K>(queue.entries[e], map, coarse, bv, states, nn_pos, track);
     }
 }
 template <int K>

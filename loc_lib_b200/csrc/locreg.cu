@@ -479,8 +479,8 @@ bool icp_run_persistent(locreg_handle* h, const IcpJob& job) {
     h->d_same.reserve(job.n_scratch_points);
     h->d_plane.reserve(job.n_scratch_points * 4 * sizeof(double));
     h->d_pstat.reserve(job.n_scratch_points);
-    h->d_ringc.reserve(2 * sizeof(unsigned int));
-    LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, 2 * sizeof(unsigned int), h->stream));
+    h->d_ringc.reserve(6 * sizeof(unsigned int));  // three (count, cursor) pairs used in rotation (icp_persist.cuh)
+    LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, 6 * sizeof(unsigned int), h->stream));
     (void)cache;
     // every block of the grid lends its warps to the stage-2 queue, so the grid is the full co-resident capacity even
     // when the scan has fewer tiles
