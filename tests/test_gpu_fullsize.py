@@ -77,6 +77,25 @@ def test_fullsize_batch_equals_single_and_recovers_ground_truth(full):
     assert np.median([pose_delta(p, g)[1] for p, g in zip(poses, full.gt)]) < 0.006
 
 
+def test_fullsize_single_scan_of_many_tiles_through_the_one_launch_kernel(full):
+    """A 128-beam scan (~230 k points = ~900 tiles, six tiles per block of the persistent grid) through the one-launch
+    single-scan kernel - grid-wide and in-block stage 2, the rotating queue counters - against the per-iteration pipeline
+    (a batch of one): the same neighbours and planes, sums in another fixed order."""
+    scan = full.world.scan(full.gt[3], beams=128, azimuth=1953)
+    assert len(scan) > 150_000
+    _, cloud, pose = full.reg.ScanMatch(scan, full.init[3])
+    assert full.reg.last_timing()[1] <= 3  # the loop is one launch (+ the cloud transform)
+    res1 = dict(full.reg.last_result)
+    offsets = np.array([0, len(scan)], np.int64)
+    poses, res = full.reg.ScanMatchBatch(scan, offsets, full.init[3:4])
+    dr, dt = pose_delta(pose, poses[0])
+    assert dr < 1e-9 and dt < 1e-9, (dr, dt)
+    assert res1["iters"] == res[0]["iters"] == 10 and res1["n_effective"] == res[0]["n_effective"]
+    assert res1["n_inlier"] == res[0]["n_inlier"]
+    dr, dt = pose_delta(pose, full.gt[3])
+    assert dt < 0.05 and dr < 5e-3
+
+
 def test_fullsize_pipelined_batch_equals_plain_batch(full):
     """locreg_align_batch from PINNED host memory overlaps chunked copies with compute; same poses, bit for bit."""
     import torch
