@@ -25,10 +25,13 @@ class DeviceVoxelMap {
     // Turns this map into a coarse level of `fine`: every entry's w (original index) is replaced by the point's
     // canonical position in fine's pts, which is what the search reports on every level.
     void attach_to(const VoxelMapView& fine, const unsigned int* fine_pos_of_index, cudaStream_t stream);
+    // Block pyramid over this (fine) level for the ball-query stage 2 (voxel_map.cuh); no synchronisation.
+    void build_pyramid(cudaStream_t stream);
+    const PyrView& pyramid() const { return pyr_view_; }
     const VoxelMapView& view() const { return view_; }
     bool empty() const { return view_.n_pts == 0; }
     void clear() { release(); }  // forgets the map, keeps the memory
-    size_t bytes() const { return bytes_; }
+    size_t bytes() const { return bytes_ + pyr_bytes_; }
     unsigned int n_cells() const { return n_cells_; }
     unsigned int n_blocks() const { return n_blocks_; }
     unsigned int n_lists() const { return n_lists_; }
@@ -57,6 +60,9 @@ class DeviceVoxelMap {
     Grow<unsigned int> cell_start_buf_;
     Grow<float4> pts_buf_;
     Grow<NbrSlot> nbr_buf_;
+    Grow<PyrSlot> pyr_buf_;
+    PyrView pyr_view_{};
+    size_t pyr_bytes_ = 0;
     VoxelSlot* slots_ = nullptr;
     unsigned int* cell_start_ = nullptr;
     float4* pts_ = nullptr;

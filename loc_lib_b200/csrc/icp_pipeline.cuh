@@ -354,9 +354,9 @@ __global__ void __launch_bounds__(kTile, TRACKED ? LR_NN_TRACK_MIN_BLOCKS : LR_N
 template <int K>
 __global__ void __launch_bounds__(128, LR_FINISH_MIN_BLOCKS) k_icp_nn_finish(VoxelMapView map, CoarseLevels coarse, BatchView bv,
                                                        const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
-                                                       KnnTrack* track, RingQueue queue, unsigned int min_count) {
+                                                       KnnTrack* track, RingQueue queue, unsigned int min_count, unsigned int max_count) {
     const unsigned int n = *queue.count;
-    if (n < min_count) return;  // short queues are k_icp_nn_rings'
+    if (n < min_count || n >= max_count) return;  // short queues are k_icp_nn_rings', very long ones k_icp_nn_pyr's
     // Queries differ several-fold in cost, so warps do not own a fixed share of the queue: each one takes the next
     // 32 entries from a shared cursor whenever it has finished its last batch.
     const unsigned int lane = threadIdx.x & 31;
@@ -396,6 +396,135 @@ __global__ void __launch_bounds__(128, LR_FINISH_MIN_BLOCKS) k_icp_nn_finish(Vox
             KnnTrack tr;
             tr.qx = qx; tr.qy = qy; tr.qz = qz; tr.margin = margin;
             track[q.x] = tr;
+        }
+    }
+}
+
+// ---- stage-2 queue in SPATIAL order --------------------------------------------------------------------------------------
+// The queue's order is the arrival order of tiles and, inside a tile, of atomics: the 32 queries of a warp lie metres
+// apart, walk different cells for different lengths, and 9 lanes of 32 are busy on average.  For the long queues of a
+// global relocalisation (thousands of hypotheses of ONE scan: the queued queries of a wave fill the space around the
+// map many times over) a counting sort by the query's bin (a cube of `bin` metres, hashed into a table of buckets) puts
+// queries that walk the SAME cells into neighbouring lanes: same branches, same addresses (broadcast loads).
+// Three kernels behind the device-side queue length: count (also remembers each entry's bucket), scan (exclusive_scan_u32),
+// scatter.  Which entry a lane serves never changes a result.
+__device__ __forceinline__ void queue_entry_query(const uint2 q, const BatchView& bv, const AlignState* __restrict__ states,
+                                                  float& qx, float& qy, float& qz) {
+    const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
+    const float4 sp = bv.src[src_idx];
+    Pose T;
+    pose_load(T, states[q.y].pose);
+    double wx, wy, wz;
+    pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
+    qx = static_cast<float>(wx); qy = static_cast<float>(wy); qz = static_cast<float>(wz);
+}
+__global__ void __launch_bounds__(256) k_queue_bin_count(BatchView bv, const AlignState* __restrict__ states, RingQueue queue,
+                                                         unsigned int min_count, float inv_bin, unsigned int bucket_mask, int sub_bits,
+                                                         unsigned int* __restrict__ bucket_of, unsigned int* hist) {
+    const unsigned int n = *queue.count;
+    if (n < min_count) return;
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        float qx, qy, qz;
+        queue_entry_query(queue.entries[e], bv, states, qx, qy, qz);
+        // bucket = hash of the group of 2^sub_bits bins per axis the query's bin belongs to, then the bin's Morton code
+        // inside the group: neighbouring buckets of a group are neighbouring bins
+        const int bx = cell_of(cell_coord_f(qx, inv_bin)), by = cell_of(cell_coord_f(qy, inv_bin)), bz = cell_of(cell_coord_f(qz, inv_bin));
+        const unsigned long long key = pack_cell(bx >> sub_bits, by >> sub_bits, bz >> sub_bits);
+        unsigned int mort = 0u;
+        for (int j = 0; j < sub_bits; ++j)
+            mort |= (((static_cast<unsigned int>(bx) >> j) & 1u) << (3 * j)) | (((static_cast<unsigned int>(by) >> j) & 1u) << (3 * j + 1)) |
+                    (((static_cast<unsigned int>(bz) >> j) & 1u) << (3 * j + 2));
+        const unsigned int b = ((hash_block(key) << (3 * sub_bits)) | mort) & bucket_mask;
+        bucket_of[e] = b;
+        atomicAdd(&hist[b], 1u);
+    }
+}
+__global__ void __launch_bounds__(256) k_queue_bin_scatter(RingQueue queue, unsigned int min_count, const unsigned int* __restrict__ bucket_of,
+                                                           unsigned int* cursor, uint2* __restrict__ sorted) {
+    const unsigned int n = *queue.count;
+    if (n < min_count) return;
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+        sorted[atomicAdd(&cursor[bucket_of[e]], 1u)] = queue.entries[e];
+}
+
+// Stage 2 of VERY LONG queues (global relocalisation: half the points of a wrong hypothesis hang metres away from every
+// surface; the unseeded first iteration of a batch): ball queries through the block pyramid (PyrWalk, voxel_map.cuh),
+// one walk per LANE, every lane of a warp in the same step loop, and a lane whose walk has ended takes the next queued
+// query as soon as kPyrRefill lanes are free - no lane waits for the longest walk of its warp.
+#ifndef LR_PYR_MIN_BLOCKS
+#define LR_PYR_MIN_BLOCKS 8
+#endif
+#ifndef LR_PYR_REFILL
+#define LR_PYR_REFILL 8
+#endif
+template <int K>
+__global__ void __launch_bounds__(128, LR_PYR_MIN_BLOCKS) k_icp_nn_pyr(VoxelMapView map, const __grid_constant__ PyrView py, BatchView bv,
+                                                    const AlignState* __restrict__ states, unsigned int* __restrict__ nn_pos,
+                                                    KnnTrack* track, RingQueue queue, unsigned int min_count) {
+    const unsigned int n = *queue.count;
+    if (n < min_count) return;
+    const unsigned int lane = threadIdx.x & 31;
+    PyrWalk<K> w;
+    unsigned long long todo[kPyrStack];
+    constexpr int kFree = 4, kDead = 5;
+    int st = kFree, bit = 0;
+    bool exhausted = false;  // warp-uniform: the queue's cursor has passed its end
+    unsigned int row = 0;
+    while (true) {
+        // two kinds of step - a point of an opened cell, or the next child of the node on top of the stack (test, open) -
+        // and the warp runs the kind more lanes are due for; the other lanes wait for their turn.  Free lanes are handed
+        // the next queued queries once LR_PYR_REFILL of them have gathered (or nothing else is left to do).
+        const unsigned int b_node = __ballot_sync(0xffffffffu, st == kPyrNode), b_point = __ballot_sync(0xffffffffu, st == kPyrPoint),
+                           b_free = __ballot_sync(0xffffffffu, st == kFree);
+        const int n_node = __popc(b_node), n_point = __popc(b_point), n_free = __popc(b_free);
+        if ((b_node | b_point | b_free) == 0u) break;
+        if (n_free >= LR_PYR_REFILL || (b_node | b_point) == 0u) {  // hand out queued queries
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(queue.count + 1, static_cast<unsigned int>(n_free));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            exhausted = base + static_cast<unsigned int>(n_free) >= n;
+            if (st == kFree) {
+                const unsigned int e = base + static_cast<unsigned int>(__popc(b_free & ((1u << lane) - 1u)));
+                st = kDead;
+                if (e < n) {
+                    const uint2 q = queue.entries[e];
+                    const size_t src_idx = bv.offsets ? static_cast<size_t>(q.x) : static_cast<size_t>(q.x) - static_cast<size_t>(q.y) * bv.n_single;
+                    const float4 sp = bv.src[src_idx];
+                    Pose T;
+                    pose_load(T, states[q.y].pose);
+                    double wx, wy, wz;
+                    pose_apply(T, static_cast<double>(sp.x), static_cast<double>(sp.y), static_cast<double>(sp.z), wx, wy, wz);
+                    const float qx = static_cast<float>(wx), qy = static_cast<float>(wy), qz = static_cast<float>(wz);
+                    row = q.x;
+                    const unsigned int* out = nn_pos + static_cast<size_t>(row) * K;
+                    knn_init(w.res);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const unsigned int sp_j = out[j];
+                        if (sp_j < map.n_pts) {
+                            const float4 c = map.pts[sp_j];
+                            knn_offer(map.pts, w.res, dis2_f32(qx, qy, qz, c.x, c.y, c.z), sp_j);
+                        }
+                    }
+                    w.start(map, py, qx, qy, qz);
+                    st = kPyrNode;
+                }
+            }
+        } else if (n_point >= n_node) {
+            if (st == kPyrPoint) st = w.point_step(map);
+        } else if (st == kPyrNode) {
+            st = w.node_step(map, py, todo, bit);
+            if (st == kPyrDone) {
+                unsigned int* out = nn_pos + static_cast<size_t>(row) * K;
+#pragma unroll
+                for (int j = 0; j < K; ++j) out[j] = w.res.pos[j];
+                if (track) {
+                    KnnTrack tr;
+                    tr.qx = w.qx; tr.qy = w.qy; tr.qz = w.qz; tr.margin = -1.0f;
+                    track[row] = tr;
+                }
+                st = exhausted ? kDead : kFree;
+            }
         }
     }
 }

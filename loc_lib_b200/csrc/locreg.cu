@@ -89,6 +89,8 @@ struct locreg_handle {
         CoarseLevels c{};
         for (int l = 0; l < kCoarseLevels; ++l) c.lv[l] = icp_coarse[l].view();
         c.mid = icp_mid.view();
+        c.pyr = icp_map.pyramid();  // levels == 0 unless LOCREG_PYR_KERNEL=1 asked for it (build_icp_maps)
+        c.pyr_mode = 0;             // the thread-per-query stage 2 uses the shells; k_icp_nn_pyr walks the pyramid
         return c;
     }
     DeviceNdtMap ndt_map;
@@ -99,7 +101,7 @@ struct locreg_handle {
     int comm_rank = 0, comm_world = 1;
     DevBuf d_gather_pose, d_gather_res, d_bcast;
     DevBuf d_raw, d_src4, d_out, d_partials, d_state, d_acc, d_gate, d_nn, d_offsets, d_poses_in, d_poses_out, d_results,
-        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_rescanq, d_rescanc, d_lmap_new, d_global, d_local, d_same, d_plane, d_pstat, d_track;
+        d_scores, d_misc, d_target, d_nnpos, d_tile_begin, d_tiles, d_states, d_ringq, d_ringc, d_sortq, d_sortb, d_sorth, d_rescanq, d_rescanc, d_lmap_new, d_global, d_local, d_same, d_plane, d_pstat, d_track;
     size_t n_global = 0, global_stride = 0;  // Loc's global map kept on the device (locreg_set_global_map)
     // Lio's sliding local map (locreg_local_map_add_keyframe): transformed key frames + the filtered local map
     struct KeyFrame { void* p = nullptr; size_t n = 0; };
@@ -401,9 +403,48 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
                   small ? 0xFFFFFFFFu : kWarpFinishMax);
     }
     if (!small) {
+        const PyrView pyr = h->icp_map.pyramid();
+        // Relocalisation (hypotheses of one scan; LOCREG_SORT_BATCH=1: batches too): queues of LOCREG_SORT_FRAC x the job's
+        // points or more are put in spatial order first (k_queue_bin_count / scan / k_queue_bin_scatter).
+        static const int sort_on = getenv("LOCREG_SORT") ? atoi(getenv("LOCREG_SORT")) : 1;
+        static const int sort_batch = getenv("LOCREG_SORT_BATCH") ? atoi(getenv("LOCREG_SORT_BATCH")) : 0;
+        static const double sort_frac = getenv("LOCREG_SORT_FRAC") ? atof(getenv("LOCREG_SORT_FRAC")) : 0.1;
+        static const double sort_bin = getenv("LOCREG_SORT_BIN") ? atof(getenv("LOCREG_SORT_BIN")) : 1.0;  // metres
+        static const int sort_bits = getenv("LOCREG_SORT_BITS") ? atoi(getenv("LOCREG_SORT_BITS")) : 24;
+        static const int sort_sub = getenv("LOCREG_SORT_SUB") ? std::min(5, std::max(0, atoi(getenv("LOCREG_SORT_SUB")))) : 3;  // Morton-ordered bins per hashed group: 2^sub per axis
+        // LOCREG_PYR_KERNEL: which kernel serves the long (sorted) queues - 0 (default) the shells (k_icp_nn_finish), 1 the
+        // block-pyramid walks with lane refill (k_icp_nn_pyr: 4x fewer candidates, measured slower - DESIGN section 8)
+        static const int pyr_kernel = getenv("LOCREG_PYR_KERNEL") ? atoi(getenv("LOCREG_PYR_KERNEL")) : 0;
+        RingQueue long_queue = queue;
+        unsigned int long_min = 0xFFFFFFFFu;  // queues from this length on take the long-queue path
+        const bool sortable = sort_on && (job.bv.offsets == nullptr || sort_batch) && job.n_scratch_points < 0xFFFFFFFFull;
+        if (sortable) {
+            long_min = static_cast<unsigned int>(std::max<double>(kWarpFinishMax, std::min<double>(4.0e9, sort_frac * static_cast<double>(job.n_scratch_points))));
+            const unsigned int buckets = 1u << sort_bits;
+            h->d_sortq.reserve(job.n_scratch_points * sizeof(uint2));
+            h->d_sortb.reserve(job.n_scratch_points * sizeof(unsigned int));
+            h->d_sorth.reserve(static_cast<size_t>(buckets) * sizeof(unsigned int));
+            LR_CUDA(cudaMemsetAsync(h->d_sorth.p, 0, static_cast<size_t>(buckets) * sizeof(unsigned int), h->stream));
+            const unsigned int gs = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 255) / 256, static_cast<size_t>(h->num_sms) * 8));
+            LR_LAUNCH(k_queue_bin_count, gs, 256, 0, h->stream, job.bv, job.states, queue, long_min, static_cast<float>(1.0 / sort_bin), buckets - 1, sort_sub,
+                      h->d_sortb.as<unsigned int>(), h->d_sorth.as<unsigned int>());
+            exclusive_scan_u32(h->d_sorth.as<unsigned int>(), h->d_sorth.as<unsigned int>(), buckets, nullptr, h->stream);
+            LR_LAUNCH(k_queue_bin_scatter, gs, 256, 0, h->stream, queue, long_min, h->d_sortb.as<unsigned int>(), h->d_sorth.as<unsigned int>(),
+                      h->d_sortq.as<uint2>());
+            long_queue = RingQueue{queue.count, h->d_sortq.as<uint2>()};
+        }
         const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * LR_FINISH_MIN_BLOCKS));
         LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), stage2_track, queue,
-                  kWarpFinishMax);
+                  kWarpFinishMax, long_min);
+        if (long_min != 0xFFFFFFFFu) {
+            if (pyr_kernel == 1 && pyr.levels != 0) {
+                const unsigned int gp = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * LR_PYR_MIN_BLOCKS));
+                LR_LAUNCH(k_icp_nn_pyr<K>, gp, 128, 0, h->stream, map, pyr, job.bv, job.states, h->d_nnpos.as<unsigned int>(), stage2_track, long_queue, long_min);
+            } else {
+                LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), stage2_track,
+                          long_queue, long_min, 0xFFFFFFFFu);
+            }
+        }
     }
     prof_mark(h, 3, false);
     prof_mark(h, 1, true);

@@ -73,6 +73,37 @@ LR_HD bool build_insert_body(size_t i, const void* xyz, size_t stride, float inv
     return true;
 }
 
+// Block pyramid (voxel_map.cuh): the node with packed coordinate `child_key` registers itself with its parent on the
+// next level (coordinate >> 2 per axis).  counters: [0] nodes created on the parent level, [1] overflow flag
+template <class A>
+LR_HD void build_pyr_body(unsigned long long child_key, PyrSlot* slots, unsigned int slot_mask, unsigned int* counters) {
+    const int x = static_cast<int>((child_key >> 42) & 0x1FFFFFull) - kCoordBias, y = static_cast<int>((child_key >> 21) & 0x1FFFFFull) - kCoordBias,
+              z = static_cast<int>(child_key & 0x1FFFFFull) - kCoordBias;
+    const unsigned long long key = pack_block(x >> 2, y >> 2, z >> 2);
+    const int bit = ((z & 3) << 4) | ((y & 3) << 2) | (x & 3);
+    unsigned int h = hash_block(key) & slot_mask;
+    unsigned int probes = 0;
+    while (true) {
+        const unsigned long long k = A::cas64(&slots[h].key, kEmptyKey, key);
+        if (k == kEmptyKey) { A::add32(&counters[0], 1u); break; }
+        if (k == key) break;
+        h = (h + 1) & slot_mask;
+        if (++probes > slot_mask) { counters[1] = 1u; return; }
+    }
+    A::or64(&slots[h].mask, 1ull << bit);
+}
+// number of pyramid levels for occupied cell bounds [cmin, cmax]: the smallest P >= 1 whose top nodes (2^(2P+2) cells
+// per axis) span the bounds with at most two nodes per axis
+inline int pyr_levels_for(const int* cmin, const int* cmax) {
+    for (int P = 1; P <= kPyrMaxLevels; ++P) {
+        const int s = 2 * P + 2;
+        bool ok = true;
+        for (int a = 0; a < 3; ++a) ok = ok && ((cmax[a] >> s) - (cmin[a] >> s)) <= 1;
+        if (ok) return P;
+    }
+    return kPyrMaxLevels;  // (cannot happen within the 21-bit coordinate clamp; the search copes with more top nodes)
+}
+
 // Step 3.  pt_slot[i] is rewritten in place with the point's cell id.
 template <class A>
 LR_HD void build_count_body(size_t i, const VoxelSlot* slots, unsigned int* pt_slot, const unsigned char* pt_bit,

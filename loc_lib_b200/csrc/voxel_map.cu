@@ -1,5 +1,6 @@
 // Voxel-hash map build kernels (K1) and the scan primitive.  See voxel_build.cuh for the pipeline.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "device_map.cuh"
@@ -253,12 +254,13 @@ __global__ void k_nbr_gather(VoxelMapView map, NbrSlot* nbr, unsigned int nbr_ca
 
 // ------------------------------------------------------------------------------------------------
 DeviceVoxelMap::~DeviceVoxelMap() {
-    slots_buf_.free(); cell_start_buf_.free(); pts_buf_.free(); nbr_buf_.free();
+    slots_buf_.free(); cell_start_buf_.free(); pts_buf_.free(); nbr_buf_.free(); pyr_buf_.free();
 }
 void DeviceVoxelMap::release() {  // forgets the map, keeps the memory
     slots_ = nullptr; cell_start_ = nullptr; pts_ = nullptr; nbr_ = nullptr;
     view_ = VoxelMapView{};
     bytes_ = 0; n_cells_ = 0; n_blocks_ = 0; n_lists_ = 0; n_list_entries_ = 0;
+    pyr_view_ = PyrView{}; pyr_bytes_ = 0;
 }
 
 static unsigned int next_pow2(size_t v) {
@@ -408,6 +410,44 @@ void DeviceVoxelMap::build(const void* d_xyz, size_t n, size_t stride, float cel
              static_cast<size_t>(n_kept) * sizeof(float4) * (lists ? 28 : 1) + static_cast<size_t>(nbr_cap) * sizeof(NbrSlot);
 }
 
+// ---- block pyramid (voxel_map.cuh: PyrView) ---------------------------------------------------------------------------
+__global__ void k_pyr_clear(PyrSlot* slots, size_t n) {
+    const size_t s = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (s < n) slots[s] = PyrSlot{kEmptyKey, 0ull};
+}
+__global__ void k_pyr_from_blocks(const VoxelSlot* __restrict__ slots, unsigned int cap, PyrSlot* up, unsigned int up_mask, unsigned int* counters) {
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap && slots[s].key != kEmptyKey) build_pyr_body<DeviceAtomics>(slots[s].key, up, up_mask, counters);
+}
+__global__ void k_pyr_from_pyr(const PyrSlot* __restrict__ slots, unsigned int cap, PyrSlot* up, unsigned int up_mask, unsigned int* counters) {
+    const unsigned int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < cap && slots[s].key != kEmptyKey) build_pyr_body<DeviceAtomics>(slots[s].key, up, up_mask, counters);
+}
+void DeviceVoxelMap::build_pyramid(cudaStream_t stream) {
+    pyr_view_ = PyrView{};
+    pyr_bytes_ = 0;
+    if (view_.n_pts == 0) return;
+    const int P = pyr_levels_for(view_.cmin, view_.cmax);
+    // a level never has more nodes than the level below, and the fine level has n_blocks_ of them: load <= 0.5 everywhere
+    const unsigned int cap = next_pow2(static_cast<size_t>(n_blocks_) * 2);
+    PyrSlot* base = pyr_buf_.ensure(static_cast<size_t>(cap) * P);
+    unsigned int* counters = nullptr;
+    LR_CUDA(cudaMallocAsync(&counters, 2 * sizeof(unsigned int), stream));
+    LR_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream));
+    const unsigned int T = 256;
+    const size_t total = static_cast<size_t>(cap) * P;
+    LR_LAUNCH(k_pyr_clear, static_cast<unsigned int>((total + T - 1) / T), T, 0, stream, base, total);
+    const unsigned int fine_cap = view_.slot_mask + 1;
+    LR_LAUNCH(k_pyr_from_blocks, (fine_cap + T - 1) / T, T, 0, stream, view_.slots, fine_cap, base, cap - 1, counters);
+    for (int l = 1; l < P; ++l)
+        LR_LAUNCH(k_pyr_from_pyr, (cap + T - 1) / T, T, 0, stream, base + static_cast<size_t>(cap) * (l - 1), cap,
+                  base + static_cast<size_t>(cap) * l, cap - 1, counters);
+    LR_CUDA(cudaFreeAsync(counters, stream));
+    for (int l = 0; l < P; ++l) { pyr_view_.slots[l] = base + static_cast<size_t>(cap) * l; pyr_view_.mask[l] = cap - 1; }
+    pyr_view_.levels = P;
+    pyr_bytes_ = total * sizeof(PyrSlot);
+}
+
 __global__ void k_coarse_remap(float4* pts, unsigned int n, const unsigned int* __restrict__ fine_pos_of_index) {
     const unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) pts[j].w = __int_as_float(static_cast<int>(fine_pos_of_index[__float_as_int(pts[j].w)]));
@@ -432,6 +472,9 @@ void build_icp_maps(DeviceVoxelMap& fine, DeviceVoxelMap* coarse, DeviceVoxelMap
     unsigned int* pos = nullptr;
     DeviceVoxelMap::DupFlags dups;
     fine.build(d_xyz, n, stride, cell, want_lists, stream, &pos, &dups);
+    // the block pyramid is only built for the experimental ball-query kernel (LOCREG_PYR_KERNEL=1, locreg.cu)
+    static const bool want_pyramid = getenv("LOCREG_PYR_KERNEL") != nullptr && atoi(getenv("LOCREG_PYR_KERNEL")) == 1;
+    if (want_pyramid) fine.build_pyramid(stream);
     DeviceVoxelMap::DupFlags* dp = dups.flags ? &dups : nullptr;
     if (mid) {
         mid->build(d_xyz, n, stride, cell * kMidFactor, want_lists, stream, nullptr, dp);

@@ -664,6 +664,8 @@ LR_HD void knn_shell_block(const VoxelMapView& m, const KnnCellFrame& c, const K
         const unsigned int cid = base + popc64(occ & ((1ull << bit) - 1ull));
         const unsigned int beg = m.cell_start[cid], end = m.cell_start[cid + 1];
         LR_STAT(7, end - beg);  // shell candidates
+        // (kScanBatch independent loads in flight, as in the list scans, measured SLOWER here: relocalisation stage 2
+        // 18.3 -> 25.8 ms, a batch's 0.27 -> 0.31 ms - 36 more spilled bytes at 64 registers)
         for (unsigned int i = beg; i < end; ++i) {
             const float4 p = m.pts[i];
             const float d2 = dis2_f32(qx, qy, qz, p.x, p.y, p.z);
@@ -728,10 +730,256 @@ constexpr float kMidFactor = LR_MID_FACTOR;  // the mid level's cell edge / the 
 #define LR_MID_SHELLS 4  // measured 1..8: 4 (batch stage 2 -25 % against 2; relocalisation indifferent)
 #endif
 constexpr int kMidShells = LR_MID_SHELLS;  // shells on the mid level when a coarse level can take over
+// ---- the block pyramid: a 64-ary tree over the fine level's blocks --------------------------------------------------------
+// Level l of the pyramid holds one 16 B record {key, 64-bit child mask} per node of 4^(l+1) fine blocks per axis
+// (coordinates = block coordinates >> 2(l+1), pure integer arithmetic on the fine grid, so the levels nest for every
+// cell size); a child of a level-0 node is a fine block of m.slots, a child of a block a cell.  It turns stage 2 of the
+// search into a depth-first BALL QUERY: from the top, only children whose box can hold a point at or below the current
+// K-th distance are opened, nearest child first, so a far-off query (a wrong relocalisation hypothesis: its points hang
+// metres away from every surface) costs a dozen 16-32 B records and the points of the few fine cells its ball touches,
+// where Chebyshev shells had to look at every cell of a (2R + 1)^2 patch of the nearest surface before they could prune.
+struct __attribute__((aligned(16))) PyrSlot {
+    unsigned long long key;   // pack_block(node coordinate), kEmptyKey if unused
+    unsigned long long mask;  // bit (z&3)<<4 | (y&3)<<2 | (x&3) set iff that child exists
+};
+constexpr int kPyrMaxLevels = 8;   // 4^(8+1) blocks per axis at the top: more than the 21-bit coordinates can hold
+struct PyrView {
+    const PyrSlot* slots[kPyrMaxLevels];
+    unsigned int mask[kPyrMaxLevels];  // capacity - 1 per level
+    int levels;                        // 0: no pyramid; the top level spans the occupied bounds with <= 2 nodes per axis
+};
 struct CoarseLevels {
     VoxelMapView lv[kCoarseLevels];  // n_pts == 0: level absent
     VoxelMapView mid;                // cells kMidFactor times the fine ones WITH neighbourhood lists; n_pts == 0: absent
+    PyrView pyr;                     // block pyramid over the FINE level (levels == 0: absent)
+    int pyr_mode;                    // 0: shells only; 1: pyramid after the mid level's list; 2: pyramid instead of the mid level
 };
+LR_HD const PyrSlot* find_pyr(const PyrView& py, int l, int nx, int ny, int nz) {
+    const unsigned long long key = pack_block(nx, ny, nz);
+    unsigned int h = hash_block(key) & py.mask[l];
+    while (true) {
+        const PyrSlot* s = py.slots[l] + h;
+        const unsigned long long k = s->key;
+        if (k == key) return s;
+        if (k == kEmptyKey) return nullptr;
+        h = (h + 1) & py.mask[l];
+    }
+}
+// bit i of the result = bit (i ^ a) of m: children in the order of i ^ a start with child a
+LR_HD unsigned long long xor_permute64(unsigned long long m, unsigned int a) {
+    if (a & 1u) m = ((m & 0x5555555555555555ull) << 1) | ((m >> 1) & 0x5555555555555555ull);
+    if (a & 2u) m = ((m & 0x3333333333333333ull) << 2) | ((m >> 2) & 0x3333333333333333ull);
+    if (a & 4u) m = ((m & 0x0F0F0F0F0F0F0F0Full) << 4) | ((m >> 4) & 0x0F0F0F0F0F0F0F0Full);
+    if (a & 8u) m = ((m & 0x00FF00FF00FF00FFull) << 8) | ((m >> 8) & 0x00FF00FF00FF00FFull);
+    if (a & 16u) m = ((m & 0x0000FFFF0000FFFFull) << 16) | ((m >> 16) & 0x0000FFFF0000FFFFull);
+    if (a & 32u) m = (m << 32) | (m >> 32);
+    return m;
+}
+// children (4 per axis, each 2^shift cells wide) of the node at coordinate n whose cells meet [lo, hi]; 4-bit mask
+LR_HD unsigned int axis_child_mask(int n, int shift, int lo, int hi) {
+    const int o = n << 2;
+    int a = (lo >> shift) - o, b = (hi >> shift) - o;
+    a = a < 0 ? 0 : a;
+    b = b > 3 ? 3 : b;
+    if (a > b) return 0u;
+    return ((1u << (b + 1)) - 1u) & ~((1u << a) - 1u);
+}
+// index (0..3) of the child of node n nearest to cell f along one axis
+LR_HD unsigned int axis_near_child(int n, int shift, int f) {
+    const int a = (f >> shift) - (n << 2);
+    return static_cast<unsigned int>(a < 0 ? 0 : (a > 3 ? 3 : a));
+}
+// The ball query as a STATE MACHINE: one call of step() looks at one point, opens one child or pops one node, so that
+// a kernel can run 32 walks in the lanes of a warp, every lane in the same loop whatever the depth of its walk, and
+// hand a lane the next query the moment its walk ends (k_icp_nn_pyr) - the shells' 9 active lanes of 32 came from
+// queries of very different length sharing a warp from start to end.
+// Soundness: a subtree is skipped only when the conservative distance to its box exceeds the current K-th distance, or
+// when it lies outside the cell range that the points at or below that distance can occupy given the box's gaps along
+// the other two axes; every point of an opened cell at or below the K-th distance is offered; candidates already in
+// the set are rejected by the membership test, ties are decided by the original index as everywhere else.  The set
+// may start from any real, distinct points (seeds) or empty.
+// todo[] (children still to visit per depth, XOR-permuted: nearest child first) is the caller's array: the one
+// dynamically indexed piece of state stays in local memory on its own and everything in the struct in registers.
+constexpr int kPyrStack = kPyrMaxLevels + 1;
+constexpr int kPyrDone = 0, kPyrNode = 1, kPyrPoint = 2, kPyrPush = 3;
+template <int K>
+struct PyrWalk {
+    KnnResult<K> res;
+    float qx, qy, qz;        // the query
+    float ux, uy, uz;        // ... in cell units
+    int fx, fy, fz;          // its cell
+    float eps;               // rounding allowance of a gap, in cell units (safe_gap)
+    unsigned long long near_pack;                // 6 bits per depth: the XOR order's first child
+    unsigned long long occ;                      // occupancy of the fine block on top of the stack
+    unsigned int base;                           // its first cell id
+    unsigned int pi, pend;                       // points of the opened cell still to look at
+    int nx, ny, nz;                              // coordinate of the node on top of the stack
+    int d;                                       // its depth (level P - 1 - d; P: a fine block); -1: at the root
+    unsigned int root_todo, root_near;           // the <= 2x2x2 top nodes, same ordering trick
+    int rlx, rhx, rly, rhy, rlz, rhz;            // cells a point at or below the K-th distance can lie in (reach box)
+
+    // conservative (never over-estimated) gaps in metres between the query and the box of 2^shift cells per axis at
+    // coordinate (cx, cy, cz) (in units of 2^shift cells)
+    LR_HD void box_gaps(const VoxelMapView& m, int cx, int cy, int cz, int shift, float& sx, float& sy, float& sz) const {
+        const float wdt = static_cast<float>(1 << shift), cs = m.cell * 0.99999f;
+        const float lx = static_cast<float>(cx << shift), ly = static_cast<float>(cy << shift), lz = static_cast<float>(cz << shift);
+        sx = fmaxf(fmaxf(lx - ux, ux - (lx + wdt)) - eps, 0.0f) * cs;
+        sy = fmaxf(fmaxf(ly - uy, uy - (ly + wdt)) - eps, 0.0f) * cs;
+        sz = fmaxf(fmaxf(lz - uz, uz - (lz + wdt)) - eps, 0.0f) * cs;
+    }
+    // The reach box: the cells per axis that a point at or below the current K-th distance can lie in.  Kept in
+    // registers and refreshed whenever the K-th distance changes (an insertion into a full set), so that opening a
+    // node costs three range masks and no square root.
+    LR_HD void refresh_reach(const VoxelMapView& m) {
+        const float worst = res.d2[K - 1];
+        if (!(worst < INFINITY)) {
+            rlx = rly = rlz = -0x40000000; rhx = rhy = rhz = 0x40000000;
+            return;
+        }
+        const float dc = fminf(sqrtf(worst * 1.000001f) * m.inv_cell * 1.0001f + 4.0f * eps + 1e-3f, 4.0e6f);
+        rlx = static_cast<int>(floorf(ux - dc)); rhx = static_cast<int>(floorf(ux + dc));
+        rly = static_cast<int>(floorf(uy - dc)); rhy = static_cast<int>(floorf(uy + dc));
+        rlz = static_cast<int>(floorf(uz - dc)); rhz = static_cast<int>(floorf(uz + dc));
+    }
+    LR_HD void start(const VoxelMapView& m, const PyrView& py, float x, float y, float z) {
+        qx = x; qy = y; qz = z;
+        ux = cell_coord_f(x, m.inv_cell); uy = cell_coord_f(y, m.inv_cell); uz = cell_coord_f(z, m.inv_cell);
+        fx = cell_of(ux); fy = cell_of(uy); fz = cell_of(uz);
+        float mag = fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz));
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            mag = fmaxf(mag, fmaxf(fabsf(static_cast<float>(m.cmin[a])), fabsf(static_cast<float>(m.cmax[a]))));
+        eps = 4.8e-7f * (mag + 8.0f);
+        pi = pend = 0u;
+        d = -1;
+        near_pack = 0ull;
+        occ = 0ull; base = 0u;
+        nx = ny = nz = 0;
+        const int ts = 2 * py.levels + 2;
+        const int t0x = m.cmin[0] >> ts, t0y = m.cmin[1] >> ts, t0z = m.cmin[2] >> ts;
+        const int wx = (m.cmax[0] >> ts) - t0x, wy = (m.cmax[1] >> ts) - t0y, wz = (m.cmax[2] >> ts) - t0z;  // 0 or 1
+        root_todo = 1u | (wx ? 2u : 0u);
+        root_todo |= wy ? root_todo << 2 : 0u;
+        root_todo |= wz ? root_todo << 4 : 0u;
+        const int ax = (fx >> ts) - t0x, ay = (fy >> ts) - t0y, az = (fz >> ts) - t0z;
+        root_near = (ax > 0 && wx ? 1u : 0u) | (ay > 0 && wy ? 2u : 0u) | (az > 0 && wz ? 4u : 0u);
+        root_todo = static_cast<unsigned int>(xor_permute64(root_todo, root_near));
+        refresh_reach(m);
+        LR_STAT(10, 1);  // pyramid queries
+    }
+    // pushes node (cx, cy, cz) at depth nd with child mask cm
+    LR_HD void push(const VoxelMapView& m, const PyrView& py, unsigned long long* todo, int nd, int cx, int cy, int cz, unsigned long long cm) {
+        const int gs = 2 * (py.levels - nd);  // cells per child of the new node = 2^gs
+        unsigned int na = 0u;
+        if (res.d2[K - 1] < INFINITY) {  // children outside the reach box are dropped at once; the order hardly matters any more
+            cm &= spread_x(axis_child_mask(cx, gs, rlx, rhx)) & spread_y(axis_child_mask(cy, gs, rly, rhy)) & spread_z(axis_child_mask(cz, gs, rlz, rhz));
+            if (cm == 0ull) return;
+        } else {  // nothing to prune with yet: nearest child first
+            na = axis_near_child(cx, gs, fx) | (axis_near_child(cy, gs, fy) << 2) | (axis_near_child(cz, gs, fz) << 4);
+            cm = xor_permute64(cm, na);
+        }
+        d = nd;
+        nx = cx; ny = cy; nz = cz;
+        near_pack = (near_pack << 6) | na;
+        todo[nd] = cm;
+    }
+    // The walk is cut into three kinds of step so that a warp can run ONE kind at a time for all the lanes that are
+    // due for it (k_icp_nn_pyr): node_step (take the next child of the node on top of the stack and test its box, or
+    // pop), push_step (open the interior child that passed: hash probe, reach masks, ordering - the long one) and
+    // point_step (one point of the opened cell).  Each returns the kind of step the walk needs next.
+    // node_step: kPyrNode again, kPyrPoint (a cell was opened), kPyrPush (child `bit` passed and waits to be opened:
+    // a top node when d < 0), or kPyrDone (res is final).
+    LR_HD int node_step(const VoxelMapView& m, const PyrView& py, unsigned long long* todo, int& bit_out) {
+        const int P = py.levels;
+        if (d < 0) {  // the next top node
+            if (root_todo == 0u) return kPyrDone;
+            const unsigned int i = static_cast<unsigned int>(ffs64(root_todo) - 1) ^ root_near;
+            root_todo &= root_todo - 1u;
+            const int ts = 2 * P + 2;
+            float sx, sy, sz;
+            box_gaps(m, (m.cmin[0] >> ts) + static_cast<int>(i & 1u), (m.cmin[1] >> ts) + static_cast<int>((i >> 1) & 1u),
+                     (m.cmin[2] >> ts) + static_cast<int>(i >> 2), ts, sx, sy, sz);
+            LR_STAT(13, 1);  // box tests
+            if ((sx * sx + sy * sy + sz * sz) * 0.99999f > res.d2[K - 1]) return kPyrNode;
+            (void)bit_out;
+            push_step(m, py, todo, static_cast<int>(i));
+            return kPyrNode;
+        }
+        const unsigned long long t = todo[d];
+        if (t == 0ull) {  // node exhausted
+            --d;
+            nx >>= 2; ny >>= 2; nz >>= 2;
+            near_pack >>= 6;
+            return kPyrNode;
+        }
+        const int bit = (ffs64(t) - 1) ^ static_cast<int>(near_pack & 63ull);
+        todo[d] = t & (t - 1ull);
+        const int cx = (nx << 2) + (bit & 3), cy = (ny << 2) + ((bit >> 2) & 3), cz = (nz << 2) + (bit >> 4);
+        float sx, sy, sz;
+        box_gaps(m, cx, cy, cz, 2 * (P - d), sx, sy, sz);
+        LR_STAT(13, 1);
+        if ((sx * sx + sy * sy + sz * sz) * 0.99999f > res.d2[K - 1]) return kPyrNode;
+        if (d == P) {  // a cell of the fine block on top of the stack
+            const unsigned int cid = base + popc64(occ & ((1ull << bit) - 1ull));
+            pi = m.cell_start[cid];
+            pend = m.cell_start[cid + 1];
+            LR_STAT(12, pend - pi); LR_STAT(14, 1);  // candidates, cells opened
+            return pi < pend ? kPyrPoint : kPyrNode;
+        }
+        push_step(m, py, todo, bit);
+        return kPyrNode;
+    }
+    LR_HD void push_step(const VoxelMapView& m, const PyrView& py, unsigned long long* todo, int bit) {
+        const int P = py.levels;
+        LR_STAT(11, 1);  // node probes
+        if (d < 0) {
+            const int ts = 2 * P + 2;
+            const int tx = (m.cmin[0] >> ts) + (bit & 1), ty = (m.cmin[1] >> ts) + ((bit >> 1) & 1), tz = (m.cmin[2] >> ts) + (bit >> 2);
+            const PyrSlot* s = find_pyr(py, P - 1, tx, ty, tz);
+            if (s != nullptr) push(m, py, todo, 0, tx, ty, tz, s->mask);
+            return;
+        }
+        const int cx = (nx << 2) + (bit & 3), cy = (ny << 2) + ((bit >> 2) & 3), cz = (nz << 2) + (bit >> 4);
+        if (d == P - 1) {  // the child is a fine block
+            const VoxelSlot* s = find_block(m, cx, cy, cz);
+            if (s == nullptr) return;
+            const unsigned long long cm = s->mask;
+            const unsigned int cb = s->cell_base;
+            const int d_was = d;
+            push(m, py, todo, d + 1, cx, cy, cz, cm);
+            if (d != d_was) { occ = cm; base = cb; }
+        } else {
+            const PyrSlot* s = find_pyr(py, P - 2 - d, cx, cy, cz);
+            if (s != nullptr) push(m, py, todo, d + 1, cx, cy, cz, s->mask);
+        }
+    }
+    LR_HD int point_step(const VoxelMapView& m) {
+        const float4 p = m.pts[pi];
+        const float d2 = dis2_f32(qx, qy, qz, p.x, p.y, p.z);
+        const unsigned int pos = m.w_is_pos ? static_cast<unsigned int>(float_as_int(p.w)) : pi;
+        if (knn_accepts(m.canon, res, d2, pos)) {
+            knn_insert(m.canon, res, d2, pos);
+            refresh_reach(m);
+        }
+        ++pi;
+        return pi < pend ? kPyrPoint : kPyrNode;
+    }
+};
+template <int K>
+LR_HD void knn_query_pyr(const VoxelMapView& m, const PyrView& py, float qx, float qy, float qz, KnnResult<K>& res) {
+    PyrWalk<K> w;
+    unsigned long long todo[kPyrStack];
+    w.res = res;
+    w.start(m, py, qx, qy, qz);
+    int st = kPyrNode, bit = 0;
+    while (st != kPyrDone) {
+        if (st == kPyrNode) st = w.node_step(m, py, todo, bit);
+        else if (st == kPyrPoint) st = w.point_step(m);
+        else { w.push_step(m, py, todo, bit); st = kPyrNode; }
+    }
+    res = w.res;
+}
+
 // Stage 2 through the mid level: one list of the mid level covers a box three mid cells wide around the query - what
 // the corner lists and the first fine shells would have to collect from up to eight lists and dozens of hash-probed
 // blocks is one probe and one contiguous scan here.  Returns true when `res` is final; false: coarse levels next.
@@ -739,7 +987,7 @@ struct CoarseLevels {
 // a seeded scan knows d6 as in knn_query_fast_track), else -1.
 template <int K>
 LR_HD bool knn_query_mid(const VoxelMapView& md, bool have_coarse, float qx, float qy, float qz, KnnResult<K>& res,
-                         float* margin = nullptr) {
+                         float* margin = nullptr, bool list_only = false) {
     const KnnCellFrame c = knn_frame(md, qx, qy, qz);
     int boxes_done = 0;
     if (margin) *margin = -1.0f;
@@ -760,6 +1008,7 @@ LR_HD bool knn_query_mid(const VoxelMapView& md, bool have_coarse, float qx, flo
         }
         boxes_done = 1;
     }
+    if (list_only) return false;  // the caller continues with the block pyramid
     if (have_coarse && c.R0 > kMidShells) return false;
     return knn_query_rings<K>(md, qx, qy, qz, res, boxes_done, have_coarse ? kMidShells : kBruteForceShell);
 }
@@ -768,10 +1017,26 @@ LR_HD void knn_query_finish(const VoxelMapView& m, const CoarseLevels& coarse, f
                             float* margin = nullptr) {
     const bool have_coarse = coarse.lv[0].n_pts != 0;
     if (margin) *margin = -1.0f;
+    // (pyr_mode is honoured on the host - tests/hostsim, which checks PyrWalk against brute force - and in device builds
+    // with -DLR_FINISH_PYR; the product's thread-per-query kernels stay free of the walk's stack and registers: on the
+    // device the pyramid is walked by k_icp_nn_pyr only)
+#if !defined(__CUDA_ARCH__) || defined(LR_FINISH_PYR)
+    const bool pyr = coarse.pyr.levels != 0 && coarse.pyr_mode != 0;
+#else
+    const bool pyr = false;
+#endif
+    if (pyr && (coarse.pyr_mode == 2 || coarse.mid.n_pts == 0)) {  // the ball query does all of stage 2
+        knn_query_pyr<K>(m, coarse.pyr, qx, qy, qz, res);
+        return;
+    }
     if (coarse.mid.n_pts != 0) {
         LR_STAT(2, 1);  // queries entering stage 2a
-        if (knn_query_mid<K>(coarse.mid, have_coarse, qx, qy, qz, res, margin)) return;
+        if (knn_query_mid<K>(coarse.mid, have_coarse || pyr, qx, qy, qz, res, margin, pyr)) return;
         if (margin) *margin = -1.0f;
+        if (pyr) {  // what the mid level's list could not settle: ball query instead of shells
+            knn_query_pyr<K>(m, coarse.pyr, qx, qy, qz, res);
+            return;
+        }
     } else {
         const KnnCellFrame c = knn_frame(m, qx, qy, qz);
         int boxes_done = knn_uses_list(m, c) ? 1 : 0;

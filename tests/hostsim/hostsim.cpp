@@ -27,6 +27,7 @@ struct HsMap {
     HsMap* coarse_map[kCoarseLevels] = {};   // coarser levels (no lists), or nullptr
     CoarseLevels coarse{};                   // lv[l].n_pts == 0: level absent
     HsMap* mid_map = nullptr;                // mid level (lists), or nullptr
+    std::vector<PyrSlot> pyr;                // block pyramid of the fine level, levels back to back
     ~HsMap() { for (HsMap* c : coarse_map) delete c; delete mid_map; }
 };
 
@@ -135,8 +136,28 @@ HsMap* hs_map_create(const float* xyz, size_t n, size_t stride, float cell, unsi
         m->coarse_map[l] = c;
         m->coarse.lv[l] = c->view;
     }
+    if (m->view.n_pts) {  // block pyramid (what DeviceVoxelMap::build_pyramid does)
+        const int P = pyr_levels_for(m->view.cmin, m->view.cmax);
+        unsigned int nb = 0;
+        for (const VoxelSlot& s : m->slots) nb += s.key != kEmptyKey;
+        const unsigned int cap = std::max(1024u, next_pow2(nb * 2));
+        m->pyr.assign(static_cast<size_t>(cap) * P, PyrSlot{kEmptyKey, 0ull});
+        unsigned int counters[2] = {0, 0};
+        for (const VoxelSlot& s : m->slots)
+            if (s.key != kEmptyKey) build_pyr_body<HostAtomics>(s.key, m->pyr.data(), cap - 1, counters);
+        for (int l = 1; l < P; ++l)
+            for (unsigned int j = 0; j < cap; ++j) {
+                const PyrSlot& s = m->pyr[static_cast<size_t>(cap) * (l - 1) + j];
+                if (s.key != kEmptyKey) build_pyr_body<HostAtomics>(s.key, m->pyr.data() + static_cast<size_t>(cap) * l, cap - 1, counters);
+            }
+        for (int l = 0; l < P; ++l) { m->coarse.pyr.slots[l] = m->pyr.data() + static_cast<size_t>(cap) * l; m->coarse.pyr.mask[l] = cap - 1; }
+        m->coarse.pyr.levels = P;
+        m->coarse.pyr_mode = 0;
+    }
     return m;
 }
+// 0: shells only (default), 1: pyramid after the mid level's list, 2: pyramid for all of stage 2
+void hs_map_set_pyr_mode(HsMap* m, int mode) { m->coarse.pyr_mode = mode; }
 void hs_map_destroy(HsMap* m) { delete m; }
 // search-stage counters since the last call (see LR_STAT in voxel_map.cuh); reading clears them
 void hs_knn_stats(unsigned long long* out16) {

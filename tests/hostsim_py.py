@@ -20,6 +20,7 @@ def lib():
         L.hs_map_create.restype = vp
         L.hs_map_create.argtypes = [vp, sz, sz, C.c_float, C.c_uint]
         L.hs_map_destroy.argtypes = [vp]
+        L.hs_map_set_pyr_mode.argtypes = [vp, i32]
         L.hs_map_stats.argtypes = [vp, vp]
         L.hs_knn.argtypes = [vp, vp, sz, sz, i32, vp]
         L.hs_knn_stats.argtypes = [vp]
@@ -45,7 +46,8 @@ def _cloud(a):
 
 
 STAT_NAMES = ["fast_queries", "fast_candidates", "corner_queries", "corner_lists", "corner_candidates", "ring_queries",
-              "ring_block_probes", "ring_candidates", "linear_scans", "skipped_searches"]
+              "ring_block_probes", "ring_candidates", "linear_scans", "skipped_searches", "pyr_queries", "pyr_probes",
+              "pyr_candidates", "pyr_child_tests", "pyr_cells"]
 
 
 def knn_stats():
@@ -70,6 +72,10 @@ class HsMap:
         if getattr(self, "_h", None):
             lib().hs_map_destroy(self._h)
             self._h = None
+
+    def set_pyr_mode(self, mode):
+        """Stage 2 of the search: 0 = shells, 1 = block-pyramid ball query after the mid level's list, 2 = instead of it."""
+        lib().hs_map_set_pyr_mode(self._h, mode)
 
     def stats(self):
         out = np.zeros(4, np.uint32)

@@ -67,6 +67,59 @@ def test_far_queries_use_the_coarse_level_not_a_linear_scan(scene, ref_icp):
     assert HS.knn_stats()["linear_scans"] == 2
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["after-mid-list", "all-of-stage-2"])
+@pytest.mark.parametrize("cell,hint", [(0.5, 0), (0.3, 0), (1.3, 0xFFFFFFFD), (0.5, 0xFFFFFFFF)])
+def test_knn_pyramid_ball_query_is_exact(scene, ref_icp, cell, hint, mode):
+    """Stage 2 as a depth-first ball query through the block pyramid (PyrWalk - what k_icp_nn_pyr runs per lane): near,
+    far, out-of-bounds and way-out queries, unseeded and seeded, lattice ties; never a shell, never a linear scan."""
+    m = HS.HsMap(scene.map, cell=cell, capacity_hint=hint)
+    m.set_pyr_mode(mode)
+    rng = np.random.default_rng(17)
+    far = rng.uniform(-60, 60, (1500, 3)).astype(np.float32)
+    far[:, 2] = rng.uniform(-4, 40, 1500)
+    way_out = rng.uniform(-900, 900, (60, 3)).astype(np.float32)
+    near = _queries(scene)[:3000]
+    HS.knn_stats()
+    for q in (near, far, way_out):
+        for k in (1, 5):
+            assert np.array_equal(m.knn(q, k), ref_icp.knn(q, k))
+    st = HS.knn_stats()
+    assert st["pyr_queries"] > 0 and st["ring_queries"] == 0 and st["linear_scans"] == 0, st
+    for q in (near, far):
+        exp = ref_icp.knn(q, 5)
+        for sigma in (0.02, 0.3, 5.0):
+            assert np.array_equal(m.knn_seeded(q, (q + rng.normal(0, sigma, q.shape)).astype(np.float32)), exp)
+
+
+def test_knn_pyramid_ties_and_tiny_maps():
+    g = np.arange(-6, 7, dtype=np.float32) * np.float32(0.25)
+    x, y, z = np.meshgrid(g, g, g[:3])
+    pts = np.stack([x.ravel(), y.ravel(), z.ravel(), np.zeros(x.size)], 1).astype(np.float32)
+    rng = np.random.default_rng(0)
+    pts = pts[rng.permutation(len(pts))]
+    q = np.concatenate([np.stack([x.ravel(), y.ravel(), z.ravel()], 1).astype(np.float32)[::3] + np.float32(0.125),
+                        rng.uniform(-30, 30, (300, 3)).astype(np.float32)])
+    for n in (len(pts), 7, 3, 1):  # fewer points than K: the result is padded, as the shells' is
+        m = HS.HsMap(pts[:n], cell=0.5)
+        exp = m.knn(q, 5)
+        if n >= 5:
+            assert np.array_equal(exp, O.bfnn(pts[:n], q, 5))
+        for mode in (1, 2):
+            m.set_pyr_mode(mode)
+            assert np.array_equal(m.knn(q, 5), exp)
+            assert np.array_equal(m.knn_seeded(q, q + np.float32(0.25)), exp)
+        m.set_pyr_mode(0)
+    # a map far from the origin on negative and positive sides (top nodes on both sides of zero)
+    big = np.concatenate([pts[:, :3] + np.float32([-700, 300, 5]), pts[:, :3] + np.float32([900, -20, -3])]).astype(np.float32)
+    big = np.concatenate([big, np.zeros((len(big), 1), np.float32)], 1)
+    m = HS.HsMap(big, cell=0.5)
+    qq = np.concatenate([q + np.float32([-700, 300, 5]), q + np.float32([900, -20, -3]), q]).astype(np.float32)
+    exp = O.bfnn(big, qq, 5)
+    for mode in (0, 1, 2):
+        m.set_pyr_mode(mode)
+        assert np.array_equal(m.knn(qq, 5), exp)
+
+
 @pytest.mark.parametrize("k", [1, 5])
 def test_knn_tracked_shortcut_is_exact(scene, hs_map, ref_icp, k):
     """Queries that moved less than their margin since their last full search only re-sort their k neighbours
