@@ -397,29 +397,32 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
     // stage 2 leaves margins behind only while the loop tracks (LOCREG_TRACK=0: every query searches every time)
     static const int track_env = getenv("LOCREG_TRACK") ? atoi(getenv("LOCREG_TRACK")) : 1;
     KnnTrack* stage2_track = track_env ? h->d_track.as<KnnTrack>() : nullptr;
+    // Relocalisation (hypotheses of one scan; LOCREG_SORT_BATCH=1: batches too): queues of LOCREG_SORT_FRAC x the job's
+    // points or more are put in spatial order first (k_queue_bin_count / scan / k_queue_bin_scatter).
+    static const int sort_on = getenv("LOCREG_SORT") ? atoi(getenv("LOCREG_SORT")) : 1;
+    static const int sort_batch = getenv("LOCREG_SORT_BATCH") ? atoi(getenv("LOCREG_SORT_BATCH")) : 0;
+    static const double sort_frac = getenv("LOCREG_SORT_FRAC") ? atof(getenv("LOCREG_SORT_FRAC")) : 0.1;
+    static const double sort_bin = getenv("LOCREG_SORT_BIN") ? atof(getenv("LOCREG_SORT_BIN")) : 1.0;  // metres
+    static const int sort_bits = getenv("LOCREG_SORT_BITS") ? atoi(getenv("LOCREG_SORT_BITS")) : 24;
+    static const int sort_sub = getenv("LOCREG_SORT_SUB") ? std::min(5, std::max(0, atoi(getenv("LOCREG_SORT_SUB")))) : 3;  // Morton-ordered bins per hashed group: 2^sub per axis
+    // LOCREG_PYR_KERNEL: which kernel serves the long (sorted) queues - 0 (default) the shells (k_icp_nn_finish), 1 the
+    // block-pyramid walks with lane refill (k_icp_nn_pyr: 4x fewer candidates, measured slower - DESIGN section 8)
+    static const int pyr_kernel = getenv("LOCREG_PYR_KERNEL") ? atoi(getenv("LOCREG_PYR_KERNEL")) : 0;
+    // LOCREG_SORT_MIN: shortest queue that is sorted (tools/sanitize_reloc.py lowers it so that a tiny job runs the path)
+    static const unsigned int sort_min = getenv("LOCREG_SORT_MIN") ? static_cast<unsigned int>(std::max(1, atoi(getenv("LOCREG_SORT_MIN")))) : kWarpFinishMax;
+    const bool sortable = !small && sort_on && (job.bv.offsets == nullptr || sort_batch) && job.n_scratch_points < 0xFFFFFFFFull;
+    unsigned int long_min = 0xFFFFFFFFu;  // queues from this length on take the long-queue path (spatial order)
+    if (sortable)
+        long_min = static_cast<unsigned int>(std::max<double>(sort_min, std::min<double>(4.0e9, sort_frac * static_cast<double>(job.n_scratch_points))));
     {
         const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 3) / 4, static_cast<size_t>(h->num_sms) * 8));
         LR_LAUNCH(k_icp_nn_rings<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), stage2_track, queue,
-                  small ? 0xFFFFFFFFu : kWarpFinishMax);
+                  small ? 0xFFFFFFFFu : std::min(kWarpFinishMax, long_min));
     }
     if (!small) {
         const PyrView pyr = h->icp_map.pyramid();
-        // Relocalisation (hypotheses of one scan; LOCREG_SORT_BATCH=1: batches too): queues of LOCREG_SORT_FRAC x the job's
-        // points or more are put in spatial order first (k_queue_bin_count / scan / k_queue_bin_scatter).
-        static const int sort_on = getenv("LOCREG_SORT") ? atoi(getenv("LOCREG_SORT")) : 1;
-        static const int sort_batch = getenv("LOCREG_SORT_BATCH") ? atoi(getenv("LOCREG_SORT_BATCH")) : 0;
-        static const double sort_frac = getenv("LOCREG_SORT_FRAC") ? atof(getenv("LOCREG_SORT_FRAC")) : 0.1;
-        static const double sort_bin = getenv("LOCREG_SORT_BIN") ? atof(getenv("LOCREG_SORT_BIN")) : 1.0;  // metres
-        static const int sort_bits = getenv("LOCREG_SORT_BITS") ? atoi(getenv("LOCREG_SORT_BITS")) : 24;
-        static const int sort_sub = getenv("LOCREG_SORT_SUB") ? std::min(5, std::max(0, atoi(getenv("LOCREG_SORT_SUB")))) : 3;  // Morton-ordered bins per hashed group: 2^sub per axis
-        // LOCREG_PYR_KERNEL: which kernel serves the long (sorted) queues - 0 (default) the shells (k_icp_nn_finish), 1 the
-        // block-pyramid walks with lane refill (k_icp_nn_pyr: 4x fewer candidates, measured slower - DESIGN section 8)
-        static const int pyr_kernel = getenv("LOCREG_PYR_KERNEL") ? atoi(getenv("LOCREG_PYR_KERNEL")) : 0;
         RingQueue long_queue = queue;
-        unsigned int long_min = 0xFFFFFFFFu;  // queues from this length on take the long-queue path
-        const bool sortable = sort_on && (job.bv.offsets == nullptr || sort_batch) && job.n_scratch_points < 0xFFFFFFFFull;
         if (sortable) {
-            long_min = static_cast<unsigned int>(std::max<double>(kWarpFinishMax, std::min<double>(4.0e9, sort_frac * static_cast<double>(job.n_scratch_points))));
             const unsigned int buckets = 1u << sort_bits;
             h->d_sortq.reserve(job.n_scratch_points * sizeof(uint2));
             h->d_sortb.reserve(job.n_scratch_points * sizeof(unsigned int));
@@ -435,7 +438,7 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
         }
         const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * LR_FINISH_MIN_BLOCKS));
         LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), stage2_track, queue,
-                  kWarpFinishMax, long_min);
+                  std::min(kWarpFinishMax, long_min), long_min);
         if (long_min != 0xFFFFFFFFu) {
             if (pyr_kernel == 1 && pyr.levels != 0) {
                 const unsigned int gp = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * LR_PYR_MIN_BLOCKS));

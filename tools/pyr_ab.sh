@@ -1,8 +1,9 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-run() { echo "--- reloc $*"; env "$@" HYP=${HYP:-2048} timeout 300 python tools/reloc_breakdown.py 2>&1 | tail -1 | sed 's/.*total/total/'; }
 {
-run LOCREG_SORT=1
-for v in v1 v2 v3 v4; do run LOCREG_SO=liblocreg_$v.so; done
+for f in "LOCREG_SORT=0" "LOCREG_SORT_BATCH=1 LOCREG_SORT_FRAC=0.05" "LOCREG_SORT_BATCH=1 LOCREG_SORT_FRAC=0.05 LOCREG_SORT_BIN=2" "LOCREG_SORT_BATCH=1 LOCREG_SORT_FRAC=0.05 LOCREG_SORT_BIN=0.5 LOCREG_SORT_SUB=4" "LOCREG_SORT_BATCH=1 LOCREG_SORT_FRAC=0.001"; do
+  echo "--- batch $f"
+  env $f S=512 timeout 300 python tools/icp_breakdown.py 2>&1 | tail -1 | sed 's/.*total/total/'
+done
 } 2>&1 | tee gpurun_out/pyr_ab.log
