@@ -35,6 +35,10 @@ extern unsigned long long g_knn_stats[16];
 #define LR_STAT(i, v) ((void)0)
 #endif
 
+#ifndef LR_BLOCK_PRUNE
+#define LR_BLOCK_PRUNE 1
+#endif
+
 namespace locreg {
 
 struct __attribute__((aligned(32))) VoxelSlot {
@@ -648,11 +652,26 @@ LR_HD unsigned long long knn_shell_block_cells(const VoxelMapView& m, const KnnS
 // Cells of block (bx, by, bz) that belong to the shell: their points are offered to `res`.  bound (<= INFINITY) is an
 // additional acceptance / pruning bound on dis2 that does not come from `res` itself (the warp-cooperative search
 // passes the replicated global k-th distance while `res` is a lane's private set).
+// Conservative squared distance from the query to the 4x4x4 cells of block (bx, by, bz) (as knn_cell_min_d2)
+LR_HD float knn_block_min_d2(const VoxelMapView& m, const KnnCellFrame& c, int bx, int by, int bz, float magR) {
+    const int ox = bx << 2, oy = by << 2, oz = bz << 2;
+    const float gx = ox > c.fx ? static_cast<float>(ox - c.fx) - c.frx : (ox + 3 < c.fx ? static_cast<float>(c.fx - ox - 4) + c.frx : 0.0f);
+    const float gy = oy > c.fy ? static_cast<float>(oy - c.fy) - c.fry : (oy + 3 < c.fy ? static_cast<float>(c.fy - oy - 4) + c.fry : 0.0f);
+    const float gz = oz > c.fz ? static_cast<float>(oz - c.fz) - c.frz : (oz + 3 < c.fz ? static_cast<float>(c.fz - oz - 4) + c.frz : 0.0f);
+    const float sx = safe_gap(gx, magR, m.cell), sy = safe_gap(gy, magR, m.cell), sz = safe_gap(gz, magR, m.cell);
+    return (sx * sx + sy * sy + sz * sz) * 0.99999f;
+}
 template <int K>
 LR_HD void knn_shell_block(const VoxelMapView& m, const KnnCellFrame& c, const KnnShell& sh, int bx, int by, int bz,
                            float qx, float qy, float qz, float bound, KnnResult<K>& res) {
     unsigned long long occ = 0ull;
     unsigned int base = 0;
+#if LR_BLOCK_PRUNE
+    {   // a block the ball of the current K-th distance cannot reach is not even looked up
+        const float worst0 = fminf(bound, res.d2[K - 1]);
+        if (worst0 < INFINITY && knn_block_min_d2(m, c, bx, by, bz, c.mag + static_cast<float>(sh.R)) > worst0) { LR_STAT(15, 1); return; }
+    }
+#endif
     unsigned long long todo = knn_shell_block_cells(m, sh, bx, by, bz, occ, base);
     const int ox = bx << 2, oy = by << 2, oz = bz << 2;
     const float magR = c.mag + static_cast<float>(sh.R);

@@ -47,7 +47,7 @@ def _cloud(a):
 
 STAT_NAMES = ["fast_queries", "fast_candidates", "corner_queries", "corner_lists", "corner_candidates", "ring_queries",
               "ring_block_probes", "ring_candidates", "linear_scans", "skipped_searches", "pyr_queries", "pyr_probes",
-              "pyr_candidates", "pyr_child_tests", "pyr_cells"]
+              "pyr_candidates", "pyr_child_tests", "pyr_cells", "blocks_pruned"]
 
 
 def knn_stats():
