@@ -85,8 +85,9 @@ struct locreg_handle {
     DeviceVoxelMap icp_map;     // level 0: cells of knn_cell_size, neighbourhood lists
     DeviceVoxelMap icp_coarse[kCoarseLevels];  // cells 4x, 16x larger, block tables only (far queries)
     DeviceVoxelMap icp_mid;     // cells 2x larger, neighbourhood lists: stage 2 of the search (LOCREG_MID=0: off)
-    CoarseLevels coarse_views() const {
+    CoarseLevels coarse_views(int mid_shells = -1) const {  // -1: the default of the build (kMidShells)
         CoarseLevels c{};
+        c.mid_shells_p1 = mid_shells + 1;
         for (int l = 0; l < kCoarseLevels; ++l) c.lv[l] = icp_coarse[l].view();
         c.mid = icp_mid.view();
         c.pyr = icp_map.pyramid();  // levels == 0 unless LOCREG_PYR_KERNEL=1 asked for it (build_icp_maps)
@@ -444,8 +445,11 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
                 const unsigned int gp = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * LR_PYR_MIN_BLOCKS));
                 LR_LAUNCH(k_icp_nn_pyr<K>, gp, 128, 0, h->stream, map, pyr, job.bv, job.states, h->d_nnpos.as<unsigned int>(), stage2_track, long_queue, long_min);
             } else {
-                LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(), job.bv, job.states, h->d_nnpos.as<unsigned int>(), stage2_track,
-                          long_queue, long_min, 0xFFFFFFFFu);
+                // far-off hypotheses leave the mid level after two shells (LOCREG_RELOC_MID_SHELLS; measured -4 % against the
+                // batches' four, which in turn lose 25 % at two)
+                static const int reloc_mid_shells = getenv("LOCREG_RELOC_MID_SHELLS") ? std::max(0, atoi(getenv("LOCREG_RELOC_MID_SHELLS"))) : 1;
+                LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(job.bv.offsets == nullptr ? reloc_mid_shells : -1), job.bv, job.states,
+                          h->d_nnpos.as<unsigned int>(), stage2_track, long_queue, long_min, 0xFFFFFFFFu);
             }
         }
     }
@@ -1172,7 +1176,16 @@ static unsigned long long* relocalise_core(locreg_handle* h, const float4* src4,
         // scratch - planes, margins, queues - scales with it: ~4.5 GiB in all for P2Plane)
         const int K = h->opt.method == LOCREG_ICP_P2P ? 1 : 5;
         const size_t per_hyp = std::max<size_t>(n, 1) * K * sizeof(unsigned int);
-        const size_t wave = std::max<size_t>(1, std::min<size_t>(n_local, (size_t(1) << 30) / per_hyp));
+        // LOCREG_RELOC_WAVE_GIB: neighbour scratch per wave in GiB.  Default 4 (7857 hypotheses of a 27 k-point scan, ~20 GB
+        // of scratch in all; measured on 8192 hypotheses: 1.82 s at 1 GiB, 1.75 s at 2, 1.69 s at 4 - larger waves fill the
+        // bins of the spatially ordered stage-2 queue better), never more than a third of the free device memory
+        static const double wave_gib = getenv("LOCREG_RELOC_WAVE_GIB") ? std::min(16.0, std::max(0.01, atof(getenv("LOCREG_RELOC_WAVE_GIB")))) : 4.0;
+        size_t free_b = 0, total_b = 0;
+        LR_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_hyp_all = std::max<size_t>(n, 1) * (K * sizeof(unsigned int) + 80);  // + planes, margins, queues, flags
+        size_t wave = std::max<size_t>(1, std::min<size_t>(n_local, static_cast<size_t>(wave_gib * static_cast<double>(size_t(1) << 30)) / per_hyp));
+        wave = std::max<size_t>(1, std::min<size_t>(wave, free_b / 3 / per_hyp_all));
+        wave = std::min<size_t>(wave, (size_t(1) << 32) / std::max<size_t>(n, 1) - 1);  // scratch rows are 32-bit
         h->d_states.reserve(wave * sizeof(AlignState));
         for (size_t w0 = 0; w0 < n_local; w0 += wave) {
             const unsigned int W = static_cast<unsigned int>(std::min(wave, n_local - w0));

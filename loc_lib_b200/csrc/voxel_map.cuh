@@ -772,6 +772,7 @@ struct CoarseLevels {
     VoxelMapView mid;                // cells kMidFactor times the fine ones WITH neighbourhood lists; n_pts == 0: absent
     PyrView pyr;                     // block pyramid over the FINE level (levels == 0: absent)
     int pyr_mode;                    // 0: shells only; 1: pyramid after the mid level's list; 2: pyramid instead of the mid level
+    int mid_shells_p1;               // 1 + shells on the mid level before a coarse level takes over; 0: kMidShells (batches)
 };
 LR_HD const PyrSlot* find_pyr(const PyrView& py, int l, int nx, int ny, int nz) {
     const unsigned long long key = pack_block(nx, ny, nz);
@@ -1006,7 +1007,7 @@ LR_HD void knn_query_pyr(const VoxelMapView& m, const PyrView& py, float qx, flo
 // a seeded scan knows d6 as in knn_query_fast_track), else -1.
 template <int K>
 LR_HD bool knn_query_mid(const VoxelMapView& md, bool have_coarse, float qx, float qy, float qz, KnnResult<K>& res,
-                         float* margin = nullptr, bool list_only = false) {
+                         float* margin = nullptr, bool list_only = false, int mid_shells = kMidShells) {
     const KnnCellFrame c = knn_frame(md, qx, qy, qz);
     int boxes_done = 0;
     if (margin) *margin = -1.0f;
@@ -1028,8 +1029,8 @@ LR_HD bool knn_query_mid(const VoxelMapView& md, bool have_coarse, float qx, flo
         boxes_done = 1;
     }
     if (list_only) return false;  // the caller continues with the block pyramid
-    if (have_coarse && c.R0 > kMidShells) return false;
-    return knn_query_rings<K>(md, qx, qy, qz, res, boxes_done, have_coarse ? kMidShells : kBruteForceShell);
+    if (have_coarse && c.R0 > mid_shells) return false;
+    return knn_query_rings<K>(md, qx, qy, qz, res, boxes_done, have_coarse ? mid_shells : kBruteForceShell);
 }
 template <int K>
 LR_HD void knn_query_finish(const VoxelMapView& m, const CoarseLevels& coarse, float qx, float qy, float qz, KnnResult<K>& res,
@@ -1050,7 +1051,7 @@ LR_HD void knn_query_finish(const VoxelMapView& m, const CoarseLevels& coarse, f
     }
     if (coarse.mid.n_pts != 0) {
         LR_STAT(2, 1);  // queries entering stage 2a
-        if (knn_query_mid<K>(coarse.mid, have_coarse || pyr, qx, qy, qz, res, margin, pyr)) return;
+        if (knn_query_mid<K>(coarse.mid, have_coarse || pyr, qx, qy, qz, res, margin, pyr, coarse.mid_shells_p1 > 0 ? coarse.mid_shells_p1 - 1 : kMidShells)) return;
         if (margin) *margin = -1.0f;
         if (pyr) {  // what the mid level's list could not settle: ball query instead of shells
             knn_query_pyr<K>(m, coarse.pyr, qx, qy, qz, res);

@@ -497,3 +497,25 @@ def test_gpu_matches_golden_fixture():
     _, _, pose = ndt.ScanMatch(scan, init, want_cloud=False)
     dr, dt = pose_delta(pose, g["ndt_trace"][-1])
     assert dr < ROT_TOL and dt < TRANS_TOL
+
+
+@pytest.mark.gpu
+def test_relocalise_long_queue_paths_agree_bit_for_bit():
+    """Stage 2 of long queues: arrival order, spatial order (k_queue_bin_count / scatter) and the block-pyramid ball query
+    (k_icp_nn_pyr) must give the same neighbours, hence bit-identical poses of EVERY hypothesis.  Two Gauss-Newton
+    iterations + the score pass: all before the tracked iterations, whose margin shortcut keeps a neighbour SET in the
+    order of its last full search (which stage-2 kernel leaves which margins behind then shows up in the last bits of a
+    plane).  The switches are read once per process, so each variant runs tools/sanitize_reloc.py (96 hypotheses, two
+    thirds far off, LOCREG_SORT_MIN=1 so that the small queue takes the long-queue path) in its own process."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for name, env in (("arrival", {"LOCREG_SORT": "0", "LOCREG_SORT_MIN": "1"}), ("sorted", {}), ("pyramid", {"LOCREG_PYR_KERNEL": "1"})):
+        e = dict(os.environ); e.update(env); e["SANITIZE_RELOC_ITERS"] = "2"
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_reloc.py")], env=e, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [l.split(" launches")[0] for l in out.stdout.splitlines() if l.startswith("method")]
+        assert len(lines) == 2, out.stdout
+        outs[name] = (lines, [int(l.split("launches ")[1]) for l in out.stdout.splitlines() if l.startswith("method")])
+    assert outs["arrival"][0] == outs["sorted"][0] == outs["pyramid"][0], outs
+    assert outs["sorted"][1][0] > outs["arrival"][1][0]  # the sort kernels really ran

@@ -1,9 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-run() { echo "--- reloc $*"; env "$@" HYP=${HYP:-2048} timeout 300 python tools/reloc_breakdown.py 2>&1 | tail -1 | sed 's/.*total/total/'; }
+run() { echo "--- reloc $*"; env "$@" HYP=${HYP:-8192} timeout 300 python tools/reloc_breakdown.py 2>&1 | tail -1 | sed 's/.*total/total/'; }
 {
-run LOCREG_SORT=1
-echo "--- batch"; S=512 timeout 300 python tools/icp_breakdown.py 2>&1 | tail -1 | sed 's/.*total/total/'
-echo "--- track"; timeout 300 python tools/track_latency.py 2>&1 | tail -3
+run LOCREG_RELOC_MID_SHELLS=0
+run LOCREG_RELOC_MID_SHELLS=1
 } 2>&1 | tee gpurun_out/pyr_ab.log

@@ -21,8 +21,10 @@ hyp = np.stack([synth.perturb_pose(gt, synth.SEED_POSE + i) for i in range(96)])
 hyp[32:, 4:6] += rng.uniform(-12, 12, (64, 2))
 hyp[64:, 6] += rng.uniform(2, 9, 32)
 for method, k in ((L.IcpMethod.P2PLANE, 5), (L.IcpMethod.P2P, 1)):
-    r = L.IcpRegistration(L.IcpOptions(method_=method, max_iteration_=4, eps_=0.0))
+    r = L.IcpRegistration(L.IcpOptions(method_=method, max_iteration_=int(os.environ.get("SANITIZE_RELOC_ITERS", "4")), eps_=0.0))
     r.SetInputTarget(m)
     pose, idx, score, poses, results = r.Relocalise(scan, hyp, want_all=True)
-    print("method", int(method), "winner", idx, "score", score, "launches", r.last_timing()[1])
+    import hashlib
+    print("method", int(method), "winner", idx, "score", score, "poses", hashlib.sha1(np.ascontiguousarray(poses).tobytes()).hexdigest()[:16],
+          "launches", r.last_timing()[1])
 print("sanitize_reloc ok (sort_min=%s pyr_kernel=%s)" % (os.environ["LOCREG_SORT_MIN"], os.environ.get("LOCREG_PYR_KERNEL", "0")))
