@@ -630,12 +630,13 @@ def bench_reloc(ctx, reg, world, map_cloud):
                                   "%d rank(s)" % (len(hyp), len(scan), W), "hypotheses": len(hyp),
                       "collective": "ncclAllReduce(MIN, uint64 (score bits << 32 | global index), count 1) + ncclBroadcast(8 doubles) "
                                     "on the handle's stream inside locreg_relocalise_sharded" if W > 1 else "none (one rank)",
-                      "timing": "CUDA events of the handle (kernels + both collectives), max over ranks; per-point scratch of a wave ~4.5 GB (larger than L2)"},
+                      "stage2_queue": "spatial order (counting sort of the queued queries by 1 m bin, Morton order inside hashed 8 m groups), waves of 4 GiB neighbour scratch",
+                      "timing": "CUDA events of the handle (kernels + both collectives), max over ranks; per-point scratch of a wave ~20 GB (larger than L2)"},
            "e2e": {"value": len(hyp) / step_s, "unit": "hypotheses/s", "ms_per_step": step_s * 1e3,
                    "h2d_bytes_per_step": int(scan.nbytes + hyp.nbytes // W), "d2h_bytes_per_step": 8 + 8 * 8,
                    "api": "locreg_relocalise_sharded (host scan + hypotheses in, winner out; wall clock between barriers)"},
            "gpu_launches": int(launches), "clocks": clocks,
-           "roofline": {"bound": "hbm", "kernel": "whole pipeline (stage-2 search dominates: far hypotheses)",
+           "roofline": {"bound": "hbm", "kernel": "whole pipeline (stage-2 search k_icp_nn_finish on the spatially ordered queue dominates: far hypotheses)",
                         "achieved": algo / (kern_ms * 1e-3) / 1e9 / W, "peak": ctx.peak, "unit": "GB/s per GPU",
                         "frac": algo / (kern_ms * 1e-3) / 1e9 / W / ctx.peak, "traffic": None, "peak_source": ctx.peak_src,
                         "note": "96 B x scan points x 11 evaluations x hypotheses"},
