@@ -1179,7 +1179,7 @@ static unsigned long long* relocalise_core(locreg_handle* h, const float4* src4,
         // LOCREG_RELOC_WAVE_GIB: neighbour scratch per wave in GiB.  Default 4 (7857 hypotheses of a 27 k-point scan, ~20 GB
         // of scratch in all; measured on 8192 hypotheses: 1.82 s at 1 GiB, 1.75 s at 2, 1.69 s at 4 - larger waves fill the
         // bins of the spatially ordered stage-2 queue better), never more than a third of the free device memory
-        static const double wave_gib = getenv("LOCREG_RELOC_WAVE_GIB") ? std::min(16.0, std::max(0.01, atof(getenv("LOCREG_RELOC_WAVE_GIB")))) : 4.0;
+        static const double wave_gib = getenv("LOCREG_RELOC_WAVE_GIB") ? std::min(16.0, std::max(1e-5, atof(getenv("LOCREG_RELOC_WAVE_GIB")))) : 4.0;
         size_t free_b = 0, total_b = 0;
         LR_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const size_t per_hyp_all = std::max<size_t>(n, 1) * (K * sizeof(unsigned int) + 80);  // + planes, margins, queues, flags

@@ -510,12 +510,15 @@ def test_relocalise_long_queue_paths_agree_bit_for_bit():
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for name, env in (("arrival", {"LOCREG_SORT": "0", "LOCREG_SORT_MIN": "1"}), ("sorted", {}), ("pyramid", {"LOCREG_PYR_KERNEL": "1"})):
+    # "waves": 96 hypotheses in waves of 17 (0.0005 GiB of neighbour scratch) instead of one
+    for name, env in (("arrival", {"LOCREG_SORT": "0", "LOCREG_SORT_MIN": "1"}), ("sorted", {}), ("pyramid", {"LOCREG_PYR_KERNEL": "1"}),
+                      ("waves", {"LOCREG_RELOC_WAVE_GIB": "0.0005"})):
         e = dict(os.environ); e.update(env); e["SANITIZE_RELOC_ITERS"] = "2"
         out = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_reloc.py")], env=e, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
         lines = [l.split(" launches")[0] for l in out.stdout.splitlines() if l.startswith("method")]
         assert len(lines) == 2, out.stdout
         outs[name] = (lines, [int(l.split("launches ")[1]) for l in out.stdout.splitlines() if l.startswith("method")])
-    assert outs["arrival"][0] == outs["sorted"][0] == outs["pyramid"][0], outs
+    assert outs["arrival"][0] == outs["sorted"][0] == outs["pyramid"][0] == outs["waves"][0], outs
     assert outs["sorted"][1][0] > outs["arrival"][1][0]  # the sort kernels really ran
+    assert outs["waves"][1][0] > 2 * outs["arrival"][1][0]  # ... and so did six waves
