@@ -85,9 +85,10 @@ struct locreg_handle {
     DeviceVoxelMap icp_map;     // level 0: cells of knn_cell_size, neighbourhood lists
     DeviceVoxelMap icp_coarse[kCoarseLevels];  // cells 4x, 16x larger, block tables only (far queries)
     DeviceVoxelMap icp_mid;     // cells 2x larger, neighbourhood lists: stage 2 of the search (LOCREG_MID=0: off)
-    CoarseLevels coarse_views(int mid_shells = -1) const {  // -1: the default of the build (kMidShells)
+    CoarseLevels coarse_views(int mid_shells = -1, int coarse_shells = -1) const {  // -1: the defaults of the build
         CoarseLevels c{};
         c.mid_shells_p1 = mid_shells + 1;
+        c.coarse_shells_p1 = coarse_shells + 1;
         for (int l = 0; l < kCoarseLevels; ++l) c.lv[l] = icp_coarse[l].view();
         c.mid = icp_mid.view();
         c.pyr = icp_map.pyramid();  // levels == 0 unless LOCREG_PYR_KERNEL=1 asked for it (build_icp_maps)
@@ -448,7 +449,9 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
                 // far-off hypotheses leave the mid level after two shells (LOCREG_RELOC_MID_SHELLS; measured -4 % against the
                 // batches' four, which in turn lose 25 % at two)
                 static const int reloc_mid_shells = getenv("LOCREG_RELOC_MID_SHELLS") ? std::max(0, atoi(getenv("LOCREG_RELOC_MID_SHELLS"))) : 1;
-                LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map, h->coarse_views(job.bv.offsets == nullptr ? reloc_mid_shells : -1), job.bv, job.states,
+                static const int reloc_coarse_shells = getenv("LOCREG_RELOC_COARSE_SHELLS") ? std::max(1, atoi(getenv("LOCREG_RELOC_COARSE_SHELLS"))) : -1;
+                LR_LAUNCH(k_icp_nn_finish<K>, g, 128, 0, h->stream, map,
+                          h->coarse_views(job.bv.offsets == nullptr ? reloc_mid_shells : -1, job.bv.offsets == nullptr ? reloc_coarse_shells : -1), job.bv, job.states,
                           h->d_nnpos.as<unsigned int>(), stage2_track, long_queue, long_min, 0xFFFFFFFFu);
             }
         }

@@ -773,6 +773,7 @@ struct CoarseLevels {
     PyrView pyr;                     // block pyramid over the FINE level (levels == 0: absent)
     int pyr_mode;                    // 0: shells only; 1: pyramid after the mid level's list; 2: pyramid instead of the mid level
     int mid_shells_p1;               // 1 + shells on the mid level before a coarse level takes over; 0: kMidShells (batches)
+    int coarse_shells_p1;            // 1 + shells on a coarse level that has a coarser one behind it; 0: kCoarseShells
 };
 LR_HD const PyrSlot* find_pyr(const PyrView& py, int l, int nx, int ny, int nz) {
     const unsigned long long key = pack_block(nx, ny, nz);
@@ -1074,8 +1075,9 @@ LR_HD void knn_query_finish(const VoxelMapView& m, const CoarseLevels& coarse, f
         if (cl.n_pts == 0) break;
         const bool last = l + 1 == kCoarseLevels || coarse.lv[l + 1].n_pts == 0;
         // leave a level early (6 shells) when a coarser one can take over, so that far queries climb quickly
-        if (!last && knn_frame(cl, qx, qy, qz).R0 > kCoarseShells) continue;
-        if (knn_query_rings<K>(cl, qx, qy, qz, res, 0, last ? kBruteForceShell : kCoarseShells)) return;
+        const int shells = coarse.coarse_shells_p1 > 0 ? coarse.coarse_shells_p1 - 1 : kCoarseShells;
+        if (!last && knn_frame(cl, qx, qy, qz).R0 > shells) continue;
+        if (knn_query_rings<K>(cl, qx, qy, qz, res, 0, last ? kBruteForceShell : shells)) return;
     }
     LR_STAT(8, 1);  // linear scans
     knn_init(res);
