@@ -224,7 +224,7 @@ def _traffic(kernel_names, grid=None):
     if not recs:
         return None
     if grid is None:
-        grid = max(r["grid"] for r in recs)  # the whole batch (halves of it = the e2e chunks, small grids = single scans)
+        grid = max(r["grid"] for r in recs)  # the whole batch (smaller grids = the e2e chunks and single scans)
     tot = sum(r["mean_bytes"] * r["launches"] for r in recs if r["grid"] == grid)
     cnt = sum(r["launches"] for r in recs if r["grid"] == grid)
     return tot / cnt if cnt else None

@@ -82,6 +82,8 @@ struct locreg_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t copy_stream = nullptr;        // host->device copies of later chunks overlap the compute of earlier ones
     std::vector<cudaEvent_t> chunk_events;     // locreg_align_batch
+    std::vector<cudaStream_t> chunk_streams;   // compute streams of the chunks after the first (they run concurrently)
+    std::vector<cudaEvent_t> chunk_done;       // ... and the events that join them into `stream`
     DeviceVoxelMap icp_map;     // level 0: cells of knn_cell_size, neighbourhood lists
     DeviceVoxelMap icp_coarse[kCoarseLevels];  // cells 4x, 16x larger, block tables only (far queries)
     DeviceVoxelMap icp_mid;     // cells 2x larger, neighbourhood lists: stage 2 of the search (LOCREG_MID=0: off)
@@ -318,6 +320,10 @@ struct IcpJob {
     AlignState* states = nullptr;
     unsigned int n_tiles = 0;       // grid of the per-point kernels (an upper bound is fine: surplus tiles exit)
     size_t n_scratch_points = 0;    // rows of the per-point scratch arrays
+    // Chunks of one batch that run CONCURRENTLY on their own streams (align_batch_resident) each own a slice of the
+    // handle's per-job scratch: partial rows (doubles into d_partials), queue counters (uints into d_ringc), queue
+    // entries (into d_ringq).  The per-point arrays are indexed by absolute point number and need no slicing.
+    size_t partials_off = 0, ringc_off = 0, ringq_off = 0;
 };
 
 // nn_mode: kNnSeeds when the per-point neighbour scratch still holds THIS job's previous iteration, kNnTwoPass for the
@@ -329,7 +335,6 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
     constexpr int K = METHOD == kIcpP2P ? 1 : 5;
     const VoxelMapView map = h->icp_map.view();
     h->d_nnpos.reserve(job.n_scratch_points * K * sizeof(unsigned int));
-    h->d_partials.reserve(2 * static_cast<size_t>(job.n_tiles) * kPartialDoubles * sizeof(double));
     h->d_ringq.reserve(job.n_scratch_points * sizeof(uint2));
     h->d_track.reserve(job.n_scratch_points * sizeof(KnnTrack));
     // P2Plane: per-point plane (k_icp_fit) and the flag that says it still belongs to the point's current neighbours
@@ -340,15 +345,18 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
         h->d_plane.reserve(job.n_scratch_points * 4 * sizeof(double));
         h->d_pstat.reserve(job.n_scratch_points);
     }
-    h->d_ringc.reserve(2 * sizeof(unsigned int));
     // k_icp_post re-zeroes the counters after every use; the first evaluation of a job starts from a known state
-    if (!(nn_mode & kNnSeeds)) LR_CUDA(cudaMemsetAsync(h->d_ringc.p, 0, 2 * sizeof(unsigned int), h->stream));
+    h->d_partials.reserve((job.partials_off + 2 * static_cast<size_t>(job.n_tiles) * kPartialDoubles) * sizeof(double));
+    h->d_ringc.reserve((job.ringc_off + 2) * sizeof(unsigned int));
+    unsigned int* const ringc = h->d_ringc.as<unsigned int>() + job.ringc_off;
+    double* const partials_a = h->d_partials.as<double>() + job.partials_off;
+    if (!(nn_mode & kNnSeeds)) LR_CUDA(cudaMemsetAsync(ringc, 0, 2 * sizeof(unsigned int), h->stream));
     if (job.n_tiles == 0) return nullptr;
-    const RingQueue queue{h->d_ringc.as<unsigned int>(), h->d_ringq.as<uint2>()};
+    const RingQueue queue{ringc, h->d_ringq.as<uint2>() + job.ringq_off};
     // P2Plane, tracked iterations: search + residual + normal equations in one pass (icp_fused.cuh)
     static const int fused_on = getenv("LOCREG_FUSED") ? atoi(getenv("LOCREG_FUSED")) : 0;
     const bool fused = METHOD == kIcpP2Plane && (nn_mode & kNnFused) && !gate && !nn_idx && fused_on;
-    double* partials_b = h->d_partials.as<double>() + static_cast<size_t>(job.n_tiles) * kPartialDoubles;
+    double* partials_b = partials_a + static_cast<size_t>(job.n_tiles) * kPartialDoubles;
     // searches that look at every point of the tile: candidate lists staged in shared memory (icp_staged.cuh)
     // LOCREG_STAGED: bit 0 = the unseeded first iteration (measured 1.51 ms against 1.75 ms per 14.1 M points), bit 1 =
     // seeded searches, bit 2 = the first tracked one (both measured slower than k_icp_nn, 1.8 against 1.5-1.7 ms: with
@@ -371,7 +379,7 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
         const RingQueue rescan{h->d_rescanc.as<unsigned int>(), h->d_rescanq.as<uint2>()};
         LR_CUDA(cudaMemsetAsync(h->d_rescanc.p, 0, 2 * sizeof(unsigned int), h->stream));
         LR_LAUNCH(k_icp_track_p2plane, job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
-                  h->d_track.as<KnnTrack>(), rescan, h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(), h->d_partials.as<double>());
+                  h->d_track.as<KnnTrack>(), rescan, h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(), partials_a);
         const unsigned int g = static_cast<unsigned int>(std::min<size_t>((job.n_scratch_points + 127) / 128, static_cast<size_t>(h->num_sms) * 8));
         LR_LAUNCH(k_icp_rescan, g, 128, 0, h->stream, map, job.bv, job.states, h->d_nnpos.as<unsigned int>(), h->d_same.as<unsigned char>(),
                   h->d_track.as<KnnTrack>(), queue, rescan);
@@ -466,7 +474,7 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
                   h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(), rescan);
         LR_LAUNCH(k_icp_pending, (job.n_tiles + group - 1) / group, kTile, 0, h->stream, h->icp_params(), job.bv, job.states, ignore_stop,
                   h->d_same.as<unsigned char>(), h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(), group, partials_b,
-                  h->d_ringc.as<unsigned int>());
+                  ringc);
         prof_mark(h, 1, false);
         return partials_b;
     }
@@ -478,7 +486,7 @@ const double* icp_launch_eval(locreg_handle* h, const IcpJob& job, int ignore_st
                   h->d_nnpos.as<unsigned int>(), h->d_same.as<unsigned char>(), h->d_plane.as<double>(), h->d_pstat.as<unsigned char>(), group);
     }
     LR_LAUNCH(k_icp_post<METHOD>, job.n_tiles, kTile, 0, h->stream, map, h->icp_params(), job.bv, job.states, ignore_stop,
-              h->d_nnpos.as<unsigned int>(), h->d_partials.as<double>(), gate, nn_idx, h->d_ringc.as<unsigned int>(),
+              h->d_nnpos.as<unsigned int>(), partials_a, gate, nn_idx, ringc,
               cache ? h->d_plane.as<double>() : nullptr, cache ? h->d_pstat.as<unsigned char>() : nullptr);
     prof_mark(h, 1, false);
     return nullptr;
@@ -487,7 +495,7 @@ template <int METHOD>
 void icp_launch_solve(locreg_handle* h, const IcpJob& job, int mode, double* acc_out, const double* partials_b = nullptr) {
     prof_mark(h, 2, true);
     LR_LAUNCH(k_icp_solve<METHOD>, (job.bv.S + 3) / 4, 128, 0, h->stream, h->icp_params(), job.bv, job.states,
-              h->d_partials.as<double>(), partials_b, mode, acc_out);
+              h->d_partials.as<double>() + job.partials_off, partials_b, mode, acc_out);
     prof_mark(h, 2, false);
 }
 // The whole Gauss-Newton loop, queued on the stream without a host round-trip; stopped scans make their tiles exit.
@@ -593,21 +601,24 @@ IcpJob icp_single_job(locreg_handle* h, const float4* src, unsigned int n) {
     return job;
 }
 // offsets on the device; total = number of points covered by the offsets
-IcpJob icp_batch_job(locreg_handle* h, const float4* src, const long long* d_offsets, unsigned int S, size_t total) {
+// tile_off / tb_off: this job's slice of d_tiles / d_tile_begin (chunks of a batch that run concurrently)
+IcpJob icp_batch_job(locreg_handle* h, const float4* src, const long long* d_offsets, unsigned int S, size_t total, size_t tile_off = 0,
+                     size_t tb_off = 0) {
     IcpJob job;
-    h->d_tile_begin.reserve((static_cast<size_t>(S) + 1) * sizeof(unsigned int));
+    h->d_tile_begin.reserve((tb_off + static_cast<size_t>(S) + 1) * sizeof(unsigned int));
     h->d_states.reserve(static_cast<size_t>(S) * sizeof(AlignState));
-    LR_LAUNCH(k_tile_begin, 1, 1024, 0, h->stream, d_offsets, S, h->d_tile_begin.as<unsigned int>());
-    job.bv.src = src; job.bv.offsets = d_offsets; job.bv.tile_begin = h->d_tile_begin.as<unsigned int>();
+    unsigned int* const tile_begin = h->d_tile_begin.as<unsigned int>() + tb_off;
+    LR_LAUNCH(k_tile_begin, 1, 1024, 0, h->stream, d_offsets, S, tile_begin);
+    job.bv.src = src; job.bv.offsets = d_offsets; job.bv.tile_begin = tile_begin;
     job.bv.n_single = 0; job.bv.tiles_per_item = 0; job.bv.S = S;
     job.states = h->d_states.as<AlignState>();
     job.n_tiles = static_cast<unsigned int>(std::min<size_t>(total / kTile + S, 0x7fffffffu));
     job.n_scratch_points = total;
     job.bv.tiles = nullptr;
     if (job.n_tiles) {
-        h->d_tiles.reserve(static_cast<size_t>(job.n_tiles) * sizeof(TileRec));
-        LR_LAUNCH(k_tile_table, (job.n_tiles + 255) / 256, 256, 0, h->stream, job.bv, job.n_tiles, h->d_tiles.as<TileRec>());
-        job.bv.tiles = h->d_tiles.as<TileRec>();
+        h->d_tiles.reserve((tile_off + static_cast<size_t>(job.n_tiles)) * sizeof(TileRec));
+        LR_LAUNCH(k_tile_table, (job.n_tiles + 255) / 256, 256, 0, h->stream, job.bv, job.n_tiles, h->d_tiles.as<TileRec>() + tile_off);
+        job.bv.tiles = h->d_tiles.as<TileRec>() + tile_off;
         job.bv.n_table_tiles = job.n_tiles;
     }
     return job;
@@ -736,6 +747,8 @@ int locreg_destroy(locreg_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->chunk_done) cudaEventDestroy(e);
+    for (cudaStream_t st : h->chunk_streams) cudaStreamDestroy(st);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->comm && nccl_api().ok()) nccl_api().CommDestroy(h->comm);
     h->clear_keyframes();
@@ -1002,7 +1015,45 @@ static void align_batch_resident(locreg_handle* h, const float* srcs, const int6
     LR_CUDA(cudaStreamSynchronize(h->stream));  // rel[] is pageable
     const unsigned int Su = static_cast<unsigned int>(S);
     if (pipelined) {
-        static const size_t kChunks = getenv("LOCREG_CHUNKS") ? std::max(1, atoi(getenv("LOCREG_CHUNKS"))) : 2;  // measured on B200 together with the size ratio below: 2 chunks at 1:8 give 712 M points/s end to end, equal halves 674 M, 3 chunks 658-682 M, 4 chunks 621 M
+        // LOCREG_CHUNK_STREAMS (default 1): every chunk runs its Gauss-Newton loop on its own stream as soon as its copy has
+        // landed, concurrently with the chunks before it.  A chunk's loop is ~70 dependent kernels, each ending in a tail
+        // in which the GPU drains (measured: +1.1 to 1.8 ms per additional chunk when the chunks run one after the other);
+        // the blocks of another chunk's kernels fill those tails.  Each chunk owns a slice of the per-job scratch (IcpJob).
+        static const int streams_env = getenv("LOCREG_CHUNK_STREAMS") ? atoi(getenv("LOCREG_CHUNK_STREAMS")) : 1;
+        static const bool fused_env = getenv("LOCREG_FUSED") && atoi(getenv("LOCREG_FUSED")) != 0;
+        static const bool sort_batch_env = getenv("LOCREG_SORT_BATCH") && atoi(getenv("LOCREG_SORT_BATCH")) != 0;
+        const bool may_run_concurrently = streams_env && !h->profile && !fused_env && !sort_batch_env;
+        // Chunk weights (relative point counts): LOCREG_CHUNK_WEIGHTS="w0,w1,...", else LOCREG_CHUNKS chunks growing by
+        // LOCREG_CHUNK_RATIO, else the measured optimum.  Only the first chunk's copy is exposed, and a chunk's copy hides
+        // behind the compute of the chunks before it (compute takes ~4x as long as the copy of the same points).
+        // Measured on B200 (512 scans, 226 MB, profiles/r2_chunk_streams.txt), M points/s end to end:
+        //   concurrent chunks: 1:2:3:3 782, 1:3:3:3 780, 1:4:4 777, 1:1:1:1 772, 1:4 726, 1:8 707   (resident: 827)
+        //   one after the other: 1:8 707, 1:4:4 669, 1:3:4:4 616, equal halves 674
+        static const std::vector<double> kEnvWeights = []() {
+            std::vector<double> w;
+            if (const char* e = getenv("LOCREG_CHUNK_WEIGHTS")) {
+                for (const char* p = e; *p;) {
+                    char* end = nullptr;
+                    const double v = strtod(p, &end);
+                    if (end == p) break;
+                    if (v > 0.0) w.push_back(v);
+                    if (*end != ',') break;
+                    p = end + 1;
+                }
+                if (w.size() > 16) w.resize(16);
+            } else if (getenv("LOCREG_CHUNKS") || getenv("LOCREG_CHUNK_RATIO")) {
+                const size_t n = getenv("LOCREG_CHUNKS") ? std::max(1, std::min(16, atoi(getenv("LOCREG_CHUNKS")))) : 2;
+                const double ratio = getenv("LOCREG_CHUNK_RATIO") ? std::min(16.0, std::max(1.0, atof(getenv("LOCREG_CHUNK_RATIO")))) : 8.0;
+                double v = 1.0;
+                for (size_t c = 0; c < n; ++c, v *= ratio) w.push_back(v);
+            }
+            return w;
+        }();
+        static const std::vector<double> kConcurrentWeights{1.0, 2.0, 3.0, 3.0}, kSerialWeights{1.0, 8.0};
+        // (four chunks only where every one of them still fills the GPU: from 4 M points on)
+        const std::vector<double>& kWeights =
+            !kEnvWeights.empty() ? kEnvWeights : (may_run_concurrently && n_pts >= (4u << 20) ? kConcurrentWeights : kSerialWeights);
+        const size_t kChunks = kWeights.size();
         if (!h->copy_stream) LR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         while (h->chunk_events.size() < kChunks) {
             cudaEvent_t e;
@@ -1014,16 +1065,10 @@ static void align_batch_resident(locreg_handle* h, const float* srcs, const int6
         h->d_states.reserve(S * sizeof(AlignState));
         // chunk boundaries: whole scans, about equal point counts
         std::vector<size_t> cut{0};
-        // The first chunk's copy is the one nothing hides, and a chunk's copy hides behind the compute of the chunk before
-        // it (compute takes ~4x as long as the copy of the same points): chunk sizes grow geometrically, ratio
-        // LOCREG_CHUNK_RATIO (default 8; 1 = equal chunks).
-        static const double kRatio = getenv("LOCREG_CHUNK_RATIO") ? std::min(16.0, std::max(1.0, atof(getenv("LOCREG_CHUNK_RATIO")))) : 8.0;
-        double total_w = 0.0, acc_w = 0.0, w = 1.0;
-        for (size_t c = 0; c < kChunks; ++c, w *= kRatio) total_w += w;
-        w = 1.0;
+        double total_w = 0.0, acc_w = 0.0;
+        for (size_t c = 0; c < kChunks; ++c) total_w += kWeights[c];
         for (size_t c = 1; c < kChunks; ++c) {
-            acc_w += w;
-            w *= kRatio;
+            acc_w += kWeights[c - 1];
             const long long want = static_cast<long long>(static_cast<double>(n_pts) * acc_w / total_w);
             size_t s = std::lower_bound(rel.begin(), rel.end(), want) - rel.begin();
             s = std::min(std::max(s, cut.back()), S);
@@ -1037,31 +1082,73 @@ static void align_batch_resident(locreg_handle* h, const float* srcs, const int6
                                         (p1 - p0) * stride, cudaMemcpyHostToDevice, h->copy_stream));
             LR_CUDA(cudaEventRecord(h->chunk_events[c], h->copy_stream));
         }
+        const bool concurrent = may_run_concurrently && kChunks > 1;
+        std::vector<size_t> tile_off(kChunks + 1, 0);
+        for (size_t c = 0; c < kChunks; ++c) {
+            const size_t pts = static_cast<size_t>(rel[cut[c + 1]] - rel[cut[c]]);
+            tile_off[c + 1] = tile_off[c] + pts / kTile + (cut[c + 1] - cut[c]);  // icp_batch_job's n_tiles
+        }
+        if (concurrent) {
+            // everything the chunks share is allocated before the first launch: a later reserve() must never move a buffer
+            const size_t K5 = h->opt.method == LOCREG_ICP_P2P ? 1 : 5;
+            h->d_partials.reserve(2 * tile_off[kChunks] * kPartialDoubles * sizeof(double));
+            h->d_tiles.reserve(tile_off[kChunks] * sizeof(TileRec));
+            h->d_tile_begin.reserve((S + kChunks) * sizeof(unsigned int));
+            h->d_ringc.reserve(2 * kChunks * sizeof(unsigned int));
+            h->d_nnpos.reserve(n_pts * K5 * sizeof(unsigned int));
+            h->d_ringq.reserve(n_pts * sizeof(uint2));
+            h->d_track.reserve(n_pts * sizeof(KnnTrack));
+            if (h->opt.method == LOCREG_ICP_P2PLANE) {
+                h->d_same.reserve(n_pts);
+                h->d_plane.reserve(n_pts * 4 * sizeof(double));
+                h->d_pstat.reserve(n_pts);
+            }
+            while (h->chunk_streams.size() + 1 < kChunks) {
+                cudaStream_t st;
+                LR_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                h->chunk_streams.push_back(st);
+                cudaEvent_t e;
+                LR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->chunk_done.push_back(e);
+            }
+        }
         h->begin_timing();
-        long long launches = 0;
+        cudaStream_t const main_stream = h->stream;
         for (size_t c = 0; c < kChunks; ++c) {
             const size_t s0 = cut[c], s1 = cut[c + 1];
+            // (the launch helpers below issue on h->stream: it is the chunk's stream while the chunk is being queued)
+            if (concurrent && c > 0) h->stream = h->chunk_streams[c - 1];
+            struct Restore { locreg_handle* h; cudaStream_t s; ~Restore() { h->stream = s; } } restore{h, main_stream};
             LR_CUDA(cudaStreamWaitEvent(h->stream, h->chunk_events[c], 0));
-            if (s1 == s0) continue;
-            const size_t p0 = static_cast<size_t>(rel[s0]), p1 = static_cast<size_t>(rel[s1]);
-            const unsigned int Sc = static_cast<unsigned int>(s1 - s0);
-            if (stride != 16 && p1 > p0) {
-                const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((p1 - p0 + 255) / 256, 4096));
-                LR_LAUNCH(k_pack_float4, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>() + p0 * stride, p1 - p0, stride,
-                          h->d_src4.as<float4>() + p0);
+            if (s1 > s0) {
+                const size_t p0 = static_cast<size_t>(rel[s0]), p1 = static_cast<size_t>(rel[s1]);
+                const unsigned int Sc = static_cast<unsigned int>(s1 - s0);
+                if (stride != 16 && p1 > p0) {
+                    const unsigned int grid = static_cast<unsigned int>(std::min<size_t>((p1 - p0 + 255) / 256, 4096));
+                    LR_LAUNCH(k_pack_float4, grid, 256, 0, h->stream, h->d_raw.as<unsigned char>() + p0 * stride, p1 - p0, stride,
+                              h->d_src4.as<float4>() + p0);
+                }
+                const float4* all4 = stride == 16 ? h->d_raw.as<float4>() : h->d_src4.as<float4>();
+                // offsets stay absolute (into the whole batch); only the scan range of the job moves
+                IcpJob job = icp_batch_job(h, all4, h->d_offsets.as<long long>() + s0, Sc, p1 - p0, concurrent ? tile_off[c] : 0,
+                                           concurrent ? s0 + c : 0);
+                job.states = h->d_states.as<AlignState>() + s0;
+                job.n_scratch_points = n_pts;  // scratch rows are indexed by absolute point number
+                if (concurrent) {
+                    job.partials_off = 2 * tile_off[c] * kPartialDoubles;
+                    job.ringc_off = 2 * c;
+                    job.ringq_off = p0;
+                }
+                LR_LAUNCH(k_states_init, (Sc + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>() + s0 * 7, Sc, h->opt.max_iteration, h->opt.zero_initial_translation, job.states);
+                ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
+                LR_LAUNCH(k_states_export, (Sc + 255) / 256, 256, 0, h->stream, job.states, Sc, h->d_poses_out.as<double>() + s0 * 7,
+                          h->d_results.as<DevResult>() + s0);
             }
-            const float4* all4 = stride == 16 ? h->d_raw.as<float4>() : h->d_src4.as<float4>();
-            // offsets stay absolute (into the whole batch); only the scan range of the job moves
-            IcpJob job = icp_batch_job(h, all4, h->d_offsets.as<long long>() + s0, Sc, p1 - p0);
-            job.states = h->d_states.as<AlignState>() + s0;
-            job.n_scratch_points = n_pts;  // scratch rows are indexed by absolute point number
-            LR_LAUNCH(k_states_init, (Sc + 255) / 256, 256, 0, h->stream, h->d_poses_in.as<double>() + s0 * 7, Sc, h->opt.max_iteration, h->opt.zero_initial_translation, job.states);
-            ICP_DISPATCH(h, icp_run_loop<M>(h, job, 0));
-            LR_LAUNCH(k_states_export, (Sc + 255) / 256, 256, 0, h->stream, job.states, Sc, h->d_poses_out.as<double>() + s0 * 7,
-                      h->d_results.as<DevResult>() + s0);
-            launches = g_launch_count;
+            if (concurrent && c > 0) {  // the handle's stream ends after every chunk has
+                LR_CUDA(cudaEventRecord(h->chunk_done[c - 1], h->stream));
+                LR_CUDA(cudaStreamWaitEvent(main_stream, h->chunk_done[c - 1], 0));
+            }
         }
-        (void)launches;
         h->end_timing();
     } else {
         h->begin_timing();

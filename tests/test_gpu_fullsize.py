@@ -113,6 +113,18 @@ def test_fullsize_pipelined_batch_equals_plain_batch(full):
     wide[:, :3] = clouds[:, :3]
     piped32, _ = full.reg.ScanMatchBatch(wide, offsets, init)
     assert np.array_equal(plain, piped32)
+    # from 4 M points on the batch is cut into four chunks that run concurrently on their own streams, each on its own
+    # slice of the per-job scratch (locreg.cu, align_batch_resident): the same poses again
+    reps = 7  # 168 scans, 4.6 M points
+    clouds = np.concatenate(full.scans * reps)
+    offsets = np.concatenate([[0], np.cumsum([len(s) for s in full.scans * reps])]).astype(np.int64)
+    init = np.concatenate([full.init] * reps)
+    assert len(clouds) >= (4 << 20)
+    pinned = torch.from_numpy(clouds).pin_memory().numpy()
+    piped4, res4 = full.reg.ScanMatchBatch(pinned, offsets, init)
+    for r in range(reps):
+        assert np.array_equal(piped4[r * full.S:(r + 1) * full.S], plain[:full.S])
+        assert res4[r * full.S:(r + 1) * full.S] == res_plain[:full.S]
 
 
 def test_fullsize_idempotent_at_convergence_and_oracle_spot_check(full):
