@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scans-per-gpu", type=int, default=512)
     ap.add_argument("--map-points", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample-scans", type=int, default=8)
+    ap.add_argument("--cpu-sample-scans", type=int, default=32)  # ~11 s of one host core (the contract asks for 10-30 s)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--configs", default="C4S,C3,C5,LIO",
                     help="comma list of the extra measurements after the headline (C4S, C3, C5, LIO); 'none' = headline only")
