@@ -1049,10 +1049,13 @@ static void align_batch_resident(locreg_handle* h, const float* srcs, const int6
             }
             return w;
         }();
-        static const std::vector<double> kConcurrentWeights{1.0, 2.0, 3.0, 3.0}, kSerialWeights{1.0, 8.0};
-        // (four chunks only where every one of them still fills the GPU: from 4 M points on)
-        const std::vector<double>& kWeights =
-            !kEnvWeights.empty() ? kEnvWeights : (may_run_concurrently && n_pts >= (4u << 20) ? kConcurrentWeights : kSerialWeights);
+        static const std::vector<double> kConcurrentWeights{1.0, 2.0, 3.0, 3.0}, kSerialWeights{1.0, 8.0}, kHugeWeights{1.0, 3.0, 9.0, 27.0, 41.0};
+        // (four chunks only where every one of them still fills the GPU: from 4 M points on.  What is exposed is the FIRST
+        // chunk's copy, and ~25 MB is as small as it usefully gets: a 4096-scan batch (113 M points, 1.8 GB) measured 875 M
+        // points/s end to end at 1:3:9:27:41 against 824 M at 1:2:3:3 and 936 M resident - profiles/r2_chunk_streams.txt)
+        const std::vector<double>& kWeights = !kEnvWeights.empty() ? kEnvWeights
+                                              : !may_run_concurrently || n_pts < (4u << 20) ? kSerialWeights
+                                              : n_pts < (32u << 20) ? kConcurrentWeights : kHugeWeights;
         const size_t kChunks = kWeights.size();
         if (!h->copy_stream) LR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         while (h->chunk_events.size() < kChunks) {
