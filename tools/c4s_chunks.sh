@@ -1,3 +1,5 @@
+# Config 4 as written (4096 scans, 1.8 GB pinned) end to end on one GPU for two chunkings of the copy / compute overlap:
+# weights:streams pairs, one bench.py run each (GPU box: bash tools/c4s_chunks.sh > gpurun_out/r2_c4s_chunks.txt).
 for cfg in "1,3,9,27,41:1" "1,3,9,27,41:0"; do
   w=${cfg%%:*}; s=${cfg##*:}
   line=$(LOCREG_CHUNK_WEIGHTS="$w" LOCREG_CHUNK_STREAMS=$s timeout 27 python bench.py --configs C4S --no-cpu-baseline --steps 5 --warmup 3 2>/dev/null | tail -1)
